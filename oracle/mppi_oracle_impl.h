@@ -1,0 +1,420 @@
+/*
+ * TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+ *
+ * CPU restatement of the NicolayP/mppi-tf update step, one C function per
+ * reference sub-graph, written op-for-op so that every known-answer test of
+ * the reference (test/test_{model,cost,controller,utile}.cpp) can be replayed
+ * against it.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference leg may use it.
+ *
+ * This file is included twice by mppi_oracle.c: once with REAL=float
+ * (the reference's DT_FLOAT graph) and once with REAL=double (the Python
+ * twin's fp64 graph, used as the "exact" value in tolerance tests).
+ *
+ * All file:line citations are relative to /root/reference.
+ *
+ * Layouts (row-major, the reference's trailing singleton dim dropped):
+ *   state  [k][s]      reference [k, s, 1]
+ *   action [k][a]      reference [k, a, 1]
+ *   noise  [k][T][a]   reference [k, T, a, 1]
+ *   U      [T][a]      reference [T, a, 1]
+ */
+
+#ifndef REAL
+#error "include from mppi_oracle.c"
+#endif
+
+#define CAT_(a, b) a##b
+#define CAT(a, b) CAT_(a, b)
+#define FN(name) CAT(name, SUFFIX)
+
+/* utile::blockDiag — src/utile.cpp:10-43.  `in` is [rows][cols]; the result is
+ * the nb-fold block diagonal [nb*rows][nb*cols] (zero padding elsewhere). */
+void FN(orc_block_diag)(const REAL *in, int rows, int cols, int nb, REAL *out)
+{
+    int R = rows * nb, C = cols * nb;
+    for (int i = 0; i < R * C; i++) out[i] = (REAL)0;
+    for (int b = 0; b < nb; b++)
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < cols; c++)
+                out[(b * rows + r) * C + (b * cols + c)] = in[r * cols + c];
+}
+
+/* A = blockDiag([[1,dt],[0,1]], s/2) — src/model_base.cpp:59-64.
+ * B = blockDiag([[dt*dt/2],[dt]] / mass, a) — src/model_base.cpp:70-78; the
+ * mass is the constructor argument as pinned by test/test_model.cpp:123-125
+ * (the "mass" Variable of :27-32 is never assigned at HEAD). */
+void FN(orc_model_matrices)(REAL mass, REAL dt, int s, int a, REAL *A, REAL *B)
+{
+    REAL a_blk[4] = {(REAL)1, dt, (REAL)0, (REAL)1};
+    REAL b_blk[2] = {(dt * dt) / (REAL)2 / mass, dt / mass};
+    FN(orc_block_diag)(a_blk, 2, 2, s / 2, A);
+    FN(orc_block_diag)(b_blk, 2, 1, a, B);
+}
+
+/* BatchMatMul(M[r][c], v[k|1][c][1]) with the matrix broadcast over the batch
+ * (model_base.cpp:65-67, :79-81).  Dense on purpose: the reference multiplies
+ * by the full block-diagonal matrix, zeros included. */
+static void FN(orc_bmm_bcast)(const REAL *M, int r, int c, const REAL *v, int k, REAL *out)
+{
+    for (int i = 0; i < k; i++)
+        for (int row = 0; row < r; row++) {
+            REAL acc = (REAL)0;
+            for (int col = 0; col < c; col++) acc += M[row * c + col] * v[i * c + col];
+            out[i * r + row] = acc;
+        }
+}
+
+/* ModelBase::mBuildFreeStepGraph — src/model_base.cpp:59-68.  A x, state [kst][s]. */
+void FN(orc_model_free_step)(REAL mass, REAL dt, int s, int a, int kst, const REAL *state, REAL *out)
+{
+    REAL A[ORC_MAX_S * ORC_MAX_S], B[ORC_MAX_S * ORC_MAX_A];
+    FN(orc_model_matrices)(mass, dt, s, a, A, B);
+    FN(orc_bmm_bcast)(A, s, s, state, kst, out);
+}
+
+/* ModelBase::mBuildActionStepGraph — src/model_base.cpp:70-82.  (B/m) u, action [k][a]. */
+void FN(orc_model_action_step)(REAL mass, REAL dt, int s, int a, int k, const REAL *action, REAL *out)
+{
+    REAL A[ORC_MAX_S * ORC_MAX_S], B[ORC_MAX_S * ORC_MAX_A];
+    FN(orc_model_matrices)(mass, dt, s, a, A, B);
+    FN(orc_bmm_bcast)(B, s, a, action, k, out);
+}
+
+/* ModelBase::mBuildModelStepGraph — src/model_base.cpp:53-57.  state is
+ * [kst][s] with kst in {1, k}: kst == 1 broadcasts against [k][a] actions
+ * (test/test_model.cpp:216-255, src/controller_base.cpp:247). out [k][s]. */
+void FN(orc_model_step)(REAL mass, REAL dt, int s, int a, int kst, int k,
+                        const REAL *state, const REAL *action, REAL *out)
+{
+    REAL A[ORC_MAX_S * ORC_MAX_S], B[ORC_MAX_S * ORC_MAX_A];
+    REAL fr[ORC_MAX_S], ac[ORC_MAX_S];
+    FN(orc_model_matrices)(mass, dt, s, a, A, B);
+    for (int i = 0; i < k; i++) {
+        const REAL *st = state + (kst == 1 ? 0 : i * s);
+        FN(orc_bmm_bcast)(A, s, s, st, 1, fr);
+        FN(orc_bmm_bcast)(B, s, a, action + i * a, 1, ac);
+        for (int j = 0; j < s; j++) out[i * s + j] = fr[j] + ac[j];
+    }
+}
+
+/* MatrixInverse — src/cost_base.cpp:39.  Gauss-Jordan with partial pivoting,
+ * carried out in double so both instantiations share one inverse. */
+int FN(orc_mat_inverse)(const REAL *M, int n, REAL *inv)
+{
+    double w[ORC_MAX_A][2 * ORC_MAX_A];
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            w[i][j] = (double)M[i * n + j];
+            w[i][n + j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int c = 0; c < n; c++) {
+        int p = c;
+        for (int r = c + 1; r < n; r++)
+            if (fabs(w[r][c]) > fabs(w[p][c])) p = r;
+        if (w[p][c] == 0.0) return 1;
+        if (p != c)
+            for (int j = 0; j < 2 * n; j++) { double t = w[c][j]; w[c][j] = w[p][j]; w[p][j] = t; }
+        double d = w[c][c];
+        for (int j = 0; j < 2 * n; j++) w[c][j] /= d;
+        for (int r = 0; r < n; r++) {
+            if (r == c) continue;
+            double f = w[r][c];
+            if (f == 0.0) continue;
+            for (int j = 0; j < 2 * n; j++) w[r][j] -= f * w[c][j];
+        }
+    }
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) inv[i * n + j] = (REAL)w[i][n + j];
+    return 0;
+}
+
+/* CostBase::mStateCost — src/cost_base.cpp:56-61 with Q = Diag(q) (:40):
+ * diff = x - g; left = Q diff (dense); cost = diff^T left. */
+void FN(orc_cost_state)(int k, int s, const REAL *state, const REAL *goal, const REAL *q, REAL *out)
+{
+    for (int i = 0; i < k; i++) {
+        REAL diff[ORC_MAX_S], left[ORC_MAX_S];
+        for (int j = 0; j < s; j++) diff[j] = state[i * s + j] - goal[j];
+        for (int r = 0; r < s; r++) {
+            REAL acc = (REAL)0;
+            for (int c = 0; c < s; c++) acc += ((r == c) ? q[r] : (REAL)0) * diff[c];
+            left[r] = acc;
+        }
+        REAL acc = (REAL)0;
+        for (int j = 0; j < s; j++) acc += diff[j] * left[j];
+        out[i] = acc;
+    }
+}
+
+/* CostBase::mActionCost — src/cost_base.cpp:63-68:
+ * lambda * action^T (Sigma^-1 noise); action [a] is the UN-perturbed U[t]. */
+void FN(orc_cost_action)(int k, int a, REAL lambda, const REAL *sigma, const REAL *action,
+                         const REAL *noise, REAL *out)
+{
+    REAL inv[ORC_MAX_A * ORC_MAX_A];
+    FN(orc_mat_inverse)(sigma, a, inv);
+    for (int i = 0; i < k; i++) {
+        REAL nc[ORC_MAX_A];
+        FN(orc_bmm_bcast)(inv, a, a, noise + i * a, 1, nc);
+        REAL acc = (REAL)0;
+        for (int j = 0; j < a; j++) acc += action[j] * nc[j];
+        out[i] = lambda * acc;
+    }
+}
+
+/* CostBase::mBuildStepCostGraph — src/cost_base.cpp:43-50. */
+void FN(orc_cost_step)(int k, int s, int a, REAL lambda, const REAL *sigma, const REAL *goal,
+                       const REAL *q, const REAL *state, const REAL *action, const REAL *noise,
+                       REAL *out)
+{
+    REAL *ac = (REAL *)malloc(sizeof(REAL) * (size_t)k);
+    FN(orc_cost_state)(k, s, state, goal, q, out);
+    FN(orc_cost_action)(k, a, lambda, sigma, action, noise, ac);
+    for (int i = 0; i < k; i++) out[i] = out[i] + ac[i];
+    free(ac);
+}
+
+/* mNoiseGenGraph scaling — src/controller_base.cpp:201: eps = Sigma z. */
+void FN(orc_scale_noise)(int n, int a, const REAL *sigma, const REAL *z, REAL *eps)
+{
+    FN(orc_bmm_bcast)(sigma, a, a, z, n, eps);
+}
+
+/* mPrepareAction / mPrepareNoise — src/controller_base.cpp:205-213. */
+void FN(orc_prepare_action)(int T, int a, const REAL *U, int t, REAL *out)
+{
+    (void)T;
+    for (int j = 0; j < a; j++) out[j] = U[t * a + j];
+}
+void FN(orc_prepare_noise)(int k, int T, int a, const REAL *noise, int t, REAL *out)
+{
+    for (int i = 0; i < k; i++)
+        for (int j = 0; j < a; j++) out[i * a + j] = noise[((size_t)i * T + t) * a + j];
+}
+
+/* mBeta / mExpArg / mExp / mNabla / mWeights / mWeightedNoise —
+ * src/controller_base.cpp:166-192.  Any output pointer may be NULL. */
+void FN(orc_update_stages)(int k, int T, int a, REAL lambda, const REAL *cost, const REAL *noise,
+                           REAL *beta_o, REAL *arg_o, REAL *exp_o, REAL *nabla_o, REAL *w_o,
+                           REAL *wn_o)
+{
+    REAL beta = cost[0];
+    for (int i = 1; i < k; i++) beta = cost[i] < beta ? cost[i] : beta;     /* Min :167 */
+    REAL *e = (REAL *)malloc(sizeof(REAL) * (size_t)k);
+    REAL nabla = (REAL)0;
+    REAL neg_inv_lambda = (REAL)(-1) / lambda;                               /* :171 */
+    for (int i = 0; i < k; i++) {
+        REAL arg = neg_inv_lambda * (cost[i] - beta);                        /* :171-173 */
+        if (arg_o) arg_o[i] = arg;
+        e[i] = REAL_EXP(arg);                                                /* :177 */
+        if (exp_o) exp_o[i] = e[i];
+        nabla += e[i];                                                       /* :181 */
+    }
+    if (beta_o) *beta_o = beta;
+    if (nabla_o) *nabla_o = nabla;
+    if (wn_o) for (int j = 0; j < T * a; j++) wn_o[j] = (REAL)0;
+    for (int i = 0; i < k; i++) {
+        REAL w = e[i] / nabla;                                               /* :185 */
+        if (w_o) w_o[i] = w;
+        if (wn_o)
+            for (int j = 0; j < T * a; j++) wn_o[j] += w * noise[(size_t)i * T * a + j]; /* :189-191 */
+    }
+    free(e);
+}
+
+/* mGetNew — src/controller_base.cpp:327-329: first nb rows. */
+void FN(orc_get_new)(int T, int a, const REAL *cur, int nb, REAL *out)
+{
+    (void)T;
+    for (int j = 0; j < nb * a; j++) out[j] = cur[j];
+}
+
+/* mShift — src/controller_base.cpp:310-324: concat(cur[nb:], init[nb]). */
+void FN(orc_shift)(int T, int a, const REAL *cur, const REAL *init, int nb, REAL *out)
+{
+    for (int j = 0; j < (T - nb) * a; j++) out[j] = cur[nb * a + j];
+    for (int j = 0; j < nb * a; j++) out[(T - nb) * a + j] = init[j];
+}
+
+/* Rollout + cost for samples [k0, k1) — mBuildModelGraph, src/controller_base.cpp:226-273:
+ *   x <- x0 (broadcast, :247); S <- 0 (:248)
+ *   for t: u = U[t] + eps[:,t] (:256-258); x <- A x + (B/m) u (:260);
+ *          S += q(x) + lambda U[t]^T Sigma^-1 eps[:,t] (:264-268, un-noised U[t])
+ *   S += q(x_T) (:271-272, on top of step T-1's q(x_T)).
+ * eps_sample_stride lets the caller pass a slice of a larger [K][T][a] tensor. */
+void FN(orc_rollout_costs)(int k0, int k1, int T, int s, int a, REAL dt, REAL mass, REAL lambda,
+                           const REAL *sigma, const REAL *goal, const REAL *q, const REAL *x0,
+                           const REAL *U, const REAL *eps, REAL *costs)
+{
+    REAL A[ORC_MAX_S * ORC_MAX_S], B[ORC_MAX_S * ORC_MAX_A], inv[ORC_MAX_A * ORC_MAX_A];
+    FN(orc_model_matrices)(mass, dt, s, a, A, B);
+    FN(orc_mat_inverse)(sigma, a, inv);
+    for (int i = k0; i < k1; i++) {
+        REAL x[ORC_MAX_S], xn[ORC_MAX_S], u[ORC_MAX_A], nc[ORC_MAX_A], fr[ORC_MAX_S], ac[ORC_MAX_S];
+        REAL S = (REAL)0, c;
+        for (int j = 0; j < s; j++) x[j] = x0[j];
+        for (int t = 0; t < T; t++) {
+            const REAL *e = eps + ((size_t)i * T + t) * a;
+            const REAL *ut = U + t * a;
+            for (int j = 0; j < a; j++) u[j] = ut[j] + e[j];
+            FN(orc_bmm_bcast)(A, s, s, x, 1, fr);
+            FN(orc_bmm_bcast)(B, s, a, u, 1, ac);
+            for (int j = 0; j < s; j++) xn[j] = fr[j] + ac[j];
+            FN(orc_cost_state)(1, s, xn, goal, q, &c);
+            FN(orc_bmm_bcast)(inv, a, a, e, 1, nc);
+            REAL acc = (REAL)0;
+            for (int j = 0; j < a; j++) acc += ut[j] * nc[j];
+            S = S + (c + lambda * acc);
+            for (int j = 0; j < s; j++) x[j] = xn[j];
+        }
+        FN(orc_cost_state)(1, s, x, goal, q, &c);
+        costs[i] = S + c;
+    }
+}
+
+/* One full update — ControllerBase::next's graph, src/controller_base.cpp:135-153,
+ * 275-308: rollout costs -> update stages -> U' = U + sum_k w_k eps_k (:223) ->
+ * next = U'[0] (:303) -> shifted = concat(U'[1:], 0) (:305-307).
+ * Outputs: costs [k], U_new [T][a] (pre-shift), next [a], U_shift [T][a]. */
+void FN(orc_mppi_update)(int k, int T, int s, int a, REAL dt, REAL mass, REAL lambda,
+                         const REAL *sigma, const REAL *goal, const REAL *q, const REAL *x0,
+                         const REAL *U, const REAL *eps, REAL *costs, REAL *U_new, REAL *next,
+                         REAL *U_shift)
+{
+    REAL *wn = (REAL *)malloc(sizeof(REAL) * (size_t)T * a);
+    REAL *zero = (REAL *)calloc((size_t)a, sizeof(REAL));
+#pragma omp parallel
+    {
+        int nt = 1, id = 0;
+#ifdef _OPENMP
+        nt = omp_get_num_threads();
+        id = omp_get_thread_num();
+#endif
+        int lo = (int)((long long)k * id / nt), hi = (int)((long long)k * (id + 1) / nt);
+        FN(orc_rollout_costs)(lo, hi, T, s, a, dt, mass, lambda, sigma, goal, q, x0, U, eps, costs);
+    }
+    FN(orc_update_stages)(k, T, a, lambda, costs, eps, NULL, NULL, NULL, NULL, NULL, wn);
+    for (int j = 0; j < T * a; j++) U_new[j] = U[j] + wn[j];
+    FN(orc_get_new)(T, a, U_new, 1, next);
+    FN(orc_shift)(T, a, U_new, zero, 1, U_shift);
+    free(wn);
+    free(zero);
+}
+
+/* Rank-partial of the update over samples [k0,k1): (beta_r, eta_r, N_r[T*a]) with
+ * N_r = sum_k exp(-(S_k-beta_r)/lambda) eps_k — the payload exchanged between ranks
+ * (SURVEY.md section 8e).  New design, no reference line; checked against
+ * orc_update_stages by tests/test_oracle_kats.py. */
+void FN(orc_partial)(int k0, int k1, int T, int a, REAL lambda, const REAL *costs, const REAL *eps,
+                     REAL *beta_r, REAL *eta_r, REAL *N_r)
+{
+    REAL beta = costs[k0];
+    for (int i = k0 + 1; i < k1; i++) beta = costs[i] < beta ? costs[i] : beta;
+    REAL eta = (REAL)0;
+    for (int j = 0; j < T * a; j++) N_r[j] = (REAL)0;
+    for (int i = k0; i < k1; i++) {
+        REAL e = REAL_EXP(-(costs[i] - beta) / lambda);
+        eta += e;
+        for (int j = 0; j < T * a; j++) N_r[j] += e * eps[(size_t)i * T * a + j];
+    }
+    *beta_r = beta;
+    *eta_r = eta;
+}
+
+/* Learned-MLP dynamics step (row A13): behaviour of NNAUVModel.build_step_graph,
+ * scripts/src/models/nn_model.py:215-239,289-304 with the Keras Sequential of :54-60
+ * re-shaped to BASELINE config 4 (input [x(s), u(a)] -> H -> H -> s, ReLU, linear head):
+ *   X = (concat(x,u) - Xmean)/Xstd; h1 = relu(W1^T X + b1); h2 = relu(W2^T h1 + b2);
+ *   d = W3^T h2 + b3; x' = x + d*Ystd + Ymean.
+ * Weights are Keras-layout [in][out] row-major.  PARITY UNPINNED in the reference (no
+ * forward-value KAT exists for this shape; scripts/test.py:592-682 only covers data prep). */
+void FN(orc_mlp_step)(int s, int a, int H, const REAL *W1, const REAL *b1, const REAL *W2,
+                      const REAL *b2, const REAL *W3, const REAL *b3, const REAL *Xmean,
+                      const REAL *Xstd, const REAL *Ymean, const REAL *Ystd, const REAL *x,
+                      const REAL *u, REAL *xn)
+{
+    REAL X[ORC_MAX_S + ORC_MAX_A], h1[ORC_MAX_H], h2[ORC_MAX_H];
+    int in = s + a;
+    for (int j = 0; j < s; j++) X[j] = (x[j] - Xmean[j]) / Xstd[j];
+    for (int j = 0; j < a; j++) X[s + j] = (u[j] - Xmean[s + j]) / Xstd[s + j];
+    for (int o = 0; o < H; o++) {
+        REAL acc = b1[o];
+        for (int i = 0; i < in; i++) acc += X[i] * W1[i * H + o];
+        h1[o] = acc > (REAL)0 ? acc : (REAL)0;
+    }
+    for (int o = 0; o < H; o++) {
+        REAL acc = b2[o];
+        for (int i = 0; i < H; i++) acc += h1[i] * W2[i * H + o];
+        h2[o] = acc > (REAL)0 ? acc : (REAL)0;
+    }
+    for (int o = 0; o < s; o++) {
+        REAL acc = b3[o];
+        for (int i = 0; i < H; i++) acc += h2[i] * W3[i * s + o];
+        xn[o] = x[o] + (acc * Ystd[o] + Ymean[o]);
+    }
+}
+
+/* Rollout costs with the MLP dynamics in place of the point mass (same cost and
+ * loop structure as orc_rollout_costs). */
+void FN(orc_rollout_costs_mlp)(int k0, int k1, int T, int s, int a, int H, REAL lambda,
+                               const REAL *sigma, const REAL *goal, const REAL *q, const REAL *W1,
+                               const REAL *b1, const REAL *W2, const REAL *b2, const REAL *W3,
+                               const REAL *b3, const REAL *Xmean, const REAL *Xstd,
+                               const REAL *Ymean, const REAL *Ystd, const REAL *x0, const REAL *U,
+                               const REAL *eps, REAL *costs)
+{
+    REAL inv[ORC_MAX_A * ORC_MAX_A];
+    FN(orc_mat_inverse)(sigma, a, inv);
+    for (int i = k0; i < k1; i++) {
+        REAL x[ORC_MAX_S], xn[ORC_MAX_S], u[ORC_MAX_A], nc[ORC_MAX_A];
+        REAL S = (REAL)0, c;
+        for (int j = 0; j < s; j++) x[j] = x0[j];
+        for (int t = 0; t < T; t++) {
+            const REAL *e = eps + ((size_t)i * T + t) * a;
+            const REAL *ut = U + t * a;
+            for (int j = 0; j < a; j++) u[j] = ut[j] + e[j];
+            FN(orc_mlp_step)(s, a, H, W1, b1, W2, b2, W3, b3, Xmean, Xstd, Ymean, Ystd, x, u, xn);
+            FN(orc_cost_state)(1, s, xn, goal, q, &c);
+            FN(orc_bmm_bcast)(inv, a, a, e, 1, nc);
+            REAL acc = (REAL)0;
+            for (int j = 0; j < a; j++) acc += ut[j] * nc[j];
+            S = S + (c + lambda * acc);
+            for (int j = 0; j < s; j++) x[j] = xn[j];
+        }
+        FN(orc_cost_state)(1, s, x, goal, q, &c);
+        costs[i] = S + c;
+    }
+}
+
+void FN(orc_mppi_update_mlp)(int k, int T, int s, int a, int H, REAL lambda, const REAL *sigma,
+                             const REAL *goal, const REAL *q, const REAL *W1, const REAL *b1,
+                             const REAL *W2, const REAL *b2, const REAL *W3, const REAL *b3,
+                             const REAL *Xmean, const REAL *Xstd, const REAL *Ymean,
+                             const REAL *Ystd, const REAL *x0, const REAL *U, const REAL *eps,
+                             REAL *costs, REAL *U_new, REAL *next, REAL *U_shift)
+{
+    REAL *wn = (REAL *)malloc(sizeof(REAL) * (size_t)T * a);
+    REAL *zero = (REAL *)calloc((size_t)a, sizeof(REAL));
+#pragma omp parallel
+    {
+        int nt = 1, id = 0;
+#ifdef _OPENMP
+        nt = omp_get_num_threads();
+        id = omp_get_thread_num();
+#endif
+        int lo = (int)((long long)k * id / nt), hi = (int)((long long)k * (id + 1) / nt);
+        FN(orc_rollout_costs_mlp)(lo, hi, T, s, a, H, lambda, sigma, goal, q, W1, b1, W2, b2, W3, b3,
+                                  Xmean, Xstd, Ymean, Ystd, x0, U, eps, costs);
+    }
+    FN(orc_update_stages)(k, T, a, lambda, costs, eps, NULL, NULL, NULL, NULL, NULL, wn);
+    for (int j = 0; j < T * a; j++) U_new[j] = U[j] + wn[j];
+    FN(orc_get_new)(T, a, U_new, 1, next);
+    FN(orc_shift)(T, a, U_new, zero, 1, U_shift);
+    free(wn);
+    free(zero);
+}
+
+#undef FN
+#undef CAT
+#undef CAT_

@@ -1,0 +1,278 @@
+"""TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+ctypes wrapper over oracle/_build/libmppi_oracle.so (see mppi_oracle.c /
+mppi_oracle_impl.h for the reference file:line each function restates).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libmppi_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    """Compile the C oracle (gcc, OpenMP).  Building the checker is not using it."""
+    src = [os.path.join(_HERE, f) for f in ("mppi_oracle.c", "mppi_oracle_impl.h", "Makefile")]
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+    return _lib
+
+
+def _c(arr, dt):
+    return np.ascontiguousarray(arr, dtype=dt)
+
+
+def _p(arr):
+    return arr.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """One instance per precision ("f32" = the reference's DT_FLOAT graph, "f64" = the
+    Python twin's precision, used as the exact value in tolerance tests)."""
+
+    def __init__(self, precision="f32"):
+        assert precision in ("f32", "f64")
+        self.sfx = "_" + precision
+        self.dt = np.float32 if precision == "f32" else np.float64
+        self.creal = C.c_float if precision == "f32" else C.c_double
+        self.lib = load()
+
+    def _fn(self, name):
+        return getattr(self.lib, name + self.sfx)
+
+    # --- utile::blockDiag -------------------------------------------------------------
+    def block_diag(self, block, nb):
+        block = _c(block, self.dt)
+        r, c = block.shape
+        out = np.empty((r * nb, c * nb), self.dt)
+        self._fn("orc_block_diag")(_p(block), r, c, nb, _p(out))
+        return out
+
+    def model_matrices(self, mass, dt, s, a):
+        A = np.empty((s, s), self.dt)
+        B = np.empty((s, a), self.dt)
+        self._fn("orc_model_matrices")(self.creal(mass), self.creal(dt), s, a, _p(A), _p(B))
+        return A, B
+
+    # --- ModelBase ----------------------------------------------------------------------
+    def model_free_step(self, mass, dt, s, a, state):
+        state = _c(state, self.dt).reshape(-1, s)
+        out = np.empty_like(state)
+        self._fn("orc_model_free_step")(self.creal(mass), self.creal(dt), s, a, state.shape[0],
+                                        _p(state), _p(out))
+        return out
+
+    def model_action_step(self, mass, dt, s, a, action):
+        action = _c(action, self.dt).reshape(-1, a)
+        out = np.empty((action.shape[0], s), self.dt)
+        self._fn("orc_model_action_step")(self.creal(mass), self.creal(dt), s, a, action.shape[0],
+                                          _p(action), _p(out))
+        return out
+
+    def model_step(self, mass, dt, s, a, state, action):
+        state = _c(state, self.dt).reshape(-1, s)
+        action = _c(action, self.dt).reshape(-1, a)
+        k = action.shape[0]
+        out = np.empty((k, s), self.dt)
+        self._fn("orc_model_step")(self.creal(mass), self.creal(dt), s, a, state.shape[0], k,
+                                   _p(state), _p(action), _p(out))
+        return out
+
+    # --- CostBase -----------------------------------------------------------------------
+    def mat_inverse(self, M):
+        M = _c(M, self.dt)
+        out = np.empty_like(M)
+        rc = self._fn("orc_mat_inverse")(_p(M), M.shape[0], _p(out))
+        if rc:
+            raise np.linalg.LinAlgError("singular")
+        return out
+
+    def cost_state(self, state, goal, q):
+        goal = _c(goal, self.dt).ravel()
+        s = goal.size
+        state = _c(state, self.dt).reshape(-1, s)
+        q = _c(q, self.dt).ravel()
+        out = np.empty(state.shape[0], self.dt)
+        self._fn("orc_cost_state")(state.shape[0], s, _p(state), _p(goal), _p(q), _p(out))
+        return out
+
+    def cost_action(self, lam, sigma, action, noise):
+        action = _c(action, self.dt).ravel()
+        a = action.size
+        noise = _c(noise, self.dt).reshape(-1, a)
+        sigma = _c(sigma, self.dt)
+        out = np.empty(noise.shape[0], self.dt)
+        self._fn("orc_cost_action")(noise.shape[0], a, self.creal(lam), _p(sigma), _p(action),
+                                    _p(noise), _p(out))
+        return out
+
+    def cost_step(self, lam, sigma, goal, q, state, action, noise):
+        goal = _c(goal, self.dt).ravel()
+        s = goal.size
+        action = _c(action, self.dt).ravel()
+        a = action.size
+        state = _c(state, self.dt).reshape(-1, s)
+        noise = _c(noise, self.dt).reshape(-1, a)
+        out = np.empty(state.shape[0], self.dt)
+        self._fn("orc_cost_step")(state.shape[0], s, a, self.creal(lam), _p(_c(sigma, self.dt)),
+                                  _p(goal), _p(_c(q, self.dt).ravel()), _p(state), _p(action),
+                                  _p(noise), _p(out))
+        return out
+
+    # --- ControllerBase stages ------------------------------------------------------------
+    def scale_noise(self, sigma, z):
+        sigma = _c(sigma, self.dt)
+        a = sigma.shape[0]
+        z = _c(z, self.dt)
+        out = np.empty_like(z)
+        self._fn("orc_scale_noise")(z.size // a, a, _p(sigma), _p(z), _p(out))
+        return out
+
+    def prepare_action(self, U, t):
+        U = _c(U, self.dt)
+        T, a = U.shape
+        out = np.empty(a, self.dt)
+        self._fn("orc_prepare_action")(T, a, _p(U), t, _p(out))
+        return out
+
+    def prepare_noise(self, noise, t):
+        noise = _c(noise, self.dt)
+        k, T, a = noise.shape
+        out = np.empty((k, a), self.dt)
+        self._fn("orc_prepare_noise")(k, T, a, _p(noise), t, _p(out))
+        return out
+
+    def update_stages(self, lam, cost, noise):
+        cost = _c(cost, self.dt).ravel()
+        noise = _c(noise, self.dt)
+        k, T, a = noise.shape
+        beta = self.creal()
+        nabla = self.creal()
+        arg = np.empty(k, self.dt)
+        e = np.empty(k, self.dt)
+        w = np.empty(k, self.dt)
+        wn = np.empty((T, a), self.dt)
+        self._fn("orc_update_stages")(k, T, a, self.creal(lam), _p(cost), _p(noise), C.byref(beta),
+                                      _p(arg), _p(e), C.byref(nabla), _p(w), _p(wn))
+        return dict(beta=beta.value, exp_arg=arg, exp=e, nabla=nabla.value, weights=w,
+                    weighted_noise=wn)
+
+    def get_new(self, cur, nb):
+        cur = _c(cur, self.dt)
+        T, a = cur.shape
+        out = np.empty((nb, a), self.dt)
+        self._fn("orc_get_new")(T, a, _p(cur), nb, _p(out))
+        return out
+
+    def shift(self, cur, init, nb):
+        cur = _c(cur, self.dt)
+        init = _c(init, self.dt)
+        T, a = cur.shape
+        out = np.empty((T, a), self.dt)
+        self._fn("orc_shift")(T, a, _p(cur), _p(init), nb, _p(out))
+        return out
+
+    def rollout_costs(self, cfg, x0, U, eps):
+        k, T, s, a = cfg["k"], cfg["tau"], cfg["s_dim"], cfg["a_dim"]
+        eps = _c(eps, self.dt)
+        assert eps.shape == (k, T, a)
+        costs = np.empty(k, self.dt)
+        self._fn("orc_rollout_costs")(0, k, T, s, a, self.creal(cfg["dt"]), self.creal(cfg["mass"]),
+                                      self.creal(cfg["lambda"]), _p(_c(cfg["sigma"], self.dt)),
+                                      _p(_c(cfg["goal"], self.dt)), _p(_c(cfg["q"], self.dt)),
+                                      _p(_c(x0, self.dt)), _p(_c(U, self.dt)), _p(eps), _p(costs))
+        return costs
+
+    def mppi_update(self, cfg, x0, U, eps):
+        """Full update (ControllerBase::next graph).  Returns dict(costs, U_new, next, U_shift)."""
+        k, T, s, a = cfg["k"], cfg["tau"], cfg["s_dim"], cfg["a_dim"]
+        eps = _c(eps, self.dt)
+        assert eps.shape == (k, T, a)
+        costs = np.empty(k, self.dt)
+        U_new = np.empty((T, a), self.dt)
+        nxt = np.empty(a, self.dt)
+        U_shift = np.empty((T, a), self.dt)
+        self._fn("orc_mppi_update")(k, T, s, a, self.creal(cfg["dt"]), self.creal(cfg["mass"]),
+                                    self.creal(cfg["lambda"]), _p(_c(cfg["sigma"], self.dt)),
+                                    _p(_c(cfg["goal"], self.dt)), _p(_c(cfg["q"], self.dt)),
+                                    _p(_c(x0, self.dt)), _p(_c(U, self.dt)), _p(eps), _p(costs),
+                                    _p(U_new), _p(nxt), _p(U_shift))
+        return dict(costs=costs, U_new=U_new, next=nxt, U_shift=U_shift)
+
+    def partial(self, lam, costs, eps, k0, k1):
+        costs = _c(costs, self.dt)
+        eps = _c(eps, self.dt)
+        _, T, a = eps.shape
+        beta = self.creal()
+        eta = self.creal()
+        N = np.empty((T, a), self.dt)
+        self._fn("orc_partial")(k0, k1, T, a, self.creal(lam), _p(costs), _p(eps), C.byref(beta),
+                                C.byref(eta), _p(N))
+        return beta.value, eta.value, N
+
+    # --- MLP dynamics (row A13) -----------------------------------------------------------
+    def _mlp_args(self, mlp):
+        keys = ("W1", "b1", "W2", "b2", "W3", "b3", "Xmean", "Xstd", "Ymean", "Ystd")
+        arrs = [_c(mlp[k], self.dt) for k in keys]
+        return arrs
+
+    def mlp_step(self, mlp, x, u):
+        x = _c(x, self.dt).ravel()
+        u = _c(u, self.dt).ravel()
+        s, a, H = x.size, u.size, np.asarray(mlp["b1"]).size
+        arrs = self._mlp_args(mlp)
+        out = np.empty(s, self.dt)
+        self._fn("orc_mlp_step")(s, a, H, *[_p(v) for v in arrs], _p(x), _p(u), _p(out))
+        return out
+
+    def mppi_update_mlp(self, cfg, mlp, x0, U, eps):
+        k, T, s, a = cfg["k"], cfg["tau"], cfg["s_dim"], cfg["a_dim"]
+        H = np.asarray(mlp["b1"]).size
+        eps = _c(eps, self.dt)
+        arrs = self._mlp_args(mlp)
+        costs = np.empty(k, self.dt)
+        U_new = np.empty((T, a), self.dt)
+        nxt = np.empty(a, self.dt)
+        U_shift = np.empty((T, a), self.dt)
+        self._fn("orc_mppi_update_mlp")(k, T, s, a, H, self.creal(cfg["lambda"]),
+                                        _p(_c(cfg["sigma"], self.dt)), _p(_c(cfg["goal"], self.dt)),
+                                        _p(_c(cfg["q"], self.dt)), *[_p(v) for v in arrs],
+                                        _p(_c(x0, self.dt)), _p(_c(U, self.dt)), _p(eps), _p(costs),
+                                        _p(U_new), _p(nxt), _p(U_shift))
+        return dict(costs=costs, U_new=U_new, next=nxt, U_shift=U_shift)
+
+
+# --- noise stream specification (integer part is a bit-exact contract) ---------------------
+def philox4x32_10(ctr, key):
+    lib = load()
+    c = (C.c_uint32 * 4)(*[int(v) & 0xFFFFFFFF for v in ctr])
+    k = (C.c_uint32 * 2)(*[int(v) & 0xFFFFFFFF for v in key])
+    o = (C.c_uint32 * 4)()
+    lib.orc_philox4x32_10(c, k, o)
+    return [int(v) for v in o]
+
+
+def philox_normals(seed, update, stream, k0, k1, n_per_sample):
+    lib = load()
+    z = np.empty((k1 - k0, n_per_sample), np.float32)
+    lib.orc_philox_normals(C.c_uint64(seed), C.c_uint32(update), C.c_uint32(stream),
+                           C.c_uint32(k0), C.c_uint32(k1), C.c_int(n_per_sample), _p(z))
+    return z
+
+
+def num_threads():
+    return load().orc_num_threads()
