@@ -1,0 +1,208 @@
+/*
+ * mppi_b200.h — C-ABI of the B200-native MPPI update step.
+ *
+ * This is the drop-in boundary for the hot path of NicolayP/mppi-tf: everything the reference
+ * executes inside `ClientSession::Run` for one `ControllerBase::next` call
+ * (/root/reference/src/controller_base.cpp:135-153) plus the sub-graph builders its unit tests
+ * exercise.  The reference has no FFI of its own (its boundary is the public C++ API of
+ * ControllerBase / ModelBase / CostBase, linked into one executable, CMakeLists.txt:56-64), so
+ * each entry point below names the reference C++ method it replaces.  The C++ classes in
+ * include/controller_base.hpp, model_base.hpp, cost_base.hpp, data_base.hpp keep the reference's
+ * class names and numerical method signatures and are thin callers of this ABI.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; never throws.
+ *   - every function returns an mppi_status (0 = ok); mppi_last_error() gives the text.
+ *   - all tensors are fp32, row-major, the reference's trailing singleton dimension dropped:
+ *       state [k][s]   action [k][a]   noise [k][T][a]   sequence U [T][a]
+ *     state layout per axis is interleaved (pos0, vel0, pos1, vel1, ...), s = 2a
+ *     (/root/reference/src/model_base.cpp:61-64).
+ *   - "host" pointers are ordinary host memory; the library copies in/out.  "dev" pointers are
+ *     CUDA device memory on the handle's device.
+ *   - a handle is not thread-safe; distinct handles are independent (one CUDA stream each).
+ *   - there is NO CPU fallback: every compute entry point fails with MPPI_ERR_CUDA if no
+ *     sm_100 device is usable.
+ */
+#ifndef MPPI_B200_H
+#define MPPI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MPPI_OK = 0,
+    MPPI_ERR_BAD_ARG = 1,     /* null pointer, non-positive size, s != 2a, ... */
+    MPPI_ERR_CUDA = 2,        /* CUDA runtime/driver failure (text in mppi_last_error) */
+    MPPI_ERR_COMM = 3,        /* multi-rank exchange failure */
+    MPPI_ERR_UNSUPPORTED = 4, /* size outside the compiled limits (see MPPI_MAX_*) */
+    MPPI_ERR_STATE = 5        /* call sequence error (e.g. dump_noise before any next) */
+} mppi_status;
+
+#define MPPI_MAX_A 8          /* a_dim <= 8, s_dim = 2 a_dim <= 16 */
+#define MPPI_MAX_S 16
+#define MPPI_MAX_TA 4096      /* tau * a_dim */
+
+typedef struct mppi_handle mppi_handle;
+
+/* Dynamics model selector (ModelBase vs the learning_base MLP). */
+typedef enum { MPPI_MODEL_POINT_MASS = 0, MPPI_MODEL_MLP = 1 } mppi_model_kind;
+
+/*
+ * Construction parameters.  Mirrors ControllerBase(k, tau, dt, mass, s_dim, a_dim)
+ * (/root/reference/include/controller_base.hpp:60-65) with the constants the reference
+ * hard-codes in that constructor made explicit (src/controller_base.cpp:37-69):
+ *   lambda = 1, sigma = I, goal = (1,0,1,0,...), q = ones, model mass = 1.
+ * NULL sigma/goal/q select exactly those defaults.
+ */
+typedef struct {
+    int k;                 /* samples per controller, summed over all ranks */
+    int tau;               /* horizon T */
+    int s_dim;             /* must equal 2 * a_dim for the point-mass model */
+    int a_dim;
+    float dt;
+    float mass;            /* model mass used in B = [dt^2/2; dt] / mass */
+    float lambda;
+    const float *sigma;    /* [a][a]; scale in eps = sigma z AND inverted in the action cost */
+    const float *goal;     /* [s] (shared) or [n_controllers][s] if goal_per_controller != 0 */
+    const float *q;        /* [s] diagonal of Q */
+    uint64_t seed;         /* Philox key; the reference uses RandomNormal::Seed(1) (:199) */
+    int device;            /* CUDA device ordinal, -1 = current device */
+    int rank;              /* this process's shard: samples [rank*k/world, (rank+1)*k/world) */
+    int world;             /* number of sample shards (1 = single GPU) */
+    int n_controllers;     /* independent controllers batched in one handle (>= 1) */
+    int goal_per_controller;
+    void *stream;          /* cudaStream_t to launch on; NULL = library-owned stream */
+} mppi_config;
+
+/* Fill *cfg with the reference constructor's defaults for the given sizes. */
+void mppi_config_default(mppi_config *cfg, int k, int tau, float dt, float mass, int s_dim, int a_dim);
+
+/* ---- lifetime --------------------------------------------------------------------------- */
+/* replaces ControllerBase::ControllerBase + mBuildGraph (src/controller_base.cpp:23-71,275-308) */
+int mppi_create(const mppi_config *cfg, mppi_handle **out);
+int mppi_destroy(mppi_handle *h);
+/* Text of the last error on this handle (h may be NULL for the last create/stateless error). */
+const char *mppi_last_error(const mppi_handle *h);
+
+/* ---- the update step ---------------------------------------------------------------------- */
+/*
+ * replaces ControllerBase::next (src/controller_base.cpp:135-153).
+ * x_host [n_controllers][s] -> action_host [n_controllers][a].  Draws fresh noise
+ * (counter-based Philox, regenerated in registers), rolls out, reweights, updates and shifts the
+ * stored sequence.  Synchronous: returns after the action is on the host.
+ * With world > 1 the exchange must have been wired with mppi_exchange_* first.
+ */
+int mppi_next(mppi_handle *h, const float *x_host, float *action_host);
+
+/*
+ * Same update with the noise tensor INJECTED instead of generated — the parity/debug mode
+ * required by BASELINE.json ("a debug mode reads eps from a buffer").
+ * eps [n_controllers][k_local][T][a] are the already-scaled noises eps = sigma z
+ * (the output of mNoiseGenGraph, src/controller_base.cpp:194-203) for this rank's samples.
+ */
+int mppi_next_with_noise(mppi_handle *h, const float *x_host, const float *eps_host, float *action_host);
+int mppi_next_with_noise_dev(mppi_handle *h, const float *x_host, const float *eps_dev, float *action_host);
+
+/*
+ * Asynchronous halves used by the benchmark and by multi-rank callers.
+ * mppi_enqueue_update launches the fused rollout (+ merge when world == 1) on the handle's
+ * stream and returns without synchronising; eps_dev == NULL selects Philox mode.  The state must
+ * have been staged with mppi_set_state.  With world > 1 the launch leaves this rank's payload
+ * (beta_r, eta_r, N_r) in the exchange send buffer; after the caller's all-gather,
+ * mppi_enqueue_finish merges the gathered payloads and applies the update.
+ * mppi_fetch_action copies the [n_controllers][a] action to the host and synchronises.
+ */
+int mppi_set_state(mppi_handle *h, const float *x_host);
+int mppi_enqueue_update(mppi_handle *h, const float *eps_dev);
+int mppi_enqueue_finish(mppi_handle *h);
+int mppi_fetch_action(mppi_handle *h, float *action_host);
+int mppi_synchronize(mppi_handle *h);
+
+/* ---- controller state ---------------------------------------------------------------------- */
+/* replaces ControllerBase::setGoal (src/controller_base.cpp:126-133) — and takes effect, which
+ * the reference's does not (the goal is baked into the graph as a Const, src/cost_base.cpp:57). */
+int mppi_set_goal(mppi_handle *h, const float *goal_host);       /* [s] or [n][s] */
+int mppi_set_lambda(mppi_handle *h, float lambda);
+int mppi_set_sigma(mppi_handle *h, const float *sigma_host);     /* [a][a], must be invertible */
+int mppi_set_q(mppi_handle *h, const float *q_host);             /* [s] */
+int mppi_set_sequence(mppi_handle *h, const float *U_host);      /* m_U, [n][T][a] */
+int mppi_get_sequence(mppi_handle *h, float *U_host);            /* shifted sequence kept for the next call */
+int mppi_get_update(mppi_handle *h, float *U_new_host);          /* U + sum_k w_k eps_k of the last call, pre-shift */
+int mppi_get_costs(mppi_handle *h, float *costs_host);           /* [n][k_local] per-sample costs of the last call */
+int mppi_get_weight_stats(mppi_handle *h, float *beta, float *eta); /* [n] each: min cost, sum of exp */
+int mppi_set_update_counter(mppi_handle *h, uint32_t counter);   /* Philox "update" counter word */
+/* Regenerates the eps tensor of the LAST Philox-mode update for this rank's samples
+ * ([n][k_local][T][a], host) so it can be replayed through the injected path / the oracle. */
+int mppi_dump_noise(mppi_handle *h, float *eps_host);
+int mppi_k_local(const mppi_handle *h);
+int mppi_k_offset(const mppi_handle *h);
+
+/* ---- multi-rank exchange (sample sharding) ------------------------------ */
+/* Payload per rank: n_controllers * mppi_exchange_stride(h) floats =
+ * {beta_r, eta_r, 0, 0, N_r[T*a] (padded to a multiple of 4)} per controller. */
+int mppi_exchange_stride(const mppi_handle *h);
+/* Device buffers the caller all-gathers between enqueue_update and enqueue_finish:
+ * send = this rank's payload, recv = [world] payloads in rank order.  The library owns them
+ * unless external ones are supplied (e.g. tensors registered with torch.distributed). */
+int mppi_exchange_buffers(mppi_handle *h, void **send_dev, void **recv_dev);
+int mppi_exchange_set_buffers(mppi_handle *h, void *send_dev, void *recv_dev);
+/* In-library exchange over NCCL (dlopen'ed libnccl.so.2): every rank passes the same 128-byte
+ * ncclUniqueId (mppi_comm_unique_id fills one on the caller that broadcasts it). */
+int mppi_comm_unique_id(void *id128);
+int mppi_comm_init(mppi_handle *h, const void *id128);
+
+/* ---- learned MLP dynamics (learning_base, row A13) ------------------------------------------- */
+/* x' = x + (W3^T relu(W2^T relu(W1^T X + b1) + b2) + b3) * Ystd + Ymean,
+ * X = (concat(x, u) - Xmean) / Xstd; weights in Keras layout [in][out]
+ * (behaviour of /root/reference/scripts/src/models/nn_model.py:54-60,215-239,289-304).
+ * Switches the handle to MPPI_MODEL_MLP; bf16 tensor-core rollout, fp32 state. */
+int mppi_set_mlp(mppi_handle *h, int hidden, const float *W1, const float *b1, const float *W2,
+                 const float *b2, const float *W3, const float *b3, const float *Xmean,
+                 const float *Xstd, const float *Ymean, const float *Ystd);
+
+/* ---- stateless stage entry points (the reference's graph-builder methods on plain buffers) ----
+ * All pointers are host memory; each call runs the corresponding CUDA kernel on `device`. */
+/* utile::blockDiag (src/utile.cpp:10-43): in [rows][cols] -> out [nb*rows][nb*cols] */
+int mppi_block_diag(const float *in, int rows, int cols, int nb, float *out);
+/* ModelBase::mBuildFreeStepGraph (src/model_base.cpp:59-68): state [kst][s] -> out [kst][s] */
+int mppi_model_free_step(int device, float mass, float dt, int s, int a, int kst, const float *state, float *out);
+/* ModelBase::mBuildActionStepGraph (src/model_base.cpp:70-82): action [k][a] -> out [k][s] */
+int mppi_model_action_step(int device, float mass, float dt, int s, int a, int k, const float *action, float *out);
+/* ModelBase::mBuildModelStepGraph (src/model_base.cpp:53-57): state [kst][s], kst in {1,k} */
+int mppi_model_step(int device, float mass, float dt, int s, int a, int kst, int k, const float *state,
+                    const float *action, float *out);
+/* CostBase::mStateCost / mBuildFinalStepCostGraph (src/cost_base.cpp:52-61) */
+int mppi_cost_state(int device, int k, int s, const float *state, const float *goal, const float *q, float *out);
+/* CostBase::mActionCost (src/cost_base.cpp:63-68): lambda * action^T sigma^-1 noise */
+int mppi_cost_action(int device, int k, int a, float lambda, const float *sigma, const float *action,
+                     const float *noise, float *out);
+/* CostBase::mBuildStepCostGraph (src/cost_base.cpp:43-50) */
+int mppi_cost_step(int device, int k, int s, int a, float lambda, const float *sigma, const float *goal,
+                   const float *q, const float *state, const float *action, const float *noise, float *out);
+/* ControllerBase::mPrepareAction / mPrepareNoise (src/controller_base.cpp:205-213) */
+int mppi_prepare_action(int T, int a, const float *U, int t, float *out);
+int mppi_prepare_noise(int device, int k, int T, int a, const float *noise, int t, float *out);
+/* ControllerBase::mBeta, mExpArg, mExp, mNabla, mWeights, mWeightedNoise
+ * (src/controller_base.cpp:166-192); any output pointer may be NULL. */
+int mppi_update_stages(int device, int k, int T, int a, float lambda, const float *cost, const float *noise,
+                       float *beta, float *exp_arg, float *exp_out, float *nabla, float *weights,
+                       float *weighted_noise);
+/* ControllerBase::mGetNew / mShift (src/controller_base.cpp:310-329) */
+int mppi_get_new(int T, int a, const float *cur, int nb, float *out);
+int mppi_shift(int T, int a, const float *cur, const float *init, int nb, float *out);
+/* Raw Philox4x32-10 words of the noise stream (integer contract, bit-exact vs the oracle):
+ * out [n_calls][4] for counter (call0 + i, sample, update, stream). */
+int mppi_philox_raw(int device, uint64_t seed, uint32_t call0, uint32_t sample, uint32_t update,
+                    uint32_t stream, int n_calls, uint32_t *out);
+
+/* Library/version info: returns a static string such as "mppi_b200 0.1 sm_100a". */
+const char *mppi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPPI_B200_H */

@@ -1,0 +1,113 @@
+"""ctypes binding of include/mppi_b200.h (libmppi_b200.so).
+
+There is no Python/CPU fallback here on purpose: if the shared library is missing, or no
+sm_100 device is present, every compute entry point raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libmppi_b200.so")
+
+MPPI_OK = 0
+MPPI_ERR_BAD_ARG, MPPI_ERR_CUDA, MPPI_ERR_COMM, MPPI_ERR_UNSUPPORTED, MPPI_ERR_STATE = 1, 2, 3, 4, 5
+MPPI_MAX_A = 8
+
+_fp = C.POINTER(C.c_float)
+
+
+class MppiConfig(C.Structure):
+    """struct mppi_config, field for field."""
+    _fields_ = [
+        ("k", C.c_int), ("tau", C.c_int), ("s_dim", C.c_int), ("a_dim", C.c_int),
+        ("dt", C.c_float), ("mass", C.c_float), ("lambda_", C.c_float),
+        ("sigma", _fp), ("goal", _fp), ("q", _fp),
+        ("seed", C.c_uint64),
+        ("device", C.c_int), ("rank", C.c_int), ("world", C.c_int),
+        ("n_controllers", C.c_int), ("goal_per_controller", C.c_int),
+        ("stream", C.c_void_p),
+    ]
+
+
+class MppiError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mppi_b200 error {code}: {msg}")
+        self.code = code
+
+
+# every exported symbol of include/mppi_b200.h: name -> (restype, argtypes)
+_i, _f, _u32, _u64, _vp = C.c_int, C.c_float, C.c_uint32, C.c_uint64, C.c_void_p
+_H = C.c_void_p
+SYMBOLS = {
+    "mppi_version": (C.c_char_p, []),
+    "mppi_config_default": (None, [C.POINTER(MppiConfig), _i, _i, _f, _f, _i, _i]),
+    "mppi_create": (_i, [C.POINTER(MppiConfig), C.POINTER(_H)]),
+    "mppi_destroy": (_i, [_H]),
+    "mppi_last_error": (C.c_char_p, [_H]),
+    "mppi_next": (_i, [_H, _fp, _fp]),
+    "mppi_next_with_noise": (_i, [_H, _fp, _fp, _fp]),
+    "mppi_next_with_noise_dev": (_i, [_H, _fp, _vp, _fp]),
+    "mppi_set_state": (_i, [_H, _fp]),
+    "mppi_enqueue_update": (_i, [_H, _vp]),
+    "mppi_enqueue_finish": (_i, [_H]),
+    "mppi_fetch_action": (_i, [_H, _fp]),
+    "mppi_synchronize": (_i, [_H]),
+    "mppi_set_goal": (_i, [_H, _fp]),
+    "mppi_set_lambda": (_i, [_H, _f]),
+    "mppi_set_sigma": (_i, [_H, _fp]),
+    "mppi_set_q": (_i, [_H, _fp]),
+    "mppi_set_sequence": (_i, [_H, _fp]),
+    "mppi_get_sequence": (_i, [_H, _fp]),
+    "mppi_get_update": (_i, [_H, _fp]),
+    "mppi_get_costs": (_i, [_H, _fp]),
+    "mppi_get_weight_stats": (_i, [_H, _fp, _fp]),
+    "mppi_set_update_counter": (_i, [_H, _u32]),
+    "mppi_dump_noise": (_i, [_H, _fp]),
+    "mppi_k_local": (_i, [_H]),
+    "mppi_k_offset": (_i, [_H]),
+    "mppi_exchange_stride": (_i, [_H]),
+    "mppi_exchange_buffers": (_i, [_H, C.POINTER(_vp), C.POINTER(_vp)]),
+    "mppi_exchange_set_buffers": (_i, [_H, _vp, _vp]),
+    "mppi_comm_unique_id": (_i, [_vp]),
+    "mppi_comm_init": (_i, [_H, _vp]),
+    "mppi_set_mlp": (_i, [_H, _i] + [_fp] * 10),
+    "mppi_block_diag": (_i, [_fp, _i, _i, _i, _fp]),
+    "mppi_model_free_step": (_i, [_i, _f, _f, _i, _i, _i, _fp, _fp]),
+    "mppi_model_action_step": (_i, [_i, _f, _f, _i, _i, _i, _fp, _fp]),
+    "mppi_model_step": (_i, [_i, _f, _f, _i, _i, _i, _i, _fp, _fp, _fp]),
+    "mppi_cost_state": (_i, [_i, _i, _i, _fp, _fp, _fp, _fp]),
+    "mppi_cost_action": (_i, [_i, _i, _i, _f, _fp, _fp, _fp, _fp]),
+    "mppi_cost_step": (_i, [_i, _i, _i, _i, _f, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "mppi_prepare_action": (_i, [_i, _i, _fp, _i, _fp]),
+    "mppi_prepare_noise": (_i, [_i, _i, _i, _i, _fp, _i, _fp]),
+    "mppi_update_stages": (_i, [_i, _i, _i, _i, _f, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "mppi_get_new": (_i, [_i, _i, _fp, _i, _fp]),
+    "mppi_shift": (_i, [_i, _i, _fp, _fp, _i, _fp]),
+    "mppi_philox_raw": (_i, [_i, _u64, _u32, _u32, _u32, _u32, _i, C.POINTER(_u32)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libmppi_b200.so.  Raises (never falls back) when the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C mppi_tf_b200/csrc` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)      # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, handle=None):
+    if rc != MPPI_OK:
+        msg = load().mppi_last_error(handle)
+        raise MppiError(rc, msg.decode() if msg else "unknown error")

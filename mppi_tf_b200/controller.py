@@ -1,0 +1,322 @@
+"""Python mirror of the reference's C++ classes over the C-ABI (used by tests and bench.py).
+
+Same names and argument meaning as /root/reference/include/{controller,model,cost}_base.hpp;
+the TensorFlow graph-builder methods become calls on plain numpy buffers.  All arithmetic runs in
+libmppi_b200.so on the GPU — nothing here computes.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import MppiConfig, check
+
+_fp = C.POINTER(C.c_float)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_fp)
+
+
+class ModelBase:
+    """ModelBase(mass, dt, s_dim, a_dim) — include/model_base.hpp:58-61."""
+
+    def __init__(self, mass=1.0, dt=0.01, s_dim=2, a_dim=1, device=-1):
+        self.mass, self.dt, self.s_dim, self.a_dim, self.device = float(mass), float(dt), s_dim, a_dim, device
+        self._lib = _capi.load()
+
+    def freeStep(self, state):
+        """mBuildFreeStepGraph: state [k|1, s] -> [k|1, s]."""
+        st = _f32(state).reshape(-1, self.s_dim)
+        out = np.empty_like(st)
+        check(self._lib.mppi_model_free_step(self.device, self.mass, self.dt, self.s_dim, self.a_dim,
+                                             st.shape[0], _ptr(st), _ptr(out)))
+        return out
+
+    def actionStep(self, action):
+        """mBuildActionStepGraph: action [k, a] -> [k, s]."""
+        ac = _f32(action).reshape(-1, self.a_dim)
+        out = np.empty((ac.shape[0], self.s_dim), np.float32)
+        check(self._lib.mppi_model_action_step(self.device, self.mass, self.dt, self.s_dim, self.a_dim,
+                                               ac.shape[0], _ptr(ac), _ptr(out)))
+        return out
+
+    def predict(self, state, action):
+        """mBuildModelStepGraph: state [k|1, s], action [k, a] -> next state [k, s]."""
+        st = _f32(state).reshape(-1, self.s_dim)
+        ac = _f32(action).reshape(-1, self.a_dim)
+        out = np.empty((ac.shape[0], self.s_dim), np.float32)
+        check(self._lib.mppi_model_step(self.device, self.mass, self.dt, self.s_dim, self.a_dim, st.shape[0],
+                                        ac.shape[0], _ptr(st), _ptr(ac), _ptr(out)))
+        return out
+
+
+class CostBase:
+    """CostBase(lambda, sigma[a,a], goal[s], Q[s]) — include/cost_base.hpp:77-80."""
+
+    def __init__(self, lam, sigma, goal, Q, device=-1):
+        self.lam = float(lam)
+        self.sigma = _f32(sigma)
+        self.goal = _f32(goal).ravel()
+        self.Q = _f32(Q).ravel()
+        self.a_dim = self.sigma.shape[0]
+        self.s_dim = self.goal.size
+        self.device = device
+        self._lib = _capi.load()
+
+    def setGoal(self, goal):
+        goal = _f32(goal).ravel()
+        if goal.size != self.s_dim:
+            return False
+        self.goal = goal
+        return True
+
+    def stateCost(self, state):
+        st = _f32(state).reshape(-1, self.s_dim)
+        out = np.empty(st.shape[0], np.float32)
+        check(self._lib.mppi_cost_state(self.device, st.shape[0], self.s_dim, _ptr(st), _ptr(self.goal),
+                                        _ptr(self.Q), _ptr(out)))
+        return out
+
+    finalCost = stateCost   # mBuildFinalStepCostGraph, src/cost_base.cpp:52-54
+
+    def actionCost(self, action, noise):
+        ac = _f32(action).ravel()
+        nz = _f32(noise).reshape(-1, self.a_dim)
+        out = np.empty(nz.shape[0], np.float32)
+        check(self._lib.mppi_cost_action(self.device, nz.shape[0], self.a_dim, self.lam, _ptr(self.sigma),
+                                         _ptr(ac), _ptr(nz), _ptr(out)))
+        return out
+
+    def stepCost(self, state, action, noise):
+        st = _f32(state).reshape(-1, self.s_dim)
+        ac = _f32(action).ravel()
+        nz = _f32(noise).reshape(-1, self.a_dim)
+        out = np.empty(st.shape[0], np.float32)
+        check(self._lib.mppi_cost_step(self.device, st.shape[0], self.s_dim, self.a_dim, self.lam,
+                                       _ptr(self.sigma), _ptr(self.goal), _ptr(self.Q), _ptr(st), _ptr(ac),
+                                       _ptr(nz), _ptr(out)))
+        return out
+
+
+def blockDiag(block, nb):
+    """utile::blockDiag — src/utile.cpp:10-43."""
+    lib = _capi.load()
+    b = _f32(block)
+    out = np.empty((b.shape[0] * nb, b.shape[1] * nb), np.float32)
+    check(lib.mppi_block_diag(_ptr(b), b.shape[0], b.shape[1], nb, _ptr(out)))
+    return out
+
+
+class ControllerBase:
+    """ControllerBase(k, tau, dt, mass, s_dim, a_dim) — include/controller_base.hpp:60-65.
+
+    Extra keyword arguments expose what the reference hard-codes in its constructor
+    (lambda=1, sigma=I, goal=(1,0,..), Q=1; src/controller_base.cpp:37-69) and the B200 additions:
+    rank/world sample sharding, n_controllers batching, an external CUDA stream.
+    """
+
+    def __init__(self, k, tau, dt, mass, s_dim, a_dim, lam=1.0, sigma=None, goal=None, Q=None, seed=1,
+                 device=-1, rank=0, world=1, n_controllers=1, goal_per_controller=False, stream=None):
+        self._lib = _capi.load()
+        self.k, self.tau, self.dt, self.mass, self.s_dim, self.a_dim = k, tau, dt, mass, s_dim, a_dim
+        self.n = n_controllers
+        self.device = device
+        cfg = MppiConfig()
+        self._lib.mppi_config_default(C.byref(cfg), k, tau, dt, mass, s_dim, a_dim)
+        cfg.lambda_ = lam
+        keep = []
+        for name, val in (("sigma", sigma), ("goal", goal), ("q", Q)):
+            if val is not None:
+                arr = _f32(val)
+                keep.append(arr)
+                setattr(cfg, name, _ptr(arr))
+        cfg.seed = seed
+        cfg.device = device
+        cfg.rank, cfg.world = rank, world
+        cfg.n_controllers = n_controllers
+        cfg.goal_per_controller = 1 if goal_per_controller else 0
+        cfg.stream = stream
+        self._h = C.c_void_p()
+        check(self._lib.mppi_create(C.byref(cfg), C.byref(self._h)))
+        self.k_local = self._lib.mppi_k_local(self._h)
+        self.k_offset = self._lib.mppi_k_offset(self._h)
+        self._action = np.empty((n_controllers, a_dim), np.float32)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.mppi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _shape_out(self, arr):
+        return arr[0].copy() if self.n == 1 else arr.copy()
+
+    # ---- reference API -------------------------------------------------------------------------
+    def next(self, x):
+        """ControllerBase::next — src/controller_base.cpp:135-153."""
+        x = _f32(x).reshape(self.n, self.s_dim)
+        check(self._lib.mppi_next(self._h, _ptr(x), _ptr(self._action)), self._h)
+        return self._shape_out(self._action)
+
+    def setGoal(self, goal):
+        """ControllerBase::setGoal — src/controller_base.cpp:126-133 (size mismatch -> False)."""
+        g = _f32(goal).ravel()
+        if g.size not in (self.s_dim, self.n * self.s_dim):
+            return False
+        check(self._lib.mppi_set_goal(self._h, _ptr(g)), self._h)
+        return True
+
+    # ---- parity / debug ---------------------------------------------------------------------------
+    def nextWithNoise(self, x, eps):
+        """Same update with eps [n, k_local, tau, a] injected (host buffer)."""
+        x = _f32(x).reshape(self.n, self.s_dim)
+        eps = _f32(eps)
+        assert eps.size == self.n * self.k_local * self.tau * self.a_dim, "eps has the wrong size"
+        check(self._lib.mppi_next_with_noise(self._h, _ptr(x), _ptr(eps), _ptr(self._action)), self._h)
+        return self._shape_out(self._action)
+
+    def nextWithNoiseDev(self, x, eps_dev_ptr):
+        x = _f32(x).reshape(self.n, self.s_dim)
+        check(self._lib.mppi_next_with_noise_dev(self._h, _ptr(x), C.c_void_p(eps_dev_ptr), _ptr(self._action)),
+              self._h)
+        return self._shape_out(self._action)
+
+    def getCosts(self):
+        out = np.empty((self.n, self.k_local), np.float32)
+        check(self._lib.mppi_get_costs(self._h, _ptr(out)), self._h)
+        return out[0] if self.n == 1 else out
+
+    def getSequence(self):
+        out = np.empty((self.n, self.tau, self.a_dim), np.float32)
+        check(self._lib.mppi_get_sequence(self._h, _ptr(out)), self._h)
+        return out[0] if self.n == 1 else out
+
+    def setSequence(self, U):
+        U = _f32(U)
+        assert U.size == self.n * self.tau * self.a_dim
+        check(self._lib.mppi_set_sequence(self._h, _ptr(U)), self._h)
+
+    def getUpdate(self):
+        out = np.empty((self.n, self.tau, self.a_dim), np.float32)
+        check(self._lib.mppi_get_update(self._h, _ptr(out)), self._h)
+        return out[0] if self.n == 1 else out
+
+    def getWeightStats(self):
+        beta = np.empty(self.n, np.float32)
+        eta = np.empty(self.n, np.float32)
+        check(self._lib.mppi_get_weight_stats(self._h, _ptr(beta), _ptr(eta)), self._h)
+        return beta, eta
+
+    def dumpNoise(self):
+        out = np.empty((self.n, self.k_local, self.tau, self.a_dim), np.float32)
+        check(self._lib.mppi_dump_noise(self._h, _ptr(out)), self._h)
+        return out[0] if self.n == 1 else out
+
+    def setLambda(self, lam):
+        check(self._lib.mppi_set_lambda(self._h, float(lam)), self._h)
+
+    def setSigma(self, sigma):
+        check(self._lib.mppi_set_sigma(self._h, _ptr(_f32(sigma))), self._h)
+
+    def setQ(self, q):
+        check(self._lib.mppi_set_q(self._h, _ptr(_f32(q))), self._h)
+
+    def setUpdateCounter(self, c):
+        check(self._lib.mppi_set_update_counter(self._h, int(c)), self._h)
+
+    # ---- asynchronous halves (bench / multi-rank) ---------------------------------------------------
+    def setState(self, x):
+        x = _f32(x).reshape(self.n, self.s_dim)
+        check(self._lib.mppi_set_state(self._h, _ptr(x)), self._h)
+
+    def enqueueUpdate(self, eps_dev_ptr=None):
+        check(self._lib.mppi_enqueue_update(self._h, C.c_void_p(eps_dev_ptr) if eps_dev_ptr else None), self._h)
+
+    def enqueueFinish(self):
+        check(self._lib.mppi_enqueue_finish(self._h), self._h)
+
+    def fetchAction(self):
+        check(self._lib.mppi_fetch_action(self._h, _ptr(self._action)), self._h)
+        return self._shape_out(self._action)
+
+    def synchronize(self):
+        check(self._lib.mppi_synchronize(self._h), self._h)
+
+    def exchangeStride(self):
+        return self._lib.mppi_exchange_stride(self._h)
+
+    def exchangeBuffers(self):
+        s, r = C.c_void_p(), C.c_void_p()
+        check(self._lib.mppi_exchange_buffers(self._h, C.byref(s), C.byref(r)), self._h)
+        return s.value, r.value
+
+    def setExchangeBuffers(self, send_ptr, recv_ptr):
+        check(self._lib.mppi_exchange_set_buffers(self._h, C.c_void_p(send_ptr), C.c_void_p(recv_ptr)), self._h)
+
+    def commInit(self, unique_id_bytes):
+        buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
+        check(self._lib.mppi_comm_init(self._h, C.cast(buf, C.c_void_p)), self._h)
+
+    # ---- stage entry points (the reference's m* graph builders) ---------------------------------------
+    def prepareAction(self, actions, t):
+        U = _f32(actions).reshape(-1, self.a_dim)
+        out = np.empty(self.a_dim, np.float32)
+        check(self._lib.mppi_prepare_action(U.shape[0], self.a_dim, _ptr(U), t, _ptr(out)))
+        return out
+
+    def prepareNoise(self, noises, t):
+        nz = _f32(noises)
+        k, T, a = nz.shape
+        out = np.empty((k, a), np.float32)
+        check(self._lib.mppi_prepare_noise(self.device, k, T, a, _ptr(nz), t, _ptr(out)))
+        return out
+
+    def updateStages(self, cost, noises, lam=1.0):
+        """mBeta/mExpArg/mExp/mNabla/mWeights/mWeightedNoise on given costs [k] and noises [k,T,a]."""
+        c = _f32(cost).ravel()
+        nz = _f32(noises)
+        k, T, a = nz.shape
+        beta, nabla = C.c_float(), C.c_float()
+        arg, e, w = (np.empty(k, np.float32) for _ in range(3))
+        wn = np.empty((T, a), np.float32)
+        check(self._lib.mppi_update_stages(self.device, k, T, a, float(lam), _ptr(c), _ptr(nz), C.byref(beta),
+                                           _ptr(arg), _ptr(e), C.byref(nabla), _ptr(w), _ptr(wn)))
+        return dict(beta=beta.value, exp_arg=arg, exp=e, nabla=nabla.value, weights=w, weighted_noise=wn)
+
+    def getNew(self, current, nb):
+        cur = _f32(current).reshape(-1, self.a_dim)
+        out = np.empty((nb, self.a_dim), np.float32)
+        check(self._lib.mppi_get_new(cur.shape[0], self.a_dim, _ptr(cur), nb, _ptr(out) if nb else None))
+        return out
+
+    def shift(self, current, init, nb):
+        cur = _f32(current).reshape(-1, self.a_dim)
+        ini = _f32(init).reshape(-1, self.a_dim)
+        out = np.empty_like(cur)
+        check(self._lib.mppi_shift(cur.shape[0], self.a_dim, _ptr(cur), _ptr(ini), nb, _ptr(out)))
+        return out
+
+
+def comm_unique_id():
+    lib = _capi.load()
+    buf = C.create_string_buffer(128)
+    check(lib.mppi_comm_unique_id(C.cast(buf, C.c_void_p)))
+    return bytes(buf.raw)
+
+
+def philox_raw(seed, call0, sample, update, stream, n_calls, device=-1):
+    lib = _capi.load()
+    out = np.empty((n_calls, 4), np.uint32)
+    check(lib.mppi_philox_raw(device, seed, call0, sample, update, stream, n_calls,
+                              out.ctypes.data_as(C.POINTER(C.c_uint32))))
+    return out

@@ -1,0 +1,747 @@
+// C-ABI of libmppi_b200.so (see include/mppi_b200.h for the contract and the reference
+// methods each entry point replaces).  Host-side only: owns the device buffers, builds the kernel
+// parameter block and launches the kernels of mppi_rollout.cu / mppi_stages.cu.
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mppi_device.cuh"
+#include "mppi_internal.h"
+
+using namespace mppi;
+
+// ---- minimal NCCL surface, resolved with dlopen so single-GPU users need no NCCL at all -----------
+namespace {
+struct NcclUniqueId { char internal[128]; };
+typedef void *NcclComm;
+typedef int (*fn_ncclGetUniqueId)(NcclUniqueId *);
+typedef int (*fn_ncclCommInitRank)(NcclComm *, int, NcclUniqueId, int);
+typedef int (*fn_ncclAllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t);
+typedef int (*fn_ncclCommDestroy)(NcclComm);
+typedef const char *(*fn_ncclGetErrorString)(int);
+struct NcclApi {
+    void *lib = nullptr;
+    fn_ncclGetUniqueId GetUniqueId = nullptr;
+    fn_ncclCommInitRank CommInitRank = nullptr;
+    fn_ncclAllGather AllGather = nullptr;
+    fn_ncclCommDestroy CommDestroy = nullptr;
+    fn_ncclGetErrorString GetErrorString = nullptr;
+};
+NcclApi g_nccl;
+std::string g_last_error;   // errors without a handle (create / stateless stages)
+
+bool load_nccl(std::string &err)
+{
+    if (g_nccl.lib) return true;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+    g_nccl.GetUniqueId = (fn_ncclGetUniqueId)dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (fn_ncclCommInitRank)dlsym(lib, "ncclCommInitRank");
+    g_nccl.AllGather = (fn_ncclAllGather)dlsym(lib, "ncclAllGather");
+    g_nccl.CommDestroy = (fn_ncclCommDestroy)dlsym(lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (fn_ncclGetErrorString)dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) {
+        err = "libnccl.so.2 lacks a required symbol";
+        return false;
+    }
+    g_nccl.lib = lib;
+    return true;
+}
+}  // namespace
+
+struct mppi_handle {
+    int k = 0, tau = 0, s = 0, a = 0, n_ctrl = 1, rank = 0, world = 1;
+    int K_local = 0, k_offset = 0, TA = 0, stride = 0;
+    float dt = 0, mass = 1, lambda = 1;
+    float sigma[kMaxA * kMaxA], lam_inv_sigma_T[kMaxA * kMaxA], q[kMaxS];
+    int sigma_diag = 1, goal_per_ctrl = 0;
+    uint64_t seed = 1;
+    uint32_t update_counter = 0, last_update = 0;
+    bool have_philox_update = false, last_philox = true, pending_finish = false;
+    int device = 0, num_sms = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int max_gx = 1;
+    // device buffers
+    float *d_x = nullptr, *d_goal = nullptr, *d_U = nullptr, *d_Unew = nullptr, *d_next = nullptr;
+    float *d_costs = nullptr, *d_partials = nullptr, *d_payload = nullptr, *d_gather = nullptr, *d_stats = nullptr;
+    unsigned int *d_counters = nullptr;
+    float *d_eps_tmp = nullptr;
+    bool ext_exchange = false;
+    // pinned host staging
+    float *h_x = nullptr, *h_next = nullptr;
+    bool x_staged = false;
+    NcclComm comm = nullptr;
+    std::string err;
+};
+
+namespace {
+
+int fail(mppi_handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+#define CU_TRY(h, expr)                                                                          \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(h, MPPI_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+int select_device(mppi_handle *h, int device, int *dev_out, cudaDeviceProp *prop)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(h, MPPI_ERR_CUDA,
+                    std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                        " (libmppi_b200 has no CPU fallback)");
+    int dev = device;
+    if (dev < 0) CU_TRY(h, cudaGetDevice(&dev));
+    if (dev >= n) return fail(h, MPPI_ERR_BAD_ARG, "device ordinal out of range");
+    CU_TRY(h, cudaSetDevice(dev));
+    CU_TRY(h, cudaGetDeviceProperties(prop, dev));
+    if (prop->major != 10)
+        return fail(h, MPPI_ERR_CUDA, std::string("device ") + prop->name + " is sm_" + std::to_string(prop->major) +
+                                          std::to_string(prop->minor) + "; this library carries sm_100a code only");
+    *dev_out = dev;
+    return MPPI_OK;
+}
+
+void derive_sigma(mppi_handle *h)
+{
+    const int a = h->a;
+    float inv[kMaxA * kMaxA];
+    invert_matrix(h->sigma, a, inv);
+    h->sigma_diag = 1;
+    for (int i = 0; i < a; i++)
+        for (int j = 0; j < a; j++) {
+            if (i != j && h->sigma[i * a + j] != 0.f) h->sigma_diag = 0;
+            h->lam_inv_sigma_T[i * a + j] = h->lambda * inv[j * a + i];   // lambda * (Sigma^-1)^T
+        }
+}
+
+RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
+{
+    RolloutParams p;
+    memset(&p, 0, sizeof(p));
+    p.K_local = h->K_local;
+    p.k_offset = h->k_offset;
+    p.T = h->tau;
+    p.TA = h->TA;
+    p.n_ctrl = h->n_ctrl;
+    p.n_iter = 1;
+    p.world = h->world;
+    p.dt = h->dt;
+    p.c_pu = (h->dt * h->dt) / 2.0f / h->mass;
+    p.c_vu = h->dt / h->mass;
+    p.lambda = h->lambda;
+    p.neg_inv_lambda_log2e = -kLog2e / h->lambda;
+    memcpy(p.q, h->q, sizeof(p.q));
+    memcpy(p.sigma, h->sigma, sizeof(p.sigma));
+    memcpy(p.lam_inv_sigma_T, h->lam_inv_sigma_T, sizeof(p.lam_inv_sigma_T));
+    p.sigma_diag = h->sigma_diag;
+    p.goal_per_ctrl = h->goal_per_ctrl;
+    p.key0 = (uint32_t)h->seed;
+    p.key1 = (uint32_t)(h->seed >> 32);
+    p.update = h->update_counter;
+    p.x_inline = (h->n_ctrl == 1);
+    if (p.x_inline) memcpy(p.x0, h->h_x, sizeof(float) * h->s);
+    p.x = h->d_x;
+    p.goal = h->d_goal;
+    p.U = h->d_U;
+    p.U_new = h->d_Unew;
+    p.next = h->d_next;
+    p.costs = h->d_costs;
+    p.partials = h->d_partials;
+    p.payload = h->d_payload;
+    p.stats = h->d_stats;
+    p.counters = h->d_counters;
+    p.eps = eps_dev;
+    return p;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 4); }
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *mppi_version(void) { return "mppi_b200 0.1 sm_100a"; }
+
+void mppi_config_default(mppi_config *cfg, int k, int tau, float dt, float mass, int s_dim, int a_dim)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->k = k; cfg->tau = tau; cfg->dt = dt; cfg->mass = mass; cfg->s_dim = s_dim; cfg->a_dim = a_dim;
+    cfg->lambda = 1.0f;       // src/controller_base.cpp:40
+    cfg->seed = 1;            // RandomNormal::Seed(1), src/controller_base.cpp:199
+    cfg->device = -1;
+    cfg->rank = 0; cfg->world = 1; cfg->n_controllers = 1;
+}
+
+const char *mppi_last_error(const mppi_handle *h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int mppi_create(const mppi_config *cfg, mppi_handle **out)
+{
+    if (!cfg || !out) return fail(nullptr, MPPI_ERR_BAD_ARG, "null cfg/out");
+    *out = nullptr;
+    const int n_ctrl = cfg->n_controllers > 0 ? cfg->n_controllers : 1;
+    const int world = cfg->world > 0 ? cfg->world : 1;
+    if (cfg->k <= 0 || cfg->tau <= 0 || cfg->a_dim <= 0 || cfg->s_dim <= 0)
+        return fail(nullptr, MPPI_ERR_BAD_ARG, "k, tau, s_dim, a_dim must be positive");
+    if (cfg->s_dim != 2 * cfg->a_dim)
+        return fail(nullptr, MPPI_ERR_BAD_ARG, "point-mass model needs s_dim == 2 * a_dim");
+    if (cfg->a_dim > MPPI_MAX_A) return fail(nullptr, MPPI_ERR_UNSUPPORTED, "a_dim > MPPI_MAX_A");
+    if ((long long)cfg->tau * cfg->a_dim > MPPI_MAX_TA) return fail(nullptr, MPPI_ERR_UNSUPPORTED, "tau*a_dim > MPPI_MAX_TA");
+    if (!(cfg->lambda > 0.f) || !(cfg->mass != 0.f)) return fail(nullptr, MPPI_ERR_BAD_ARG, "lambda must be > 0, mass != 0");
+    if (cfg->rank < 0 || cfg->rank >= world) return fail(nullptr, MPPI_ERR_BAD_ARG, "rank outside [0, world)");
+    if (cfg->k < world) return fail(nullptr, MPPI_ERR_BAD_ARG, "fewer samples than ranks");
+
+    mppi_handle *h = new (std::nothrow) mppi_handle();
+    if (!h) return fail(nullptr, MPPI_ERR_CUDA, "out of host memory");
+    cudaDeviceProp prop;
+    int rc = select_device(h, cfg->device, &h->device, &prop);
+    if (rc != MPPI_OK) { g_last_error = h->err; delete h; return rc; }
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+
+    h->k = cfg->k; h->tau = cfg->tau; h->s = cfg->s_dim; h->a = cfg->a_dim;
+    h->n_ctrl = n_ctrl; h->rank = cfg->rank; h->world = world;
+    h->dt = cfg->dt; h->mass = cfg->mass; h->lambda = cfg->lambda; h->seed = cfg->seed;
+    h->TA = cfg->tau * cfg->a_dim;
+    h->stride = partial_stride(h->TA);
+    // rank r owns samples [r*k/world, (r+1)*k/world)  
+    h->k_offset = (int)((long long)cfg->k * cfg->rank / world);
+    h->K_local = (int)((long long)cfg->k * (cfg->rank + 1) / world) - h->k_offset;
+    h->goal_per_ctrl = cfg->goal_per_controller ? 1 : 0;
+
+    const int a = h->a, s = h->s;
+    memset(h->sigma, 0, sizeof(h->sigma));
+    memset(h->q, 0, sizeof(h->q));
+    for (int i = 0; i < a; i++)
+        for (int j = 0; j < a; j++) h->sigma[i * a + j] = cfg->sigma ? cfg->sigma[i * a + j] : (i == j ? 1.f : 0.f);
+    for (int i = 0; i < s; i++) h->q[i] = cfg->q ? cfg->q[i] : 1.f;
+    {
+        float inv[kMaxA * kMaxA];
+        if (!invert_matrix(h->sigma, a, inv)) { delete h; return fail(nullptr, MPPI_ERR_BAD_ARG, "sigma is singular"); }
+    }
+    derive_sigma(h);
+
+    auto bail = [&](int code, const std::string &msg) {
+        g_last_error = msg;
+        mppi_destroy(h);
+        return code;
+    };
+#define CU_TRY_C(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) return bail(MPPI_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+    if (cfg->stream) { h->stream = (cudaStream_t)cfg->stream; h->own_stream = false; }
+    else { CU_TRY_C(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+
+    h->max_gx = max_grid_x(h->K_local, n_ctrl, h->num_sms);
+    const size_t n_goal = (size_t)(h->goal_per_ctrl ? n_ctrl : 1) * s;
+    CU_TRY_C(cudaMalloc(&h->d_x, sizeof(float) * n_ctrl * s));
+    CU_TRY_C(cudaMalloc(&h->d_goal, sizeof(float) * n_goal));
+    CU_TRY_C(cudaMalloc(&h->d_U, sizeof(float) * n_ctrl * h->TA));
+    CU_TRY_C(cudaMalloc(&h->d_Unew, sizeof(float) * n_ctrl * h->TA));
+    CU_TRY_C(cudaMalloc(&h->d_next, sizeof(float) * n_ctrl * a));
+    CU_TRY_C(cudaMalloc(&h->d_costs, sizeof(float) * (size_t)n_ctrl * h->K_local));
+    CU_TRY_C(cudaMalloc(&h->d_partials, sizeof(float) * (size_t)n_ctrl * h->max_gx * h->stride));
+    CU_TRY_C(cudaMalloc(&h->d_payload, sizeof(float) * (size_t)n_ctrl * h->stride));
+    CU_TRY_C(cudaMalloc(&h->d_gather, sizeof(float) * (size_t)world * n_ctrl * h->stride));
+    CU_TRY_C(cudaMalloc(&h->d_stats, sizeof(float) * 2 * n_ctrl));
+    CU_TRY_C(cudaMalloc(&h->d_counters, sizeof(unsigned int) * n_ctrl));
+    CU_TRY_C(cudaMemset(h->d_counters, 0, sizeof(unsigned int) * n_ctrl));
+    CU_TRY_C(cudaMemset(h->d_U, 0, sizeof(float) * n_ctrl * h->TA));
+    CU_TRY_C(cudaMemset(h->d_Unew, 0, sizeof(float) * n_ctrl * h->TA));
+    CU_TRY_C(cudaMemset(h->d_stats, 0, sizeof(float) * 2 * n_ctrl));
+    CU_TRY_C(cudaMemset(h->d_x, 0, sizeof(float) * n_ctrl * s));
+    CU_TRY_C(cudaMallocHost(&h->h_x, sizeof(float) * n_ctrl * s));
+    CU_TRY_C(cudaMallocHost(&h->h_next, sizeof(float) * n_ctrl * a));
+    memset(h->h_x, 0, sizeof(float) * n_ctrl * s);
+
+    std::vector<float> goal(n_goal);
+    for (size_t i = 0; i < n_goal; i++)
+        goal[i] = cfg->goal ? cfg->goal[i] : ((i % s) % 2 == 0 ? 1.f : 0.f);   // (1,0,1,0,..), :43-46
+    CU_TRY_C(cudaMemcpy(h->d_goal, goal.data(), sizeof(float) * n_goal, cudaMemcpyHostToDevice));
+#undef CU_TRY_C
+    *out = h;
+    return MPPI_OK;
+}
+
+int mppi_destroy(mppi_handle *h)
+{
+    if (!h) return MPPI_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    cudaFree(h->d_x); cudaFree(h->d_goal); cudaFree(h->d_U); cudaFree(h->d_Unew); cudaFree(h->d_next);
+    cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_counters);
+    cudaFree(h->d_eps_tmp);
+    if (!h->ext_exchange) { cudaFree(h->d_payload); cudaFree(h->d_gather); }
+    if (h->h_x) cudaFreeHost(h->h_x);
+    if (h->h_next) cudaFreeHost(h->h_next);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MPPI_OK;
+}
+
+int mppi_k_local(const mppi_handle *h) { return h ? h->K_local : 0; }
+int mppi_k_offset(const mppi_handle *h) { return h ? h->k_offset : 0; }
+int mppi_exchange_stride(const mppi_handle *h) { return h ? h->stride : 0; }
+
+// ---- update step --------------------------------------------------------------------------------
+int mppi_set_state(mppi_handle *h, const float *x_host)
+{
+    if (!h || !x_host) return fail(h, MPPI_ERR_BAD_ARG, "null handle/state");
+    CU_TRY(h, cudaSetDevice(h->device));
+    memcpy(h->h_x, x_host, sizeof(float) * h->n_ctrl * h->s);
+    if (h->n_ctrl > 1)
+        CU_TRY(h, cudaMemcpyAsync(h->d_x, h->h_x, sizeof(float) * h->n_ctrl * h->s, cudaMemcpyHostToDevice, h->stream));
+    h->x_staged = true;
+    return MPPI_OK;
+}
+
+int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
+{
+    if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
+    if (!h->x_staged) return fail(h, MPPI_ERR_STATE, "mppi_set_state must precede mppi_enqueue_update");
+    CU_TRY(h, cudaSetDevice(h->device));
+    RolloutParams p = make_params(h, eps_dev);
+    int gx = 0;
+    if (eps_dev) {
+        cudaError_t e = launch_rollout_injected(p, h->a, h->num_sms, h->smem_optin, h->stream, &gx);
+        if (e == cudaErrorInvalidConfiguration)
+            return fail(h, MPPI_ERR_UNSUPPORTED, "injected-noise mode: one 32-sample tile of tau*a_dim floats does not fit shared memory");
+        CU_TRY(h, e);
+        h->last_philox = false;
+    } else {
+        CU_TRY(h, launch_rollout_philox(p, h->a, h->num_sms, h->stream, &gx));
+        h->last_philox = true;
+        h->have_philox_update = true;
+        h->last_update = h->update_counter;
+        h->update_counter++;
+    }
+    h->pending_finish = (h->world > 1);
+    return MPPI_OK;
+}
+
+int mppi_enqueue_finish(mppi_handle *h)
+{
+    if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
+    if (h->world <= 1) return MPPI_OK;
+    if (!h->pending_finish) return fail(h, MPPI_ERR_STATE, "no update awaiting a finish");
+    CU_TRY(h, cudaSetDevice(h->device));
+    RolloutParams p = make_params(h, nullptr);
+    CU_TRY(h, launch_finish(p, h->a, h->last_philox, h->d_gather, h->stream));
+    h->pending_finish = false;
+    return MPPI_OK;
+}
+
+static int exchange(mppi_handle *h)
+{
+    if (h->world <= 1) return MPPI_OK;
+    if (!h->comm)
+        return fail(h, MPPI_ERR_COMM, "world > 1 needs mppi_comm_init (in-library NCCL) or a caller-side all-gather "
+                                      "between mppi_enqueue_update and mppi_enqueue_finish");
+    const int rc = g_nccl.AllGather(h->d_payload, h->d_gather, (size_t)h->n_ctrl * h->stride, /*ncclFloat*/ 7, h->comm, h->stream);
+    if (rc != 0)
+        return fail(h, MPPI_ERR_COMM, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    return MPPI_OK;
+}
+
+int mppi_fetch_action(mppi_handle *h, float *action_host)
+{
+    if (!h || !action_host) return fail(h, MPPI_ERR_BAD_ARG, "null handle/action");
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaMemcpyAsync(h->h_next, h->d_next, sizeof(float) * h->n_ctrl * h->a, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    memcpy(action_host, h->h_next, sizeof(float) * h->n_ctrl * h->a);
+    return MPPI_OK;
+}
+
+int mppi_synchronize(mppi_handle *h)
+{
+    if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+static int next_common(mppi_handle *h, const float *x_host, const float *eps_dev, float *action_host)
+{
+    int rc = mppi_set_state(h, x_host);
+    if (rc) return rc;
+    rc = mppi_enqueue_update(h, eps_dev);
+    if (rc) return rc;
+    if (h->world > 1) {
+        rc = exchange(h);
+        if (rc) return rc;
+        rc = mppi_enqueue_finish(h);
+        if (rc) return rc;
+    }
+    return mppi_fetch_action(h, action_host);
+}
+
+int mppi_next(mppi_handle *h, const float *x_host, float *action_host)
+{
+    if (!h || !x_host || !action_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    return next_common(h, x_host, nullptr, action_host);
+}
+
+int mppi_next_with_noise_dev(mppi_handle *h, const float *x_host, const float *eps_dev, float *action_host)
+{
+    if (!h || !x_host || !eps_dev || !action_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    return next_common(h, x_host, eps_dev, action_host);
+}
+
+int mppi_next_with_noise(mppi_handle *h, const float *x_host, const float *eps_host, float *action_host)
+{
+    if (!h || !x_host || !eps_host || !action_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t bytes = sizeof(float) * (size_t)h->n_ctrl * h->K_local * h->TA;
+    if (!h->d_eps_tmp) CU_TRY(h, cudaMalloc(&h->d_eps_tmp, bytes));
+    CU_TRY(h, cudaMemcpyAsync(h->d_eps_tmp, eps_host, bytes, cudaMemcpyHostToDevice, h->stream));
+    return next_common(h, x_host, h->d_eps_tmp, action_host);
+}
+
+// ---- controller state ------------------------------------------------------------------------------
+static int d2h(mppi_handle *h, float *dst, const float *src, size_t n)
+{
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaMemcpyAsync(dst, src, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+static int h2d(mppi_handle *h, float *dst, const float *src, size_t n)
+{
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaMemcpyAsync(dst, src, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_set_goal(mppi_handle *h, const float *goal_host)
+{
+    if (!h || !goal_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    return h2d(h, h->d_goal, goal_host, (size_t)(h->goal_per_ctrl ? h->n_ctrl : 1) * h->s);
+}
+int mppi_set_lambda(mppi_handle *h, float lambda)
+{
+    if (!h || !(lambda > 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "lambda must be > 0");
+    h->lambda = lambda;
+    derive_sigma(h);
+    return MPPI_OK;
+}
+int mppi_set_sigma(mppi_handle *h, const float *sigma_host)
+{
+    if (!h || !sigma_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    float inv[kMaxA * kMaxA];
+    if (!invert_matrix(sigma_host, h->a, inv)) return fail(h, MPPI_ERR_BAD_ARG, "sigma is singular");
+    memcpy(h->sigma, sigma_host, sizeof(float) * h->a * h->a);
+    derive_sigma(h);
+    return MPPI_OK;
+}
+int mppi_set_q(mppi_handle *h, const float *q_host)
+{
+    if (!h || !q_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    memcpy(h->q, q_host, sizeof(float) * h->s);
+    return MPPI_OK;
+}
+int mppi_set_sequence(mppi_handle *h, const float *U_host)
+{
+    if (!h || !U_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    return h2d(h, h->d_U, U_host, (size_t)h->n_ctrl * h->TA);
+}
+int mppi_get_sequence(mppi_handle *h, float *U_host)
+{
+    if (!h || !U_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    return d2h(h, U_host, h->d_U, (size_t)h->n_ctrl * h->TA);
+}
+int mppi_get_update(mppi_handle *h, float *U_new_host)
+{
+    if (!h || !U_new_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    return d2h(h, U_new_host, h->d_Unew, (size_t)h->n_ctrl * h->TA);
+}
+int mppi_get_costs(mppi_handle *h, float *costs_host)
+{
+    if (!h || !costs_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    return d2h(h, costs_host, h->d_costs, (size_t)h->n_ctrl * h->K_local);
+}
+int mppi_get_weight_stats(mppi_handle *h, float *beta, float *eta)
+{
+    if (!h || !beta || !eta) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    std::vector<float> st(2 * (size_t)h->n_ctrl);
+    int rc = d2h(h, st.data(), h->d_stats, st.size());
+    if (rc) return rc;
+    for (int c = 0; c < h->n_ctrl; c++) { beta[c] = st[2 * c]; eta[c] = st[2 * c + 1]; }
+    return MPPI_OK;
+}
+int mppi_set_update_counter(mppi_handle *h, uint32_t counter)
+{
+    if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
+    h->update_counter = counter;
+    return MPPI_OK;
+}
+
+int mppi_dump_noise(mppi_handle *h, float *eps_host)
+{
+    if (!h || !eps_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    if (!h->have_philox_update) return fail(h, MPPI_ERR_STATE, "no Philox-mode update has run yet");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n_ctrl * h->K_local * h->TA;
+    DevBuf buf;
+    CU_TRY(h, buf.alloc(sizeof(float) * n));
+    RolloutParams p = make_params(h, nullptr);
+    p.update = h->last_update;
+    CU_TRY(h, launch_dump_noise(p, h->a, buf.as<float>(), h->stream));
+    return d2h(h, eps_host, buf.as<float>(), n);
+}
+
+// ---- exchange ------------------------------------------------------------------------------------
+int mppi_exchange_buffers(mppi_handle *h, void **send_dev, void **recv_dev)
+{
+    if (!h || !send_dev || !recv_dev) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    *send_dev = h->d_payload;
+    *recv_dev = h->d_gather;
+    return MPPI_OK;
+}
+int mppi_exchange_set_buffers(mppi_handle *h, void *send_dev, void *recv_dev)
+{
+    if (!h || !send_dev || !recv_dev) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (!h->ext_exchange) { cudaFree(h->d_payload); cudaFree(h->d_gather); }
+    h->d_payload = (float *)send_dev;
+    h->d_gather = (float *)recv_dev;
+    h->ext_exchange = true;
+    return MPPI_OK;
+}
+int mppi_comm_unique_id(void *id128)
+{
+    if (!id128) return fail(nullptr, MPPI_ERR_BAD_ARG, "null id");
+    std::string err;
+    if (!load_nccl(err)) return fail(nullptr, MPPI_ERR_COMM, err);
+    NcclUniqueId id;
+    const int rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0) return fail(nullptr, MPPI_ERR_COMM, "ncclGetUniqueId failed");
+    memcpy(id128, &id, sizeof(id));
+    return MPPI_OK;
+}
+int mppi_comm_init(mppi_handle *h, const void *id128)
+{
+    if (!h || !id128) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    std::string err;
+    if (!load_nccl(err)) return fail(h, MPPI_ERR_COMM, err);
+    CU_TRY(h, cudaSetDevice(h->device));
+    NcclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    const int rc = g_nccl.CommInitRank(&h->comm, h->world, id, h->rank);
+    if (rc != 0)
+        return fail(h, MPPI_ERR_COMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    return MPPI_OK;
+}
+
+int mppi_set_mlp(mppi_handle *h, int, const float *, const float *, const float *, const float *, const float *,
+                 const float *, const float *, const float *, const float *, const float *)
+{
+    return fail(h, MPPI_ERR_UNSUPPORTED, "MLP dynamics are not built into this library version");
+}
+
+// ---- stateless stages -------------------------------------------------------------------------------
+int mppi_block_diag(const float *in, int rows, int cols, int nb, float *out)
+{
+    if (!in || !out || rows <= 0 || cols <= 0 || nb <= 0) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad block_diag argument");
+    const int R = rows * nb, C = cols * nb;
+    for (int i = 0; i < R * C; i++) out[i] = 0.f;
+    for (int b = 0; b < nb; b++)
+        for (int r = 0; r < rows; r++)
+            memcpy(out + (size_t)(b * rows + r) * C + b * cols, in + (size_t)r * cols, sizeof(float) * cols);
+    return MPPI_OK;
+}
+
+static int stage_device(int device)
+{
+    cudaDeviceProp prop;
+    int dev;
+    return select_device(nullptr, device, &dev, &prop);
+}
+#define CU_TRY_S(expr) CU_TRY((mppi_handle *)nullptr, expr)
+
+static int model_stage(int device, float mass, float dt, int s, int a, int kst, int k, const float *state,
+                       const float *action, float *out, int mode)
+{
+    if (!out || s != 2 * a || a <= 0 || (mode != 1 && (!state || kst <= 0)) || (mode != 0 && (!action || k <= 0)))
+        return fail(nullptr, MPPI_ERR_BAD_ARG, "bad model stage argument");
+    if (mode == 2 && kst != 1 && kst != k) return fail(nullptr, MPPI_ERR_BAD_ARG, "state batch must be 1 or k");
+    int rc = stage_device(device);
+    if (rc) return rc;
+    const int n_out = (mode == 0 ? kst : k);
+    DevBuf ds, da, dout;
+    CU_TRY_S(ds.alloc(sizeof(float) * (size_t)(mode != 1 ? kst : 1) * s));
+    CU_TRY_S(da.alloc(sizeof(float) * (size_t)(mode != 0 ? k : 1) * a));
+    CU_TRY_S(dout.alloc(sizeof(float) * (size_t)n_out * s));
+    if (mode != 1) CU_TRY_S(cudaMemcpy(ds.p, state, sizeof(float) * (size_t)kst * s, cudaMemcpyHostToDevice));
+    if (mode != 0) CU_TRY_S(cudaMemcpy(da.p, action, sizeof(float) * (size_t)k * a, cudaMemcpyHostToDevice));
+    CU_TRY_S(launch_model_step(mass, dt, s, a, kst, k, ds.as<float>(), da.as<float>(), dout.as<float>(), mode, 0));
+    CU_TRY_S(cudaMemcpy(out, dout.p, sizeof(float) * (size_t)n_out * s, cudaMemcpyDeviceToHost));
+    return MPPI_OK;
+}
+int mppi_model_free_step(int device, float mass, float dt, int s, int a, int kst, const float *state, float *out)
+{
+    return model_stage(device, mass, dt, s, a, kst, kst, state, nullptr, out, 0);
+}
+int mppi_model_action_step(int device, float mass, float dt, int s, int a, int k, const float *action, float *out)
+{
+    return model_stage(device, mass, dt, s, a, 1, k, nullptr, action, out, 1);
+}
+int mppi_model_step(int device, float mass, float dt, int s, int a, int kst, int k, const float *state,
+                    const float *action, float *out)
+{
+    return model_stage(device, mass, dt, s, a, kst, k, state, action, out, 2);
+}
+
+static int cost_stage(int device, int k, int s, int a, float lambda, const float *sigma, const float *goal,
+                      const float *q, const float *state, const float *action, const float *noise, float *out, int mode)
+{
+    if (!out || k <= 0) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad cost stage argument");
+    if (mode != 1 && (!state || !goal || !q || s <= 0 || s > 64)) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad state-cost argument");
+    if (mode != 0 && (!sigma || !action || !noise || a <= 0 || a > MPPI_MAX_A)) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad action-cost argument");
+    int rc = stage_device(device);
+    if (rc) return rc;
+    float inv[kMaxA * kMaxA] = {0};
+    if (mode != 0 && !invert_matrix(sigma, a, inv)) return fail(nullptr, MPPI_ERR_BAD_ARG, "sigma is singular");
+    DevBuf dinv, dg, dq, dst, dac, dn, dout;
+    const int ss = s > 0 ? s : 1, aa = a > 0 ? a : 1;
+    CU_TRY_S(dinv.alloc(sizeof(inv)));
+    CU_TRY_S(dg.alloc(sizeof(float) * ss)); CU_TRY_S(dq.alloc(sizeof(float) * ss));
+    CU_TRY_S(dst.alloc(sizeof(float) * (size_t)k * ss));
+    CU_TRY_S(dac.alloc(sizeof(float) * aa)); CU_TRY_S(dn.alloc(sizeof(float) * (size_t)k * aa));
+    CU_TRY_S(dout.alloc(sizeof(float) * (size_t)k));
+    CU_TRY_S(cudaMemcpy(dinv.p, inv, sizeof(inv), cudaMemcpyHostToDevice));
+    if (mode != 1) {
+        CU_TRY_S(cudaMemcpy(dg.p, goal, sizeof(float) * s, cudaMemcpyHostToDevice));
+        CU_TRY_S(cudaMemcpy(dq.p, q, sizeof(float) * s, cudaMemcpyHostToDevice));
+        CU_TRY_S(cudaMemcpy(dst.p, state, sizeof(float) * (size_t)k * s, cudaMemcpyHostToDevice));
+    }
+    if (mode != 0) {
+        CU_TRY_S(cudaMemcpy(dac.p, action, sizeof(float) * a, cudaMemcpyHostToDevice));
+        CU_TRY_S(cudaMemcpy(dn.p, noise, sizeof(float) * (size_t)k * a, cudaMemcpyHostToDevice));
+    }
+    CU_TRY_S(launch_cost(k, s, a, lambda, dinv.as<float>(), dg.as<float>(), dq.as<float>(), dst.as<float>(),
+                         dac.as<float>(), dn.as<float>(), dout.as<float>(), mode, 0));
+    CU_TRY_S(cudaMemcpy(out, dout.p, sizeof(float) * (size_t)k, cudaMemcpyDeviceToHost));
+    return MPPI_OK;
+}
+int mppi_cost_state(int device, int k, int s, const float *state, const float *goal, const float *q, float *out)
+{
+    return cost_stage(device, k, s, 0, 1.f, nullptr, goal, q, state, nullptr, nullptr, out, 0);
+}
+int mppi_cost_action(int device, int k, int a, float lambda, const float *sigma, const float *action,
+                     const float *noise, float *out)
+{
+    return cost_stage(device, k, 0, a, lambda, sigma, nullptr, nullptr, nullptr, action, noise, out, 1);
+}
+int mppi_cost_step(int device, int k, int s, int a, float lambda, const float *sigma, const float *goal,
+                   const float *q, const float *state, const float *action, const float *noise, float *out)
+{
+    return cost_stage(device, k, s, a, lambda, sigma, goal, q, state, action, noise, out, 2);
+}
+
+int mppi_prepare_action(int T, int a, const float *U, int t, float *out)
+{
+    if (!U || !out || t < 0 || t >= T || a <= 0) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad prepare_action argument");
+    memcpy(out, U + (size_t)t * a, sizeof(float) * a);
+    return MPPI_OK;
+}
+int mppi_prepare_noise(int device, int k, int T, int a, const float *noise, int t, float *out)
+{
+    if (!noise || !out || k <= 0 || a <= 0 || t < 0 || t >= T) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad prepare_noise argument");
+    int rc = stage_device(device);
+    if (rc) return rc;
+    DevBuf dn, dout;
+    CU_TRY_S(dn.alloc(sizeof(float) * (size_t)k * T * a));
+    CU_TRY_S(dout.alloc(sizeof(float) * (size_t)k * a));
+    CU_TRY_S(cudaMemcpy(dn.p, noise, sizeof(float) * (size_t)k * T * a, cudaMemcpyHostToDevice));
+    CU_TRY_S(launch_prepare_noise(k, T, a, dn.as<float>(), t, dout.as<float>(), 0));
+    CU_TRY_S(cudaMemcpy(out, dout.p, sizeof(float) * (size_t)k * a, cudaMemcpyDeviceToHost));
+    return MPPI_OK;
+}
+
+int mppi_update_stages(int device, int k, int T, int a, float lambda, const float *cost, const float *noise,
+                       float *beta, float *exp_arg, float *exp_out, float *nabla, float *weights,
+                       float *weighted_noise)
+{
+    if (!cost || !noise || k <= 0 || T <= 0 || a <= 0 || !(lambda > 0.f)) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad update_stages argument");
+    int rc = stage_device(device);
+    if (rc) return rc;
+    DevBuf dc, dn, dscal, darg, dexp, dw, dwn;
+    CU_TRY_S(dc.alloc(sizeof(float) * (size_t)k));
+    CU_TRY_S(dn.alloc(sizeof(float) * (size_t)k * T * a));
+    CU_TRY_S(dscal.alloc(sizeof(float) * 2));
+    CU_TRY_S(darg.alloc(sizeof(float) * (size_t)k));
+    CU_TRY_S(dexp.alloc(sizeof(float) * (size_t)k));
+    CU_TRY_S(dw.alloc(sizeof(float) * (size_t)k));
+    CU_TRY_S(dwn.alloc(sizeof(float) * (size_t)T * a));
+    CU_TRY_S(cudaMemcpy(dc.p, cost, sizeof(float) * (size_t)k, cudaMemcpyHostToDevice));
+    CU_TRY_S(cudaMemcpy(dn.p, noise, sizeof(float) * (size_t)k * T * a, cudaMemcpyHostToDevice));
+    CU_TRY_S(launch_update_stages(k, T, a, lambda, dc.as<float>(), dn.as<float>(), dscal.as<float>(), darg.as<float>(),
+                                  dexp.as<float>(), dw.as<float>(), dwn.as<float>(), 0));
+    float scal[2];
+    CU_TRY_S(cudaMemcpy(scal, dscal.p, sizeof(scal), cudaMemcpyDeviceToHost));
+    if (beta) *beta = scal[0];
+    if (nabla) *nabla = scal[1];
+    if (exp_arg) CU_TRY_S(cudaMemcpy(exp_arg, darg.p, sizeof(float) * (size_t)k, cudaMemcpyDeviceToHost));
+    if (exp_out) CU_TRY_S(cudaMemcpy(exp_out, dexp.p, sizeof(float) * (size_t)k, cudaMemcpyDeviceToHost));
+    if (weights) CU_TRY_S(cudaMemcpy(weights, dw.p, sizeof(float) * (size_t)k, cudaMemcpyDeviceToHost));
+    if (weighted_noise) CU_TRY_S(cudaMemcpy(weighted_noise, dwn.p, sizeof(float) * (size_t)T * a, cudaMemcpyDeviceToHost));
+    return MPPI_OK;
+}
+
+int mppi_get_new(int T, int a, const float *cur, int nb, float *out)
+{
+    if (!cur || nb < 0 || nb > T || a <= 0 || (nb > 0 && !out)) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad get_new argument");
+    if (nb > 0) memcpy(out, cur, sizeof(float) * (size_t)nb * a);
+    return MPPI_OK;
+}
+int mppi_shift(int T, int a, const float *cur, const float *init, int nb, float *out)
+{
+    if (!cur || !out || nb < 0 || nb > T || a <= 0 || (nb > 0 && !init)) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad shift argument");
+    memmove(out, cur + (size_t)nb * a, sizeof(float) * (size_t)(T - nb) * a);
+    if (nb > 0) memcpy(out + (size_t)(T - nb) * a, init, sizeof(float) * (size_t)nb * a);
+    return MPPI_OK;
+}
+
+int mppi_philox_raw(int device, uint64_t seed, uint32_t call0, uint32_t sample, uint32_t update, uint32_t stream,
+                    int n_calls, uint32_t *out)
+{
+    if (!out || n_calls <= 0) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad philox_raw argument");
+    int rc = stage_device(device);
+    if (rc) return rc;
+    DevBuf d;
+    CU_TRY_S(d.alloc(sizeof(uint32_t) * 4 * (size_t)n_calls));
+    CU_TRY_S(launch_philox_raw(seed, call0, sample, update, stream, n_calls, d.as<uint32_t>(), 0));
+    CU_TRY_S(cudaMemcpy(out, d.p, sizeof(uint32_t) * 4 * (size_t)n_calls, cudaMemcpyDeviceToHost));
+    return MPPI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+// Device-side building blocks shared by the rollout kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mppi_b200.h"
+
+namespace mppi {
+
+constexpr int kMaxA = MPPI_MAX_A;
+constexpr int kMaxS = MPPI_MAX_S;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kInf = __builtin_huge_valf();
+
+// Exchange / partial record layout: {beta, eta, 0, 0, N[TA padded to 4]}.
+__host__ __device__ inline int partial_stride(int TA) { return 4 + ((TA + 3) & ~3); }
+
+// Kernel parameters (one struct, passed by value as __grid_constant__).
+struct RolloutParams {
+    // sizes
+    int K_local;      // samples of this rank, per controller
+    int k_offset;     // global index of the first local sample (Philox counter word 1)
+    int T, TA;        // horizon, T * a
+    int n_ctrl;
+    int n_iter;       // samples per thread in the Philox kernel
+    int world;        // > 1: the last CTA writes the rank payload instead of applying the update
+    // model (ModelBase: A = blkdiag([[1,dt],[0,1]]), B = blkdiag([[dt^2/2],[dt]]) / mass)
+    float dt, c_pu, c_vu;
+    // cost (CostBase): lambda, diag(Q), Sigma (scale) and lambda * Sigma^-T (action cost)
+    float lambda, neg_inv_lambda_log2e;
+    float q[kMaxS];
+    float sigma[kMaxA * kMaxA];
+    float lam_inv_sigma_T[kMaxA * kMaxA];   // v_t = lam_inv_sigma_T * U_t  (injected mode)
+    int sigma_diag;
+    int goal_per_ctrl;
+    // Philox key / counter words
+    uint32_t key0, key1, update;
+    // single-controller fast path: state passed by value (no H2D copy)
+    int x_inline;
+    float x0[kMaxS];
+    // device buffers
+    const float *x;          // [n_ctrl][s]
+    const float *goal;       // [1 or n_ctrl][s]
+    float *U;                // [n_ctrl][T][a]   in: mean sequence, out: shifted sequence
+    float *U_new;            // [n_ctrl][T][a]   pre-shift update
+    float *next;             // [n_ctrl][a]
+    float *costs;            // [n_ctrl][K_local]
+    float *partials;         // [n_ctrl][gridDim.x][stride]
+    float *payload;          // [n_ctrl][stride]   (world > 1)
+    float *stats;            // [n_ctrl][2]        beta, eta of the last update
+    unsigned int *counters;  // [n_ctrl] last-CTA election
+    const float *eps;        // injected noise [n_ctrl][K_local][T][a] or nullptr
+};
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  Integer contract shared with oracle/mppi_oracle.c.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+        const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += kPhiloxW0;
+        k1 += kPhiloxW1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ float bits_to_1_2(uint32_t x)
+{
+    return __uint_as_float((x >> 9) | 0x3f800000u);   // [1, 2)
+}
+
+// Box-Muller on two 32-bit words -> two standard normals (MUFU lg2 / sqrt / sin / cos).
+__device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float &z0, float &z1)
+{
+    const float u1 = 2.0f - bits_to_1_2(xa);                       // (0, 1]
+    const float th = fmaf(bits_to_1_2(xb), 6.2831853071795865f, -6.2831853071795865f);  // [0, 2pi)
+    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));      // sqrt(-2 ln u1)
+    float sn, cs;
+    __sincosf(th, &sn, &cs);
+    z0 = r * cs;
+    z1 = r * sn;
+}
+
+// Four standard normals z[4c .. 4c+3] of sample `k` (global index).
+__device__ __forceinline__ void normals4(uint32_t call, uint32_t k, uint32_t update, uint32_t stream,
+                                         uint32_t key0, uint32_t key1, float z[4])
+{
+    const uint4 x = philox4x32_10(call, k, update, stream, key0, key1);
+    box_muller(x.x, x.y, z[0], z[1]);
+    box_muller(x.z, x.w, z[2], z[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp / block reductions
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Reduce-scatter of 32 per-lane values across the warp: on return v[0] of lane l holds
+// sum over lanes of the input v[l].  31 shuffles for 32 sums.
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane)
+{
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; i++) {
+            const float send = up ? v[i] : v[i + half];
+            const float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+// exp(-(S - beta)/lambda) through ex2 with the max-shift already applied.
+__device__ __forceinline__ float weight_exp(float S, float beta, float neg_inv_lambda_log2e)
+{
+    return exp2f((S - beta) * neg_inv_lambda_log2e);
+}
+
+// ------------------------------------------------------------------------------------------
+// Point-mass model + quadratic cost, one sample in registers.
+//   x' = A x + (B/m) u  (src/model_base.cpp:53-82), block structure exploited per axis:
+//   p' = (p + dt v) + (dt^2/2m) u ;  v' = v + (dt/m) u
+//   q(x) = sum_i q_i (x_i - g_i)^2   (src/cost_base.cpp:56-61, Q = Diag(q))
+// ------------------------------------------------------------------------------------------
+template <int A>
+struct PointMass {
+    float p[A], v[A];
+    __device__ __forceinline__ void init(const float *x0)
+    {
+#pragma unroll
+        for (int j = 0; j < A; j++) { p[j] = x0[2 * j]; v[j] = x0[2 * j + 1]; }
+    }
+    __device__ __forceinline__ void step(const float (&u)[A], float dt, float c_pu, float c_vu)
+    {
+#pragma unroll
+        for (int j = 0; j < A; j++) {
+            p[j] = fmaf(c_pu, u[j], fmaf(dt, v[j], p[j]));
+            v[j] = fmaf(c_vu, u[j], v[j]);
+        }
+    }
+    __device__ __forceinline__ float state_cost(const float (&g)[2 * A], const float (&q)[2 * A]) const
+    {
+        float c = 0.f;
+#pragma unroll
+        for (int j = 0; j < A; j++) {
+            const float dp = p[j] - g[2 * j], dv = v[j] - g[2 * j + 1];
+            c = fmaf(q[2 * j] * dp, dp, c);
+            c = fmaf(q[2 * j + 1] * dv, dv, c);
+        }
+        return c;
+    }
+};
+
+// mbarrier / bulk-copy (TMA) helpers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (UBLKCP in SASS).
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+}  // namespace mppi

@@ -1,0 +1,37 @@
+// Host-side declarations shared between the translation units of libmppi_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace mppi {
+
+struct RolloutParams;
+
+// mppi_rollout.cu
+cudaError_t launch_rollout_philox(RolloutParams p, int a, int num_sms, cudaStream_t st, int *grid_x_out);
+cudaError_t launch_rollout_injected(RolloutParams p, int a, int num_sms, size_t smem_limit, cudaStream_t st,
+                                    int *grid_x_out);
+cudaError_t launch_finish(RolloutParams p, int a, bool philox, const float *gathered, cudaStream_t st);
+cudaError_t launch_dump_noise(RolloutParams p, int a, float *out_dev, cudaStream_t st);
+int max_grid_x(int K_local, int n_ctrl, int num_sms);
+bool injected_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sms, size_t smem_limit,
+                       int *nw_out, int *stages_out, int *grid_x_out, size_t *smem_out);
+
+// mppi_stages.cu  (device pointers)
+cudaError_t launch_model_step(float mass, float dt, int s, int a, int kst, int k, const float *state,
+                              const float *action, float *out, int mode, cudaStream_t st);
+cudaError_t launch_cost(int k, int s, int a, float lambda, const float *inv_sigma, const float *goal,
+                        const float *q, const float *state, const float *action, const float *noise,
+                        float *out, int mode, cudaStream_t st);
+cudaError_t launch_prepare_noise(int k, int T, int a, const float *noise, int t, float *out, cudaStream_t st);
+cudaError_t launch_update_stages(int k, int T, int a, float lambda, const float *cost, const float *noise,
+                                 float *scal /*beta,nabla*/, float *exp_arg, float *exp_out, float *weights,
+                                 float *weighted_noise, cudaStream_t st);
+cudaError_t launch_philox_raw(uint64_t seed, uint32_t call0, uint32_t sample, uint32_t update, uint32_t stream,
+                              int n_calls, uint32_t *out, cudaStream_t st);
+
+// Host helper: inverse of an a x a matrix (Gauss-Jordan, double); returns false when singular.
+bool invert_matrix(const float *m, int n, float *inv);
+
+}  // namespace mppi

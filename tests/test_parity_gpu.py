@@ -1,0 +1,254 @@
+"""Parity of the fused CUDA update (through the C-ABI) against the CPU oracle on the same state
+and the same injected noise tensor.  Bar (BASELINE.json): control sequence and per-sample costs
+within 1e-5 relative in fp32 — measured norm-wise against the exact (fp64) oracle, see
+tests/util.py:assert_update_close."""
+import numpy as np
+import pytest
+
+from tests.util import (CFG1, CFG2, assert_update_close, controller_from_cfg, make_cfg, parity_noise, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_injected(cfg, x0, U0, eps, oracle32, oracle64, check_costs=True):
+    ctrl = controller_from_cfg(cfg)
+    try:
+        ctrl.setSequence(U0)
+        act = ctrl.nextWithNoise(x0, eps)
+        got = dict(next=act, U_new=ctrl.getUpdate(), U_shift=ctrl.getSequence(), costs=ctrl.getCosts())
+    finally:
+        ctrl.close()
+    r64 = oracle64.mppi_update(cfg, x0, U0, eps)
+    r32 = oracle32.mppi_update(cfg, x0, U0, eps)
+    errs = {}
+    for key in ("U_new", "next", "U_shift"):
+        errs[key] = assert_update_close(got[key], r64[key], r32[key], what=key)
+    if check_costs:
+        # per-sample costs: element-wise relative 1e-5 (plus the fp32 oracle's own distance)
+        np.testing.assert_allclose(got["costs"], r64["costs"], rtol=1e-5,
+                                   atol=1e-5 * np.abs(r64["costs"]).max() * 1e-2)
+    # structure of shift / next (src/controller_base.cpp:310-329)
+    np.testing.assert_array_equal(got["next"], got["U_new"][0])
+    np.testing.assert_array_equal(got["U_shift"][:-1], got["U_new"][1:])
+    np.testing.assert_array_equal(got["U_shift"][-1], 0)
+    return got, r64, errs
+
+
+def _inputs(cfg, seed=0, warm=True):
+    rng = np.random.default_rng(seed)
+    x0 = rng.uniform(-1, 1, cfg["s_dim"]).astype(np.float32)
+    U0 = (0.2 * rng.standard_normal((cfg["tau"], cfg["a_dim"]))).astype(np.float32) if warm else \
+        np.zeros((cfg["tau"], cfg["a_dim"]), np.float32)
+    eps = parity_noise(cfg["k"], cfg["tau"], cfg["a_dim"], cfg["sigma"])
+    return x0, U0, eps
+
+
+def test_config1_reference_scale(oracle32, oracle64):
+    """BASELINE config 1: point_mass1d, K=1024, T=20 (the reference's CPU-runnable case)."""
+    cfg = make_cfg(**CFG1)
+    x0, U0, eps = _inputs(cfg, warm=False)
+    x0[:] = 0
+    _run_injected(cfg, x0, U0, eps, oracle32, oracle64)
+    x0, U0, eps = _inputs(cfg, seed=3)
+    _run_injected(cfg, x0, U0, eps, oracle32, oracle64)
+
+
+def test_config2_full_size(oracle32, oracle64):
+    """BASELINE config 2: point_mass2d, K=65536, T=50."""
+    cfg = make_cfg(**CFG2)
+    x0, U0, eps = _inputs(cfg, seed=1)
+    _run_injected(cfg, x0, U0, eps, oracle32, oracle64)
+
+
+@pytest.mark.parametrize("k,tau,a", [
+    (5, 3, 2),          # the controller KAT shape, test/test_controller.cpp:17-19
+    (1, 1, 1),          # single sample, single step
+    (31, 4, 1), (33, 4, 3), (1000, 7, 3),      # ragged K (not a multiple of the 32-sample tile)
+    (257, 5, 3),        # T*a = 15: not a multiple of 4 -> generic (non-TMA) tile path
+    (512, 9, 2),        # T*a = 18
+    (4096, 100, 3),     # config-3 row length (T*a = 300)
+    (2048, 30, 2),      # config-5 row length
+    (300, 16, 4), (200, 12, 5), (129, 8, 6), (64, 4, 7), (96, 10, 8),   # every compiled a_dim
+])
+def test_shapes(oracle32, oracle64, k, tau, a):
+    cfg = make_cfg(k, tau, 2 * a, a)
+    x0, U0, eps = _inputs(cfg, seed=k + tau)
+    _run_injected(cfg, x0, U0, eps, oracle32, oracle64)
+
+
+def test_general_sigma_mass_goal_q(oracle32, oracle64):
+    rng = np.random.default_rng(11)
+    a = 3
+    L = 0.3 * rng.standard_normal((a, a))
+    sigma = L @ L.T + 0.2 * np.eye(a)                       # full (non-diagonal) scale matrix
+    cfg = make_cfg(3000, 25, 6, 3, lam=0.5, sigma=sigma, mass=5.0, dt=0.05,
+                   goal=rng.uniform(-1, 1, 6), q=1 + 9 * rng.random(6))
+    x0, U0, eps = _inputs(cfg, seed=5)
+    _run_injected(cfg, x0, U0, eps, oracle32, oracle64)
+
+
+@pytest.mark.parametrize("lam", [0.05, 10.0])
+def test_lambda_extremes(oracle32, oracle64, lam):
+    """Small lambda: eta dominated by a few samples (the fp32-reproducibility hard part)."""
+    cfg = make_cfg(8192, 20, 4, 2, lam=lam)
+    x0, U0, eps = _inputs(cfg, seed=2)
+    _run_injected(cfg, x0, U0, eps, oracle32, oracle64)
+
+
+def test_consecutive_updates_keep_state(oracle64):
+    """m_U persists across next() calls (src/controller_base.cpp:144): three chained updates."""
+    cfg = make_cfg(2048, 15, 4, 2)
+    rng = np.random.default_rng(9)
+    ctrl = controller_from_cfg(cfg)
+    U = np.zeros((15, 2), np.float32)
+    x = rng.uniform(-1, 1, 4).astype(np.float32)
+    try:
+        for step in range(3):
+            eps = parity_noise(cfg["k"], 15, 2, cfg["sigma"], seed=100 + step)
+            act = ctrl.nextWithNoise(x, eps)
+            ref = oracle64.mppi_update(cfg, x, U, eps)
+            assert rel_err(act, ref["next"]) < 2e-5
+            assert rel_err(ctrl.getSequence(), ref["U_shift"]) < 2e-5
+            U = ref["U_shift"].astype(np.float32)
+            ctrl.setSequence(U)      # re-sync so errors do not compound across steps
+            x = (x + 0.1 * rng.standard_normal(4)).astype(np.float32)
+    finally:
+        ctrl.close()
+
+
+def test_set_goal_changes_the_update(oracle64):
+    cfg = make_cfg(1024, 10, 2, 1)
+    x0, U0, eps = _inputs(cfg, seed=4)
+    ctrl = controller_from_cfg(cfg)
+    try:
+        ctrl.setSequence(U0)
+        assert ctrl.setGoal([-2.0, 0.5]) is True
+        act = ctrl.nextWithNoise(x0, eps)
+    finally:
+        ctrl.close()
+    cfg2 = dict(cfg, goal=np.array([-2.0, 0.5], np.float32))
+    ref = oracle64.mppi_update(cfg2, x0, U0, eps)
+    assert rel_err(act, ref["next"]) < 2e-5
+
+
+def test_setters_lambda_sigma_q(oracle64):
+    cfg = make_cfg(1024, 10, 4, 2)
+    x0, U0, eps_unit = _inputs(cfg, seed=6)
+    sigma = np.array([[0.5, 0.1], [0.0, 0.3]], np.float32)
+    q = np.array([2.0, 0.5, 1.0, 3.0], np.float32)
+    eps = parity_noise(1024, 10, 2, sigma)
+    ctrl = controller_from_cfg(cfg)
+    try:
+        ctrl.setSequence(U0)
+        ctrl.setLambda(2.5)
+        ctrl.setSigma(sigma)
+        ctrl.setQ(q)
+        act = ctrl.nextWithNoise(x0, eps)
+        costs = ctrl.getCosts()
+    finally:
+        ctrl.close()
+    cfg2 = dict(cfg, sigma=sigma, q=q)
+    cfg2["lambda"] = 2.5
+    ref = oracle64.mppi_update(cfg2, x0, U0, eps)
+    assert rel_err(act, ref["next"]) < 2e-5
+    np.testing.assert_allclose(costs, ref["costs"], rtol=1e-5, atol=1e-6)
+
+
+def test_weight_stats(oracle64):
+    cfg = make_cfg(4096, 12, 4, 2)
+    x0, U0, eps = _inputs(cfg, seed=8)
+    ctrl = controller_from_cfg(cfg)
+    try:
+        ctrl.setSequence(U0)
+        ctrl.nextWithNoise(x0, eps)
+        beta, eta = ctrl.getWeightStats()
+    finally:
+        ctrl.close()
+    costs = oracle64.rollout_costs(cfg, x0, U0, eps)
+    st = oracle64.update_stages(cfg["lambda"], costs, eps)
+    assert abs(beta[0] - st["beta"]) <= 1e-5 * abs(st["beta"])
+    assert abs(eta[0] - st["nabla"]) <= 1e-4 * st["nabla"]
+
+
+def test_batched_controllers(oracle64):
+    """Config-5 style: independent controllers (own state, goal, sequence) in one handle."""
+    n, k, tau, a = 37, 1024, 30, 2
+    rng = np.random.default_rng(5)
+    goals = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+    xs = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+    U0 = (0.1 * rng.standard_normal((n, tau, a))).astype(np.float32)
+    cfg = make_cfg(k, tau, 4, a)
+    eps = np.stack([parity_noise(k, tau, a, cfg["sigma"], seed=500 + c) for c in range(n)])
+    from mppi_tf_b200 import ControllerBase
+    ctrl = ControllerBase(k, tau, cfg["dt"], cfg["mass"], 4, a, lam=1.0, sigma=cfg["sigma"], goal=goals,
+                          Q=cfg["q"], n_controllers=n, goal_per_controller=True)
+    try:
+        ctrl.setSequence(U0)
+        act = ctrl.nextWithNoise(xs, eps)
+        Ush = ctrl.getSequence()
+        costs = ctrl.getCosts()
+    finally:
+        ctrl.close()
+    for c in range(n):
+        cc = dict(cfg, goal=goals[c])
+        ref = oracle64.mppi_update(cc, xs[c], U0[c], eps[c])
+        assert rel_err(act[c], ref["next"]) < 2e-5, c
+        assert rel_err(Ush[c], ref["U_shift"]) < 2e-5, c
+        np.testing.assert_allclose(costs[c], ref["costs"], rtol=1e-5, atol=1e-6)
+
+
+def test_size_independent_properties_at_config3_rows():
+    """At sizes the oracle would take long on: properties that hold for any K.
+    (i) zero noise -> Delta = 0 and every cost equals the noiseless rollout cost;
+    (ii) the update is invariant to a permutation of the samples (up to fp32 summation order)."""
+    import torch
+    k, tau, a = 262144, 100, 3
+    cfg = make_cfg(k, tau, 6, a)
+    rng = np.random.default_rng(0)
+    x0 = rng.uniform(-1, 1, 6).astype(np.float32)
+    U0 = (0.1 * rng.standard_normal((tau, a))).astype(np.float32)
+    ctrl = controller_from_cfg(cfg)
+    try:
+        zeros = torch.zeros(k, tau, a, device="cuda")
+        ctrl.setSequence(U0)
+        ctrl.nextWithNoiseDev(x0, zeros.data_ptr())
+        np.testing.assert_allclose(ctrl.getUpdate(), U0, rtol=0, atol=0)
+        costs = ctrl.getCosts()
+        assert costs.min() == costs.max()
+        g = torch.Generator(device="cuda").manual_seed(1)
+        eps = 0.25 * torch.randn(k, tau, a, device="cuda", generator=g)
+        ctrl.setSequence(U0)
+        ctrl.nextWithNoiseDev(x0, eps.data_ptr())
+        u1 = ctrl.getUpdate()
+        c1 = ctrl.getCosts()
+        perm = torch.randperm(k, device="cuda", generator=g)
+        eps2 = eps[perm].contiguous()
+        ctrl.setSequence(U0)
+        ctrl.nextWithNoiseDev(x0, eps2.data_ptr())
+        u2 = ctrl.getUpdate()
+        c2 = ctrl.getCosts()
+        np.testing.assert_array_equal(c2, c1[perm.cpu().numpy()])       # costs are per-sample exact
+        assert rel_err(u2, u1) < 1e-5
+    finally:
+        ctrl.close()
+
+
+def test_error_codes():
+    from mppi_tf_b200 import ControllerBase, MppiError
+    from mppi_tf_b200 import _capi
+    with pytest.raises(MppiError) as e:
+        ControllerBase(1024, 20, 0.1, 1.0, 3, 1)          # s != 2a
+    assert e.value.code == _capi.MPPI_ERR_BAD_ARG
+    with pytest.raises(MppiError) as e:
+        ControllerBase(1024, 20, 0.1, 1.0, 18, 9)         # a > MPPI_MAX_A
+    assert e.value.code == _capi.MPPI_ERR_UNSUPPORTED
+    with pytest.raises(MppiError) as e:
+        ControllerBase(1024, 20, 0.1, 1.0, 4, 2, sigma=np.zeros((2, 2)))   # singular sigma
+    assert e.value.code == _capi.MPPI_ERR_BAD_ARG
+    c = ControllerBase(64, 4, 0.1, 1.0, 2, 1)
+    try:
+        with pytest.raises(MppiError) as e:
+            c.dumpNoise()                                  # before any Philox update
+        assert e.value.code == _capi.MPPI_ERR_STATE
+    finally:
+        c.close()

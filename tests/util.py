@@ -1,0 +1,59 @@
+"""Shared helpers for the parity tests: synthetic inputs as SURVEY.md section 8(d) specifies."""
+import numpy as np
+
+# (s, a) of the reference's environments: envs/point_mass{1,2,3}d.xml
+ENVS = {"point_mass1d": (2, 1), "point_mass2d": (4, 2), "point_mass3d": (6, 3)}
+
+# BASELINE.json configs (K, T, s, a)
+CFG1 = dict(k=1024, tau=20, s_dim=2, a_dim=1)
+CFG2 = dict(k=65536, tau=50, s_dim=4, a_dim=2)
+CFG3 = dict(k=1048576, tau=100, s_dim=6, a_dim=3)
+CFG5 = dict(k=1024, tau=30, s_dim=4, a_dim=2, n_controllers=4096)
+
+
+def make_cfg(k, tau, s_dim, a_dim, lam=1.0, sigma=None, mass=1.0, dt=0.1, goal=None, q=None, **extra):
+    a = a_dim
+    if sigma is None:
+        sigma = 0.25 * np.eye(a)                       # config/envs/point_mass.default.yaml:17-26
+    if goal is None:
+        goal = np.tile([1.0, 0.0], a)                  # src/controller_base.cpp:43-46
+    if q is None:
+        q = np.ones(s_dim)
+    cfg = dict(k=k, tau=tau, s_dim=s_dim, a_dim=a_dim, dt=dt, mass=mass,
+               sigma=np.asarray(sigma, np.float32), goal=np.asarray(goal, np.float32),
+               q=np.asarray(q, np.float32))
+    cfg["lambda"] = lam
+    cfg.update(extra)
+    return cfg
+
+
+def parity_noise(k, tau, a, sigma, seed=1234):
+    """eps = Sigma z with z = default_rng(1234).standard_normal((K,T,a), float32)."""
+    z = np.random.default_rng(seed).standard_normal((k, tau, a), dtype=np.float32)
+    return np.einsum("ij,ktj->kti", np.asarray(sigma, np.float32), z).astype(np.float32)
+
+
+def controller_from_cfg(cfg, **kw):
+    from mppi_tf_b200 import ControllerBase
+    return ControllerBase(cfg["k"], cfg["tau"], cfg["dt"], cfg["mass"], cfg["s_dim"], cfg["a_dim"],
+                          lam=cfg["lambda"], sigma=cfg["sigma"], goal=cfg["goal"], Q=cfg["q"], **kw)
+
+
+def rel_err(got, want):
+    """Norm-wise relative error max|got-want| / max|want|."""
+    want = np.asarray(want, np.float64)
+    got = np.asarray(got, np.float64)
+    scale = np.abs(want).max()
+    return np.abs(got - want).max() / (scale if scale > 0 else 1.0)
+
+
+def assert_update_close(got, ref64, ref32=None, tol=1e-5, what=""):
+    """The parity bar of BASELINE.json: 1e-5 relative (norm-wise) against the exact (fp64) oracle.
+    Where the reference's own fp32 arithmetic (the op-for-op fp32 oracle) is further than that
+    from fp64 — ill-conditioned softmin, few dominant samples — allow twice its error."""
+    err = rel_err(got, ref64)
+    bar = tol
+    if ref32 is not None:
+        bar = max(bar, 2.0 * rel_err(ref32, ref64))
+    assert err <= bar, f"{what}: rel err {err:.3e} > {bar:.3e}"
+    return err
