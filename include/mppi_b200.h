@@ -118,6 +118,7 @@ int mppi_next_with_noise_dev(mppi_handle *h, const float *x_host, const float *e
  */
 int mppi_set_state(mppi_handle *h, const float *x_host);
 int mppi_enqueue_update(mppi_handle *h, const float *eps_dev);
+int mppi_enqueue_exchange(mppi_handle *h);   /* in-library ncclAllGather of the payloads (after mppi_comm_init) */
 int mppi_enqueue_finish(mppi_handle *h);
 int mppi_fetch_action(mppi_handle *h, float *action_host);
 int mppi_synchronize(mppi_handle *h);
@@ -129,6 +130,7 @@ int mppi_set_goal(mppi_handle *h, const float *goal_host);       /* [s] or [n][s
 int mppi_set_lambda(mppi_handle *h, float lambda);
 int mppi_set_sigma(mppi_handle *h, const float *sigma_host);     /* [a][a], must be invertible */
 int mppi_set_q(mppi_handle *h, const float *q_host);             /* [s] */
+int mppi_set_mass(mppi_handle *h, float mass);                   /* model mass in B = [dt^2/2; dt] / mass */
 int mppi_set_sequence(mppi_handle *h, const float *U_host);      /* m_U, [n][T][a] */
 int mppi_get_sequence(mppi_handle *h, float *U_host);            /* shifted sequence kept for the next call */
 int mppi_get_update(mppi_handle *h, float *U_new_host);          /* U + sum_k w_k eps_k of the last call, pre-shift */
@@ -191,6 +193,16 @@ int mppi_prepare_noise(int device, int k, int T, int a, const float *noise, int 
 int mppi_update_stages(int device, int k, int T, int a, float lambda, const float *cost, const float *noise,
                        float *beta, float *exp_arg, float *exp_out, float *nabla, float *weights,
                        float *weighted_noise);
+/* The same stages one at a time, as the reference's test chains them (test/test_controller.cpp:146-151):
+ *   MPPI_OP_MIN      mBeta     out[0] = min_k in[k]
+ *   MPPI_OP_EXP_ARG  mExpArg   out[k] = (-1/s1) * (in[k] - s0)        s0 = beta, s1 = lambda
+ *   MPPI_OP_EXP      mExp      out[k] = exp(in[k])
+ *   MPPI_OP_SUM      mNabla    out[0] = sum_k in[k]
+ *   MPPI_OP_DIV      mWeights  out[k] = in[k] / s0                    s0 = nabla */
+typedef enum { MPPI_OP_MIN = 0, MPPI_OP_EXP_ARG = 1, MPPI_OP_EXP = 2, MPPI_OP_SUM = 3, MPPI_OP_DIV = 4 } mppi_stage_op;
+int mppi_stage_vector_op(int device, int op, int k, const float *in, float s0, float s1, float *out);
+/* ControllerBase::mWeightedNoise alone (src/controller_base.cpp:188-192): weights [k], noise [k][TA] */
+int mppi_weighted_noise(int device, int k, int TA, const float *weights, const float *noise, float *out);
 /* ControllerBase::mGetNew / mShift (src/controller_base.cpp:310-329) */
 int mppi_get_new(int T, int a, const float *cur, int nb, float *out);
 int mppi_shift(int T, int a, const float *cur, const float *init, int nb, float *out);

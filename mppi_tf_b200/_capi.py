@@ -49,6 +49,7 @@ SYMBOLS = {
     "mppi_next_with_noise_dev": (_i, [_H, _fp, _vp, _fp]),
     "mppi_set_state": (_i, [_H, _fp]),
     "mppi_enqueue_update": (_i, [_H, _vp]),
+    "mppi_enqueue_exchange": (_i, [_H]),
     "mppi_enqueue_finish": (_i, [_H]),
     "mppi_fetch_action": (_i, [_H, _fp]),
     "mppi_synchronize": (_i, [_H]),
@@ -56,6 +57,7 @@ SYMBOLS = {
     "mppi_set_lambda": (_i, [_H, _f]),
     "mppi_set_sigma": (_i, [_H, _fp]),
     "mppi_set_q": (_i, [_H, _fp]),
+    "mppi_set_mass": (_i, [_H, _f]),
     "mppi_set_sequence": (_i, [_H, _fp]),
     "mppi_get_sequence": (_i, [_H, _fp]),
     "mppi_get_update": (_i, [_H, _fp]),
@@ -81,6 +83,8 @@ SYMBOLS = {
     "mppi_prepare_action": (_i, [_i, _i, _fp, _i, _fp]),
     "mppi_prepare_noise": (_i, [_i, _i, _i, _i, _fp, _i, _fp]),
     "mppi_update_stages": (_i, [_i, _i, _i, _i, _f, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "mppi_stage_vector_op": (_i, [_i, _i, _i, _fp, _f, _f, _fp]),
+    "mppi_weighted_noise": (_i, [_i, _i, _i, _fp, _fp, _fp]),
     "mppi_get_new": (_i, [_i, _i, _fp, _i, _fp]),
     "mppi_shift": (_i, [_i, _i, _fp, _fp, _i, _fp]),
     "mppi_philox_raw": (_i, [_i, _u64, _u32, _u32, _u32, _u32, _i, C.POINTER(_u32)]),

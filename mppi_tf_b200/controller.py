@@ -242,6 +242,9 @@ class ControllerBase:
     def enqueueUpdate(self, eps_dev_ptr=None):
         check(self._lib.mppi_enqueue_update(self._h, C.c_void_p(eps_dev_ptr) if eps_dev_ptr else None), self._h)
 
+    def enqueueExchange(self):
+        check(self._lib.mppi_enqueue_exchange(self._h), self._h)
+
     def enqueueFinish(self):
         check(self._lib.mppi_enqueue_finish(self._h), self._h)
 

@@ -370,6 +370,13 @@ static int exchange(mppi_handle *h)
     return MPPI_OK;
 }
 
+int mppi_enqueue_exchange(mppi_handle *h)
+{
+    if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
+    CU_TRY(h, cudaSetDevice(h->device));
+    return exchange(h);
+}
+
 int mppi_fetch_action(mppi_handle *h, float *action_host)
 {
     if (!h || !action_host) return fail(h, MPPI_ERR_BAD_ARG, "null handle/action");
@@ -466,6 +473,12 @@ int mppi_set_q(mppi_handle *h, const float *q_host)
 {
     if (!h || !q_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
     memcpy(h->q, q_host, sizeof(float) * h->s);
+    return MPPI_OK;
+}
+int mppi_set_mass(mppi_handle *h, float mass)
+{
+    if (!h || !(mass != 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "mass must be non-zero");
+    h->mass = mass;
     return MPPI_OK;
 }
 int mppi_set_sequence(mppi_handle *h, const float *U_host)
@@ -714,6 +727,38 @@ int mppi_update_stages(int device, int k, int T, int a, float lambda, const floa
     if (exp_out) CU_TRY_S(cudaMemcpy(exp_out, dexp.p, sizeof(float) * (size_t)k, cudaMemcpyDeviceToHost));
     if (weights) CU_TRY_S(cudaMemcpy(weights, dw.p, sizeof(float) * (size_t)k, cudaMemcpyDeviceToHost));
     if (weighted_noise) CU_TRY_S(cudaMemcpy(weighted_noise, dwn.p, sizeof(float) * (size_t)T * a, cudaMemcpyDeviceToHost));
+    return MPPI_OK;
+}
+
+int mppi_stage_vector_op(int device, int op, int k, const float *in, float s0, float s1, float *out)
+{
+    if (!in || !out || k <= 0 || op < MPPI_OP_MIN || op > MPPI_OP_DIV) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad stage_vector_op argument");
+    if (op == MPPI_OP_EXP_ARG && !(s1 != 0.f)) return fail(nullptr, MPPI_ERR_BAD_ARG, "lambda must be non-zero");
+    int rc = stage_device(device);
+    if (rc) return rc;
+    const size_t n_out = (op == MPPI_OP_MIN || op == MPPI_OP_SUM) ? 1 : (size_t)k;
+    DevBuf din, dout;
+    CU_TRY_S(din.alloc(sizeof(float) * (size_t)k));
+    CU_TRY_S(dout.alloc(sizeof(float) * n_out));
+    CU_TRY_S(cudaMemcpy(din.p, in, sizeof(float) * (size_t)k, cudaMemcpyHostToDevice));
+    CU_TRY_S(launch_vector_op(op, k, din.as<float>(), s0, s1, dout.as<float>(), 0));
+    CU_TRY_S(cudaMemcpy(out, dout.p, sizeof(float) * n_out, cudaMemcpyDeviceToHost));
+    return MPPI_OK;
+}
+
+int mppi_weighted_noise(int device, int k, int TA, const float *weights, const float *noise, float *out)
+{
+    if (!weights || !noise || !out || k <= 0 || TA <= 0) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad weighted_noise argument");
+    int rc = stage_device(device);
+    if (rc) return rc;
+    DevBuf dw, dn, dout;
+    CU_TRY_S(dw.alloc(sizeof(float) * (size_t)k));
+    CU_TRY_S(dn.alloc(sizeof(float) * (size_t)k * TA));
+    CU_TRY_S(dout.alloc(sizeof(float) * (size_t)TA));
+    CU_TRY_S(cudaMemcpy(dw.p, weights, sizeof(float) * (size_t)k, cudaMemcpyHostToDevice));
+    CU_TRY_S(cudaMemcpy(dn.p, noise, sizeof(float) * (size_t)k * TA, cudaMemcpyHostToDevice));
+    CU_TRY_S(launch_weighted_noise(k, TA, dw.as<float>(), dn.as<float>(), dout.as<float>(), 0));
+    CU_TRY_S(cudaMemcpy(out, dout.p, sizeof(float) * (size_t)TA, cudaMemcpyDeviceToHost));
     return MPPI_OK;
 }
 

@@ -28,6 +28,8 @@ cudaError_t launch_prepare_noise(int k, int T, int a, const float *noise, int t,
 cudaError_t launch_update_stages(int k, int T, int a, float lambda, const float *cost, const float *noise,
                                  float *scal /*beta,nabla*/, float *exp_arg, float *exp_out, float *weights,
                                  float *weighted_noise, cudaStream_t st);
+cudaError_t launch_vector_op(int op, int k, const float *in, float s0, float s1, float *out, cudaStream_t st);
+cudaError_t launch_weighted_noise(int k, int TA, const float *weights, const float *noise, float *out, cudaStream_t st);
 cudaError_t launch_philox_raw(uint64_t seed, uint32_t call0, uint32_t sample, uint32_t update, uint32_t stream,
                               int n_calls, uint32_t *out, cudaStream_t st);
 

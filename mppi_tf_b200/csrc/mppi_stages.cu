@@ -115,6 +115,41 @@ __global__ void __launch_bounds__(1024) update_stages_kernel(int k, int T, int a
     }
 }
 
+// One stage at a time (mBeta / mExpArg / mExp / mNabla / mWeights), single CTA.
+__global__ void __launch_bounds__(1024) vector_op_kernel(int op, int k, const float *in, float s0, float s1, float *out)
+{
+    __shared__ float sRed[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    if (op == MPPI_OP_MIN || op == MPPI_OP_SUM) {
+        float v = (op == MPPI_OP_MIN) ? kInf : 0.f;
+        for (int i = tid; i < k; i += blockDim.x) v = (op == MPPI_OP_MIN) ? fminf(v, in[i]) : v + in[i];
+        v = (op == MPPI_OP_MIN) ? warp_min(v) : warp_sum(v);
+        if (lane == 0) sRed[warp] = v;
+        __syncthreads();
+        if (tid == 0) {
+            float r = sRed[0];
+            for (int w = 1; w < nw; w++) r = (op == MPPI_OP_MIN) ? fminf(r, sRed[w]) : r + sRed[w];
+            out[0] = r;
+        }
+        return;
+    }
+    const float neg_inv = -1.0f / s1;
+    for (int i = tid; i < k; i += blockDim.x) {
+        const float x = in[i];
+        out[i] = (op == MPPI_OP_EXP_ARG) ? neg_inv * (x - s0) : (op == MPPI_OP_EXP ? expf(x) : x / s0);
+    }
+}
+
+// mWeightedNoise (src/controller_base.cpp:188-192): out[j] = sum_k w_k noise[k][j]
+__global__ void weighted_noise_kernel(int k, int TA, const float *weights, const float *noise, float *out)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < TA; j += gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int i = 0; i < k; i++) acc = fmaf(weights[i], noise[(size_t)i * TA + j], acc);
+        out[j] = acc;
+    }
+}
+
 __global__ void philox_raw_kernel(uint32_t key0, uint32_t key1, uint32_t call0, uint32_t sample, uint32_t update,
                                   uint32_t stream, int n_calls, uint32_t *out)
 {
@@ -161,6 +196,18 @@ cudaError_t launch_update_stages(int k, int T, int a, float lambda, const float 
 {
     update_stages_kernel<<<1, 1024, 0, st>>>(k, T, a, lambda, cost, noise, scal, exp_arg, exp_out, weights,
                                              weighted_noise);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vector_op(int op, int k, const float *in, float s0, float s1, float *out, cudaStream_t st)
+{
+    vector_op_kernel<<<1, 1024, 0, st>>>(op, k, in, s0, s1, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_weighted_noise(int k, int TA, const float *weights, const float *noise, float *out, cudaStream_t st)
+{
+    weighted_noise_kernel<<<blocks_for(TA, 128), 128, 0, st>>>(k, TA, weights, noise, out);
     return cudaGetLastError();
 }
 
