@@ -147,6 +147,10 @@ int mppi_k_offset(const mppi_handle *h);
 /* Payload per rank: n_controllers * mppi_exchange_stride(h) floats =
  * {beta_r, eta_r, 0, 0, N_r[T*a] (padded to a multiple of 4)} per controller. */
 int mppi_exchange_stride(const mppi_handle *h);
+/* Pure host helpers (no GPU needed): the shard of rank `rank` of `world` over k samples, and the
+ * payload stride for a given tau * a_dim — the contract multi-rank callers and tests rely on. */
+int mppi_shard_range(int k, int rank, int world, int *k_offset, int *k_local);
+int mppi_payload_stride(int tau_times_a);
 /* Device buffers the caller all-gathers between enqueue_update and enqueue_finish:
  * send = this rank's payload, recv = [world] payloads in rank order.  The library owns them
  * unless external ones are supplied (e.g. tensors registered with torch.distributed). */

@@ -68,6 +68,8 @@ SYMBOLS = {
     "mppi_k_local": (_i, [_H]),
     "mppi_k_offset": (_i, [_H]),
     "mppi_exchange_stride": (_i, [_H]),
+    "mppi_shard_range": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "mppi_payload_stride": (_i, [_i]),
     "mppi_exchange_buffers": (_i, [_H, C.POINTER(_vp), C.POINTER(_vp)]),
     "mppi_exchange_set_buffers": (_i, [_H, _vp, _vp]),
     "mppi_comm_unique_id": (_i, [_vp]),

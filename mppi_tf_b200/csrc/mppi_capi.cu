@@ -148,6 +148,7 @@ RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
     p.lambda = h->lambda;
     p.neg_inv_lambda_log2e = -kLog2e / h->lambda;
     memcpy(p.q, h->q, sizeof(p.q));
+    for (int i = 0; i < kMaxS; i++) p.sqrt_q[i] = sqrtf(h->q[i] > 0.f ? h->q[i] : 0.f);
     memcpy(p.sigma, h->sigma, sizeof(p.sigma));
     memcpy(p.lam_inv_sigma_T, h->lam_inv_sigma_T, sizeof(p.lam_inv_sigma_T));
     p.sigma_diag = h->sigma_diag;
@@ -155,6 +156,10 @@ RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
     p.key0 = (uint32_t)h->seed;
     p.key1 = (uint32_t)(h->seed >> 32);
     p.update = h->update_counter;
+    for (int r = 0; r < 10; r++) {
+        p.rk0[r] = p.key0 + (uint32_t)r * kPhiloxW0;
+        p.rk1[r] = p.key1 + (uint32_t)r * kPhiloxW1;
+    }
     p.x_inline = (h->n_ctrl == 1);
     if (p.x_inline) memcpy(p.x0, h->h_x, sizeof(float) * h->s);
     p.x = h->d_x;
@@ -228,8 +233,7 @@ int mppi_create(const mppi_config *cfg, mppi_handle **out)
     h->TA = cfg->tau * cfg->a_dim;
     h->stride = partial_stride(h->TA);
     // rank r owns samples [r*k/world, (r+1)*k/world)  
-    h->k_offset = (int)((long long)cfg->k * cfg->rank / world);
-    h->K_local = (int)((long long)cfg->k * (cfg->rank + 1) / world) - h->k_offset;
+    mppi_shard_range(cfg->k, cfg->rank, world, &h->k_offset, &h->K_local);
     h->goal_per_ctrl = cfg->goal_per_controller ? 1 : 0;
 
     const int a = h->a, s = h->s;
@@ -238,6 +242,8 @@ int mppi_create(const mppi_config *cfg, mppi_handle **out)
     for (int i = 0; i < a; i++)
         for (int j = 0; j < a; j++) h->sigma[i * a + j] = cfg->sigma ? cfg->sigma[i * a + j] : (i == j ? 1.f : 0.f);
     for (int i = 0; i < s; i++) h->q[i] = cfg->q ? cfg->q[i] : 1.f;
+    for (int i = 0; i < s; i++)
+        if (!(h->q[i] >= 0.f)) { delete h; return fail(nullptr, MPPI_ERR_BAD_ARG, "q must be non-negative (diag of a PSD Q)"); }
     {
         float inv[kMaxA * kMaxA];
         if (!invert_matrix(h->sigma, a, inv)) { delete h; return fail(nullptr, MPPI_ERR_BAD_ARG, "sigma is singular"); }
@@ -309,6 +315,16 @@ int mppi_destroy(mppi_handle *h)
 int mppi_k_local(const mppi_handle *h) { return h ? h->K_local : 0; }
 int mppi_k_offset(const mppi_handle *h) { return h ? h->k_offset : 0; }
 int mppi_exchange_stride(const mppi_handle *h) { return h ? h->stride : 0; }
+int mppi_payload_stride(int tau_times_a) { return tau_times_a > 0 ? partial_stride(tau_times_a) : 0; }
+int mppi_shard_range(int k, int rank, int world, int *k_offset, int *k_local)
+{
+    if (k <= 0 || world <= 0 || rank < 0 || rank >= world || k < world || !k_offset || !k_local)
+        return fail(nullptr, MPPI_ERR_BAD_ARG, "bad shard_range argument");
+    const int lo = (int)((long long)k * rank / world), hi = (int)((long long)k * (rank + 1) / world);
+    *k_offset = lo;
+    *k_local = hi - lo;
+    return MPPI_OK;
+}
 
 // ---- update step --------------------------------------------------------------------------------
 int mppi_set_state(mppi_handle *h, const float *x_host)
@@ -472,6 +488,8 @@ int mppi_set_sigma(mppi_handle *h, const float *sigma_host)
 int mppi_set_q(mppi_handle *h, const float *q_host)
 {
     if (!h || !q_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    for (int i = 0; i < h->s; i++)
+        if (!(q_host[i] >= 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "q must be non-negative (diag of a PSD Q)");
     memcpy(h->q, q_host, sizeof(float) * h->s);
     return MPPI_OK;
 }

@@ -29,12 +29,14 @@ struct RolloutParams {
     // cost (CostBase): lambda, diag(Q), Sigma (scale) and lambda * Sigma^-T (action cost)
     float lambda, neg_inv_lambda_log2e;
     float q[kMaxS];
+    float sqrt_q[kMaxS];                    // state cost as sum (sqrt(q_i) x_i - sqrt(q_i) g_i)^2
     float sigma[kMaxA * kMaxA];
     float lam_inv_sigma_T[kMaxA * kMaxA];   // v_t = lam_inv_sigma_T * U_t  (injected mode)
     int sigma_diag;
     int goal_per_ctrl;
     // Philox key / counter words
     uint32_t key0, key1, update;
+    uint32_t rk0[10], rk1[10];              // Philox round keys key + r * W (hoisted to the host)
     // single-controller fast path: state passed by value (no H2D copy)
     int x_inline;
     float x0[kMaxS];
@@ -77,6 +79,25 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+// Same generator with the ten round keys read from the kernel parameter block (constant bank
+// operands of LOP3: no per-call key arithmetic, no registers).
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  const uint32_t (&rk0)[10], const uint32_t (&rk1)[10])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+        const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk0[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk1[r];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 __device__ __forceinline__ float bits_to_1_2(uint32_t x)
 {
     return __uint_as_float((x >> 9) | 0x3f800000u);   // [1, 2)
@@ -87,7 +108,8 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float &z0, 
 {
     const float u1 = 2.0f - bits_to_1_2(xa);                       // (0, 1]
     const float th = fmaf(bits_to_1_2(xb), 6.2831853071795865f, -6.2831853071795865f);  // [0, 2pi)
-    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));      // sqrt(-2 ln u1)
+    float r;                                                        // sqrt(-2 ln u1), one MUFU.SQRT
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(u1)));
     float sn, cs;
     __sincosf(th, &sn, &cs);
     z0 = r * cs;
@@ -95,10 +117,10 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float &z0, 
 }
 
 // Four standard normals z[4c .. 4c+3] of sample `k` (global index).
-__device__ __forceinline__ void normals4(uint32_t call, uint32_t k, uint32_t update, uint32_t stream,
-                                         uint32_t key0, uint32_t key1, float z[4])
+__device__ __forceinline__ void normals4(uint32_t call, uint32_t k, uint32_t stream, const RolloutParams &p,
+                                         float z[4])
 {
-    const uint4 x = philox4x32_10(call, k, update, stream, key0, key1);
+    const uint4 x = philox4x32_10_rk(call, k, p.update, stream, p.rk0, p.rk1);
     box_muller(x.x, x.y, z[0], z[1]);
     box_muller(x.z, x.w, z[2], z[3]);
 }
@@ -164,14 +186,16 @@ struct PointMass {
             v[j] = fmaf(c_vu, u[j], v[j]);
         }
     }
-    __device__ __forceinline__ float state_cost(const float (&g)[2 * A], const float (&q)[2 * A]) const
+    // q(x) with sq = sqrt(q), sg = sqrt(q) * g:  sum_i (sq_i x_i - sg_i)^2  — two FMAs per component
+    __device__ __forceinline__ float state_cost(const float (&sg)[2 * A], const float (&sq)[2 * A]) const
     {
         float c = 0.f;
 #pragma unroll
         for (int j = 0; j < A; j++) {
-            const float dp = p[j] - g[2 * j], dv = v[j] - g[2 * j + 1];
-            c = fmaf(q[2 * j] * dp, dp, c);
-            c = fmaf(q[2 * j + 1] * dv, dv, c);
+            const float dp = fmaf(sq[2 * j], p[j], -sg[2 * j]);
+            const float dv = fmaf(sq[2 * j + 1], v[j], -sg[2 * j + 1]);
+            c = fmaf(dp, dp, c);
+            c = fmaf(dv, dv, c);
         }
         return c;
     }

@@ -227,8 +227,8 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
         const float *xp = p.x + (size_t)ctrl * 2 * A;
 #pragma unroll
         for (int i = 0; i < 2 * A; i++) {
-            g[i] = gp[i];
-            q[i] = p.q[i];
+            q[i] = p.sqrt_q[i];
+            g[i] = q[i] * gp[i];
             x0[i] = p.x_inline ? p.x0[i] : xp[i];
         }
     }
@@ -237,7 +237,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     float *costs = p.costs + (size_t)ctrl * p.K_local;
     const int kstride = gridDim.x * kPhiloxThreads;
     const int kfirst = blockIdx.x * kPhiloxThreads + tid;
-    const int nblk = (p.T + 3) >> 2;
+    const int nfull = p.T >> 2, trem = p.T & 3;
     const uint32_t stream = (uint32_t)ctrl;
 
     // ---- phase 1: rollout + cost ---------------------------------------------------------------
@@ -248,15 +248,24 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
         PointMass<A> x;
         x.init(x0);
         float S = 0.f;
-        for (int tb = 0; tb < nblk; tb++) {
+        const float *uv = sUV;
+        uint32_t call = 0;
+        for (int tb = 0; tb < nfull; tb++) {       // full blocks of 4 steps = A Philox calls, no guards
             float z[4 * A];
 #pragma unroll
-            for (int c = 0; c < A; c++) normals4((uint32_t)(tb * A + c), kg, p.update, stream, p.key0, p.key1, &z[4 * c]);
+            for (int c = 0; c < A; c++) normals4(call + c, kg, stream, p, &z[4 * c]);
+            call += A;
 #pragma unroll
-            for (int tt = 0; tt < 4; tt++) {
-                const int t = 4 * tb + tt;
-                if (t < p.T) rollout_step<A, true, DIAG>(x, S, sUV + t * RS, &z[tt * A], p, g, q);
-            }
+            for (int tt = 0; tt < 4; tt++) rollout_step<A, true, DIAG>(x, S, uv + tt * RS, &z[tt * A], p, g, q);
+            uv += 4 * RS;
+        }
+        if (trem) {                                 // tail: T % 4 steps
+            float z[4 * A];
+#pragma unroll
+            for (int c = 0; c < A; c++) normals4(call + c, kg, stream, p, &z[4 * c]);
+#pragma unroll
+            for (int tt = 0; tt < 3; tt++)
+                if (tt < trem) rollout_step<A, true, DIAG>(x, S, uv + tt * RS, &z[tt * A], p, g, q);
         }
         S += x.state_cost(g, q);    // terminal cost on top of step T-1's (src/controller_base.cpp:271-272)
         costs[k] = S;
@@ -278,19 +287,29 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
         float acc[32];
 #pragma unroll
         for (int i = 0; i < 32; i++) acc[i] = 0.f;
+        const bool full = (ch * 8 + 8 <= ncall);    // warp-uniform: all 8 calls of the chunk exist
         for (int it = 0, k = kfirst; it < p.n_iter; it++, k += kstride) {
             if (k >= p.K_local) break;
             const uint32_t kg = (uint32_t)(p.k_offset + k);
             const float e = weight_exp(costs[k], beta_c, p.neg_inv_lambda_log2e);
             if (ch == 0) eta += e;
+            if (full) {
 #pragma unroll
-            for (int c8 = 0; c8 < 8; c8++) {
-                const int call = ch * 8 + c8;
-                if (call < ncall) {
+                for (int c8 = 0; c8 < 8; c8++) {
                     float z[4];
-                    normals4((uint32_t)call, kg, p.update, stream, p.key0, p.key1, z);
+                    normals4((uint32_t)(ch * 8 + c8), kg, stream, p, z);
 #pragma unroll
                     for (int j = 0; j < 4; j++) acc[4 * c8 + j] = fmaf(e, z[j], acc[4 * c8 + j]);
+                }
+            } else {
+#pragma unroll
+                for (int c8 = 0; c8 < 8; c8++) {
+                    if (ch * 8 + c8 < ncall) {
+                        float z[4];
+                        normals4((uint32_t)(ch * 8 + c8), kg, stream, p, z);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[4 * c8 + j] = fmaf(e, z[j], acc[4 * c8 + j]);
+                    }
                 }
             }
         }
@@ -376,8 +395,8 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
         const float *xp = p.x + (size_t)ctrl * 2 * A;
 #pragma unroll
         for (int i = 0; i < 2 * A; i++) {
-            g[i] = gp[i];
-            q[i] = p.q[i];
+            q[i] = p.sqrt_q[i];
+            g[i] = q[i] * gp[i];
             x0[i] = p.x_inline ? p.x0[i] : xp[i];
         }
     }
@@ -525,7 +544,7 @@ __global__ void dump_noise_kernel(const __grid_constant__ RolloutParams p, float
          i += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(i / ncall), call = (int)(i - (long long)k * ncall);
         float z[4];
-        normals4((uint32_t)call, (uint32_t)(p.k_offset + k), p.update, (uint32_t)ctrl, p.key0, p.key1, z);
+        normals4((uint32_t)call, (uint32_t)(p.k_offset + k), (uint32_t)ctrl, p, z);
         float *row = out + ((size_t)ctrl * p.K_local + k) * p.TA;
 #pragma unroll
         for (int j = 0; j < 4; j++)
