@@ -156,6 +156,10 @@ def run_reference(args, rank, world):
 
 # ---------------------------------------------------------------------------------------------------
 def main():
+    # keep stdout clean for the ONE JSON line: libraries (NCCL version banner, ...) write to fd 1
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -268,15 +272,22 @@ def main():
     value = units_per_step * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the public API (host buffers, synchronous next()) -------------------------
+    def api_next():
+        if exchange and args.exchange == "torch":      # caller-side all-gather between the async halves
+            ctrl.setState(x)
+            one_update()
+            return ctrl.fetchAction()
+        return ctrl.next(x)                             # the public synchronous call (in-library exchange)
+
     act = None
     for _ in range(args.warmup):
-        act = ctrl.next(x)
+        act = api_next()
     barrier()
     lat = []
     t_all0 = time.perf_counter()
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        act = ctrl.next(x)
+        act = api_next()
         lat.append(time.perf_counter() - t0)
     e2e_s = time.perf_counter() - t_all0
     barrier()

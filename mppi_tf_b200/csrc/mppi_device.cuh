@@ -169,36 +169,94 @@ __device__ __forceinline__ float weight_exp(float S, float beta, float neg_inv_l
 //   x' = A x + (B/m) u  (src/model_base.cpp:53-82), block structure exploited per axis:
 //   p' = (p + dt v) + (dt^2/2m) u ;  v' = v + (dt/m) u
 //   q(x) = sum_i q_i (x_i - g_i)^2   (src/cost_base.cpp:56-61, Q = Diag(q))
+// Axes are processed two at a time with Blackwell's packed fp32 instructions (FFMA2 / FADD2:
+// __ffma2_rn, __fadd2_rn); an odd last axis stays scalar.
 // ------------------------------------------------------------------------------------------
 template <int A>
+struct Vec {                       // A floats as A/2 aligned pairs + optional scalar
+    static constexpr int NP = A / 2;
+    static constexpr bool ODD = (A & 1) != 0;
+    float2 pr[NP > 0 ? NP : 1];
+    float sc;
+    __device__ __forceinline__ float get(int j) const { return (j < 2 * NP) ? ((j & 1) ? pr[j >> 1].y : pr[j >> 1].x) : sc; }
+    __device__ __forceinline__ void set(int j, float v)
+    {
+        if (j < 2 * NP) { if (j & 1) pr[j >> 1].y = v; else pr[j >> 1].x = v; } else sc = v;
+    }
+    __device__ __forceinline__ void fill(float v)
+    {
+#pragma unroll
+        for (int i = 0; i < NP; i++) pr[i] = make_float2(v, v);
+        sc = v;
+    }
+};
+
+template <int A>
+struct ModelConsts {               // everything the step needs, as pairs, built once per thread
+    float2 dt2, cpu2, cvu2;
+    float dt, cpu, cvu;
+    Vec<A> sqp, sqv, sgp, sgv;     // sqrt(q) and sqrt(q)*g for positions / velocities
+    __device__ __forceinline__ void init(float dt_, float cpu_, float cvu_, const float *sqrt_q, const float *goal)
+    {
+        dt = dt_; cpu = cpu_; cvu = cvu_;
+        dt2 = make_float2(dt_, dt_); cpu2 = make_float2(cpu_, cpu_); cvu2 = make_float2(cvu_, cvu_);
+#pragma unroll
+        for (int j = 0; j < A; j++) {
+            sqp.set(j, sqrt_q[2 * j]);
+            sqv.set(j, sqrt_q[2 * j + 1]);
+            sgp.set(j, -sqrt_q[2 * j] * goal[2 * j]);          // stored negated: d = sq*x + (-sq*g)
+            sgv.set(j, -sqrt_q[2 * j + 1] * goal[2 * j + 1]);
+        }
+    }
+};
+
+template <int A>
 struct PointMass {
-    float p[A], v[A];
+    static constexpr int NP = A / 2;
+    static constexpr bool ODD = (A & 1) != 0;
+    Vec<A> p, v;
     __device__ __forceinline__ void init(const float *x0)
     {
 #pragma unroll
-        for (int j = 0; j < A; j++) { p[j] = x0[2 * j]; v[j] = x0[2 * j + 1]; }
+        for (int j = 0; j < A; j++) { p.set(j, x0[2 * j]); v.set(j, x0[2 * j + 1]); }
     }
-    __device__ __forceinline__ void step(const float (&u)[A], float dt, float c_pu, float c_vu)
+    __device__ __forceinline__ void zero() { p.fill(0.f); v.fill(0.f); }
+    __device__ __forceinline__ void step(const Vec<A> &u, const ModelConsts<A> &c)
     {
 #pragma unroll
-        for (int j = 0; j < A; j++) {
-            p[j] = fmaf(c_pu, u[j], fmaf(dt, v[j], p[j]));
-            v[j] = fmaf(c_vu, u[j], v[j]);
+        for (int i = 0; i < NP; i++) {
+            p.pr[i] = __ffma2_rn(c.cpu2, u.pr[i], __ffma2_rn(c.dt2, v.pr[i], p.pr[i]));
+            v.pr[i] = __ffma2_rn(c.cvu2, u.pr[i], v.pr[i]);
+        }
+        if (ODD) {
+            p.sc = fmaf(c.cpu, u.sc, fmaf(c.dt, v.sc, p.sc));
+            v.sc = fmaf(c.cvu, u.sc, v.sc);
         }
     }
-    // q(x) with sq = sqrt(q), sg = sqrt(q) * g:  sum_i (sq_i x_i - sg_i)^2  — two FMAs per component
-    __device__ __forceinline__ float state_cost(const float (&sg)[2 * A], const float (&sq)[2 * A]) const
+    // adds q(x) into the running (pair, scalar) accumulators
+    __device__ __forceinline__ void state_cost(const ModelConsts<A> &c, float2 &acc2, float &acc) const
     {
-        float c = 0.f;
 #pragma unroll
-        for (int j = 0; j < A; j++) {
-            const float dp = fmaf(sq[2 * j], p[j], -sg[2 * j]);
-            const float dv = fmaf(sq[2 * j + 1], v[j], -sg[2 * j + 1]);
-            c = fmaf(dp, dp, c);
-            c = fmaf(dv, dv, c);
+        for (int i = 0; i < NP; i++) {
+            const float2 dp = __ffma2_rn(c.sqp.pr[i], p.pr[i], c.sgp.pr[i]);
+            const float2 dv = __ffma2_rn(c.sqv.pr[i], v.pr[i], c.sgv.pr[i]);
+            acc2 = __ffma2_rn(dp, dp, acc2);
+            acc2 = __ffma2_rn(dv, dv, acc2);
         }
-        return c;
+        if (ODD) {
+            const float dp = fmaf(c.sqp.sc, p.sc, c.sgp.sc), dv = fmaf(c.sqv.sc, v.sc, c.sgv.sc);
+            acc = fmaf(dp, dp, acc);
+            acc = fmaf(dv, dv, acc);
+        }
     }
+};
+
+// Per-sample cost accumulator: pair lanes + scalar, folded once at the end.
+struct CostAcc {
+    float2 a2;
+    float a;
+    __device__ __forceinline__ void zero() { a2 = make_float2(0.f, 0.f); a = 0.f; }
+    __device__ __forceinline__ float total() const { return (a2.x + a2.y) + a; }
 };
 
 // mbarrier / bulk-copy (TMA) helpers -----------------------------------------------------------

@@ -6,45 +6,47 @@
 //                            Philox counters to accumulate sum_k e_k z_k.  One launch per update:
 //                            the last CTA to finish merges all CTA partials, applies the update
 //                            and shifts the sequence.
-//   rollout_injected_kernel  parity/debug mode: eps is read from HBM exactly once.  Each warp owns
-//                            a 32-sample tile that the TMA unit (cp.async.bulk) lands in shared
-//                            memory; the tile stays resident between the rollout (one lane per
-//                            sample) and the weighted sum (one lane per column) with an online
-//                            max-shifted rescale.
+//   rollout_injected_kernel  parity/debug mode: eps is read from HBM exactly once.  A 32-sample tile
+//                            is landed in shared memory by the TMA unit (cp.async.bulk) and stays
+//                            resident between the rollout (lane = sample) and the weighted sum
+//                            (lane = column) with an online max-shifted rescale.
 //   finish_kernel            multi-rank only: merges the all-gathered rank payloads.
 //
 // Reference maths: /root/reference/src/controller_base.cpp:166-329, src/model_base.cpp:53-82,
-// src/cost_base.cpp:37-68 (restated in oracle/mppi_oracle_impl.h, which tests compare against).
+// src/cost_base.cpp:37-68 (restated in the CPU checker that tests compare against).
 #include "mppi_device.cuh"
 #include "mppi_internal.h"
 
 namespace mppi {
 
-constexpr int kPhiloxThreads = 256;
-constexpr int kMaxParts = 2048;   // CTA partials (or ranks) one merge can take
+constexpr int kPhiloxThreads = 512;
+constexpr int kPhiloxCtasPerSm = 2;
+constexpr int kMaxParts = 1024;   // CTA partials (or ranks) one merge can take
 
+// Per-step uniforms staged in shared memory, one row per step:
+//   [0, A)      U_t   mean action (src/controller_base.cpp:205-208)
+//   [H, H + A)  w_t   action-cost vector: Philox mode lambda*U_t (since eps = Sigma z,
+//                     lambda U^T Sigma^-1 eps = lambda U^T z); injected mode lambda*Sigma^-T U_t
+//                     (src/cost_base.cpp:63-68)
+// H = A rounded up to even so both halves start on an aligned pair.
 template <int A>
 struct Row {
-    static constexpr int RS = (2 * A + 3) & ~3;   // floats per staged step: U_t[A], w_t[A], pad
+    static constexpr int H = (A + 1) & ~1;
+    static constexpr int RS = (2 * H + 3) & ~3;
 };
 
-// Stage the per-step uniforms of controller `ctrl` into shared memory:
-//   sUV[t][0..A)  = U_t          (mean action, src/controller_base.cpp:205-208)
-//   sUV[t][A..2A) = w_t          action-cost vector: Philox mode lambda*U_t (since eps = Sigma z,
-//                                 lambda U^T Sigma^-1 eps = lambda U^T z); injected mode
-//                                 lambda*Sigma^-T U_t (src/cost_base.cpp:63-68)
 template <int A, bool PHILOX>
 __device__ __forceinline__ void stage_sequence(const RolloutParams &p, int ctrl, float *sUV)
 {
-    constexpr int RS = Row<A>::RS;
+    constexpr int RS = Row<A>::RS, H = Row<A>::H;
     const float *U = p.U + (size_t)ctrl * p.TA;
     for (int i = threadIdx.x; i < p.T * RS; i += blockDim.x) {
         const int t = i / RS, j = i - t * RS;
         float v = 0.f;
         if (j < A) {
             v = U[t * A + j];
-        } else if (j < 2 * A) {
-            const int r = j - A;
+        } else if (j >= H && j < H + A) {
+            const int r = j - H;
             if (PHILOX) {
                 v = p.lambda * U[t * A + r];
             } else {
@@ -56,42 +58,63 @@ __device__ __forceinline__ void stage_sequence(const RolloutParams &p, int ctrl,
     }
 }
 
-// One rollout step for one sample (src/controller_base.cpp:251-269):
-//   u = U_t + eps_t ; x <- A x + (B/m) u ; S += q(x) + lambda U_t^T Sigma^-1 eps_t
-// `n` is z_t in Philox mode (eps_t = Sigma z_t formed here) and eps_t in injected mode.
-template <int A, bool PHILOX, bool DIAG>
-__device__ __forceinline__ void rollout_step(PointMass<A> &x, float &S, const float *uv_row,
-                                             const float *n, const RolloutParams &p,
-                                             const float (&g)[2 * A], const float (&q)[2 * A])
+template <int A>
+__device__ __forceinline__ void load_uv(const float *uv_row, Vec<A> &U, Vec<A> &w)
 {
-    constexpr int RS = Row<A>::RS;
+    constexpr int RS = Row<A>::RS, H = Row<A>::H, NP = A / 2;
     float uv[RS];
 #pragma unroll
     for (int i = 0; i < RS / 4; i++) {
         const float4 v = reinterpret_cast<const float4 *>(uv_row)[i];
         uv[4 * i] = v.x; uv[4 * i + 1] = v.y; uv[4 * i + 2] = v.z; uv[4 * i + 3] = v.w;
     }
-    float u[A];
-    float ac = 0.f;
 #pragma unroll
-    for (int j = 0; j < A; j++) {
-        float e;
-        if (PHILOX) {
-            if (DIAG) {
-                e = p.sigma[j * A + j] * n[j];
-            } else {
-                e = 0.f;
-#pragma unroll
-                for (int l = 0; l < A; l++) e = fmaf(p.sigma[j * A + l], n[l], e);
-            }
-        } else {
-            e = n[j];
-        }
-        u[j] = uv[j] + e;
-        ac = fmaf(uv[A + j], n[j], ac);
+    for (int i = 0; i < NP; i++) {
+        U.pr[i] = make_float2(uv[2 * i], uv[2 * i + 1]);
+        w.pr[i] = make_float2(uv[H + 2 * i], uv[H + 2 * i + 1]);
     }
-    x.step(u, p.dt, p.c_pu, p.c_vu);
-    S += x.state_cost(g, q) + ac;
+    U.sc = uv[A - 1];
+    w.sc = uv[H + A - 1];
+}
+
+template <int A>
+__device__ __forceinline__ void vec_from(const float *z, Vec<A> &n)
+{
+#pragma unroll
+    for (int i = 0; i < A / 2; i++) n.pr[i] = make_float2(z[2 * i], z[2 * i + 1]);
+    n.sc = z[A - 1];
+}
+
+// One rollout step for one sample (src/controller_base.cpp:251-269):
+//   u = U_t + eps_t ; x <- A x + (B/m) u ; S += q(x) + lambda U_t^T Sigma^-1 eps_t
+// `n` is z_t in Philox mode (eps_t = Sigma z_t formed here) and eps_t in injected mode.
+template <int A, bool PHILOX, bool DIAG>
+__device__ __forceinline__ void rollout_step(PointMass<A> &x, CostAcc &S, const float *uv_row, const Vec<A> &n,
+                                             const RolloutParams &p, const ModelConsts<A> &mc, const Vec<A> &sigd)
+{
+    constexpr int NP = A / 2;
+    constexpr bool ODD = (A & 1) != 0;
+    Vec<A> U, w, u;
+    load_uv<A>(uv_row, U, w);
+    if (PHILOX && !DIAG) {
+#pragma unroll
+        for (int j = 0; j < A; j++) {
+            float e = 0.f;
+#pragma unroll
+            for (int l = 0; l < A; l++) e = fmaf(p.sigma[j * A + l], n.get(l), e);
+            u.set(j, U.get(j) + e);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NP; i++)
+            u.pr[i] = PHILOX ? __ffma2_rn(sigd.pr[i], n.pr[i], U.pr[i]) : __fadd2_rn(U.pr[i], n.pr[i]);
+        if (ODD) u.sc = PHILOX ? fmaf(sigd.sc, n.sc, U.sc) : U.sc + n.sc;
+    }
+#pragma unroll
+    for (int i = 0; i < NP; i++) S.a2 = __ffma2_rn(w.pr[i], n.pr[i], S.a2);
+    if (ODD) S.a = fmaf(w.sc, n.sc, S.a);
+    x.step(u, mc);
+    x.state_cost(mc, S.a2, S.a);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -126,8 +149,17 @@ __device__ Merged merge_parts(const float *parts, size_t part_stride, int nparts
     float eta = 0.f;
     for (int w = 0; w < nw; w++) eta += sRed[w];
     for (int j = tid; j < TA; j += blockDim.x) {
+        const float *col = parts + 4 + j;
         float acc = 0.f;
-        for (int c = 0; c < nparts; c++) acc = fmaf(sScale[c], __ldcg(parts + c * part_stride + 4 + j), acc);
+        int c = 0;
+        for (; c + 8 <= nparts; c += 8) {      // 8 independent loads in flight, accumulated in order
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = __ldcg(col + (size_t)(c + i) * part_stride);
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc = fmaf(sScale[c + i], v[i], acc);
+        }
+        for (; c < nparts; c++) acc = fmaf(sScale[c], __ldcg(col + (size_t)c * part_stride), acc);
         sN[j] = acc;
     }
     __syncthreads();
@@ -175,6 +207,10 @@ __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_
 {
     __shared__ int s_is_last;
     const int TA = p.TA, stride = partial_stride(TA), nparts = gridDim.x;
+    if (nparts == 1 && p.world == 1) {          // a single CTA owns the controller: nothing to merge
+        apply_update<A, PHILOX>(p, ctrl, Merged{beta_c, eta_c}, sN, sWork);
+        return;
+    }
     float *mine = p.partials + ((size_t)ctrl * nparts + blockIdx.x) * stride;
     if (threadIdx.x == 0) { mine[0] = beta_c; mine[1] = eta_c; }
     for (int j = threadIdx.x; j < TA; j += blockDim.x) mine[4 + j] = sN[j];
@@ -199,11 +235,28 @@ __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_
     apply_update<A, PHILOX>(p, ctrl, m, sN, sWork);
 }
 
+template <int A>
+__device__ __forceinline__ void thread_consts(const RolloutParams &p, int ctrl, ModelConsts<A> &mc, Vec<A> &sigd,
+                                              float (&x0)[2 * A])
+{
+    const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * 2 * A : 0);
+    const float *xp = p.x + (size_t)ctrl * 2 * A;
+    float g[2 * A];
+#pragma unroll
+    for (int i = 0; i < 2 * A; i++) {
+        g[i] = gp[i];
+        x0[i] = p.x_inline ? p.x0[i] : xp[i];
+    }
+    mc.init(p.dt, p.c_pu, p.c_vu, p.sqrt_q, g);
+#pragma unroll
+    for (int j = 0; j < A; j++) sigd.set(j, p.sigma[j * A + j]);
+}
+
 // -------------------------------------------------------------------------------------------------
 // Philox mode
 // -------------------------------------------------------------------------------------------------
 template <int A, bool DIAG>
-__global__ void __launch_bounds__(kPhiloxThreads, 4)
+__global__ void __launch_bounds__(kPhiloxThreads, kPhiloxCtasPerSm)
 rollout_philox_kernel(const __grid_constant__ RolloutParams p)
 {
     constexpr int RS = Row<A>::RS;
@@ -221,33 +274,32 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     stage_sequence<A, true>(p, ctrl, sUV);
 
-    float g[2 * A], q[2 * A], x0[2 * A];
-    {
-        const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * 2 * A : 0);
-        const float *xp = p.x + (size_t)ctrl * 2 * A;
-#pragma unroll
-        for (int i = 0; i < 2 * A; i++) {
-            q[i] = p.sqrt_q[i];
-            g[i] = q[i] * gp[i];
-            x0[i] = p.x_inline ? p.x0[i] : xp[i];
-        }
-    }
+    ModelConsts<A> mc;
+    Vec<A> sigd;
+    float x0[2 * A];
+    thread_consts<A>(p, ctrl, mc, sigd, x0);
     __syncthreads();
 
     float *costs = p.costs + (size_t)ctrl * p.K_local;
-    const int kstride = gridDim.x * kPhiloxThreads;
-    const int kfirst = blockIdx.x * kPhiloxThreads + tid;
+    // contiguous, evenly sized sample range per CTA (32-sample granularity): no whole-iteration
+    // quantisation when K_local is not a multiple of gridDim.x * blockDim.x
+    const int n_w = (p.K_local + 31) >> 5;
+    const int w_lo = (int)((long long)n_w * blockIdx.x / gridDim.x);
+    const int w_hi = (int)((long long)n_w * (blockIdx.x + 1) / gridDim.x);
+    const int kfirst = 32 * w_lo + tid;
+    const int kend = min(p.K_local, 32 * w_hi);
+    constexpr int kstride = kPhiloxThreads;
     const int nfull = p.T >> 2, trem = p.T & 3;
     const uint32_t stream = (uint32_t)ctrl;
 
     // ---- phase 1: rollout + cost ---------------------------------------------------------------
     float bmin = kInf;
-    for (int it = 0, k = kfirst; it < p.n_iter; it++, k += kstride) {
-        if (k >= p.K_local) break;
+    for (int k = kfirst; k < kend; k += kstride) {
         const uint32_t kg = (uint32_t)(p.k_offset + k);
         PointMass<A> x;
         x.init(x0);
-        float S = 0.f;
+        CostAcc S;
+        S.zero();
         const float *uv = sUV;
         uint32_t call = 0;
         for (int tb = 0; tb < nfull; tb++) {       // full blocks of 4 steps = A Philox calls, no guards
@@ -256,7 +308,11 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
             for (int c = 0; c < A; c++) normals4(call + c, kg, stream, p, &z[4 * c]);
             call += A;
 #pragma unroll
-            for (int tt = 0; tt < 4; tt++) rollout_step<A, true, DIAG>(x, S, uv + tt * RS, &z[tt * A], p, g, q);
+            for (int tt = 0; tt < 4; tt++) {
+                Vec<A> n;
+                vec_from<A>(&z[tt * A], n);
+                rollout_step<A, true, DIAG>(x, S, uv + tt * RS, n, p, mc, sigd);
+            }
             uv += 4 * RS;
         }
         if (trem) {                                 // tail: T % 4 steps
@@ -265,11 +321,16 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
             for (int c = 0; c < A; c++) normals4(call + c, kg, stream, p, &z[4 * c]);
 #pragma unroll
             for (int tt = 0; tt < 3; tt++)
-                if (tt < trem) rollout_step<A, true, DIAG>(x, S, uv + tt * RS, &z[tt * A], p, g, q);
+                if (tt < trem) {
+                    Vec<A> n;
+                    vec_from<A>(&z[tt * A], n);
+                    rollout_step<A, true, DIAG>(x, S, uv + tt * RS, n, p, mc, sigd);
+                }
         }
-        S += x.state_cost(g, q);    // terminal cost on top of step T-1's (src/controller_base.cpp:271-272)
-        costs[k] = S;
-        bmin = fminf(bmin, S);
+        x.state_cost(mc, S.a2, S.a);    // terminal cost on top of step T-1's (src/controller_base.cpp:271-272)
+        const float Sk = S.total();
+        costs[k] = Sk;
+        bmin = fminf(bmin, Sk);
     }
     bmin = warp_min(bmin);
     if (lane == 0) sRed[warp] = bmin;
@@ -284,35 +345,28 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     const int nchunk = (ncall + 7) >> 3;
     float eta = 0.f;
     for (int ch = 0; ch < nchunk; ch++) {
-        float acc[32];
+        float2 acc2[16];
 #pragma unroll
-        for (int i = 0; i < 32; i++) acc[i] = 0.f;
+        for (int i = 0; i < 16; i++) acc2[i] = make_float2(0.f, 0.f);
         const bool full = (ch * 8 + 8 <= ncall);    // warp-uniform: all 8 calls of the chunk exist
-        for (int it = 0, k = kfirst; it < p.n_iter; it++, k += kstride) {
-            if (k >= p.K_local) break;
+        for (int k = kfirst; k < kend; k += kstride) {
             const uint32_t kg = (uint32_t)(p.k_offset + k);
             const float e = weight_exp(costs[k], beta_c, p.neg_inv_lambda_log2e);
+            const float2 e2 = make_float2(e, e);
             if (ch == 0) eta += e;
-            if (full) {
 #pragma unroll
-                for (int c8 = 0; c8 < 8; c8++) {
+            for (int c8 = 0; c8 < 8; c8++) {
+                if (full || ch * 8 + c8 < ncall) {
                     float z[4];
                     normals4((uint32_t)(ch * 8 + c8), kg, stream, p, z);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) acc[4 * c8 + j] = fmaf(e, z[j], acc[4 * c8 + j]);
-                }
-            } else {
-#pragma unroll
-                for (int c8 = 0; c8 < 8; c8++) {
-                    if (ch * 8 + c8 < ncall) {
-                        float z[4];
-                        normals4((uint32_t)(ch * 8 + c8), kg, stream, p, z);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) acc[4 * c8 + j] = fmaf(e, z[j], acc[4 * c8 + j]);
-                    }
+                    acc2[2 * c8] = __ffma2_rn(e2, make_float2(z[0], z[1]), acc2[2 * c8]);
+                    acc2[2 * c8 + 1] = __ffma2_rn(e2, make_float2(z[2], z[3]), acc2[2 * c8 + 1]);
                 }
             }
         }
+        float acc[32];
+#pragma unroll
+        for (int i = 0; i < 16; i++) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
         const float r = warp_transpose_sum32(acc, lane);
         sAcc[warp * TAp + ch * 32 + lane] = r;
     }
@@ -334,11 +388,51 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
 
 // -------------------------------------------------------------------------------------------------
 // Injected-noise mode
+//
+// A tile is 32 samples x (T*a) floats, contiguous in HBM, landed in shared memory by ONE TMA bulk copy
+// and kept resident between the rollout and the weighted sum, so eps is read from HBM exactly once.
+// Large rows (config 3: 38.4 KB per tile) leave room for only a few tiles per SM, so a tile is
+// processed by a GROUP of C warps that split the horizon (lane = sample in every warp):
+//   pass 1  the model is linear, so a chunk of n steps maps x_in -> M^n x_in + b with
+//           M^n = [[1, n dt],[0, 1]] per axis and b the zero-state response.  With C = sum_t u_t and
+//           D = sum_t (exclusive prefix of u), b = (c_pu C + dt c_vu D, c_vu C); u = U_t + eps_t splits
+//           into a per-CTA part (from U, computed once) and a per-sample part (two adds per axis-step);
+//   pass 2  every warp rebuilds its true incoming state from x0 and b_0..b_{c-1}, rolls its chunk
+//           with the costs, and the chunk costs are summed in a fixed order;
+//   sum     the weighted sum over the resident tile is split by column blocks across the C warps.
+// With C = 1 this degenerates to one warp per tile and no barriers.
 // -------------------------------------------------------------------------------------------------
 struct InjectedLaunch {
-    int nw;      // consumer warps per CTA
-    int stages;  // tile buffers per warp (each warp owns a private ring: no cross-warp barrier aliasing)
+    int ng;      // tile groups per CTA
+    int c;       // warps per group (time chunks)
+    int stages;  // tile buffers per group (private ring per group)
 };
+
+__device__ __forceinline__ void group_barrier(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Noise of the 4 steps of block tb (4A floats) from the lane's resident row.
+template <int A, bool TMA, bool GUARD>
+__device__ __forceinline__ void load_block(const float *row, int tb, int TA, float (&e)[4 * A])
+{
+    if (TMA) {   // T*a % 4 == 0: rows are 16-B aligned; LDS.128 is conflict-free when T*a/4 is odd
+#pragma unroll
+        for (int c = 0; c < A; c++) {
+            const int i4 = tb * A + c;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!GUARD || 4 * i4 < TA) v = reinterpret_cast<const float4 *>(row)[i4];
+            e[4 * c] = v.x; e[4 * c + 1] = v.y; e[4 * c + 2] = v.z; e[4 * c + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4 * A; i++) {
+            const int idx = tb * 4 * A + i;
+            e[i] = (!GUARD || idx < TA) ? row[idx] : 0.f;
+        }
+    }
+}
 
 template <int A, bool TMA>
 __global__ void __launch_bounds__(512, 1)
@@ -348,27 +442,30 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
     extern __shared__ float4 smem_f4[];
     float *smem = reinterpret_cast<float *>(smem_f4);
     const int TA = p.TA, TAp = (TA + 31) & ~31;
-    const int NW = L.nw, ST = L.stages, NBUF = NW * ST;
+    const int NG = L.ng, C = L.c, ST = L.stages, NBUF = NG * ST;
     const int tile_words = 32 * TA;                // multiple of 32 words: every tile 128-B aligned
     float *sTiles = smem;                          // [NBUF][32][TA]
     float *sUV = sTiles + (size_t)NBUF * tile_words;   // [T][RS]
-    float *sAccW = sUV + p.T * RS;                 // [NW][TAp] running per-warp sums
-    float *sN = sAccW + NW * TAp;                  // [TAp]
+    float *sAccG = sUV + p.T * RS;                 // [NG][TAp] running per-group sums
+    float *sN = sAccG + NG * TAp;                  // [TAp]
     float *sWork = sN + TAp;                       // [TAp]
     float *sScale = sWork + TAp;                   // [kMaxParts]
     float *sRed = sScale + kMaxParts;              // [64]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sRed + 64);   // [NBUF]
+    float *sB = sRed + 64;                         // [NG][C][2A][32] zero-state chunk responses
+    float *sS = sB + NG * C * 2 * A * 32;          // [NG][C][32] chunk costs
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sS + NG * C * 32);   // [NBUF]
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = warp / C, cw = warp - grp * C;
     const int n_tiles = (p.K_local + 31) >> 5;
     const int nseq = (n_tiles > (int)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const float *eps = p.eps + (size_t)ctrl * p.K_local * TA;
 
-    // Warp w consumes tile sequence numbers seq = w + j*NW (j = 0,1,..) of this CTA; its j-th tile
-    // lands in its private buffer w*ST + j%ST and completes phase j/ST of that buffer's mbarrier.
-    auto issue = [&](int w, int j) {   // one elected lane; TMA bulk copy of a whole tile (contiguous in HBM)
-        const int b = w * ST + (j % ST);
-        const int seq = w + j * NW;
+    // Group g consumes tile sequence numbers seq = g + j*NG (j = 0,1,..) of this CTA; its j-th tile
+    // lands in its private buffer g*ST + j%ST and completes phase j/ST of that buffer's mbarrier.
+    auto issue = [&](int g, int j) {   // one elected lane; TMA bulk copy of a whole tile
+        const int b = g * ST + (j % ST);
+        const int seq = g + j * NG;
         const int gt = seq * gridDim.x + blockIdx.x;
         const int rows = min(32, p.K_local - 32 * gt);
         const uint32_t bytes = (uint32_t)rows * TA * 4u;
@@ -383,132 +480,205 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
         }
     }
     stage_sequence<A, false>(p, ctrl, sUV);
-    for (int i = tid; i < NW * TAp; i += blockDim.x) sAccW[i] = 0.f;
+    for (int i = tid; i < NG * TAp; i += blockDim.x) sAccG[i] = 0.f;
     __syncthreads();
-    if (TMA && lane == 0 && warp < NW) {
-        for (int j = 0; j < ST && warp + j * NW < nseq; j++) issue(warp, j);
+    if (TMA && lane == 0 && cw == 0 && grp < NG) {
+        for (int j = 0; j < ST && grp + j * NG < nseq; j++) issue(grp, j);
     }
 
-    float g[2 * A], q[2 * A], x0[2 * A];
-    {
-        const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * 2 * A : 0);
-        const float *xp = p.x + (size_t)ctrl * 2 * A;
+    ModelConsts<A> mc;
+    Vec<A> sigd;
+    float x0[2 * A];
+    thread_consts<A>(p, ctrl, mc, sigd, x0);
+
+    float *costs = p.costs + (size_t)ctrl * p.K_local;
+    float *accg = sAccG + grp * TAp;
+    // time chunk of this warp, in blocks of 4 steps
+    const int nblk = (p.T + 3) >> 2;
+    const int nb = (nblk + C - 1) / C;
+    const int tb0 = min(nblk, cw * nb), tb1 = min(nblk, tb0 + nb);
+    const int bar_id = 1 + grp, bar_n = C * 32;
+    // column blocks (32 columns each) of this warp in the weighted sum
+    const int NB = (TA + 31) >> 5;
+    const int nbw = (NB + C - 1) / C;
+    const int cb0 = min(NB, cw * nbw), cb1 = min(NB, cb0 + nbw);
+    float beta_g = kInf, eta_lane = 0.f;
+
+    // U-part of this chunk's zero-state sums (same for every sample): CU = sum U_t, DU = sum prefix
+    Vec<A> CU, DU;
+    CU.fill(0.f);
+    DU.fill(0.f);
+    if (C > 1) {
+        const int s0 = 4 * tb0, s1 = min(p.T, 4 * tb1);
+        for (int t = s0; t < s1; t++) {
 #pragma unroll
-        for (int i = 0; i < 2 * A; i++) {
-            q[i] = p.sqrt_q[i];
-            g[i] = q[i] * gp[i];
-            x0[i] = p.x_inline ? p.x0[i] : xp[i];
+            for (int j = 0; j < A; j++) {
+                DU.set(j, DU.get(j) + CU.get(j));
+                CU.set(j, CU.get(j) + sUV[t * RS + j]);
+            }
         }
     }
 
-    float *costs = p.costs + (size_t)ctrl * p.K_local;
-    float *accw = sAccW + warp * TAp;
-    const int nblk = (p.T + 3) >> 2;
-    float beta_w = kInf, eta_lane = 0.f;
-
-    if (warp < NW) {
-        for (int j = 0, seq = warp; seq < nseq; j++, seq += NW) {
-            const int b = warp * ST + (j % ST);
+    if (grp < NG) {
+        for (int j = 0, seq = grp; seq < nseq; j++, seq += NG) {
+            const int b = grp * ST + (j % ST);
             const int gt = seq * gridDim.x + blockIdx.x;
             const int rows = min(32, p.K_local - 32 * gt);
             float *tile = sTiles + (size_t)b * tile_words;
             if (TMA) {
                 mbar_wait(&bars[b], (uint32_t)((j / ST) & 1));
-                if (rows < 32) {   // zero the rows the copy did not write (e = 0 must not meet NaN garbage)
+                if (rows < 32 && cw == 0) {   // zero the rows the copy did not write (e = 0 must not meet NaN garbage)
                     for (int i = rows * TA + lane; i < tile_words; i += 32) tile[i] = 0.f;
                 }
-            } else {           // generic fallback (T*a not a multiple of 4): coalesced loads by the warp
+            } else {           // generic fallback (T*a not a multiple of 4): coalesced loads by the group
                 const float *src = eps + (size_t)gt * tile_words;
                 const int nvalid = rows * TA;
-                for (int i = lane; i < tile_words; i += 32) tile[i] = (i < nvalid) ? __ldg(src + i) : 0.f;
+                for (int i = cw * 32 + lane; i < tile_words; i += C * 32) tile[i] = (i < nvalid) ? __ldg(src + i) : 0.f;
+                if (C > 1) group_barrier(bar_id, bar_n);
             }
             __syncwarp();
-
-            // ---- phase 1: lane = sample, rollout over the row held in shared memory --------------
             const float *row = tile + lane * TA;
+
             PointMass<A> x;
-            x.init(x0);
-            float S = 0.f;
-            for (int tb = 0; tb < nblk; tb++) {
-                float e[4 * A];
-                if (TMA) {   // T*a % 4 == 0: rows are 16-B aligned, conflict-free LDS.128 when T*a/4 is odd
+            if (C > 1) {
+                // ---- pass 1: per-sample part of the chunk's zero-state sums ------------------------
+                Vec<A> Cs, Ds;
+                Cs.fill(0.f);
+                Ds.fill(0.f);
+                for (int tb = tb0; tb < tb1; tb++) {
+                    float e[4 * A];
+                    if (4 * tb + 4 <= p.T) load_block<A, TMA, false>(row, tb, TA, e);
+                    else load_block<A, TMA, true>(row, tb, TA, e);    // zeros past the row end
 #pragma unroll
-                    for (int c = 0; c < A; c++) {
-                        const int i4 = tb * A + c;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (4 * i4 < TA) v = reinterpret_cast<const float4 *>(row)[i4];
-                        e[4 * c] = v.x; e[4 * c + 1] = v.y; e[4 * c + 2] = v.z; e[4 * c + 3] = v.w;
+                    for (int tt = 0; tt < 4; tt++) {
+                        Vec<A> n;
+                        vec_from<A>(&e[tt * A], n);
+#pragma unroll
+                        for (int i = 0; i < A / 2; i++) {
+                            Ds.pr[i] = __fadd2_rn(Ds.pr[i], Cs.pr[i]);
+                            Cs.pr[i] = __fadd2_rn(Cs.pr[i], n.pr[i]);
+                        }
+                        if (A & 1) { Ds.sc += Cs.sc; Cs.sc += n.sc; }
+                    }
+                }
+                // the guarded tail appends zeros: (4*tb1 - T) extra prefix terms entered D; remove them
+                const int extra = 4 * tb1 - min(p.T, 4 * tb1);
+                float *myb = sB + ((size_t)(grp * C + cw) * 2 * A) * 32 + lane;
+                const float dtcvu = p.dt * p.c_vu;
+#pragma unroll
+                for (int i = 0; i < A; i++) {
+                    const float Ci = Cs.get(i) + CU.get(i);
+                    const float Di = (Ds.get(i) - (float)extra * Cs.get(i)) + DU.get(i);
+                    myb[(2 * i) * 32] = fmaf(p.c_pu, Ci, dtcvu * Di);
+                    myb[(2 * i + 1) * 32] = p.c_vu * Ci;
+                }
+                group_barrier(bar_id, bar_n);
+                // true incoming state: x0 pushed through chunks 0..cw-1 (free response + zero-state response)
+                x.init(x0);
+                for (int cc = 0; cc < cw; cc++) {
+                    const int s0 = 4 * min(nblk, cc * nb), s1 = min(p.T, 4 * min(nblk, cc * nb + nb));
+                    const float ndt = (float)(s1 - s0) * p.dt;
+                    const float *ob = sB + ((size_t)(grp * C + cc) * 2 * A) * 32 + lane;
+#pragma unroll
+                    for (int i = 0; i < A; i++) {
+                        const float vi = x.v.get(i);
+                        x.p.set(i, fmaf(ndt, vi, x.p.get(i)) + ob[(2 * i) * 32]);
+                        x.v.set(i, vi + ob[(2 * i + 1) * 32]);
+                    }
+                }
+            } else {
+                x.init(x0);
+            }
+
+            // ---- pass 2: rollout with costs over this warp's chunk ----------------------------------
+            CostAcc Sa;
+            Sa.zero();
+            for (int tb = tb0; tb < tb1; tb++) {
+                float e[4 * A];
+                if (4 * tb + 4 <= p.T) {
+                    load_block<A, TMA, false>(row, tb, TA, e);
+#pragma unroll
+                    for (int tt = 0; tt < 4; tt++) {
+                        Vec<A> n;
+                        vec_from<A>(&e[tt * A], n);
+                        rollout_step<A, false, false>(x, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
                     }
                 } else {
+                    load_block<A, TMA, true>(row, tb, TA, e);
 #pragma unroll
-                    for (int i = 0; i < 4 * A; i++) {
-                        const int idx = tb * 4 * A + i;
-                        e[i] = (idx < TA) ? row[idx] : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int tt = 0; tt < 4; tt++) {
-                    const int t = 4 * tb + tt;
-                    if (t < p.T) rollout_step<A, false, false>(x, S, sUV + t * RS, &e[tt * A], p, g, q);
+                    for (int tt = 0; tt < 4; tt++)
+                        if (4 * tb + tt < p.T) {
+                            Vec<A> n;
+                            vec_from<A>(&e[tt * A], n);
+                            rollout_step<A, false, false>(x, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
+                        }
                 }
             }
-            S += x.state_cost(g, q);
-            if (lane < rows) costs[32 * gt + lane] = S; else S = kInf;
+            if (tb1 == nblk && tb0 < tb1) x.state_cost(mc, Sa.a2, Sa.a);   // terminal cost (src/controller_base.cpp:271-272)
+            float S = Sa.total();
+            if (C > 1) {
+                sS[(grp * C + cw) * 32 + lane] = S;
+                group_barrier(bar_id, bar_n);
+                S = 0.f;
+                for (int cc = 0; cc < C; cc++) S += sS[(grp * C + cc) * 32 + lane];   // fixed order in every warp
+            }
+            if (cw == 0 && lane < rows) costs[32 * gt + lane] = S;
+            if (lane >= rows) S = kInf;
 
-            // ---- phase 2: online max-shifted weights; lane = column of the resident tile ---------
+            // ---- weighted sum: online max-shifted weights; lane = column of the resident tile ---------
             const float m = warp_min(S);
-            if (m < beta_w) {
-                if (beta_w != kInf) {
-                    const float f = weight_exp(beta_w, m, p.neg_inv_lambda_log2e);
-                    for (int c = lane; c < TA; c += 32) accw[c] *= f;
+            if (m < beta_g) {
+                if (beta_g != kInf) {
+                    const float f = weight_exp(beta_g, m, p.neg_inv_lambda_log2e);
+                    for (int c = cb0 * 32 + lane; c < min(TA, cb1 * 32); c += 32) accg[c] *= f;
                     eta_lane *= f;
                 }
-                beta_w = m;
+                beta_g = m;
             }
-            const float ek = (lane < rows) ? weight_exp(S, beta_w, p.neg_inv_lambda_log2e) : 0.f;
+            const float ek = (lane < rows) ? weight_exp(S, beta_g, p.neg_inv_lambda_log2e) : 0.f;
             eta_lane += ek;
-            for (int cg = 0; cg < TA; cg += 128) {
-                int col[4];
+            for (int cb = cb0; cb < cb1; cb += 4) {
+                // 4 column blocks per pass: offsets 32*mm are immediates, the row pointer advances by TA.
+                // Blocks past cb1 / columns past TA read neighbouring shared memory and are discarded.
+                const float *ptr = tile + cb * 32 + lane;
                 float a4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int mm = 0; mm < 4; mm++) col[mm] = min(cg + 32 * mm + lane, TA - 1);
 #pragma unroll 8
                 for (int k = 0; k < 32; k++) {
                     const float w = __shfl_sync(0xffffffffu, ek, k);
-                    const float *trow = tile + k * TA;
 #pragma unroll
-                    for (int mm = 0; mm < 4; mm++) a4[mm] = fmaf(w, trow[col[mm]], a4[mm]);
+                    for (int mm = 0; mm < 4; mm++) a4[mm] = fmaf(w, ptr[32 * mm], a4[mm]);
+                    ptr += TA;
                 }
 #pragma unroll
                 for (int mm = 0; mm < 4; mm++) {
-                    const int c = cg + 32 * mm + lane;
-                    if (c < TA) accw[c] += a4[mm];
+                    const int c = (cb + mm) * 32 + lane;
+                    if (cb + mm < cb1 && c < TA) accg[c] += a4[mm];
                 }
             }
-            __syncwarp();
-            if (TMA && lane == 0 && seq + ST * NW < nseq) {
+            if (C > 1) group_barrier(bar_id, bar_n); else __syncwarp();   // everyone is done with the tile
+            if (TMA && lane == 0 && cw == 0 && seq + ST * NG < nseq) {
                 fence_proxy_async();
-                issue(warp, j + ST);
+                issue(grp, j + ST);
             }
         }
         eta_lane = warp_sum(eta_lane);
-        if (lane == 0) { sRed[warp] = beta_w; sRed[32 + warp] = eta_lane; }
+        if (lane == 0 && cw == 0) { sRed[grp] = beta_g; sRed[32 + grp] = eta_lane; }
     }
     __syncthreads();
 
-    // ---- CTA merge of the per-warp running sums -------------------------------------------------
+    // ---- CTA merge of the per-group running sums ---------------------------------------------------
     float beta_c = kInf;
-    for (int w = 0; w < NW; w++) beta_c = fminf(beta_c, sRed[w]);
+    for (int w = 0; w < NG; w++) beta_c = fminf(beta_c, sRed[w]);
     float eta_c = 0.f;
-    for (int w = 0; w < NW; w++) {
+    for (int w = 0; w < NG; w++) {
         const float bw = sRed[w];
         if (bw != kInf) eta_c = fmaf(weight_exp(bw, beta_c, p.neg_inv_lambda_log2e), sRed[32 + w], eta_c);
     }
     for (int j = tid; j < TA; j += blockDim.x) {
         float s = 0.f;
-        for (int w = 0; w < NW; w++) {
+        for (int w = 0; w < NG; w++) {
             const float bw = sRed[w];
-            if (bw != kInf) s = fmaf(weight_exp(bw, beta_c, p.neg_inv_lambda_log2e), sAccW[w * TAp + j], s);
+            if (bw != kInf) s = fmaf(weight_exp(bw, beta_c, p.neg_inv_lambda_log2e), sAccG[w * TAp + j], s);
         }
         sN[j] = s;
     }
@@ -562,9 +732,13 @@ __global__ void scale_noise_kernel(const __grid_constant__ RolloutParams p, floa
         for (int j = 0; j < A; j++) z[j] = io[i * A + j];
 #pragma unroll
         for (int j = 0; j < A; j++) {
-            e[j] = 0.f;
+            if (p.sigma_diag) {
+                e[j] = p.sigma[j * A + j] * z[j];
+            } else {
+                e[j] = 0.f;
 #pragma unroll
-            for (int l = 0; l < A; l++) e[j] = fmaf(p.sigma[j * A + l], z[l], e[j]);
+                for (int l = 0; l < A; l++) e[j] = fmaf(p.sigma[j * A + l], z[l], e[j]);
+            }
         }
 #pragma unroll
         for (int j = 0; j < A; j++) io[i * A + j] = e[j];
@@ -576,7 +750,7 @@ __global__ void scale_noise_kernel(const __grid_constant__ RolloutParams p, floa
 // -------------------------------------------------------------------------------------------------
 static size_t philox_smem_bytes(int A, int T, int TA)
 {
-    const int RS = (2 * A + 3) & ~3, TAp = (TA + 31) & ~31, NW = kPhiloxThreads / 32;
+    const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31, NW = kPhiloxThreads / 32;
     return sizeof(float) * ((size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 32);
 }
 
@@ -610,68 +784,71 @@ static cudaError_t launch_philox_A(const RolloutParams &p, dim3 grid, cudaStream
         default: return cudaErrorInvalidValue;   \
     }
 
-int philox_grid_x(int K_local, int n_ctrl, int num_sms, int *n_iter)
+int philox_grid_x(int K_local, int n_ctrl, int num_sms)
 {
-    const int ctas_total = num_sms * 4;                      // 4 resident CTAs of 256 threads per SM
+    const int ctas_total = num_sms * kPhiloxCtasPerSm;
     int per_ctrl = ctas_total / (n_ctrl > 0 ? n_ctrl : 1);
     if (per_ctrl < 1) per_ctrl = 1;
-    const int need = (K_local + kPhiloxThreads - 1) / kPhiloxThreads;
+    // at least 128 samples (4 warps) per CTA so small problems do not pay for empty CTAs
+    const int need = (K_local + 127) / 128;
     int gx = need < per_ctrl ? need : per_ctrl;
     if (gx > kMaxParts) gx = kMaxParts;
-    int it = (K_local + gx * kPhiloxThreads - 1) / (gx * kPhiloxThreads);
-    gx = (K_local + it * kPhiloxThreads - 1) / (it * kPhiloxThreads);   // rebalance
-    *n_iter = it;
+    if (gx < 1) gx = 1;
     return gx;
 }
 
 cudaError_t launch_rollout_philox(RolloutParams p, int a, int num_sms, cudaStream_t st, int *grid_x_out)
 {
-    int n_iter = 1;
-    const int gx = philox_grid_x(p.K_local, p.n_ctrl, num_sms, &n_iter);
-    p.n_iter = n_iter;
+    const int gx = philox_grid_x(p.K_local, p.n_ctrl, num_sms);
+    p.n_iter = (p.K_local + gx * kPhiloxThreads - 1) / (gx * kPhiloxThreads);
     if (grid_x_out) *grid_x_out = gx;
     dim3 grid(gx, p.n_ctrl);
     MPPI_DISPATCH_A(a, return launch_philox_A<A_>(p, grid, st));
     return cudaSuccess;
 }
 
-// Injected mode geometry: how many consumer warps / tile buffers fit in shared memory.
+// Injected mode geometry: tile groups / warps per group / stages that fit in shared memory.
 bool injected_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sms, size_t smem_limit,
-                       int *nw_out, int *stages_out, int *grid_x_out, size_t *smem_out)
+                       int *ng_out, int *c_out, int *stages_out, int *grid_x_out, size_t *smem_out)
 {
-    const int RS = (2 * A + 3) & ~3, TAp = (TA + 31) & ~31;
+    const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31;
     const size_t tile_b = (size_t)128 * TA;
     const int n_tiles = (K_local + 31) / 32;
+    const int nblk = (T + 3) / 4;
     // several CTAs per SM when there are many small controllers
     int ctas_per_sm = 1;
     if (n_ctrl >= 2 * num_sms) ctas_per_sm = 4;
+    const int max_warps = 16 / ctas_per_sm;         // 512 threads per SM: <= 128 registers per thread
     const size_t budget = smem_limit / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
     const size_t fixed = sizeof(float) * ((size_t)T * RS + 2 * TAp + kMaxParts + 64) + 8 * 64 + 64;
-    const size_t per_warp = sizeof(float) * (size_t)TAp;
-    if (fixed + per_warp + tile_b > budget) return false;
-    int nw = (int)((budget - fixed) / (per_warp + tile_b));
-    if (nw > 16) nw = 16;
-    if (nw > n_tiles) nw = n_tiles > 0 ? n_tiles : 1;
-    int st = (int)((budget - fixed - nw * per_warp) / (nw * tile_b));
+    // per group: running sums + chunk responses/costs for up to 4 warps
+    const size_t per_group = sizeof(float) * ((size_t)TAp + 4 * (2 * A + 1) * 32);
+    if (fixed + per_group + tile_b > budget) return false;
+    int ng = (int)((budget - fixed) / (per_group + tile_b));
+    if (ng > max_warps) ng = max_warps;
+    if (ng > n_tiles) ng = n_tiles > 0 ? n_tiles : 1;
+    int c = max_warps / ng;
+    if (c > 4) c = 4;
+    if (c > nblk / 6) c = nblk / 6;                 // at least 24 steps per time chunk
+    if (c < 1) c = 1;
+    if (c > 1 && ng > 15) c = 1;                    // named barriers 1..15
+    int st = (int)((budget - fixed - ng * per_group) / (ng * tile_b));
     if (st > 3) st = 3;
     if (st < 1) st = 1;
     int gx;
-    const int need = (n_tiles + nw - 1) / nw;
-    if (n_ctrl == 1) {
-        gx = num_sms * ctas_per_sm;
-    } else {
-        gx = (num_sms * ctas_per_sm) / n_ctrl;
-    }
+    const int need = (n_tiles + ng - 1) / ng;
+    if (n_ctrl == 1) gx = num_sms * ctas_per_sm;
+    else gx = (num_sms * ctas_per_sm) / n_ctrl;
     if (gx > need) gx = need;
     if (gx < 1) gx = 1;
     if (gx > kMaxParts) gx = kMaxParts;
-    // do not keep more stages than this CTA has tiles per warp
-    const int tiles_per_warp = (n_tiles + gx * nw - 1) / (gx * nw);
-    if (st > tiles_per_warp) st = tiles_per_warp > 0 ? tiles_per_warp : 1;
-    *nw_out = nw;
+    const int tiles_per_group = (n_tiles + gx * ng - 1) / (gx * ng);
+    if (st > tiles_per_group) st = tiles_per_group > 0 ? tiles_per_group : 1;
+    *ng_out = ng;
+    *c_out = c;
     *stages_out = st;
     *grid_x_out = gx;
-    *smem_out = fixed + nw * per_warp + (size_t)nw * st * tile_b;
+    *smem_out = fixed + ng * per_group + (size_t)ng * st * tile_b;
     return true;
 }
 
@@ -680,7 +857,7 @@ static cudaError_t launch_injected_A(const RolloutParams &p, InjectedLaunch L, d
                                      cudaStream_t st)
 {
     cudaError_t err;
-    const int threads = L.nw * 32;
+    const int threads = L.ng * L.c * 32;
     if (tma) {
         err = cudaFuncSetAttribute(rollout_injected_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
@@ -699,7 +876,7 @@ cudaError_t launch_rollout_injected(RolloutParams p, int a, int num_sms, size_t 
     InjectedLaunch L;
     int gx = 1;
     size_t smem = 0;
-    if (!injected_geometry(a, p.T, p.TA, p.K_local, p.n_ctrl, num_sms, smem_limit, &L.nw, &L.stages, &gx, &smem))
+    if (!injected_geometry(a, p.T, p.TA, p.K_local, p.n_ctrl, num_sms, smem_limit, &L.ng, &L.c, &L.stages, &gx, &smem))
         return cudaErrorInvalidConfiguration;
     if (grid_x_out) *grid_x_out = gx;
     // TMA path needs 16-byte aligned tiles and rows: T*a % 4 == 0 and an aligned base pointer.
@@ -711,8 +888,7 @@ cudaError_t launch_rollout_injected(RolloutParams p, int a, int num_sms, size_t 
 
 int max_grid_x(int K_local, int n_ctrl, int num_sms)
 {
-    int n_iter;
-    int g1 = philox_grid_x(K_local, n_ctrl, num_sms, &n_iter);
+    int g1 = philox_grid_x(K_local, n_ctrl, num_sms);
     int g2 = num_sms * 4;
     return g1 > g2 ? g1 : g2;
 }

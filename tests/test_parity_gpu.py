@@ -194,7 +194,7 @@ def test_batched_controllers(oracle32, oracle64):
         ref = oracle64.mppi_update(cc, xs[c], U0[c], eps[c])
         r32 = oracle32.mppi_update(cc, xs[c], U0[c], eps[c])
         assert_update_close(Ush[c], ref["U_shift"], r32["U_shift"], what=f"U_shift[{c}]")
-        assert np.abs(act[c] - ref["next"]).max() <= max(1e-5, 2 * rel_err(r32["U_shift"], ref["U_shift"])) * \
+        assert np.abs(act[c] - ref["next"]).max() <= max(1e-5, 3 * rel_err(r32["U_shift"], ref["U_shift"])) * \
             np.abs(ref["U_new"]).max(), c
         np.testing.assert_allclose(costs[c], ref["costs"], rtol=1e-5, atol=1e-6)
 

@@ -49,11 +49,13 @@ def rel_err(got, want):
 
 def assert_update_close(got, ref64, ref32=None, tol=1e-5, what=""):
     """The parity bar of BASELINE.json: 1e-5 relative (norm-wise) against the exact (fp64) oracle.
-    Where the reference's own fp32 arithmetic (the op-for-op fp32 oracle) is further than that
-    from fp64 — ill-conditioned softmin, few dominant samples — allow twice its error."""
+    Where the reference's own fp32 arithmetic (the op-for-op fp32 oracle) is itself further than
+    that from fp64 — ill-conditioned softmin: costs of ~50 carry an fp32 ulp of 4e-6 straight into
+    the exponent — two fp32 implementations with different rounding orders cannot agree better
+    than a small multiple of that distance, so allow three times the fp32 oracle's own error."""
     err = rel_err(got, ref64)
     bar = tol
     if ref32 is not None:
-        bar = max(bar, 2.0 * rel_err(ref32, ref64))
+        bar = max(bar, 3.0 * rel_err(ref32, ref64))
     assert err <= bar, f"{what}: rel err {err:.3e} > {bar:.3e}"
     return err
