@@ -109,7 +109,9 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float &z0, 
     const float u1 = 2.0f - bits_to_1_2(xa);                       // (0, 1]
     const float th = fmaf(bits_to_1_2(xb), 6.2831853071795865f, -6.2831853071795865f);  // [0, 2pi)
     float r;                                                        // sqrt(-2 ln u1), one MUFU.SQRT
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(u1)));
+    float l2;                                                       // raw MUFU.LG2: u1 is never denormal
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));
     float sn, cs;
     __sincosf(th, &sn, &cs);
     z0 = r * cs;

@@ -1,0 +1,148 @@
+"""Minimal numpy-backed stand-in for the handful of TensorFlow ops the reference's Python twin
+(/root/reference/scripts/src) executes on the MPPI update path.  TEST TOOLING ONLY: it exists so that
+tests/golden/gen_python_twin_fixtures.py can run the REFERENCE'S OWN Python code (its op sequence,
+its constants, its shift/next logic) here, where TensorFlow cannot be installed, and record golden
+vectors.  Each function implements the documented semantics of the TF op of the same name for the
+argument patterns the reference uses; nothing here is imported by the product or by the tests."""
+import contextlib
+import types
+
+import numpy as np
+
+float64, float32, int32, int64 = np.float64, np.float32, np.int32, np.int64
+
+
+class Variable(np.ndarray):
+    def __new__(cls, initial_value, trainable=False, dtype=None, name=None):
+        return np.asarray(initial_value, dtype=dtype).view(cls).copy()
+
+    def assign(self, v):
+        self[...] = v
+        return self
+
+    def numpy(self):
+        return np.asarray(self)
+
+
+class Module:
+    pass
+
+
+def _a(x, dtype=None):
+    return np.asarray(x, dtype=dtype)
+
+
+def convert_to_tensor(x, dtype=None, name=None):
+    return np.array(x, dtype=dtype)
+
+
+constant = convert_to_tensor
+
+
+def is_tensor(x):
+    return isinstance(x, np.ndarray)
+
+
+def zeros(shape, dtype=float32, name=None):
+    return np.zeros(tuple(int(s) for s in np.atleast_1d(shape)), dtype=dtype)
+
+
+def ones(shape, dtype=float32, name=None):
+    return np.ones(tuple(int(s) for s in np.atleast_1d(shape)), dtype=dtype)
+
+
+def shape(x):
+    return np.array(np.shape(x))
+
+
+def cast(x, dtype=None):
+    return np.asarray(x, dtype=dtype)
+
+
+def add(a, b, name=None):
+    return _a(a) + _a(b)
+
+
+def divide(a, b, name=None):
+    return _a(a) / _a(b)
+
+
+realdiv = divide
+
+
+def expand_dims(x, axis, name=None):
+    return np.expand_dims(_a(x), axis)
+
+
+def broadcast_to(x, shape, name=None):
+    return np.broadcast_to(_a(x), tuple(int(s) for s in shape)).copy()
+
+
+def squeeze(x, axis=None, name=None):
+    return np.squeeze(_a(x), axis=axis)
+
+
+def slice(x, begin, size, name=None):          # noqa: A001  (tf.slice)
+    x = _a(x)
+    idx = tuple(np.s_[b:(None if s == -1 else b + s)] for b, s in zip(begin, size))
+    return x[idx]
+
+
+def concat(values, axis, name=None):
+    return np.concatenate([_a(v) for v in values], axis=axis)
+
+
+def reduce_min(x, axis=None, name=None):
+    return np.min(_a(x), axis=axis)
+
+
+def reduce_max(x, axis=None, name=None):
+    return np.max(_a(x), axis=axis)
+
+
+def reduce_sum(x, axis=None, name=None):
+    return np.sum(_a(x), axis=axis)
+
+
+def clip_by_value(x, lo, hi, name=None):
+    return np.clip(_a(x), lo, hi)
+
+
+@contextlib.contextmanager
+def name_scope(name):
+    yield name
+
+
+def function(f=None, **kw):
+    return f if f is not None else (lambda g: g)
+
+
+def _matmul(a, b, transpose_a=False, transpose_b=False, name=None):
+    a, b = _a(a), _a(b)
+    if transpose_a:
+        a = np.swapaxes(a, -1, -2)
+    if transpose_b:
+        b = np.swapaxes(b, -1, -2)
+    return np.matmul(a, b)
+
+
+linalg = types.SimpleNamespace(matmul=_matmul, inv=lambda m, name=None: np.linalg.inv(_a(m)),
+                               diag=lambda v, name=None: np.diag(_a(v)))
+math = types.SimpleNamespace(
+    subtract=lambda a, b, name=None: _a(a) - _a(b), multiply=lambda a, b, name=None: _a(a) * _a(b),
+    add=add, exp=lambda x, name=None: np.exp(_a(x)), reduce_sum=reduce_sum, reduce_min=reduce_min,
+    reduce_max=reduce_max, divide=divide)
+
+
+def _normal(shape, mean=0.0, stddev=1.0, dtype=float32, seed=None, name=None):
+    return np.random.default_rng(seed).normal(mean, stddev, tuple(int(s) for s in shape)).astype(dtype)
+
+
+random = types.SimpleNamespace(normal=_normal)
+optimizers = types.SimpleNamespace(Adam=lambda **kw: None)
+config = types.SimpleNamespace(experimental=types.SimpleNamespace(
+    list_physical_devices=lambda kind=None: ["shim:0"], set_memory_growth=lambda dev, flag: None))
+summary = types.SimpleNamespace(create_file_writer=lambda *a, **k: None, scalar=lambda *a, **k: None,
+                                histogram=lambda *a, **k: None)
+profiler = types.SimpleNamespace(experimental=types.SimpleNamespace(start=lambda *a, **k: None,
+                                                                    stop=lambda *a, **k: None))
