@@ -165,10 +165,15 @@ int mppi_comm_init(mppi_handle *h, const void *id128);
 /* x' = x + (W3^T relu(W2^T relu(W1^T X + b1) + b2) + b3) * Ystd + Ymean,
  * X = (concat(x, u) - Xmean) / Xstd; weights in Keras layout [in][out]
  * (behaviour of /root/reference/scripts/src/models/nn_model.py:54-60,215-239,289-304).
- * Switches the handle to MPPI_MODEL_MLP; bf16 tensor-core rollout, fp32 state. */
+ * Switches the handle to MPPI_MODEL_MLP; bf16 tensor-core rollout, fp32 state.  This build supports
+ * hidden = 128 and s + a <= 16 (a <= 5). */
 int mppi_set_mlp(mppi_handle *h, int hidden, const float *W1, const float *b1, const float *W2,
                  const float *b2, const float *W3, const float *b3, const float *Xmean,
                  const float *Xstd, const float *Ymean, const float *Ystd);
+
+/* One batched MLP step on the tensor cores (the learned model's `predict`): state [kst][s] with kst in
+ * {1, k}, action [k][a] -> next [k][s].  Requires mppi_set_mlp. */
+int mppi_mlp_predict(mppi_handle *h, int kst, int k, const float *state, const float *action, float *out);
 
 /* ---- stateless stage entry points (the reference's graph-builder methods on plain buffers) ----
  * All pointers are host memory; each call runs the corresponding CUDA kernel on `device`. */

@@ -75,6 +75,7 @@ SYMBOLS = {
     "mppi_comm_unique_id": (_i, [_vp]),
     "mppi_comm_init": (_i, [_H, _vp]),
     "mppi_set_mlp": (_i, [_H, _i] + [_fp] * 10),
+    "mppi_mlp_predict": (_i, [_H, _i, _i, _fp, _fp, _fp]),
     "mppi_block_diag": (_i, [_fp, _i, _i, _i, _fp]),
     "mppi_model_free_step": (_i, [_i, _f, _f, _i, _i, _i, _fp, _fp]),
     "mppi_model_action_step": (_i, [_i, _f, _f, _i, _i, _i, _fp, _fp]),

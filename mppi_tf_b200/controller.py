@@ -234,6 +234,24 @@ class ControllerBase:
     def setUpdateCounter(self, c):
         check(self._lib.mppi_set_update_counter(self._h, int(c)), self._h)
 
+    # ---- learned MLP dynamics (learning_base, row A13) ----------------------------------------------
+    def setMlp(self, mlp):
+        """mlp: dict W1 [s+a,H], b1 [H], W2 [H,H], b2 [H], W3 [H,s], b3 [s] (Keras layout) and optional
+        Xmean/Xstd [s+a], Ymean/Ystd [s].  Switches the rollout to the tensor-core MLP model."""
+        keep = {k: _f32(v) for k, v in mlp.items()}
+        H = keep["b1"].size
+        opt = lambda k: _ptr(keep[k]) if k in keep else None
+        check(self._lib.mppi_set_mlp(self._h, H, _ptr(keep["W1"]), _ptr(keep["b1"]), _ptr(keep["W2"]), _ptr(keep["b2"]),
+                                     _ptr(keep["W3"]), _ptr(keep["b3"]), opt("Xmean"), opt("Xstd"), opt("Ymean"),
+                                     opt("Ystd")), self._h)
+
+    def mlpPredict(self, state, action):
+        st = _f32(state).reshape(-1, self.s_dim)
+        ac = _f32(action).reshape(-1, self.a_dim)
+        out = np.empty((ac.shape[0], self.s_dim), np.float32)
+        check(self._lib.mppi_mlp_predict(self._h, st.shape[0], ac.shape[0], _ptr(st), _ptr(ac), _ptr(out)), self._h)
+        return out
+
     # ---- asynchronous halves (bench / multi-rank) ---------------------------------------------------
     def setState(self, x):
         x = _f32(x).reshape(self.n, self.s_dim)

@@ -12,6 +12,7 @@
 
 #include "mppi_device.cuh"
 #include "mppi_internal.h"
+#include "mppi_mlp.cuh"
 
 using namespace mppi;
 
@@ -79,6 +80,10 @@ struct mppi_handle {
     float *h_x = nullptr, *h_next = nullptr;
     bool x_staged = false;
     NcclComm comm = nullptr;
+    // learned-MLP dynamics (mppi_set_mlp)
+    bool mlp = false;
+    void *d_wblob = nullptr;
+    float *d_fvec = nullptr;
     std::string err;
 };
 
@@ -304,6 +309,8 @@ int mppi_destroy(mppi_handle *h)
     cudaFree(h->d_x); cudaFree(h->d_goal); cudaFree(h->d_U); cudaFree(h->d_Unew); cudaFree(h->d_next);
     cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_counters);
     cudaFree(h->d_eps_tmp);
+    cudaFree(h->d_wblob);
+    cudaFree(h->d_fvec);
     if (!h->ext_exchange) { cudaFree(h->d_payload); cudaFree(h->d_gather); }
     if (h->h_x) cudaFreeHost(h->h_x);
     if (h->h_next) cudaFreeHost(h->h_next);
@@ -345,7 +352,16 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
     CU_TRY(h, cudaSetDevice(h->device));
     RolloutParams p = make_params(h, eps_dev);
     int gx = 0;
-    if (eps_dev) {
+    if (h->mlp) {
+        MlpParams mp{h->d_wblob, h->d_fvec, h->s, h->a};
+        CU_TRY(h, launch_rollout_mlp(p, mp, h->a, eps_dev == nullptr, h->num_sms, h->stream, &gx));
+        h->last_philox = (eps_dev == nullptr);
+        if (!eps_dev) {
+            h->have_philox_update = true;
+            h->last_update = h->update_counter;
+            h->update_counter++;
+        }
+    } else if (eps_dev) {
         cudaError_t e = launch_rollout_injected(p, h->a, h->num_sms, h->smem_optin, h->stream, &gx);
         if (e == cudaErrorInvalidConfiguration)
             return fail(h, MPPI_ERR_UNSUPPORTED, "injected-noise mode: one 32-sample tile of tau*a_dim floats does not fit shared memory");
@@ -592,10 +608,54 @@ int mppi_comm_init(mppi_handle *h, const void *id128)
     return MPPI_OK;
 }
 
-int mppi_set_mlp(mppi_handle *h, int, const float *, const float *, const float *, const float *, const float *,
-                 const float *, const float *, const float *, const float *, const float *)
+int mppi_set_mlp(mppi_handle *h, int hidden, const float *W1, const float *b1, const float *W2, const float *b2,
+                 const float *W3, const float *b3, const float *Xmean, const float *Xstd, const float *Ymean,
+                 const float *Ystd)
 {
-    return fail(h, MPPI_ERR_UNSUPPORTED, "MLP dynamics are not built into this library version");
+    if (!h || !W1 || !b1 || !W2 || !b2 || !W3 || !b3) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    if (hidden != kMlpH) return fail(h, MPPI_ERR_UNSUPPORTED, "this build supports hidden = 128 only");
+    if (h->s + h->a > kMlpKin || h->a > 5) return fail(h, MPPI_ERR_UNSUPPORTED, "MLP path needs s + a <= 16 (a <= 5)");
+    CU_TRY(h, cudaSetDevice(h->device));
+    std::vector<uint8_t> blob(kWBlobBytes);
+    mlp_pack_weights(h->s, h->a, W1, W2, W3, blob.data());
+    std::vector<float> fv(kFvecFloats, 0.f);
+    const int in = h->s + h->a;
+    for (int i = 0; i < kMlpH; i++) { fv[i] = b1[i]; fv[128 + i] = b2[i]; }
+    for (int i = 0; i < h->s; i++) fv[256 + i] = b3[i];
+    for (int i = 0; i < 16; i++) { fv[288 + i] = 1.f; fv[304 + i] = 1.f; }
+    for (int i = 0; i < in; i++) {
+        fv[272 + i] = Xmean ? Xmean[i] : 0.f;
+        const float sd = Xstd ? Xstd[i] : 1.f;
+        if (!(sd != 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "Xstd must be non-zero");
+        fv[288 + i] = 1.0f / sd;
+    }
+    for (int i = 0; i < h->s; i++) {
+        fv[304 + i] = Ystd ? Ystd[i] : 1.f;
+        fv[320 + i] = Ymean ? Ymean[i] : 0.f;
+    }
+    if (!h->d_wblob) CU_TRY(h, cudaMalloc(&h->d_wblob, kWBlobBytes));
+    if (!h->d_fvec) CU_TRY(h, cudaMalloc(&h->d_fvec, sizeof(float) * kFvecFloats));
+    CU_TRY(h, cudaMemcpyAsync(h->d_wblob, blob.data(), kWBlobBytes, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_fvec, fv.data(), sizeof(float) * kFvecFloats, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->mlp = true;
+    return MPPI_OK;
+}
+
+int mppi_mlp_predict(mppi_handle *h, int kst, int k, const float *state, const float *action, float *out)
+{
+    if (!h || !state || !action || !out || k <= 0 || (kst != 1 && kst != k)) return fail(h, MPPI_ERR_BAD_ARG, "bad mlp_predict argument");
+    if (!h->mlp) return fail(h, MPPI_ERR_STATE, "mppi_set_mlp has not been called");
+    CU_TRY(h, cudaSetDevice(h->device));
+    DevBuf ds, da, dout;
+    CU_TRY(h, ds.alloc(sizeof(float) * (size_t)kst * h->s));
+    CU_TRY(h, da.alloc(sizeof(float) * (size_t)k * h->a));
+    CU_TRY(h, dout.alloc(sizeof(float) * (size_t)k * h->s));
+    CU_TRY(h, cudaMemcpyAsync(ds.p, state, sizeof(float) * (size_t)kst * h->s, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(da.p, action, sizeof(float) * (size_t)k * h->a, cudaMemcpyHostToDevice, h->stream));
+    MlpParams mp{h->d_wblob, h->d_fvec, h->s, h->a};
+    CU_TRY(h, launch_mlp_predict(mp, kst, k, ds.as<float>(), da.as<float>(), dout.as<float>(), h->stream));
+    return d2h(h, out, dout.as<float>(), (size_t)k * h->s);
 }
 
 // ---- stateless stages -------------------------------------------------------------------------------

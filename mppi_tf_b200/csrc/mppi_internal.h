@@ -18,6 +18,14 @@ int max_grid_x(int K_local, int n_ctrl, int num_sms);
 bool injected_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sms, size_t smem_limit,
                        int *ng_out, int *c_out, int *stages_out, int *grid_x_out, size_t *smem_out);
 
+// mppi_mlp.cu
+struct MlpParams;
+cudaError_t launch_mlp_predict(const MlpParams &mp, int kst, int k, const float *state, const float *action, float *out,
+                               cudaStream_t st);
+cudaError_t launch_rollout_mlp(RolloutParams p, const MlpParams &mp, int a, bool philox, int num_sms, cudaStream_t st,
+                               int *grid_x_out);
+void mlp_pack_weights(int s, int a, const float *W1, const float *W2, const float *W3, void *blob_host);
+
 // mppi_stages.cu  (device pointers)
 cudaError_t launch_model_step(float mass, float dt, int s, int a, int kst, int k, const float *state,
                               const float *action, float *out, int mode, cudaStream_t st);

@@ -1,0 +1,309 @@
+// MPPI update with the learned-MLP dynamics on tcgen05 tensor cores (BASELINE config 4), plus the
+// batched one-step `predict` stage used by ModelBase-style callers and by the unit tests.
+// Device building blocks: mppi_mlp.cuh.  The update logic (softmin partials, merge, shift) is the
+// same code the point-mass kernels use (mppi_update.cuh).
+#include "mppi_mlp.cuh"
+#include "mppi_internal.h"
+#include "mppi_update.cuh"
+
+namespace mppi {
+
+// -------------------------------------------------------------------------------------------------
+// predict: next[k][s] = mlp(state[k|1][s], action[k][a])   (one CTA per 128 samples)
+// -------------------------------------------------------------------------------------------------
+template <int S, int A>
+__global__ void __launch_bounds__(kMlpThreads) mlp_predict_kernel(MlpParams mp, int kst, int k, const float *state,
+                                                                  const float *action, float *out)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t *sW = smem_raw;
+    float *sF = reinterpret_cast<float *>(sW + kWBlobBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sF + ((kFvecFloats + 3) & ~3));
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
+    MlpTile t;
+    mlp_tile_init(t, mp, sW, sF, bars, tslot);
+    const int r = blockIdx.x * kMlpThreads + threadIdx.x;
+    float x[S], u[A];
+#pragma unroll
+    for (int i = 0; i < S; i++) x[i] = (r < k) ? state[(size_t)(kst == 1 ? 0 : r) * S + i] : 0.f;
+#pragma unroll
+    for (int i = 0; i < A; i++) u[i] = (r < k) ? action[(size_t)r * A + i] : 0.f;
+    mlp_step<S, A>(t, x, u);
+    if (r < k) {
+#pragma unroll
+        for (int i = 0; i < S; i++) out[(size_t)r * S + i] = x[i];
+    }
+    mlp_tile_fini(t);
+}
+
+// -------------------------------------------------------------------------------------------------
+// fused rollout: same structure as rollout_philox_kernel (phase 1 costs, block min, phase 2 weighted
+// sums by regenerating / re-reading the noise, last-CTA merge) with the model step on tensor cores.
+// One thread = one sample row of the 128-row tile; every thread takes part in every MMA hand-shake,
+// so out-of-range rows roll a dummy sample.
+// -------------------------------------------------------------------------------------------------
+template <int A, bool PHILOX>
+__device__ __forceinline__ void noise4(const RolloutParams &p, const float *eps_row, uint32_t call, uint32_t kg,
+                                       uint32_t stream, bool valid, float (&z)[4])
+{
+    if (PHILOX) {
+        normals4(call, kg, stream, p, z);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int idx = 4 * (int)call + j;
+            z[j] = (valid && idx < p.TA) ? __ldg(eps_row + idx) : 0.f;
+        }
+    }
+}
+
+template <int A, bool PHILOX>
+__global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __grid_constant__ RolloutParams p, MlpParams mp)
+{
+    constexpr int S = 2 * A;
+    constexpr int RS = Row<A>::RS, H = Row<A>::H;
+    constexpr int NW = kMlpThreads / 32;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int TA = p.TA, TAp = (TA + 31) & ~31;
+    uint8_t *sW = smem_raw;
+    float *sF = reinterpret_cast<float *>(sW + kWBlobBytes);
+    float *sUV = sF + ((kFvecFloats + 3) & ~3);   // [T][RS]
+    float *sAcc = sUV + p.T * RS;                 // [NW][TAp]
+    float *sN = sAcc + NW * TAp;                  // [TAp]
+    float *sWork = sN + TAp;                      // [TAp]
+    float *sScale = sWork + TAp;                  // [kMaxParts]
+    float *sRed = sScale + kMaxParts;             // [32]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sRed + 32);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
+
+    const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    MlpTile t;
+    mlp_tile_init(t, mp, sW, sF, bars, tslot);
+    stage_sequence<A, PHILOX>(p, ctrl, sUV);
+
+    float g[S], q[S], x0[S];
+    {
+        const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * S : 0);
+        const float *xp = p.x + (size_t)ctrl * S;
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+            g[i] = gp[i];
+            q[i] = p.q[i];
+            x0[i] = p.x_inline ? p.x0[i] : xp[i];
+        }
+    }
+    __syncthreads();
+
+    float *costs = p.costs + (size_t)ctrl * p.K_local;
+    const float *eps = PHILOX ? nullptr : p.eps + (size_t)ctrl * p.K_local * TA;
+    // contiguous sample range of this CTA, in tiles of 128 rows
+    const int n_t = (p.K_local + kMlpThreads - 1) / kMlpThreads;
+    const int t_lo = (int)((long long)n_t * blockIdx.x / gridDim.x);
+    const int t_hi = (int)((long long)n_t * (blockIdx.x + 1) / gridDim.x);
+    const int nblk = (p.T + 3) >> 2;
+    const uint32_t stream = (uint32_t)ctrl;
+
+    // ---- phase 1: rollout + cost -----------------------------------------------------------------
+    float bmin = kInf;
+    for (int tile = t_lo; tile < t_hi; tile++) {
+        const int k = tile * kMlpThreads + tid;
+        const bool valid = k < p.K_local;
+        const uint32_t kg = (uint32_t)(p.k_offset + k);
+        const float *eps_row = PHILOX ? nullptr : eps + (size_t)(valid ? k : 0) * TA;
+        float x[S];
+#pragma unroll
+        for (int i = 0; i < S; i++) x[i] = x0[i];
+        float Sk = 0.f;
+        for (int tb = 0; tb < nblk; tb++) {
+            float z[4 * A];
+#pragma unroll
+            for (int c = 0; c < A; c++) {
+                float z4[4];
+                noise4<A, PHILOX>(p, eps_row, (uint32_t)(tb * A + c), kg, stream, valid, z4);
+#pragma unroll
+                for (int j = 0; j < 4; j++) z[4 * c + j] = z4[j];
+            }
+#pragma unroll 1
+            for (int tt = 0; tt < 4; tt++) {
+                const int ts = 4 * tb + tt;
+                if (ts >= p.T) break;            // block-uniform
+                const float *uv = sUV + ts * RS;
+                float u[A];
+                float ac = 0.f;
+#pragma unroll
+                for (int j = 0; j < A; j++) {
+                    const float n = z[tt * A + j];
+                    float e = n;
+                    if (PHILOX) {
+                        e = 0.f;
+#pragma unroll
+                        for (int l = 0; l < A; l++) e = fmaf(p.sigma[j * A + l], z[tt * A + l], e);
+                    }
+                    u[j] = uv[j] + e;
+                    ac = fmaf(uv[H + j], n, ac);
+                }
+                mlp_step<S, A>(t, x, u);
+                float c = 0.f;
+#pragma unroll
+                for (int i = 0; i < S; i++) {
+                    const float d = x[i] - g[i];
+                    c = fmaf(q[i] * d, d, c);
+                }
+                Sk += c + ac;
+            }
+        }
+        {
+            float c = 0.f;                       // terminal cost (src/controller_base.cpp:271-272)
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                const float d = x[i] - g[i];
+                c = fmaf(q[i] * d, d, c);
+            }
+            Sk += c;
+        }
+        if (valid) {
+            costs[k] = Sk;
+            bmin = fminf(bmin, Sk);
+        }
+    }
+    mlp_tile_fini(t);
+    bmin = warp_min(bmin);
+    if (lane == 0) sRed[warp] = bmin;
+    __syncthreads();
+    float beta_c = sRed[0];
+#pragma unroll
+    for (int w = 1; w < NW; w++) beta_c = fminf(beta_c, sRed[w]);
+    __syncthreads();
+
+    // ---- phase 2: sum_k e_k n_k (n = z regenerated, or eps re-read) --------------------------------
+    const int ncall = (TA + 3) >> 2;
+    const int nchunk = (ncall + 7) >> 3;
+    float eta = 0.f;
+    for (int ch = 0; ch < nchunk; ch++) {
+        float acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) acc[i] = 0.f;
+        for (int tile = t_lo; tile < t_hi; tile++) {
+            const int k = tile * kMlpThreads + tid;
+            if (k >= p.K_local) continue;
+            const uint32_t kg = (uint32_t)(p.k_offset + k);
+            const float *eps_row = PHILOX ? nullptr : eps + (size_t)k * TA;
+            const float e = weight_exp(costs[k], beta_c, p.neg_inv_lambda_log2e);
+            if (ch == 0) eta += e;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; c8++) {
+                if (ch * 8 + c8 < ncall) {
+                    float z[4];
+                    noise4<A, PHILOX>(p, eps_row, (uint32_t)(ch * 8 + c8), kg, stream, true, z);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[4 * c8 + j] = fmaf(e, z[j], acc[4 * c8 + j]);
+                }
+            }
+        }
+        const float r = warp_transpose_sum32(acc, lane);
+        sAcc[warp * TAp + ch * 32 + lane] = r;
+    }
+    eta = warp_sum(eta);
+    if (lane == 0) sRed[warp] = eta;
+    __syncthreads();
+    float eta_c = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; w++) eta_c += sRed[w];
+    for (int j = tid; j < TA; j += kMlpThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) s += sAcc[w * TAp + j];
+        sN[j] = s;
+    }
+    __syncthreads();
+    // a CTA without samples must not win the min: beta_c = +inf is skipped by merge_parts
+    publish_and_finish<A, PHILOX>(p, ctrl, beta_c, eta_c, sN, sWork, sScale, sRed);
+}
+
+// -------------------------------------------------------------------------------------------------
+// host launchers
+// -------------------------------------------------------------------------------------------------
+static size_t mlp_predict_smem() { return kWBlobBytes + sizeof(float) * ((kFvecFloats + 3) & ~3) + 2 * 8 + 16 + 128; }
+
+static size_t mlp_rollout_smem(int A, int T, int TA)
+{
+    const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31, NW = kMlpThreads / 32;
+    return kWBlobBytes + sizeof(float) * (((kFvecFloats + 3) & ~3) + (size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 32) +
+           2 * 8 + 16 + 128;
+}
+
+#define MPPI_DISPATCH_MLP_A(a, ...)              \
+    switch (a) {                                 \
+        case 1: { constexpr int A_ = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int A_ = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int A_ = 3; __VA_ARGS__; } break; \
+        case 4: { constexpr int A_ = 4; __VA_ARGS__; } break; \
+        case 5: { constexpr int A_ = 5; __VA_ARGS__; } break; \
+        default: return cudaErrorInvalidValue;   \
+    }
+
+cudaError_t launch_mlp_predict(const MlpParams &mp, int kst, int k, const float *state, const float *action, float *out,
+                               cudaStream_t st)
+{
+    const size_t smem = mlp_predict_smem();
+    const int grid = (k + kMlpThreads - 1) / kMlpThreads;
+    MPPI_DISPATCH_MLP_A(mp.a, {
+        cudaError_t err = cudaFuncSetAttribute(mlp_predict_kernel<2 * A_, A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        mlp_predict_kernel<2 * A_, A_><<<grid, kMlpThreads, smem, st>>>(mp, kst, k, state, action, out);
+    });
+    return cudaGetLastError();
+}
+
+int mlp_grid_x(int K_local, int n_ctrl, int num_sms)
+{
+    int per_ctrl = (num_sms * 2) / (n_ctrl > 0 ? n_ctrl : 1);   // 2 CTAs (2 x 256 TMEM columns) per SM
+    if (per_ctrl < 1) per_ctrl = 1;
+    const int need = (K_local + kMlpThreads - 1) / kMlpThreads;
+    int gx = need < per_ctrl ? need : per_ctrl;
+    if (gx > kMaxParts) gx = kMaxParts;
+    return gx < 1 ? 1 : gx;
+}
+
+cudaError_t launch_rollout_mlp(RolloutParams p, const MlpParams &mp, int a, bool philox, int num_sms, cudaStream_t st,
+                               int *grid_x_out)
+{
+    const int gx = mlp_grid_x(p.K_local, p.n_ctrl, num_sms);
+    if (grid_x_out) *grid_x_out = gx;
+    const size_t smem = mlp_rollout_smem(a, p.T, p.TA);
+    dim3 grid(gx, p.n_ctrl);
+    MPPI_DISPATCH_MLP_A(a, {
+        cudaError_t err;
+        if (philox) {
+            err = cudaFuncSetAttribute(rollout_mlp_kernel<A_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return err;
+            rollout_mlp_kernel<A_, true><<<grid, kMlpThreads, smem, st>>>(p, mp);
+        } else {
+            err = cudaFuncSetAttribute(rollout_mlp_kernel<A_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return err;
+            rollout_mlp_kernel<A_, false><<<grid, kMlpThreads, smem, st>>>(p, mp);
+        }
+    });
+    return cudaGetLastError();
+}
+
+// Pack Keras-layout weights ([in][out], fp32) into the bf16 canonical K-major blob the kernels stage.
+void mlp_pack_weights(int s, int a, const float *W1, const float *W2, const float *W3, void *blob_host)
+{
+    __nv_bfloat16 *b = static_cast<__nv_bfloat16 *>(blob_host);
+    const int in = s + a;
+    for (int i = 0; i < kWBlobBytes / 2; i++) b[i] = __float2bfloat16(0.f);
+    uint8_t *base = static_cast<uint8_t *>(blob_host);
+    for (int n = 0; n < kMlpH; n++)
+        for (int k = 0; k < in; k++)
+            *reinterpret_cast<__nv_bfloat16 *>(base + canon_offset_bytes(n, k, kMlpH)) = __float2bfloat16(W1[k * kMlpH + n]);
+    for (int n = 0; n < kMlpH; n++)
+        for (int k = 0; k < kMlpH; k++)
+            *reinterpret_cast<__nv_bfloat16 *>(base + kW1Bytes + canon_offset_bytes(n, k, kMlpH)) = __float2bfloat16(W2[k * kMlpH + n]);
+    for (int n = 0; n < s; n++)
+        for (int k = 0; k < kMlpH; k++)
+            *reinterpret_cast<__nv_bfloat16 *>(base + kW1Bytes + kW2Bytes + canon_offset_bytes(n, k, kMlpNout)) =
+                __float2bfloat16(W3[k * s + n]);
+}
+
+}  // namespace mppi

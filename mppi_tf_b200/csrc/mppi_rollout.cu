@@ -16,47 +16,12 @@
 // src/cost_base.cpp:37-68 (restated in the CPU checker that tests compare against).
 #include "mppi_device.cuh"
 #include "mppi_internal.h"
+#include "mppi_update.cuh"
 
 namespace mppi {
 
 constexpr int kPhiloxThreads = 512;
 constexpr int kPhiloxCtasPerSm = 2;
-constexpr int kMaxParts = 1024;   // CTA partials (or ranks) one merge can take
-
-// Per-step uniforms staged in shared memory, one row per step:
-//   [0, A)      U_t   mean action (src/controller_base.cpp:205-208)
-//   [H, H + A)  w_t   action-cost vector: Philox mode lambda*U_t (since eps = Sigma z,
-//                     lambda U^T Sigma^-1 eps = lambda U^T z); injected mode lambda*Sigma^-T U_t
-//                     (src/cost_base.cpp:63-68)
-// H = A rounded up to even so both halves start on an aligned pair.
-template <int A>
-struct Row {
-    static constexpr int H = (A + 1) & ~1;
-    static constexpr int RS = (2 * H + 3) & ~3;
-};
-
-template <int A, bool PHILOX>
-__device__ __forceinline__ void stage_sequence(const RolloutParams &p, int ctrl, float *sUV)
-{
-    constexpr int RS = Row<A>::RS, H = Row<A>::H;
-    const float *U = p.U + (size_t)ctrl * p.TA;
-    for (int i = threadIdx.x; i < p.T * RS; i += blockDim.x) {
-        const int t = i / RS, j = i - t * RS;
-        float v = 0.f;
-        if (j < A) {
-            v = U[t * A + j];
-        } else if (j >= H && j < H + A) {
-            const int r = j - H;
-            if (PHILOX) {
-                v = p.lambda * U[t * A + r];
-            } else {
-#pragma unroll
-                for (int l = 0; l < A; l++) v = fmaf(p.lam_inv_sigma_T[r * A + l], U[t * A + l], v);
-            }
-        }
-        sUV[i] = v;
-    }
-}
 
 template <int A>
 __device__ __forceinline__ void load_uv(const float *uv_row, Vec<A> &U, Vec<A> &w)
@@ -115,124 +80,6 @@ __device__ __forceinline__ void rollout_step(PointMass<A> &x, CostAcc &S, const 
     if (ODD) S.a = fmaf(w.sc, n.sc, S.a);
     x.step(u, mc);
     x.state_cost(mc, S.a2, S.a);
-}
-
-// -------------------------------------------------------------------------------------------------
-// Merge of partial records {beta, eta, -, -, N[TA]} (CTA partials or rank payloads), block-wide and
-// in a fixed order (deterministic).  On return sN[0..TA) holds sum_c scale_c N_c and the returned
-// beta/eta are the merged values: beta = min_c beta_c, scale_c = exp(-(beta_c - beta)/lambda).
-// -------------------------------------------------------------------------------------------------
-struct Merged { float beta, eta; };
-
-__device__ Merged merge_parts(const float *parts, size_t part_stride, int nparts, int TA,
-                              float neg_inv_lambda_log2e, float *sN, float *sScale, float *sRed)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    float b = kInf;
-    for (int c = tid; c < nparts; c += blockDim.x) b = fminf(b, __ldcg(parts + c * part_stride));
-    b = warp_min(b);
-    if (lane == 0) sRed[warp] = b;
-    __syncthreads();
-    float beta = sRed[0];
-    for (int w = 1; w < nw; w++) beta = fminf(beta, sRed[w]);
-    __syncthreads();
-    float e = 0.f;
-    for (int c = tid; c < nparts; c += blockDim.x) {
-        const float bc = __ldcg(parts + c * part_stride);
-        const float sc = (bc == kInf) ? 0.f : weight_exp(bc, beta, neg_inv_lambda_log2e);
-        sScale[c] = sc;
-        e = fmaf(sc, __ldcg(parts + c * part_stride + 1), e);
-    }
-    e = warp_sum(e);
-    if (lane == 0) sRed[warp] = e;
-    __syncthreads();
-    float eta = 0.f;
-    for (int w = 0; w < nw; w++) eta += sRed[w];
-    for (int j = tid; j < TA; j += blockDim.x) {
-        const float *col = parts + 4 + j;
-        float acc = 0.f;
-        int c = 0;
-        for (; c + 8 <= nparts; c += 8) {      // 8 independent loads in flight, accumulated in order
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = __ldcg(col + (size_t)(c + i) * part_stride);
-#pragma unroll
-            for (int i = 0; i < 8; i++) acc = fmaf(sScale[c + i], v[i], acc);
-        }
-        for (; c < nparts; c++) acc = fmaf(sScale[c], __ldcg(col + (size_t)c * part_stride), acc);
-        sN[j] = acc;
-    }
-    __syncthreads();
-    return Merged{beta, eta};
-}
-
-// U' = U + Delta (src/controller_base.cpp:223), next = U'[0] (:327-329), U <- [U'[1:], 0] (:310-324).
-// In Philox mode sN holds sum e z, so Delta_t = Sigma (sN_t) / eta; injected mode sums eps directly.
-template <int A, bool PHILOX>
-__device__ void apply_update(const RolloutParams &p, int ctrl, Merged m, float *sN, float *sOut)
-{
-    const int TA = p.TA;
-    const float inv_eta = 1.0f / m.eta;
-    float *U = p.U + (size_t)ctrl * TA;
-    for (int i = threadIdx.x; i < TA; i += blockDim.x) {
-        const int t = i / A, j = i - t * A;
-        float d;
-        if (PHILOX) {
-            d = 0.f;
-#pragma unroll
-            for (int l = 0; l < A; l++) d = fmaf(p.sigma[j * A + l], sN[t * A + l], d);
-        } else {
-            d = sN[i];
-        }
-        const float un = U[i] + d * inv_eta;
-        sOut[i] = un;
-        p.U_new[(size_t)ctrl * TA + i] = un;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < TA; i += blockDim.x) {
-        U[i] = (i + A < TA) ? sOut[i + A] : 0.f;
-        if (i < A) p.next[ctrl * A + i] = sOut[i];
-    }
-    if (threadIdx.x == 0) {
-        p.stats[2 * ctrl] = m.beta;
-        p.stats[2 * ctrl + 1] = m.eta;
-    }
-}
-
-// Publish this CTA's partial; the last CTA of the controller merges and finishes the update.
-// sN: CTA sums [TA]; sWork: >= TA floats scratch; sScale: kMaxParts floats; sRed: 32 floats.
-template <int A, bool PHILOX>
-__device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_c, float eta_c, float *sN,
-                                   float *sWork, float *sScale, float *sRed)
-{
-    __shared__ int s_is_last;
-    const int TA = p.TA, stride = partial_stride(TA), nparts = gridDim.x;
-    if (nparts == 1 && p.world == 1) {          // a single CTA owns the controller: nothing to merge
-        apply_update<A, PHILOX>(p, ctrl, Merged{beta_c, eta_c}, sN, sWork);
-        return;
-    }
-    float *mine = p.partials + ((size_t)ctrl * nparts + blockIdx.x) * stride;
-    if (threadIdx.x == 0) { mine[0] = beta_c; mine[1] = eta_c; }
-    for (int j = threadIdx.x; j < TA; j += blockDim.x) mine[4 + j] = sN[j];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned prev = atomicAdd(&p.counters[ctrl], 1u);
-        s_is_last = (prev == (unsigned)nparts - 1u);
-    }
-    __syncthreads();
-    if (!s_is_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) p.counters[ctrl] = 0u;
-    Merged m = merge_parts(p.partials + (size_t)ctrl * nparts * stride, stride, nparts, TA,
-                           p.neg_inv_lambda_log2e, sN, sScale, sRed);
-    if (p.world > 1) {
-        float *pay = p.payload + (size_t)ctrl * stride;
-        if (threadIdx.x == 0) { pay[0] = m.beta; pay[1] = m.eta; pay[2] = 0.f; pay[3] = 0.f; }
-        for (int j = threadIdx.x; j < stride - 4; j += blockDim.x) pay[4 + j] = (j < TA) ? sN[j] : 0.f;
-        return;
-    }
-    apply_update<A, PHILOX>(p, ctrl, m, sN, sWork);
 }
 
 template <int A>
