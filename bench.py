@@ -34,7 +34,11 @@ WORKLOADS = {
     "cfg2": ("point_mass2d K=65536 T=50 (BASELINE config 2)", 65536, 50, 4, 2, 1),
     "cfg3": ("point_mass3d K=1048576 T=100 (BASELINE config 3)", 1048576, 100, 6, 3, 1),
     "cfg5": ("4096 x point_mass2d K=1024 T=30 (BASELINE config 5)", 1024, 30, 4, 2, 4096),
+    "cfg4": ("learned MLP 9->128->128->6 on point_mass3d state, K=262144 T=50, bf16 tcgen05 (BASELINE config 4)",
+             262144, 50, 6, 3, 1),
 }
+MLP_WORKLOADS = {"cfg4"}
+MLP_FLOPS_PER_SAMPLE_STEP = 2 * (9 * 128 + 128 * 128 + 128 * 6)      # 36 608
 METRIC = "mppi_sample_steps_per_sec"
 UNIT = "sample-steps/s"
 
@@ -45,6 +49,26 @@ def measured_peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst cuBLAS 8192^3; kernel timed alone)"
+    return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
+def glorot_mlp(s, a, H=128, seed=4):
+    """default_rng(4), Glorot-uniform like Keras Dense, biases 0, unit normalisation."""
+    rng = np.random.default_rng(seed)
+
+    def g(i, o):
+        lim = np.sqrt(6.0 / (i + o))
+        return rng.uniform(-lim, lim, (i, o)).astype(np.float32)
+
+    return dict(W1=g(s + a, H), b1=np.zeros(H, np.float32), W2=g(H, H), b2=np.zeros(H, np.float32),
+                W3=g(H, s), b3=np.zeros(s, np.float32))
 
 
 class ClockSampler:
@@ -215,6 +239,9 @@ def main():
     ctrl = ControllerBase(k_rank, T, 0.1, 1.0, s, a, lam=1.0, sigma=sigma, goal=goal, seed=1, device=local_rank,
                           rank=k_rankid, world=k_world, n_controllers=n_local,
                           goal_per_controller=(n_ctrl > 1), stream=stream)
+    is_mlp = args.workload in MLP_WORKLOADS
+    if is_mlp:
+        ctrl.setMlp(glorot_mlp(s, a))
     exchange = k_world > 1
     if exchange:
         if args.exchange == "nccl":
@@ -301,7 +328,7 @@ def main():
 
     # ---- HBM-bound injected-noise kernel (N = 1 only; inputs resident in HBM) -------------------------
     inj = None
-    if world == 1 and not args.no_injected:
+    if world == 1 and not args.no_injected and not is_mlp:
         n_eps = n_local * K * T * a
         g = torch.Generator(device=dev).manual_seed(1234)
         eps = torch.randn(n_eps, device=dev, generator=g) * 0.25
@@ -347,13 +374,21 @@ def main():
                          "note": "effective GB/s on the algorithmic bytes 4*a*K*T + 4*K; the Philox kernel moves "
                                  "almost no HBM bytes and is bound by ALU/MUFU issue (see profiles/)"},
         }
+        if is_mlp:
+            tpeak, tsrc = measured_tensor_peak()
+            tf = MLP_FLOPS_PER_SAMPLE_STEP * (K // k_world) * T / (kernel_ms * 1e-3) / 1e12
+            line["dtype"] = "bf16"
+            line["config"]["mode"] = "philox noise + bf16 tcgen05 MLP rollout (fp32 state and accumulation)"
+            line["roofline"] = {"bound": "tensor", "kernel": "rollout_mlp_kernel", "achieved": tf, "peak": tpeak,
+                                "unit": "TFLOP/s", "frac": tf / tpeak, "traffic": None, "peak_source": tsrc,
+                                "note": "algorithmic flops 2*(9*128+128*128+128*6) = 36608 per sample-step (unpadded)"}
         if inj is not None:
             ia = bytes_alg(K, T, a, n_local) / (inj * 1e-3) / 1e9
             line["roofline_injected"] = {"bound": "hbm", "kernel": "rollout_injected_kernel", "achieved": ia,
                                          "peak": peak, "unit": "GB/s", "frac": ia / peak, "traffic": None,
                                          "ms_per_launch": inj,
                                          "inputs": "eps resident in HBM" + (" (larger than L2)" if 4 * n_eps > 126e6 else " (L2 flushed)")}
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and not is_mlp:
             r = cpu_port_throughput(K, T, s, a, steps=3, warmup=1, budget_s=15.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                                     "sample": r["sample"]}

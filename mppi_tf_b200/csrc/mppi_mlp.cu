@@ -18,20 +18,27 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_predict_kernel(MlpParams mp, 
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t *sW = smem_raw;
     float *sF = reinterpret_cast<float *>(sW + kWBlobBytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sF + ((kFvecFloats + 3) & ~3));
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sF + kFvecFloats);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + kMlpNumBars);
     MlpTile t;
     mlp_tile_init(t, mp, sW, sF, bars, tslot);
-    const int r = blockIdx.x * kMlpThreads + threadIdx.x;
-    float x[S], u[A];
+    if (threadIdx.x < kMlpRows) {
+        const int r = blockIdx.x * kMlpRows + threadIdx.x;
+        float x[S], u[A];
 #pragma unroll
-    for (int i = 0; i < S; i++) x[i] = (r < k) ? state[(size_t)(kst == 1 ? 0 : r) * S + i] : 0.f;
+        for (int i = 0; i < S; i++) x[i] = (r < k) ? state[(size_t)(kst == 1 ? 0 : r) * S + i] : 0.f;
 #pragma unroll
-    for (int i = 0; i < A; i++) u[i] = (r < k) ? action[(size_t)r * A + i] : 0.f;
-    mlp_step<S, A>(t, x, u);
-    if (r < k) {
+        for (int i = 0; i < A; i++) u[i] = (r < k) ? action[(size_t)r * A + i] : 0.f;
+        mlp_row_begin<S, A>(t, x, u);
+        mlp_row_layer1(t);
+        mlp_row_layer2(t);
+        mlp_row_finish<S>(t, x);
+        if (r < k) {
 #pragma unroll
-        for (int i = 0; i < S; i++) out[(size_t)r * S + i] = x[i];
+            for (int i = 0; i < S; i++) out[(size_t)r * S + i] = x[i];
+        }
+    } else {
+        mlp_mma_loop(t, 1);
     }
     mlp_tile_fini(t);
 }
@@ -39,8 +46,8 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_predict_kernel(MlpParams mp, 
 // -------------------------------------------------------------------------------------------------
 // fused rollout: same structure as rollout_philox_kernel (phase 1 costs, block min, phase 2 weighted
 // sums by regenerating / re-reading the noise, last-CTA merge) with the model step on tensor cores.
-// One thread = one sample row of the 128-row tile; every thread takes part in every MMA hand-shake,
-// so out-of-range rows roll a dummy sample.
+// Row thread r = sample row r of the 128-row tile; every row thread takes part in every hand-over
+// with the MMA warp, so out-of-range rows roll a dummy sample.
 // -------------------------------------------------------------------------------------------------
 template <int A, bool PHILOX>
 __device__ __forceinline__ void noise4(const RolloutParams &p, const float *eps_row, uint32_t call, uint32_t kg,
@@ -67,37 +74,24 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
     const int TA = p.TA, TAp = (TA + 31) & ~31;
     uint8_t *sW = smem_raw;
     float *sF = reinterpret_cast<float *>(sW + kWBlobBytes);
-    float *sUV = sF + ((kFvecFloats + 3) & ~3);   // [T][RS]
+    float *sUV = sF + kFvecFloats;                // [T][RS]
     float *sAcc = sUV + p.T * RS;                 // [NW][TAp]
     float *sN = sAcc + NW * TAp;                  // [TAp]
     float *sWork = sN + TAp;                      // [TAp]
     float *sScale = sWork + TAp;                  // [kMaxParts]
     float *sRed = sScale + kMaxParts;             // [32]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sRed + 32);
-    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 2);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + kMlpNumBars);
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     MlpTile t;
-    mlp_tile_init(t, mp, sW, sF, bars, tslot);
     stage_sequence<A, PHILOX>(p, ctrl, sUV);
-
-    float g[S], q[S], x0[S];
-    {
-        const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * S : 0);
-        const float *xp = p.x + (size_t)ctrl * S;
-#pragma unroll
-        for (int i = 0; i < S; i++) {
-            g[i] = gp[i];
-            q[i] = p.q[i];
-            x0[i] = p.x_inline ? p.x0[i] : xp[i];
-        }
-    }
-    __syncthreads();
+    mlp_tile_init(t, mp, sW, sF, bars, tslot);    // ends with a CTA barrier: sUV is visible
 
     float *costs = p.costs + (size_t)ctrl * p.K_local;
     const float *eps = PHILOX ? nullptr : p.eps + (size_t)ctrl * p.K_local * TA;
     // contiguous sample range of this CTA, in tiles of 128 rows
-    const int n_t = (p.K_local + kMlpThreads - 1) / kMlpThreads;
+    const int n_t = (p.K_local + kMlpRows - 1) / kMlpRows;
     const int t_lo = (int)((long long)n_t * blockIdx.x / gridDim.x);
     const int t_hi = (int)((long long)n_t * (blockIdx.x + 1) / gridDim.x);
     const int nblk = (p.T + 3) >> 2;
@@ -105,66 +99,103 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
 
     // ---- phase 1: rollout + cost -----------------------------------------------------------------
     float bmin = kInf;
-    for (int tile = t_lo; tile < t_hi; tile++) {
-        const int k = tile * kMlpThreads + tid;
-        const bool valid = k < p.K_local;
-        const uint32_t kg = (uint32_t)(p.k_offset + k);
-        const float *eps_row = PHILOX ? nullptr : eps + (size_t)(valid ? k : 0) * TA;
-        float x[S];
+    if (warp < kMlpRowWarps) {
+        float g[S], q[S], x0[S];
+        {
+            const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * S : 0);
+            const float *xp = p.x + (size_t)ctrl * S;
 #pragma unroll
-        for (int i = 0; i < S; i++) x[i] = x0[i];
-        float Sk = 0.f;
-        for (int tb = 0; tb < nblk; tb++) {
-            float z[4 * A];
+            for (int i = 0; i < S; i++) {
+                g[i] = gp[i];
+                q[i] = p.q[i];
+                x0[i] = p.x_inline ? p.x0[i] : xp[i];
+            }
+        }
+        for (int tile = t_lo; tile < t_hi; tile++) {
+            const int k = tile * kMlpRows + tid;
+            const bool valid = k < p.K_local;
+            const uint32_t kg = (uint32_t)(p.k_offset + k);
+            const float *eps_row = PHILOX ? nullptr : eps + (size_t)(valid ? k : 0) * TA;
+            float x[S];
+#pragma unroll
+            for (int i = 0; i < S; i++) x[i] = x0[i];
+            float Sk = 0.f;
+            float z[4 * A], zn[4 * A];
 #pragma unroll
             for (int c = 0; c < A; c++) {
                 float z4[4];
-                noise4<A, PHILOX>(p, eps_row, (uint32_t)(tb * A + c), kg, stream, valid, z4);
+                noise4<A, PHILOX>(p, eps_row, (uint32_t)c, kg, stream, valid, z4);
 #pragma unroll
                 for (int j = 0; j < 4; j++) z[4 * c + j] = z4[j];
             }
-#pragma unroll 1
-            for (int tt = 0; tt < 4; tt++) {
-                const int ts = 4 * tb + tt;
-                if (ts >= p.T) break;            // block-uniform
-                const float *uv = sUV + ts * RS;
-                float u[A];
-                float ac = 0.f;
+            for (int tb = 0; tb < nblk; tb++) {
+                const bool more = tb + 1 < nblk;          // block-uniform
 #pragma unroll
-                for (int j = 0; j < A; j++) {
-                    const float n = z[tt * A + j];
-                    float e = n;
-                    if (PHILOX) {
-                        e = 0.f;
+                for (int tt = 0; tt < 4; tt++) {
+                    const int ts = 4 * tb + tt;
+                    if (ts >= p.T) break;                 // block-uniform
+                    const float *uv = sUV + ts * RS;
+                    float u[A];
+                    float ac = 0.f;
 #pragma unroll
-                        for (int l = 0; l < A; l++) e = fmaf(p.sigma[j * A + l], z[tt * A + l], e);
+                    for (int j = 0; j < A; j++) {
+                        const float n = z[tt * A + j];
+                        float e = n;
+                        if (PHILOX) {
+                            e = 0.f;
+#pragma unroll
+                            for (int l = 0; l < A; l++) e = fmaf(p.sigma[j * A + l], z[tt * A + l], e);
+                        }
+                        u[j] = uv[j] + e;
+                        ac = fmaf(uv[H + j], n, ac);
                     }
-                    u[j] = uv[j] + e;
-                    ac = fmaf(uv[H + j], n, ac);
+                    mlp_row_begin<S, A>(t, x, u);
+                    // in the shadow of layer 1: state cost of the state the step started from (it is
+                    // step ts-1's q(x_ts)), and this step's action cost
+                    if (ts > 0) {
+                        float c = 0.f;
+#pragma unroll
+                        for (int i = 0; i < S; i++) {
+                            const float d = x[i] - g[i];
+                            c = fmaf(q[i] * d, d, c);
+                        }
+                        Sk += c;
+                    }
+                    Sk += ac;
+                    mlp_row_layer1(t);
+                    // in the shadow of layer 2 (the long MMA): this step's share of the next block's noise
+                    if (more) {
+#pragma unroll
+                        for (int c = (tt * A) / 4; c < ((tt + 1) * A) / 4; c++) {
+                            float z4[4];
+                            noise4<A, PHILOX>(p, eps_row, (uint32_t)((tb + 1) * A + c), kg, stream, valid, z4);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) zn[4 * c + j] = z4[j];
+                        }
+                    }
+                    mlp_row_layer2(t);
+                    mlp_row_finish<S>(t, x);
                 }
-                mlp_step<S, A>(t, x, u);
-                float c = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4 * A; i++) z[i] = zn[i];
+            }
+            {
+                float c = 0.f;                       // q(x_T) of step T-1 plus the terminal cost (src/controller_base.cpp:271-272)
 #pragma unroll
                 for (int i = 0; i < S; i++) {
                     const float d = x[i] - g[i];
                     c = fmaf(q[i] * d, d, c);
                 }
-                Sk += c + ac;
+                Sk += c;
+                Sk += c;
+            }
+            if (valid) {
+                costs[k] = Sk;
+                bmin = fminf(bmin, Sk);
             }
         }
-        {
-            float c = 0.f;                       // terminal cost (src/controller_base.cpp:271-272)
-#pragma unroll
-            for (int i = 0; i < S; i++) {
-                const float d = x[i] - g[i];
-                c = fmaf(q[i] * d, d, c);
-            }
-            Sk += c;
-        }
-        if (valid) {
-            costs[k] = Sk;
-            bmin = fminf(bmin, Sk);
-        }
+    } else {
+        mlp_mma_loop(t, (t_hi - t_lo) * p.T);
     }
     mlp_tile_fini(t);
     bmin = warp_min(bmin);
@@ -175,17 +206,16 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
     for (int w = 1; w < NW; w++) beta_c = fminf(beta_c, sRed[w]);
     __syncthreads();
 
-    // ---- phase 2: sum_k e_k n_k (n = z regenerated, or eps re-read) --------------------------------
+    // ---- phase 2: sum_k e_k n_k (n = z regenerated, or eps re-read); all five warps take samples ----
     const int ncall = (TA + 3) >> 2;
     const int nchunk = (ncall + 7) >> 3;
+    const int k_lo = t_lo * kMlpRows, k_hi = min(t_hi * kMlpRows, p.K_local);
     float eta = 0.f;
     for (int ch = 0; ch < nchunk; ch++) {
         float acc[32];
 #pragma unroll
         for (int i = 0; i < 32; i++) acc[i] = 0.f;
-        for (int tile = t_lo; tile < t_hi; tile++) {
-            const int k = tile * kMlpThreads + tid;
-            if (k >= p.K_local) continue;
+        for (int k = k_lo + tid; k < k_hi; k += kMlpThreads) {
             const uint32_t kg = (uint32_t)(p.k_offset + k);
             const float *eps_row = PHILOX ? nullptr : eps + (size_t)k * TA;
             const float e = weight_exp(costs[k], beta_c, p.neg_inv_lambda_log2e);
@@ -223,13 +253,13 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
 // -------------------------------------------------------------------------------------------------
 // host launchers
 // -------------------------------------------------------------------------------------------------
-static size_t mlp_predict_smem() { return kWBlobBytes + sizeof(float) * ((kFvecFloats + 3) & ~3) + 2 * 8 + 16 + 128; }
+static size_t mlp_predict_smem() { return kWBlobBytes + sizeof(float) * kFvecFloats + kMlpNumBars * 8 + 16 + 128; }
 
 static size_t mlp_rollout_smem(int A, int T, int TA)
 {
     const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31, NW = kMlpThreads / 32;
-    return kWBlobBytes + sizeof(float) * (((kFvecFloats + 3) & ~3) + (size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 32) +
-           2 * 8 + 16 + 128;
+    return kWBlobBytes + sizeof(float) * (kFvecFloats + (size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 32) +
+           kMlpNumBars * 8 + 16 + 128;
 }
 
 #define MPPI_DISPATCH_MLP_A(a, ...)              \
@@ -246,7 +276,7 @@ cudaError_t launch_mlp_predict(const MlpParams &mp, int kst, int k, const float 
                                cudaStream_t st)
 {
     const size_t smem = mlp_predict_smem();
-    const int grid = (k + kMlpThreads - 1) / kMlpThreads;
+    const int grid = (k + kMlpRows - 1) / kMlpRows;
     MPPI_DISPATCH_MLP_A(mp.a, {
         cudaError_t err = cudaFuncSetAttribute(mlp_predict_kernel<2 * A_, A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
@@ -259,7 +289,7 @@ int mlp_grid_x(int K_local, int n_ctrl, int num_sms)
 {
     int per_ctrl = (num_sms * 2) / (n_ctrl > 0 ? n_ctrl : 1);   // 2 CTAs (2 x 256 TMEM columns) per SM
     if (per_ctrl < 1) per_ctrl = 1;
-    const int need = (K_local + kMlpThreads - 1) / kMlpThreads;
+    const int need = (K_local + kMlpRows - 1) / kMlpRows;
     int gx = need < per_ctrl ? need : per_ctrl;
     if (gx > kMaxParts) gx = kMaxParts;
     return gx < 1 ? 1 : gx;
@@ -287,23 +317,28 @@ cudaError_t launch_rollout_mlp(RolloutParams p, const MlpParams &mp, int a, bool
     return cudaGetLastError();
 }
 
-// Pack Keras-layout weights ([in][out], fp32) into the bf16 canonical K-major blob the kernels stage.
-void mlp_pack_weights(int s, int a, const float *W1, const float *W2, const float *W3, void *blob_host)
+// Pack Keras-layout weights ([in][out], fp32) and biases into the bf16 canonical K-major blob the
+// kernels stage: B[n][k] = W[k][n], with the bias of each layer in the K row that meets the constant 1.
+void mlp_pack_weights(int s, int a, const float *W1, const float *b1, const float *W2, const float *b2,
+                      const float *W3, const float *b3, void *blob_host)
 {
     __nv_bfloat16 *b = static_cast<__nv_bfloat16 *>(blob_host);
     const int in = s + a;
     for (int i = 0; i < kWBlobBytes / 2; i++) b[i] = __float2bfloat16(0.f);
     uint8_t *base = static_cast<uint8_t *>(blob_host);
-    for (int n = 0; n < kMlpH; n++)
-        for (int k = 0; k < in; k++)
-            *reinterpret_cast<__nv_bfloat16 *>(base + canon_offset_bytes(n, k, kMlpH)) = __float2bfloat16(W1[k * kMlpH + n]);
-    for (int n = 0; n < kMlpH; n++)
-        for (int k = 0; k < kMlpH; k++)
-            *reinterpret_cast<__nv_bfloat16 *>(base + kW1Bytes + canon_offset_bytes(n, k, kMlpH)) = __float2bfloat16(W2[k * kMlpH + n]);
-    for (int n = 0; n < s; n++)
-        for (int k = 0; k < kMlpH; k++)
-            *reinterpret_cast<__nv_bfloat16 *>(base + kW1Bytes + kW2Bytes + canon_offset_bytes(n, k, kMlpNout)) =
-                __float2bfloat16(W3[k * s + n]);
+    auto put = [&](int off, int n, int k, int N, float v) {
+        *reinterpret_cast<__nv_bfloat16 *>(base + off + canon_offset_bytes(n, k, N)) = __float2bfloat16(v);
+    };
+    for (int n = 0; n < kMlpH; n++) {
+        for (int k = 0; k < in; k++) put(0, n, k, kMlpH, W1[k * kMlpH + n]);
+        put(0, n, in, kMlpH, b1[n]);
+        for (int k = 0; k < kMlpH; k++) put(kW1Bytes, n, k, kMlpH, W2[k * kMlpH + n]);
+        put(kW1Bytes, n, kMlpH, kMlpH, b2[n]);
+    }
+    for (int n = 0; n < s; n++) {
+        for (int k = 0; k < kMlpH; k++) put(kW1Bytes + kW2Bytes, n, k, kMlpNout, W3[k * s + n]);
+        put(kW1Bytes + kW2Bytes, n, kMlpH, kMlpNout, b3[n]);
+    }
 }
 
 }  // namespace mppi
