@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libmppi_b200.so")
+# MPPI_B200_LIB: developer knob to load an experimental build of the same library
+LIB_PATH = os.environ.get("MPPI_B200_LIB") or os.path.join(_HERE, "_build", "libmppi_b200.so")
 
 MPPI_OK = 0
 MPPI_ERR_BAD_ARG, MPPI_ERR_CUDA, MPPI_ERR_COMM, MPPI_ERR_UNSUPPORTED, MPPI_ERR_STATE = 1, 2, 3, 4, 5

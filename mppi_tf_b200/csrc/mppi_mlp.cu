@@ -317,6 +317,16 @@ cudaError_t launch_rollout_mlp(RolloutParams p, const MlpParams &mp, int a, bool
     return cudaGetLastError();
 }
 
+#ifdef MPPI_MLP_TRACE
+extern "C" int mppi_debug_mlp_trace(long long *out /*[2][1024]*/, int *n /*[2]*/)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_mlp_trace, sizeof(long long) * 2 * 1024);
+    n[0] = n[1] = 16 * 64;
+    return 0;
+}
+#endif
+
 // Pack Keras-layout weights ([in][out], fp32) and biases into the bf16 canonical K-major blob the
 // kernels stage: B[n][k] = W[k][n], with the bias of each layer in the K row that meets the constant 1.
 void mlp_pack_weights(int s, int a, const float *W1, const float *b1, const float *W2, const float *b2,

@@ -29,6 +29,10 @@ constexpr int kMlpKh = 144;       // hidden K padded by one UMMA K step: column 
 constexpr int kMlpKin = 16;       // input features (+ constant 1) padded to one UMMA K step
 constexpr int kMlpNout = 16;      // output features padded to the minimum N for M = 128
 constexpr int kMlpRows = 128;     // samples per tile = TMEM lanes
+#ifndef MPPI_MLP_SPLIT_N
+#define MPPI_MLP_SPLIT_N 1
+#endif
+constexpr bool kMlpSplitN = MPPI_MLP_SPLIT_N != 0;   // layer 2 as two N = 64 halves (1) or one N = 128 MMA per K step (0)
 constexpr int kMlpRowWarps = 4;    // one per TMEM lane quadrant
 constexpr int kMlpThreads = 160;  // 4 row warps + 1 MMA warp
 
@@ -173,6 +177,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+#ifdef MPPI_MLP_TRACE
+// developer build only: clock stamps of every hand-over of CTA 0 (row warp 0 / MMA warp), first steps.
+// The event index lives in a register (fire-and-forget stores: a few issue slots per stamp).
+__device__ long long g_mlp_trace[2][16 * 64];
+__device__ int g_mlp_trace_n[2];
+#define MLP_TRACE(who, ev)                                                                         \
+    do {                                                                                           \
+        if (t.tr_on && t.tr_n < 16 * 64) {                                                         \
+            g_mlp_trace[who][t.tr_n] = ((long long)clock64() << 8) | (ev);                         \
+            t.tr_n++;                                                                              \
+        }                                                                                          \
+    } while (0)
+#else
+#define MLP_TRACE(who, ev)
+#endif
+
 // mbarriers of one CTA tile
 enum MlpBar : int {
     kBarW = 0,     // weights landed (TMA complete_tx)
@@ -193,6 +213,10 @@ struct MlpTile {
     const float *fvec;        // shared: normalisation vectors
     uint64_t *bars;           // [kMlpNumBars]
     uint32_t ph_d, ph_d3;     // row warps: parity of the next D0/D1 and D3 completion
+#ifdef MPPI_MLP_TRACE
+    int tr_n;
+    bool tr_on;
+#endif
 };
 
 // ---- MMA warp -------------------------------------------------------------------------------------
@@ -226,14 +250,16 @@ __device__ __forceinline__ bool elect_one()
 // The whole MMA side of `nsteps` network evaluations of this CTA's tile.  Called by the WHOLE MMA warp
 // (converged): every lane follows the mbarriers, one elected lane issues the tcgen05 instructions
 // (a warp-uniform region keeps the uniform-datapath operands of UTCHMMA free of per-thread loops).
-__device__ __forceinline__ void mlp_mma_loop(const MlpTile &t, int nsteps)
+__device__ __forceinline__ void mlp_mma_loop(MlpTile &t, int nsteps)
 {
     constexpr int KH = kMlpKh / 16, KH0 = kMlpH / 32;    // 9 K steps per hidden layer, 4 of them in K half 0
     constexpr uint32_t kHalfB = (kMlpH / 2 / 8) * 128u;  // byte offset of rows 64.. in a canonical N = 128 matrix
     uint32_t ph_x = 0, ph_a = 0;
     for (int s = 0; s < nsteps; s++) {
         // layer 1: X[128 x 16] -> D (two N halves)
+        MLP_TRACE(1, 0);
         mbar_wait(&t.bars[kBarX], ph_x);
+        MLP_TRACE(1, 1);
         ph_x ^= 1;
         tc_fence_after();
         if (elect_one()) {
@@ -244,26 +270,40 @@ __device__ __forceinline__ void mlp_mma_loop(const MlpTile &t, int nsteps)
         }
         __syncwarp();
         // layer 2: starts on K half 0 of A1 while the row warps still convert half 1
+        MLP_TRACE(1, 2);
         mbar_wait(&t.bars[kBarA0], ph_a);
+        MLP_TRACE(1, 3);
         tc_fence_after();
-        if (elect_one()) mlp_issue(t, kColD, kColA, kW1Bytes, 64, kMlpH, 0, KH0, true);
+        if (elect_one()) mlp_issue(t, kColD, kColA, kW1Bytes, kMlpSplitN ? 64 : 128, kMlpH, 0, KH0, true);
         __syncwarp();
+        MLP_TRACE(1, 4);
         mbar_wait(&t.bars[kBarA1], ph_a);
+        MLP_TRACE(1, 5);
         ph_a ^= 1;
         tc_fence_after();
         if (elect_one()) {
-            mlp_issue(t, kColD, kColA, kW1Bytes, 64, kMlpH, KH0, KH, false);
-            umma_commit(&t.bars[kBarD0]);
-            mlp_issue(t, kColD + 64, kColA, kW1Bytes + kHalfB, 64, kMlpH, 0, KH, true);
-            umma_commit(&t.bars[kBarD1]);
+            if (kMlpSplitN) {
+                mlp_issue(t, kColD, kColA, kW1Bytes, 64, kMlpH, KH0, KH, false);
+                umma_commit(&t.bars[kBarD0]);
+                mlp_issue(t, kColD + 64, kColA, kW1Bytes + kHalfB, 64, kMlpH, 0, KH, true);
+                umma_commit(&t.bars[kBarD1]);
+            } else {
+                mlp_issue(t, kColD, kColA, kW1Bytes, 128, kMlpH, KH0, KH, false);
+                umma_commit(&t.bars[kBarD0]);
+                umma_commit(&t.bars[kBarD1]);
+            }
         }
         __syncwarp();
         // output layer
+        MLP_TRACE(1, 6);
         mbar_wait(&t.bars[kBarA0], ph_a);
+        MLP_TRACE(1, 7);
         tc_fence_after();
         if (elect_one()) mlp_issue(t, kColD3, kColA, kW1Bytes + kW2Bytes, kMlpNout, kMlpNout, 0, KH0, true);
         __syncwarp();
+        MLP_TRACE(1, 8);
         mbar_wait(&t.bars[kBarA1], ph_a);
+        MLP_TRACE(1, 9);
         ph_a ^= 1;
         tc_fence_after();
         if (elect_one()) {
@@ -271,6 +311,7 @@ __device__ __forceinline__ void mlp_mma_loop(const MlpTile &t, int nsteps)
             umma_commit(&t.bars[kBarD3]);
         }
         __syncwarp();
+        MLP_TRACE(1, 10);
     }
 }
 
@@ -300,7 +341,7 @@ __device__ __forceinline__ void mlp_store_signal(const MlpTile &t, int h, const 
 
 // Step part 1: normalise (x, u), store the bf16 input row, hand it to the MMA warp.
 template <int S, int A>
-__device__ __forceinline__ void mlp_row_begin(const MlpTile &t, const float (&x)[S], const float (&u)[A])
+__device__ __forceinline__ void mlp_row_begin(MlpTile &t, const float (&x)[S], const float (&u)[A])
 {
     static_assert(S + A + 1 <= kMlpKin && S <= kMlpNout, "MLP tile supports s + a <= 15");
     const float *xmean = t.fvec, *xinv = t.fvec + 16;
@@ -319,19 +360,26 @@ __device__ __forceinline__ void mlp_row_begin(const MlpTile &t, const float (&x)
     tc_wait_st();
     tc_fence_before();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&t.bars[kBarX]);
+    MLP_TRACE(0, 1);
 }
 // Step part 2: layer-1 epilogue (the A region is dead here: the previous output layer has completed).
 __device__ __forceinline__ void mlp_row_layer1(MlpTile &t)
 {
     uint32_t o[32];
+    MLP_TRACE(0, 2);
     mbar_wait(&t.bars[kBarD0], t.ph_d);
+    MLP_TRACE(0, 3);
     tc_fence_after();
     mlp_load_pack(t, 0, o);
+    MLP_TRACE(0, 4);
     mlp_store_signal(t, 0, o);
+    MLP_TRACE(0, 5);
     mbar_wait(&t.bars[kBarD1], t.ph_d);
+    MLP_TRACE(0, 6);
     tc_fence_after();
     mlp_load_pack(t, 1, o);
     mlp_store_signal(t, 1, o);
+    MLP_TRACE(0, 7);
     t.ph_d ^= 1;
 }
 // Step part 3: layer-2 epilogue.  Half 0 is converted while the tensor pipe produces half 1, but it
@@ -339,14 +387,20 @@ __device__ __forceinline__ void mlp_row_layer1(MlpTile &t)
 __device__ __forceinline__ void mlp_row_layer2(MlpTile &t)
 {
     uint32_t o[32];
+    MLP_TRACE(0, 8);
     mbar_wait(&t.bars[kBarD0], t.ph_d);
+    MLP_TRACE(0, 9);
     tc_fence_after();
     mlp_load_pack(t, 0, o);
+    MLP_TRACE(0, 10);
     mbar_wait(&t.bars[kBarD1], t.ph_d);
+    MLP_TRACE(0, 11);
     tc_fence_after();
     mlp_store_signal(t, 0, o);
+    MLP_TRACE(0, 12);
     mlp_load_pack(t, 1, o);
     mlp_store_signal(t, 1, o);
+    MLP_TRACE(0, 13);
     t.ph_d ^= 1;
 }
 // Step part 4: x' = x + d * Ystd + Ymean
@@ -354,7 +408,9 @@ template <int S>
 __device__ __forceinline__ void mlp_row_finish(MlpTile &t, float (&x)[S])
 {
     const float *ystd = t.fvec + 32, *ymean = t.fvec + 48;
+    MLP_TRACE(0, 14);
     mbar_wait(&t.bars[kBarD3], t.ph_d3);
+    MLP_TRACE(0, 15);
     t.ph_d3 ^= 1;
     tc_fence_after();
     uint32_t v[16];
@@ -396,6 +452,10 @@ __device__ __forceinline__ void mlp_tile_init(MlpTile &t, const MlpParams &mp, u
     t.bars = bars;
     t.ph_d = 0;
     t.ph_d3 = 0;
+#ifdef MPPI_MLP_TRACE
+    t.tr_n = 0;
+    t.tr_on = blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (warp == 0 || warp == 4);
+#endif
     if (warp < kMlpRowWarps) {   // K-augmentation columns of the activation operand: k = 128 is the constant 1, k = 129..143 are 0
         uint32_t one[8] = {pack_bf16x2(1.0f, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
         tmem_st8(t.lane_addr + kColA + kMlpH / 2, one);
