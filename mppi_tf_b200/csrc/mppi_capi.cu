@@ -617,22 +617,19 @@ int mppi_set_mlp(mppi_handle *h, int hidden, const float *W1, const float *b1, c
     if (h->s + h->a + 1 > kMlpKin || h->a > 5) return fail(h, MPPI_ERR_UNSUPPORTED, "MLP path needs s + a <= 15 (a <= 5)");
     CU_TRY(h, cudaSetDevice(h->device));
     std::vector<uint8_t> blob(kWBlobBytes);
-    mlp_pack_weights(h->s, h->a, W1, b1, W2, W3, blob.data());
+    mlp_pack_weights(h->s, h->a, W1, b1, W2, b2, W3, b3, blob.data());
     std::vector<float> fv(kFvecFloats, 0.f);
     const int in = h->s + h->a;
-    // b2[128] | xmean[16] | 1/xstd[16] | ystd[16] | yc[16] = b3 * ystd + ymean
-    for (int i = 0; i < kMlpH; i++) fv[i] = b2[i];
-    for (int i = 0; i < 16; i++) { fv[144 + i] = 1.f; fv[160 + i] = 1.f; }
+    for (int i = 0; i < 16; i++) { fv[16 + i] = 1.f; fv[32 + i] = 1.f; }
     for (int i = 0; i < in; i++) {
-        fv[128 + i] = Xmean ? Xmean[i] : 0.f;
+        fv[i] = Xmean ? Xmean[i] : 0.f;
         const float sd = Xstd ? Xstd[i] : 1.f;
         if (!(sd != 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "Xstd must be non-zero");
-        fv[144 + i] = 1.0f / sd;
+        fv[16 + i] = 1.0f / sd;
     }
     for (int i = 0; i < h->s; i++) {
-        const float ys = Ystd ? Ystd[i] : 1.f;
-        fv[160 + i] = ys;
-        fv[176 + i] = b3[i] * ys + (Ymean ? Ymean[i] : 0.f);
+        fv[32 + i] = Ystd ? Ystd[i] : 1.f;
+        fv[48 + i] = Ymean ? Ymean[i] : 0.f;
     }
     if (!h->d_wblob) CU_TRY(h, cudaMalloc(&h->d_wblob, kWBlobBytes));
     if (!h->d_fvec) CU_TRY(h, cudaMalloc(&h->d_fvec, sizeof(float) * kFvecFloats));

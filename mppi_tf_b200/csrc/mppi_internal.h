@@ -24,7 +24,8 @@ cudaError_t launch_mlp_predict(const MlpParams &mp, int kst, int k, const float 
                                cudaStream_t st);
 cudaError_t launch_rollout_mlp(RolloutParams p, const MlpParams &mp, int a, bool philox, int num_sms, cudaStream_t st,
                                int *grid_x_out);
-void mlp_pack_weights(int s, int a, const float *W1, const float *b1, const float *W2, const float *W3, void *blob_host);
+void mlp_pack_weights(int s, int a, const float *W1, const float *b1, const float *W2, const float *b2,
+                      const float *W3, const float *b3, void *blob_host);
 
 // mppi_stages.cu  (device pointers)
 cudaError_t launch_model_step(float mass, float dt, int s, int a, int kst, int k, const float *state,

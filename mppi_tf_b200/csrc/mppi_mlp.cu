@@ -9,11 +9,11 @@
 namespace mppi {
 
 // -------------------------------------------------------------------------------------------------
-// predict: next[k][s] = mlp(state[k|1][s], action[k][a])   (one CTA per 4 x 128 samples)
+// predict: next[k][s] = mlp(state[k|1][s], action[k][a])   (one CTA per 128 samples)
 // -------------------------------------------------------------------------------------------------
 template <int S, int A>
-__global__ void __launch_bounds__(kMlpThreads, 1) mlp_predict_kernel(MlpParams mp, int kst, int k, const float *state,
-                                                                     const float *action, float *out)
+__global__ void __launch_bounds__(kMlpThreads) mlp_predict_kernel(MlpParams mp, int kst, int k, const float *state,
+                                                                  const float *action, float *out)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t *sW = smem_raw;
@@ -22,9 +22,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_predict_kernel(MlpParams m
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + kMlpNumBars);
     MlpTile t;
     mlp_tile_init(t, mp, sW, sF, bars, tslot);
-    if (threadIdx.x < kMlpRowThreads) {
-        reg_alloc<kMlpRowRegs>();
-        const int r = blockIdx.x * kMlpRowThreads + threadIdx.x;
+    if (threadIdx.x < kMlpRows) {
+        const int r = blockIdx.x * kMlpRows + threadIdx.x;
         float x[S], u[A];
 #pragma unroll
         for (int i = 0; i < S; i++) x[i] = (r < k) ? state[(size_t)(kst == 1 ? 0 : r) * S + i] : 0.f;
@@ -39,28 +38,23 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_predict_kernel(MlpParams m
             for (int i = 0; i < S; i++) out[(size_t)r * S + i] = x[i];
         }
     } else {
-        reg_dealloc<kMlpMmaRegs>();
         mlp_mma_loop(t, 1);
     }
-    mlp_tile_fini(*tslot);
+    mlp_tile_fini(t);
 }
 
 // -------------------------------------------------------------------------------------------------
 // fused rollout: same structure as rollout_philox_kernel (phase 1 costs, block min, phase 2 weighted
 // sums by regenerating / re-reading the noise, last-CTA merge) with the model step on tensor cores.
-// Tile slot g = 4 * blockIdx.x + (row warp / 4) owns a contiguous range of 128-sample tiles and rolls
-// them one after the other; row thread r of the slot = sample row r of the current tile.  Every row
-// thread takes part in every hand-over with the MMA warp, so out-of-range rows roll a dummy sample.
+// Row thread r = sample row r of the 128-row tile; every row thread takes part in every hand-over
+// with the MMA warp, so out-of-range rows roll a dummy sample.
 // -------------------------------------------------------------------------------------------------
 template <int A, bool PHILOX>
 __device__ __forceinline__ void noise4(const RolloutParams &p, const float *eps_row, uint32_t call, uint32_t kg,
-                                       uint32_t stream, bool valid, float *z)
+                                       uint32_t stream, bool valid, float (&z)[4])
 {
     if (PHILOX) {
-        float z4[4];
-        normals4(call, kg, stream, p, z4);
-#pragma unroll
-        for (int j = 0; j < 4; j++) z[j] = z4[j];
+        normals4(call, kg, stream, p, z);
     } else {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -71,12 +65,11 @@ __device__ __forceinline__ void noise4(const RolloutParams &p, const float *eps_
 }
 
 template <int A, bool PHILOX>
-__global__ void __launch_bounds__(kMlpThreads, 1) rollout_mlp_kernel(const __grid_constant__ RolloutParams p, MlpParams mp)
+__global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __grid_constant__ RolloutParams p, MlpParams mp)
 {
     constexpr int S = 2 * A;
     constexpr int RS = Row<A>::RS, H = Row<A>::H;
     constexpr int NW = kMlpThreads / 32;
-    constexpr int NE = (A + 3) / 4;               // noise calls a block's first step needs: made one block ahead
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int TA = p.TA, TAp = (TA + 31) & ~31;
     uint8_t *sW = smem_raw;
@@ -97,29 +90,29 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_mlp_kernel(const __gri
 
     float *costs = p.costs + (size_t)ctrl * p.K_local;
     const float *eps = PHILOX ? nullptr : p.eps + (size_t)ctrl * p.K_local * TA;
-    // tile slots: contiguous ranges of 128-row tiles
+    // contiguous sample range of this CTA, in tiles of 128 rows
     const int n_t = (p.K_local + kMlpRows - 1) / kMlpRows;
-    const int n_slots = gridDim.x * kMlpTiles;
-    const int slot = blockIdx.x * kMlpTiles + (warp < kMlpRowWarps ? (warp >> 2) : (warp - kMlpRowWarps));
-    const int t_lo = (int)((long long)n_t * slot / n_slots);
-    const int t_hi = (int)((long long)n_t * (slot + 1) / n_slots);
+    const int t_lo = (int)((long long)n_t * blockIdx.x / gridDim.x);
+    const int t_hi = (int)((long long)n_t * (blockIdx.x + 1) / gridDim.x);
     const int nblk = (p.T + 3) >> 2;
     const uint32_t stream = (uint32_t)ctrl;
 
     // ---- phase 1: rollout + cost -----------------------------------------------------------------
     float bmin = kInf;
     if (warp < kMlpRowWarps) {
-        reg_alloc<kMlpRowRegs>();
-        const int row = tid & (kMlpRows - 1);
-        float x0[S];
-        const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * S : 0);
+        float g[S], q[S], x0[S];
         {
+            const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * S : 0);
             const float *xp = p.x + (size_t)ctrl * S;
 #pragma unroll
-            for (int i = 0; i < S; i++) x0[i] = p.x_inline ? p.x0[i] : xp[i];
+            for (int i = 0; i < S; i++) {
+                g[i] = gp[i];
+                q[i] = p.q[i];
+                x0[i] = p.x_inline ? p.x0[i] : xp[i];
+            }
         }
         for (int tile = t_lo; tile < t_hi; tile++) {
-            const int k = tile * kMlpRows + row;
+            const int k = tile * kMlpRows + tid;
             const bool valid = k < p.K_local;
             const uint32_t kg = (uint32_t)(p.k_offset + k);
             const float *eps_row = PHILOX ? nullptr : eps + (size_t)(valid ? k : 0) * TA;
@@ -127,13 +120,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_mlp_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < S; i++) x[i] = x0[i];
             float Sk = 0.f;
-            float z[4 * A], zn[4 * NE];
+            float z[4 * A], zn[4 * A];
 #pragma unroll
-            for (int c = 0; c < NE; c++) noise4<A, PHILOX>(p, eps_row, (uint32_t)c, kg, stream, valid, zn + 4 * c);
+            for (int c = 0; c < A; c++) {
+                float z4[4];
+                noise4<A, PHILOX>(p, eps_row, (uint32_t)c, kg, stream, valid, z4);
+#pragma unroll
+                for (int j = 0; j < 4; j++) z[4 * c + j] = z4[j];
+            }
             for (int tb = 0; tb < nblk; tb++) {
                 const bool more = tb + 1 < nblk;          // block-uniform
-#pragma unroll
-                for (int i = 0; i < 4 * NE; i++) z[i] = zn[i];
 #pragma unroll
                 for (int tt = 0; tt < 4; tt++) {
                     const int ts = 4 * tb + tt;
@@ -160,32 +156,35 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_mlp_kernel(const __gri
                         float c = 0.f;
 #pragma unroll
                         for (int i = 0; i < S; i++) {
-                            const float d = x[i] - gp[i];
-                            c = fmaf(p.q[i] * d, d, c);
+                            const float d = x[i] - g[i];
+                            c = fmaf(q[i] * d, d, c);
                         }
                         Sk += c;
                     }
                     Sk += ac;
                     mlp_row_layer1(t);
-                    // in the shadow of layer 2 (the long MMAs): the noise calls the NEXT step starts to need
+                    // in the shadow of layer 2 (the long MMA): this step's share of the next block's noise
+                    if (more) {
 #pragma unroll
-                    for (int c = NE; c < A; c++)
-                        if ((4 * c) / A == tt + 1) noise4<A, PHILOX>(p, eps_row, (uint32_t)(tb * A + c), kg, stream, valid, z + 4 * c);
-                    if (tt == 3 && more) {
+                        for (int c = (tt * A) / 4; c < ((tt + 1) * A) / 4; c++) {
+                            float z4[4];
+                            noise4<A, PHILOX>(p, eps_row, (uint32_t)((tb + 1) * A + c), kg, stream, valid, z4);
 #pragma unroll
-                        for (int c = 0; c < NE; c++)
-                            noise4<A, PHILOX>(p, eps_row, (uint32_t)((tb + 1) * A + c), kg, stream, valid, zn + 4 * c);
+                            for (int j = 0; j < 4; j++) zn[4 * c + j] = z4[j];
+                        }
                     }
                     mlp_row_layer2(t);
                     mlp_row_finish<S>(t, x);
                 }
+#pragma unroll
+                for (int i = 0; i < 4 * A; i++) z[i] = zn[i];
             }
             {
                 float c = 0.f;                       // q(x_T) of step T-1 plus the terminal cost (src/controller_base.cpp:271-272)
 #pragma unroll
                 for (int i = 0; i < S; i++) {
-                    const float d = x[i] - gp[i];
-                    c = fmaf(p.q[i] * d, d, c);
+                    const float d = x[i] - g[i];
+                    c = fmaf(q[i] * d, d, c);
                 }
                 Sk += c;
                 Sk += c;
@@ -196,10 +195,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_mlp_kernel(const __gri
             }
         }
     } else {
-        reg_dealloc<kMlpMmaRegs>();
         mlp_mma_loop(t, (t_hi - t_lo) * p.T);
     }
-    mlp_tile_fini(*tslot);
+    mlp_tile_fini(t);
     bmin = warp_min(bmin);
     if (lane == 0) sRed[warp] = bmin;
     __syncthreads();
@@ -208,11 +206,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_mlp_kernel(const __gri
     for (int w = 1; w < NW; w++) beta_c = fminf(beta_c, sRed[w]);
     __syncthreads();
 
-    // ---- phase 2: sum_k e_k n_k (n = z regenerated, or eps re-read); all twenty warps take samples ---
+    // ---- phase 2: sum_k e_k n_k (n = z regenerated, or eps re-read); all five warps take samples ----
     const int ncall = (TA + 3) >> 2;
     const int nchunk = (ncall + 7) >> 3;
-    const int k_lo = (int)((long long)n_t * (blockIdx.x * kMlpTiles) / n_slots) * kMlpRows;
-    const int k_hi = min((int)((long long)n_t * ((blockIdx.x + 1) * kMlpTiles) / n_slots) * kMlpRows, p.K_local);
+    const int k_lo = t_lo * kMlpRows, k_hi = min(t_hi * kMlpRows, p.K_local);
     float eta = 0.f;
     for (int ch = 0; ch < nchunk; ch++) {
         float acc[32];
@@ -279,7 +276,7 @@ cudaError_t launch_mlp_predict(const MlpParams &mp, int kst, int k, const float 
                                cudaStream_t st)
 {
     const size_t smem = mlp_predict_smem();
-    const int grid = (k + kMlpRowThreads - 1) / kMlpRowThreads;
+    const int grid = (k + kMlpRows - 1) / kMlpRows;
     MPPI_DISPATCH_MLP_A(mp.a, {
         cudaError_t err = cudaFuncSetAttribute(mlp_predict_kernel<2 * A_, A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
@@ -290,9 +287,9 @@ cudaError_t launch_mlp_predict(const MlpParams &mp, int kst, int k, const float 
 
 int mlp_grid_x(int K_local, int n_ctrl, int num_sms)
 {
-    int per_ctrl = num_sms / (n_ctrl > 0 ? n_ctrl : 1);         // one CTA (4 tiles, 512 TMEM columns) per SM
+    int per_ctrl = (num_sms * 2) / (n_ctrl > 0 ? n_ctrl : 1);   // 2 CTAs (2 x 256 TMEM columns) per SM
     if (per_ctrl < 1) per_ctrl = 1;
-    const int need = (K_local + kMlpRowThreads - 1) / kMlpRowThreads;
+    const int need = (K_local + kMlpRows - 1) / kMlpRows;
     int gx = need < per_ctrl ? need : per_ctrl;
     if (gx > kMaxParts) gx = kMaxParts;
     return gx < 1 ? 1 : gx;
@@ -330,9 +327,10 @@ extern "C" int mppi_debug_mlp_trace(long long *out /*[2][1024]*/, int *n /*[2]*/
 }
 #endif
 
-// Pack Keras-layout weights ([in][out], fp32) into the bf16 canonical K-major blob the kernels stage:
-// B[n][k] = W[k][n]; b1 sits in the K row of W1 that meets the constant-1 input column.
-void mlp_pack_weights(int s, int a, const float *W1, const float *b1, const float *W2, const float *W3, void *blob_host)
+// Pack Keras-layout weights ([in][out], fp32) and biases into the bf16 canonical K-major blob the
+// kernels stage: B[n][k] = W[k][n], with the bias of each layer in the K row that meets the constant 1.
+void mlp_pack_weights(int s, int a, const float *W1, const float *b1, const float *W2, const float *b2,
+                      const float *W3, const float *b3, void *blob_host)
 {
     __nv_bfloat16 *b = static_cast<__nv_bfloat16 *>(blob_host);
     const int in = s + a;
@@ -345,9 +343,12 @@ void mlp_pack_weights(int s, int a, const float *W1, const float *b1, const floa
         for (int k = 0; k < in; k++) put(0, n, k, kMlpH, W1[k * kMlpH + n]);
         put(0, n, in, kMlpH, b1[n]);
         for (int k = 0; k < kMlpH; k++) put(kW1Bytes, n, k, kMlpH, W2[k * kMlpH + n]);
+        put(kW1Bytes, n, kMlpH, kMlpH, b2[n]);
     }
-    for (int n = 0; n < s; n++)
+    for (int n = 0; n < s; n++) {
         for (int k = 0; k < kMlpH; k++) put(kW1Bytes + kW2Bytes, n, k, kMlpNout, W3[k * s + n]);
+        put(kW1Bytes + kW2Bytes, n, kMlpH, kMlpNout, b3[n]);
+    }
 }
 
 }  // namespace mppi

@@ -4,25 +4,17 @@
 // re-shaped to BASELINE config 4):   X = (concat(x,u) - Xmean)/Xstd  ->  h1 = relu(W1^T X + b1)
 //   -> h2 = relu(W2^T h1 + b2) -> d = W3^T h2 + b3 -> x' = x + d*Ystd + Ymean.
 //
-// One evaluation of the network for a tile of 128 samples is a chain of three small GEMMs with a
-// TMEM -> registers -> TMEM conversion between them; the chain is latency-bound (about 3000 cycles
-// per step for 700 cycles of tensor-pipe time, measured), so the design goal is TILES IN FLIGHT per
-// SM, and the scarce resource is TMEM (512 columns).  A tile is squeezed into 128 columns:
-//     [0,64)    A operand: bf16x2 activations of the layer being consumed (K = 128), two 32-column
-//               slots Q = K steps 0-3, P = K steps 4-7; the K = 16 network input X aliases P[0,8)
-//     [64,128)  D: fp32 accumulator of ONE N = 64 half of a layer (the output layer uses D[0,16))
-// so one CTA per SM keeps FOUR tiles in flight.  Each layer runs as two N = 64 halves through the
-// same D columns: MMA half 0 -> row warps load D (and release it) -> MMA half 1 runs while the row
-// warps convert half 0.  Activations are written back only when the MMAs that read the previous
-// ones have completed (half 0 of layer 2 waits in registers).
-//
-// The CTA is warp-specialised: 16 ROW warps (tile i = warps 4i..4i+3, one per TMEM lane quadrant;
-// thread r of a tile owns sample row r for the whole rollout, fp32 state in registers) and 4 MMA warps
-// (one per tile; all lanes follow the mbarriers, one elected lane issues tcgen05.mma / commit).
-// Operands: A from TMEM (written by the row threads with tcgen05.st), B = bf16 weights in the
-// canonical K-major layout in shared memory, staged once per CTA by a TMA bulk copy.  b1 is folded
-// into the K = 16 input GEMM (constant-1 input column), b2 is added in the epilogue, b3 is folded
-// into the output affine map.  No __syncthreads on the step path.
+// Mapping: one CTA tile = 128 samples = the 128 TMEM lanes (UMMA_M = 128, cta_group::1).  The CTA is
+// warp-specialised: warps 0-3 are the ROW warps (thread r owns sample row r for the whole rollout,
+// fp32 state in registers), warp 4 is the MMA warp (one lane issues every tcgen05.mma).  Each layer is
+//   D[128 x N] (fp32, TMEM) = A[128 x K] (bf16, TMEM, written by the row threads with tcgen05.st)
+//                             x B[N x K]^T (bf16 weights, K-major canonical layout in shared memory,
+//                                           staged once per CTA by a TMA bulk copy)
+// and is issued as two N = 64 halves, each committed to its own mbarrier, so that the row warps
+// convert half 0 (TMEM -> F2FP.RELU -> TMEM) while the tensor pipe is still producing half 1, and
+// the next layer's first K steps start as soon as half 0 of its A operand is in place.  No
+// __syncthreads on the step path: row warps and the MMA warp hand tiles over through mbarriers only.
+// Two CTAs (2 x 256 TMEM columns) are resident per SM and fill each other's tensor-pipe gaps.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -31,34 +23,39 @@
 namespace mppi {
 
 constexpr int kMlpH = 128;        // hidden width (both hidden layers)
+constexpr int kMlpKh = 144;       // hidden K padded by one UMMA K step: column 128 is a constant 1 that
+                                  // multiplies the bias row of the next layer's weights (bias folded
+                                  // into the GEMM: no per-element bias add in the epilogue)
 constexpr int kMlpKin = 16;       // input features (+ constant 1) padded to one UMMA K step
 constexpr int kMlpNout = 16;      // output features padded to the minimum N for M = 128
 constexpr int kMlpRows = 128;     // samples per tile = TMEM lanes
-constexpr int kMlpTiles = 4;      // tiles in flight per CTA (4 x 128 TMEM columns)
-constexpr int kMlpRowWarps = 4 * kMlpTiles;
-constexpr int kMlpRowThreads = 32 * kMlpRowWarps;
-constexpr int kMlpThreads = kMlpRowThreads + 32 * kMlpTiles;   // + one MMA warp per tile
+#ifndef MPPI_MLP_SPLIT_N
+#define MPPI_MLP_SPLIT_N 1
+#endif
+constexpr bool kMlpSplitN = MPPI_MLP_SPLIT_N != 0;   // layer 2 as two N = 64 halves (1) or one N = 128 MMA per K step (0)
+constexpr int kMlpRowWarps = 4;    // one per TMEM lane quadrant
+constexpr int kMlpThreads = 160;  // 4 row warps + 1 MMA warp
 
 // shared-memory weight blob (bytes), canonical K-major no-swizzle core-matrix layout:
 //   element (n, k) of B[N x K] at ((k/8)*(N/8) + n/8)*128 + (n%8)*16 + (k%8)*2
-constexpr int kW1Bytes = kMlpH * kMlpKin * 2;      //  4 KB   N = 128, K = 16 (row s+a = b1)
-constexpr int kW2Bytes = kMlpH * kMlpH * 2;        // 32 KB   N = 128, K = 128
-constexpr int kW3Bytes = kMlpNout * kMlpH * 2;     //  4 KB   N = 16,  K = 128
+constexpr int kW1Bytes = kMlpH * kMlpKin * 2;      //  4 KB   N = 128, K = 16
+constexpr int kW2Bytes = kMlpH * kMlpKh * 2;       // 36 KB   N = 128, K = 144 (row 128 = b2)
+constexpr int kW3Bytes = kMlpNout * kMlpKh * 2;    // 4.5 KB  N = 16,  K = 144 (row 128 = b3)
 constexpr int kWBlobBytes = kW1Bytes + kW2Bytes + kW3Bytes;
 
-// TMEM column map of one tile (tile i at column 128 i of the CTA's 512-column allocation)
-constexpr uint32_t kColP = 0;      // [0,32)   A operand, K steps 4-7;  network input X = [0,8)
-constexpr uint32_t kColQ = 32;     // [32,64)  A operand, K steps 0-3
-constexpr uint32_t kColD = 64;     // [64,128) fp32 accumulator of one N = 64 half / of the output layer
-constexpr uint32_t kTileCols = 128;
-constexpr uint32_t kTmemCols = kTileCols * kMlpTiles;
+// TMEM column map of one tile (256 columns allocated)
+constexpr uint32_t kColD = 0;      // [0,128)   fp32 accumulator of layers 1 and 2, as two N = 64 halves
+constexpr uint32_t kColA = 128;    // [128,200) bf16x2 activations (next layer's A, K = 144; cols 192.. = const 1, 0..)
+constexpr uint32_t kColX = 200;    // [200,208) bf16x2 network input (K = 16)
+constexpr uint32_t kColD3 = 224;   // [224,240) fp32 accumulator of the output layer (N = 16)
+constexpr uint32_t kTmemCols = 256;
 
 struct MlpParams {
     const void *wblob;        // device, kWBlobBytes, canonical layouts W1 | W2 | W3
-    const float *fvec;        // device: b2[128] xmean[16] xinvstd[16] ystd[16] yc[16] (yc = b3*ystd + ymean)
-    int s, a;                 // state / action dims (s + a <= 15, s <= 16)
+    const float *fvec;        // device: xmean[16] xinvstd[16] ystd[16] ymean[16] (biases live in the weight blob)
+    int s, a;                 // state / action dims (s + a <= 16, s <= 16)
 };
-constexpr int kFvecFloats = 128 + 16 * 4;
+constexpr int kFvecFloats = 16 * 4;
 
 __host__ __device__ inline int canon_offset_bytes(int n, int k, int N)
 {
@@ -181,8 +178,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 
 #ifdef MPPI_MLP_TRACE
-// developer build only: clock stamps of every hand-over of CTA 0, tile 0 (row warp 0 / MMA warp 16).
+// developer build only: clock stamps of every hand-over of CTA 0 (row warp 0 / MMA warp), first steps.
+// The event index lives in a register (fire-and-forget stores: a few issue slots per stamp).
 __device__ long long g_mlp_trace[2][16 * 64];
+__device__ int g_mlp_trace_n[2];
 #define MLP_TRACE(who, ev)                                                                         \
     do {                                                                                           \
         if (t.tr_on && t.tr_n < 16 * 64) {                                                         \
@@ -193,6 +192,47 @@ __device__ long long g_mlp_trace[2][16 * 64];
 #else
 #define MLP_TRACE(who, ev)
 #endif
+
+// mbarriers of one CTA tile
+enum MlpBar : int {
+    kBarW = 0,     // weights landed (TMA complete_tx)
+    kBarX,         // network input row block stored          row warps -> MMA warp   (count 4)
+    kBarA0,        // activation K half 0 stored              row warps -> MMA warp   (count 4)
+    kBarA1,        // activation K half 1 stored
+    kBarD0,        // accumulator N half 0 complete           MMA commit -> row warps (count 1)
+    kBarD1,        // accumulator N half 1 complete
+    kBarD3,        // output-layer accumulator complete
+    kMlpNumBars
+};
+
+// Shared-memory / TMEM context of one CTA tile.
+struct MlpTile {
+    uint32_t tmem;            // TMEM base address (lane 0, column 0 of the allocation)
+    uint32_t lane_addr;       // tmem + (32 * (warp % 4)) << 16 : this warp's lane quadrant
+    uint32_t sW;              // shared address of the weight blob
+    const float *fvec;        // shared: normalisation vectors
+    uint64_t *bars;           // [kMlpNumBars]
+    uint32_t ph_d, ph_d3;     // row warps: parity of the next D0/D1 and D3 completion
+#ifdef MPPI_MLP_TRACE
+    int tr_n;
+    bool tr_on;
+#endif
+};
+
+// ---- MMA warp -------------------------------------------------------------------------------------
+// K = 16 steps [k0, k1) of D[d_col, N] (+)= A[a_col ...] * W[w_off ...]^T; weights in canonical layout
+// of a matrix with N_total rows (the N half is selected through w_off).
+__device__ __forceinline__ void mlp_issue(const MlpTile &t, uint32_t d_col, uint32_t a_col, uint32_t w_off, int N, int N_total,
+                                          int k0, int k1, bool fresh)
+{
+    const uint32_t idesc = make_idesc(128, N);
+    const uint32_t lbo = (uint32_t)(N_total >> 3) * 128u, sbo = 128u;   // adjacent k-groups / adjacent n-groups
+#pragma unroll
+    for (int k = k0; k < k1; k++) {
+        const uint64_t bdesc = make_smem_desc(t.sW + w_off + (uint32_t)k * 2u * lbo, lbo, sbo);
+        umma_ts(t.tmem + d_col, t.tmem + a_col + (uint32_t)k * 8u, bdesc, idesc, (fresh && k == k0) ? 0u : 1u);
+    }
+}
 
 __device__ __forceinline__ bool elect_one()
 {
@@ -207,159 +247,101 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
-// Register re-partitioning between the warp groups (setmaxnreg): the kernel launches with 96 registers
-// per thread (640 threads); the MMA warps give theirs up, the row warps - which hold a converted
-// half layer in registers while the next accumulator half streams in - take them.
-constexpr int kMlpRowRegs = 112, kMlpMmaRegs = 32;    // pool = 640 * 96; the MMA warps release 128 * 64 = 512 * 16
-template <int N>
-__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-
-// mbarriers of one tile
-enum MlpBar : int {
-    kBarXR = 0,    // network input stored (and the output accumulator read)   row warps -> MMA warp (count 4)
-    kBarDF,        // accumulator half read: D may be overwritten              row warps -> MMA warp (count 4)
-    kBarAR,        // activations of a whole layer stored                      row warps -> MMA warp (count 4)
-    kBarDfull,     // accumulator complete                                     MMA commit -> row warps (count 1)
-    kMlpBarsPerTile
-};
-constexpr int kMlpNumBars = 1 + kMlpBarsPerTile * kMlpTiles;   // [0] = weights landed
-
-// Shared-memory / TMEM context of one tile, as seen by one of its threads.
-struct MlpTile {
-    uint32_t tmem;            // TMEM address of the tile: lane 0, first column of the tile
-    uint32_t lane_addr;       // tmem + (32 * (warp % 4)) << 16 : this row warp's lane quadrant
-    uint32_t sW;              // shared address of the weight blob
-    const float *fvec;        // shared: b2 and the normalisation vectors
-    uint64_t *bars;           // this tile's [kMlpBarsPerTile]
-    uint32_t ph;              // row warps: parity of the next Dfull completion
-#ifdef MPPI_MLP_TRACE
-    int tr_n;
-    bool tr_on;
-#endif
-};
-
-// ---- MMA warp -------------------------------------------------------------------------------------
-// One N-wide slab of a K = 128 layer: D = A * W[rows n0 .. n0+N)^T as eight K = 16 steps.  A: K steps
-// 0-3 in slot Q, 4-7 in slot P; weights: canonical layout of an [N_total x 128] matrix at w_off.
-__device__ __forceinline__ void mlp_issue_hidden(const MlpTile &t, uint32_t w_off, int n0, int N, int N_total)
-{
-    const uint32_t idesc = make_idesc(128, N);
-    const uint32_t lbo = (uint32_t)(N_total >> 3) * 128u, sbo = 128u;   // adjacent k-groups / adjacent n-groups
-    const uint32_t w = t.sW + w_off + (uint32_t)(n0 >> 3) * 128u;
-#pragma unroll
-    for (int k = 0; k < kMlpH / 16; k++) {
-        const uint64_t bdesc = make_smem_desc(w + (uint32_t)k * 2u * lbo, lbo, sbo);
-        const uint32_t a_col = (k < 4 ? kColQ + 8u * k : kColP + 8u * (k - 4));
-        umma_ts(t.tmem + kColD, t.tmem + a_col, bdesc, idesc, k > 0 ? 1u : 0u);
-    }
-}
-// One N = 64 half of the input layer (K = 16, A = X in P[0,8))
-__device__ __forceinline__ void mlp_issue_input(const MlpTile &t, int n0)
-{
-    const uint32_t lbo = (uint32_t)(kMlpH >> 3) * 128u, sbo = 128u;
-    const uint64_t bdesc = make_smem_desc(t.sW + (uint32_t)(n0 >> 3) * 128u, lbo, sbo);
-    umma_ts(t.tmem + kColD, t.tmem + kColP, bdesc, make_idesc(128, 64), 0u);
-}
-
-// The whole MMA side of `nsteps` network evaluations of one tile.  Called by the WHOLE MMA warp
-// (converged): every lane follows the mbarriers, one elected lane issues the tcgen05 instructions.
+// The whole MMA side of `nsteps` network evaluations of this CTA's tile.  Called by the WHOLE MMA warp
+// (converged): every lane follows the mbarriers, one elected lane issues the tcgen05 instructions
+// (a warp-uniform region keeps the uniform-datapath operands of UTCHMMA free of per-thread loops).
 __device__ __forceinline__ void mlp_mma_loop(MlpTile &t, int nsteps)
 {
-    uint32_t ph_x = 0, ph_f = 0, ph_a = 0;
-    uint64_t *full = &t.bars[kBarDfull];
+    constexpr int KH = kMlpKh / 16, KH0 = kMlpH / 32;    // 9 K steps per hidden layer, 4 of them in K half 0
+    constexpr uint32_t kHalfB = (kMlpH / 2 / 8) * 128u;  // byte offset of rows 64.. in a canonical N = 128 matrix
+    uint32_t ph_x = 0, ph_a = 0;
     for (int s = 0; s < nsteps; s++) {
+        // layer 1: X[128 x 16] -> D (two N halves)
         MLP_TRACE(1, 0);
-        mbar_wait(&t.bars[kBarXR], ph_x);            // X stored; D (previous output) read
+        mbar_wait(&t.bars[kBarX], ph_x);
+        MLP_TRACE(1, 1);
         ph_x ^= 1;
         tc_fence_after();
-        MLP_TRACE(1, 1);
-        if (elect_one()) { mlp_issue_input(t, 0); umma_commit(full); }
+        if (elect_one()) {
+            mlp_issue(t, kColD, kColX, 0, 64, kMlpH, 0, 1, true);
+            umma_commit(&t.bars[kBarD0]);
+            mlp_issue(t, kColD + 64, kColX, kHalfB, 64, kMlpH, 0, 1, true);
+            umma_commit(&t.bars[kBarD1]);
+        }
         __syncwarp();
+        // layer 2: starts on K half 0 of A1 while the row warps still convert half 1
         MLP_TRACE(1, 2);
-        mbar_wait(&t.bars[kBarDF], ph_f);            // layer-1 half 0 read
-        ph_f ^= 1;
-        tc_fence_after();
+        mbar_wait(&t.bars[kBarA0], ph_a);
         MLP_TRACE(1, 3);
-        if (elect_one()) { mlp_issue_input(t, 64); umma_commit(full); }
+        tc_fence_after();
+        if (elect_one()) mlp_issue(t, kColD, kColA, kW1Bytes, kMlpSplitN ? 64 : 128, kMlpH, 0, KH0, true);
         __syncwarp();
         MLP_TRACE(1, 4);
-        mbar_wait(&t.bars[kBarAR], ph_a);            // A1 stored (implies layer-1 half 1 read)
-        ph_a ^= 1;
-        tc_fence_after();
+        mbar_wait(&t.bars[kBarA1], ph_a);
         MLP_TRACE(1, 5);
-        if (elect_one()) { mlp_issue_hidden(t, kW1Bytes, 0, 64, kMlpH); umma_commit(full); }
-        __syncwarp();
-        MLP_TRACE(1, 6);
-        mbar_wait(&t.bars[kBarDF], ph_f);            // layer-2 half 0 read
-        ph_f ^= 1;
-        tc_fence_after();
-        MLP_TRACE(1, 7);
-        if (elect_one()) { mlp_issue_hidden(t, kW1Bytes, 64, 64, kMlpH); umma_commit(full); }
-        __syncwarp();
-        MLP_TRACE(1, 8);
-        mbar_wait(&t.bars[kBarAR], ph_a);            // A2 stored (implies layer-2 half 1 read)
         ph_a ^= 1;
         tc_fence_after();
+        if (elect_one()) {
+            if (kMlpSplitN) {
+                mlp_issue(t, kColD, kColA, kW1Bytes, 64, kMlpH, KH0, KH, false);
+                umma_commit(&t.bars[kBarD0]);
+                mlp_issue(t, kColD + 64, kColA, kW1Bytes + kHalfB, 64, kMlpH, 0, KH, true);
+                umma_commit(&t.bars[kBarD1]);
+            } else {
+                mlp_issue(t, kColD, kColA, kW1Bytes, 128, kMlpH, KH0, KH, false);
+                umma_commit(&t.bars[kBarD0]);
+                umma_commit(&t.bars[kBarD1]);
+            }
+        }
+        __syncwarp();
+        // output layer: one batch (nine tiny MMAs) once both K halves of A2 are in place - an early
+        // start on half 0 would save 50 tensor cycles and cost a second issue batch (~200 cycles)
+        MLP_TRACE(1, 6);
+        mbar_wait(&t.bars[kBarA0], ph_a);
+        MLP_TRACE(1, 8);
+        mbar_wait(&t.bars[kBarA1], ph_a);
         MLP_TRACE(1, 9);
-        if (elect_one()) { mlp_issue_hidden(t, kW1Bytes + kW2Bytes, 0, kMlpNout, kMlpNout); umma_commit(full); }
+        ph_a ^= 1;
+        tc_fence_after();
+        if (elect_one()) {
+            mlp_issue(t, kColD3, kColA, kW1Bytes + kW2Bytes, kMlpNout, kMlpNout, 0, KH, true);
+            umma_commit(&t.bars[kBarD3]);
+        }
         __syncwarp();
         MLP_TRACE(1, 10);
     }
 }
 
 // ---- row warps ------------------------------------------------------------------------------------
-__device__ __forceinline__ void mlp_row_signal(const MlpTile &t, int bar)
+// accumulator N half `h` -> 32 packed bf16x2 words, ReLU folded into the conversion (the bias already
+// sits in the accumulator: K-augmented GEMM)
+__device__ __forceinline__ void mlp_load_pack(const MlpTile &t, int h, uint32_t (&o)[32])
 {
-    tc_fence_before();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(&t.bars[bar]);
-}
-__device__ __forceinline__ void mlp_row_wait_full(MlpTile &t)
-{
-    mbar_wait(&t.bars[kBarDfull], t.ph);
-    t.ph ^= 1;
-    tc_fence_after();
-}
-// the 64 fp32 accumulator columns -> registers (two 32-column loads in flight)
-__device__ __forceinline__ void mlp_load_d(const MlpTile &t, uint32_t (&v0)[32], uint32_t (&v1)[32])
-{
-    tmem_ld32(t.lane_addr + kColD, v0);
-    tmem_ld32(t.lane_addr + kColD + 32u, v1);
+    uint32_t v0[32], v1[32];
+    const uint32_t d = t.lane_addr + kColD + 64u * h;
+    tmem_ld32(d, v0);
+    tmem_ld32(d + 32u, v1);
     tc_wait_ld();
-}
-// (+ bias) -> ReLU -> bf16x2: 64 accumulator values to 32 packed words
-template <bool BIAS>
-__device__ __forceinline__ void mlp_pack(const uint32_t (&v0)[32], const uint32_t (&v1)[32], const float *bias, uint32_t (&o)[32])
-{
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        float2 p0 = make_float2(__uint_as_float(v0[4 * i]), __uint_as_float(v0[4 * i + 1]));
-        float2 p1 = make_float2(__uint_as_float(v0[4 * i + 2]), __uint_as_float(v0[4 * i + 3]));
-        float2 p2 = make_float2(__uint_as_float(v1[4 * i]), __uint_as_float(v1[4 * i + 1]));
-        float2 p3 = make_float2(__uint_as_float(v1[4 * i + 2]), __uint_as_float(v1[4 * i + 3]));
-        if (BIAS) {
-            const float4 b0 = *reinterpret_cast<const float4 *>(bias + 4 * i);        // warp-uniform address: broadcast
-            const float4 b1 = *reinterpret_cast<const float4 *>(bias + 32 + 4 * i);
-            p0 = __fadd2_rn(p0, make_float2(b0.x, b0.y));
-            p1 = __fadd2_rn(p1, make_float2(b0.z, b0.w));
-            p2 = __fadd2_rn(p2, make_float2(b1.x, b1.y));
-            p3 = __fadd2_rn(p3, make_float2(b1.z, b1.w));
-        }
-        o[2 * i] = pack_relu_bf16x2(p0.x, p0.y);
-        o[2 * i + 1] = pack_relu_bf16x2(p1.x, p1.y);
-        o[16 + 2 * i] = pack_relu_bf16x2(p2.x, p2.y);
-        o[16 + 2 * i + 1] = pack_relu_bf16x2(p3.x, p3.y);
-    }
+    for (int i = 0; i < 16; i++) o[i] = pack_relu_bf16x2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+#pragma unroll
+    for (int i = 0; i < 16; i++) o[16 + i] = pack_relu_bf16x2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+}
+// store K half `h` of the next A operand and hand it to the MMA warp
+__device__ __forceinline__ void mlp_store_signal(const MlpTile &t, int h, const uint32_t (&o)[32])
+{
+    tmem_st32(t.lane_addr + kColA + 32u * h, o);
+    tc_wait_st();
+    tc_fence_before();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&t.bars[h ? kBarA1 : kBarA0]);
 }
 
-// Step part 1: normalise (x, u), store the bf16 input row into P[0,8), hand it to the MMA warp.
-// Precondition: the previous output accumulator has been read (mlp_row_finish) - XR also releases D.
+// Step part 1: normalise (x, u), store the bf16 input row, hand it to the MMA warp.
 template <int S, int A>
 __device__ __forceinline__ void mlp_row_begin(MlpTile &t, const float (&x)[S], const float (&u)[A])
 {
     static_assert(S + A + 1 <= kMlpKin && S <= kMlpNout, "MLP tile supports s + a <= 15");
-    const float *xmean = t.fvec + 128, *xinv = t.fvec + 144;
+    const float *xmean = t.fvec, *xinv = t.fvec + 16;
     float in[kMlpKin];
 #pragma unroll
     for (int i = 0; i < kMlpKin; i++) in[i] = 0.f;
@@ -371,87 +353,84 @@ __device__ __forceinline__ void mlp_row_begin(MlpTile &t, const float (&x)[S], c
     uint32_t px[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) px[i] = pack_bf16x2(in[2 * i], in[2 * i + 1]);
-    tmem_st8(t.lane_addr + kColP, px);
+    tmem_st8(t.lane_addr + kColX, px);
     tc_wait_st();
-    mlp_row_signal(t, kBarXR);
+    tc_fence_before();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&t.bars[kBarX]);
     MLP_TRACE(0, 1);
 }
-// Step part 2: layer-1 epilogue.  Half 0 goes to Q at once (layer 1 reads only X = P[0,8)); half 1
-// overwrites P once the second input MMA has completed.
+// Step part 2: layer-1 epilogue (the A region is dead here: the previous output layer has completed).
 __device__ __forceinline__ void mlp_row_layer1(MlpTile &t)
 {
-    uint32_t v0[32], v1[32], o[32];
+    uint32_t o[32];
     MLP_TRACE(0, 2);
-    mlp_row_wait_full(t);
+    mbar_wait(&t.bars[kBarD0], t.ph_d);
     MLP_TRACE(0, 3);
-    mlp_load_d(t, v0, v1);
-    mlp_row_signal(t, kBarDF);
+    tc_fence_after();
+    mlp_load_pack(t, 0, o);
     MLP_TRACE(0, 4);
-    mlp_pack<false>(v0, v1, nullptr, o);
-    tmem_st32(t.lane_addr + kColQ, o);
+    mlp_store_signal(t, 0, o);
     MLP_TRACE(0, 5);
-    mlp_row_wait_full(t);
+    mbar_wait(&t.bars[kBarD1], t.ph_d);
     MLP_TRACE(0, 6);
-    mlp_load_d(t, v0, v1);
-    mlp_pack<false>(v0, v1, nullptr, o);
-    tmem_st32(t.lane_addr + kColP, o);
-    tc_wait_st();
-    mlp_row_signal(t, kBarAR);
+    tc_fence_after();
+    mlp_load_pack(t, 1, o);
+    mlp_store_signal(t, 1, o);
     MLP_TRACE(0, 7);
+    t.ph_d ^= 1;
 }
-// Step part 3: layer-2 epilogue.  Half 0 waits in registers: the MMAs of half 1 still read A1.
+// Step part 3: layer-2 epilogue.  Half 0 is converted while the tensor pipe produces half 1, but it
+// is stored only after half 1 has completed: until then the MMAs still read A1 from the same columns.
 __device__ __forceinline__ void mlp_row_layer2(MlpTile &t)
 {
-    uint32_t v0[32], v1[32], o0[32], o1[32];
-    const float *b2 = t.fvec;
+    uint32_t o[32];
     MLP_TRACE(0, 8);
-    mlp_row_wait_full(t);
+    mbar_wait(&t.bars[kBarD0], t.ph_d);
     MLP_TRACE(0, 9);
-    mlp_load_d(t, v0, v1);
-    mlp_row_signal(t, kBarDF);
+    tc_fence_after();
+    mlp_load_pack(t, 0, o);
     MLP_TRACE(0, 10);
-    mlp_pack<true>(v0, v1, b2, o0);
+    mbar_wait(&t.bars[kBarD1], t.ph_d);
     MLP_TRACE(0, 11);
-    mlp_row_wait_full(t);
+    tc_fence_after();
+    mlp_store_signal(t, 0, o);
     MLP_TRACE(0, 12);
-    tmem_st32(t.lane_addr + kColQ, o0);
-    mlp_load_d(t, v0, v1);
-    mlp_pack<true>(v0, v1, b2 + 64, o1);
-    tmem_st32(t.lane_addr + kColP, o1);
-    tc_wait_st();
-    mlp_row_signal(t, kBarAR);
+    mlp_load_pack(t, 1, o);
+    mlp_store_signal(t, 1, o);
     MLP_TRACE(0, 13);
+    t.ph_d ^= 1;
 }
-// Step part 4: x' = x + d * Ystd + (b3 * Ystd + Ymean)
+// Step part 4: x' = x + d * Ystd + Ymean
 template <int S>
 __device__ __forceinline__ void mlp_row_finish(MlpTile &t, float (&x)[S])
 {
-    const float *ystd = t.fvec + 160, *yc = t.fvec + 176;
+    const float *ystd = t.fvec + 32, *ymean = t.fvec + 48;
     MLP_TRACE(0, 14);
-    mlp_row_wait_full(t);
+    mbar_wait(&t.bars[kBarD3], t.ph_d3);
     MLP_TRACE(0, 15);
+    t.ph_d3 ^= 1;
+    tc_fence_after();
     uint32_t v[16];
-    tmem_ld16(t.lane_addr + kColD, v);
+    tmem_ld16(t.lane_addr + kColD3, v);
     tc_wait_ld();
 #pragma unroll
-    for (int i = 0; i < S; i++) x[i] += fmaf(__uint_as_float(v[i]), ystd[i], yc[i]);
+    for (int i = 0; i < S; i++) x[i] += fmaf(__uint_as_float(v[i]), ystd[i], ymean[i]);
 }
 
-// CTA prologue: TMEM allocation, mbarriers, TMA-staged weights, vectors.  smem_w must be 128-B aligned
-// and hold kWBlobBytes; smem_f holds kFvecFloats floats.  Ends with a CTA barrier.
+// CTA prologue: TMEM allocation (MMA warp), mbarriers, TMA-staged weights, vectors.  smem_w must be
+// 128-B aligned and hold kWBlobBytes; smem_f holds kFvecFloats floats.
 __device__ __forceinline__ void mlp_tile_init(MlpTile &t, const MlpParams &mp, uint8_t *smem_w, float *smem_f,
                                               uint64_t *bars /*[kMlpNumBars]*/, uint32_t *tmem_slot)
 {
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        for (int i = 0; i < kMlpTiles; i++) {
-            uint64_t *b = bars + 1 + i * kMlpBarsPerTile;
-            mbar_init(&b[kBarXR], 4);
-            mbar_init(&b[kBarDF], 4);
-            mbar_init(&b[kBarAR], 4);
-            mbar_init(&b[kBarDfull], 1);
-        }
+        mbar_init(&bars[kBarW], 1);
+        mbar_init(&bars[kBarX], kMlpRowWarps);
+        mbar_init(&bars[kBarA0], kMlpRowWarps);
+        mbar_init(&bars[kBarA1], kMlpRowWarps);
+        mbar_init(&bars[kBarD0], 1);
+        mbar_init(&bars[kBarD1], 1);
+        mbar_init(&bars[kBarD3], 1);
         fence_mbar_init();
     }
     for (int i = threadIdx.x; i < kFvecFloats; i += blockDim.x) smem_f[i] = mp.fvec[i];
@@ -460,30 +439,37 @@ __device__ __forceinline__ void mlp_tile_init(MlpTile &t, const MlpParams &mp, u
     __syncthreads();
     tc_fence_after();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(&bars[0], kWBlobBytes);
-        bulk_g2s(smem_w, mp.wblob, kWBlobBytes, &bars[0]);
+        mbar_expect_tx(&bars[kBarW], kWBlobBytes);
+        bulk_g2s(smem_w, mp.wblob, kWBlobBytes, &bars[kBarW]);
     }
-    const int tile = warp < kMlpRowWarps ? (warp >> 2) : (warp - kMlpRowWarps);
-    t.tmem = *tmem_slot + kTileCols * (uint32_t)tile;
+    t.tmem = *tmem_slot;
     t.lane_addr = t.tmem + ((uint32_t)(32 * (warp & 3)) << 16);
     t.sW = smem_u32(smem_w);
     t.fvec = smem_f;
-    t.bars = bars + 1 + tile * kMlpBarsPerTile;
-    t.ph = 0;
+    t.bars = bars;
+    t.ph_d = 0;
+    t.ph_d3 = 0;
 #ifdef MPPI_MLP_TRACE
     t.tr_n = 0;
-    t.tr_on = blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (warp == 0 || warp == kMlpRowWarps);
+    t.tr_on = blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (warp == 0 || warp == 4);
 #endif
-    mbar_wait(&bars[0], 0);         // every thread observes the weights (async-proxy writes) before any MMA
+    if (warp < kMlpRowWarps) {   // K-augmentation columns of the activation operand: k = 128 is the constant 1, k = 129..143 are 0
+        uint32_t one[8] = {pack_bf16x2(1.0f, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        tmem_st8(t.lane_addr + kColA + kMlpH / 2, one);
+        tc_wait_st();
+    }
+    mbar_wait(&bars[kBarW], 0);     // every thread observes the weights (async-proxy writes) before any MMA
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
 }
 
-// All MMAs have been consumed (the row warps waited for their last output accumulator) when this is called.
-__device__ __forceinline__ void mlp_tile_fini(uint32_t tmem_base)
+// All MMAs of the tile have been consumed (the row warps waited for the last D3) when this is called.
+__device__ __forceinline__ void mlp_tile_fini(MlpTile &t)
 {
     tc_fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == kMlpRowWarps) tmem_dealloc(tmem_base, kTmemCols);
+    if ((threadIdx.x >> 5) == kMlpRowWarps) tmem_dealloc(t.tmem, kTmemCols);
 }
 
 }  // namespace mppi

@@ -21,10 +21,10 @@ for who in range(2):
         ev.append((v >> 8, who, v & 255))
 ev.sort()
 t0 = ev[0][0]
-RN = {1: "X sent", 2: "wait full(L1h0)", 3: "got full(L1h0)", 4: "loaded; DF sent", 5: "Q stored; wait full(L1h1)", 6: "got full(L1h1)", 7: "A1 sent",
-      8: "wait full(L2h0)", 9: "got full(L2h0)", 10: "loaded; DF sent", 11: "packed; wait full(L2h1)", 12: "got full(L2h1)", 13: "A2 sent", 14: "wait full(L3)", 15: "got full(L3)"}
-MN = {0: "wait XR", 1: "got XR", 2: "L1h0 issued; wait DF", 3: "got DF", 4: "L1h1 issued; wait AR", 5: "got AR",
-      6: "L2h0 issued; wait DF", 7: "got DF", 8: "L2h1 issued; wait AR", 9: "got AR", 10: "L3 issued"}
+RN = {1: "X arrived(sent)", 2: "wait D0(L1)", 3: "got D0(L1)", 4: "packed h0", 5: "A0 sent", 6: "got D1(L1)", 7: "A1 sent",
+      8: "wait D0(L2)", 9: "got D0(L2)", 10: "packed h0", 11: "got D1(L2)", 12: "A0 sent", 13: "A1 sent", 14: "wait D3", 15: "got D3"}
+MN = {0: "wait X", 1: "got X", 2: "L1 issued; wait A0", 3: "got A0", 4: "L2 k0-3 issued; wait A1", 5: "got A1",
+      6: "L2 issued; wait A0", 7: "got A0", 8: "L3 k0-3 issued; wait A1", 9: "got A1", 10: "L3 issued"}
 last = {0: t0, 1: t0}
 for t, who, e in ev[:int(sys.argv[1]) if len(sys.argv) > 1 else 160]:
     print(f"{t - t0:8d}  +{t - last[who]:5d}  {'ROW' if who == 0 else '        MMA'}  {(RN if who == 0 else MN)[e]}")
