@@ -194,6 +194,7 @@ def main():
                     help="N>1: in-library ncclAllGather, or torch.distributed all_gather on external buffers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-injected", action="store_true")
+    ap.add_argument("--k-override", type=int, default=0, help="developer knob: replace the workload's K (not a bench line)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -219,6 +220,8 @@ def main():
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
     desc, K, T, s, a, n_ctrl = WORKLOADS[args.workload]
+    if args.k_override:
+        K, desc = args.k_override, desc + f" [K overridden to {args.k_override}: developer run, not the BASELINE config]"
     if n_ctrl > 1:
         # independent controllers: partition the controllers across ranks, no exchange at all
         n_local = n_ctrl // world

@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
     float *sWork = sN + TAp;                      // [TAp]
     float *sScale = sWork + TAp;                  // [kMaxParts]
     float *sRed = sScale + kMaxParts;             // [32]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sRed + 32);
+    float4 *sScratch = reinterpret_cast<float4 *>(sRed + 32);     // [kMlpThreads] merge scratch
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sScratch + kMlpThreads);
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + kMlpNumBars);
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
     }
     __syncthreads();
     // a CTA without samples must not win the min: beta_c = +inf is skipped by merge_parts
-    publish_and_finish<A, PHILOX>(p, ctrl, beta_c, eta_c, sN, sWork, sScale, sRed);
+    publish_and_finish<A, PHILOX>(p, ctrl, beta_c, eta_c, sN, sWork, sScale, sRed, sScratch, kMlpThreads);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -259,7 +260,7 @@ static size_t mlp_rollout_smem(int A, int T, int TA)
 {
     const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31, NW = kMlpThreads / 32;
     return kWBlobBytes + sizeof(float) * (kFvecFloats + (size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 32) +
-           kMlpNumBars * 8 + 16 + 128;
+           sizeof(float4) * kMlpThreads + kMlpNumBars * 8 + 16 + 128;
 }
 
 #define MPPI_DISPATCH_MLP_A(a, ...)              \

@@ -117,6 +117,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     float *sWork = sN + TAp;             // [TAp]
     float *sScale = sWork + TAp;         // [kMaxParts]
     float *sRed = sScale + kMaxParts;    // [32]
+    float4 *sScratch = reinterpret_cast<float4 *>(sRed + 32);   // [kPhiloxThreads] merge scratch
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     stage_sequence<A, true>(p, ctrl, sUV);
@@ -230,7 +231,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
         sN[j] = s;
     }
     __syncthreads();
-    publish_and_finish<A, true>(p, ctrl, beta_c, eta_c, sN, sWork, sScale, sRed);
+    publish_and_finish<A, true>(p, ctrl, beta_c, eta_c, sN, sWork, sScale, sRed, sScratch, kPhiloxThreads);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -530,7 +531,9 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
         sN[j] = s;
     }
     __syncthreads();
-    publish_and_finish<A, false>(p, ctrl, beta_c, eta_c, sN, sWork, sScale, sRed);
+    // the tile buffers are free now (every group is past its last tile): merge scratch
+    publish_and_finish<A, false>(p, ctrl, beta_c, eta_c, sN, sWork, sScale, sRed, reinterpret_cast<float4 *>(sTiles),
+                                 (NBUF * tile_words) >> 2);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -544,9 +547,10 @@ __global__ void __launch_bounds__(256) finish_kernel(const __grid_constant__ Rol
     float *smem = reinterpret_cast<float *>(smem_f4);
     const int TA = p.TA, TAp = (TA + 31) & ~31;
     float *sN = smem, *sWork = sN + TAp, *sScale = sWork + TAp, *sRed = sScale + kMaxParts;
+    float4 *sScratch = reinterpret_cast<float4 *>(sRed + 32);
     const int ctrl = blockIdx.x, stride = partial_stride(TA);
     Merged m = merge_parts(gathered + (size_t)ctrl * stride, (size_t)p.n_ctrl * stride, p.world, TA,
-                           p.neg_inv_lambda_log2e, sN, sScale, sRed);
+                           p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, 256);
     apply_update<A, PHILOX>(p, ctrl, m, sN, sWork);
 }
 
@@ -598,7 +602,7 @@ __global__ void scale_noise_kernel(const __grid_constant__ RolloutParams p, floa
 static size_t philox_smem_bytes(int A, int T, int TA)
 {
     const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31, NW = kPhiloxThreads / 32;
-    return sizeof(float) * ((size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 32);
+    return sizeof(float) * ((size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 32) + sizeof(float4) * kPhiloxThreads;
 }
 
 template <int A>
@@ -743,7 +747,7 @@ int max_grid_x(int K_local, int n_ctrl, int num_sms)
 cudaError_t launch_finish(RolloutParams p, int a, bool philox, const float *gathered, cudaStream_t st)
 {
     const int TAp = (p.TA + 31) & ~31;
-    const size_t smem = sizeof(float) * (2 * (size_t)TAp + kMaxParts + 32);
+    const size_t smem = sizeof(float) * (2 * (size_t)TAp + kMaxParts + 32) + sizeof(float4) * 256;
     MPPI_DISPATCH_A(a, {
         if (philox) finish_kernel<A_, true><<<p.n_ctrl, 256, smem, st>>>(p, gathered);
         else finish_kernel<A_, false><<<p.n_ctrl, 256, smem, st>>>(p, gathered);

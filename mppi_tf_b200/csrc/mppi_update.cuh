@@ -50,8 +50,13 @@ __device__ __forceinline__ void stage_sequence(const RolloutParams &p, int ctrl,
 // -------------------------------------------------------------------------------------------------
 struct Merged { float beta, eta; };
 
+// sScratch: `scratch_f4` float4 of shared memory, free to clobber.  The column sums are the serial tail
+// of every update (one CTA reads nparts x TA floats through L2), so they are spread over the whole CTA:
+// work item (slice, column quad) sums every nsl-th record with eight 16-byte loads in flight, then the
+// slices are added in a fixed order.
 __device__ inline Merged merge_parts(const float *parts, size_t part_stride, int nparts, int TA,
-                              float neg_inv_lambda_log2e, float *sN, float *sScale, float *sRed)
+                              float neg_inv_lambda_log2e, float *sN, float *sScale, float *sRed,
+                              float4 *sScratch, int scratch_f4)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     float b = kInf;
@@ -74,21 +79,53 @@ __device__ inline Merged merge_parts(const float *parts, size_t part_stride, int
     __syncthreads();
     float eta = 0.f;
     for (int w = 0; w < nw; w++) eta += sRed[w];
-    for (int j = tid; j < TA; j += blockDim.x) {
-        const float *col = parts + 4 + j;
-        float acc = 0.f;
-        int c = 0;
-        for (; c + 8 <= nparts; c += 8) {      // 8 independent loads in flight, accumulated in order
-            float v[8];
+
+    const int ncol4 = (TA + 3) >> 2;               // records are padded to whole quads (partial_stride)
+    int nsl = (int)blockDim.x / ncol4;
+    if (nsl > scratch_f4 / ncol4) nsl = scratch_f4 / ncol4;
+    if (nsl > nparts) nsl = nparts;
+    if (nsl < 1) nsl = 1;
+    for (int it = tid; it < ncol4 * nsl; it += blockDim.x) {
+        const int sl = it / ncol4, c4 = it - sl * ncol4;
+        const float *col = parts + 4 + 4 * c4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int c = sl;
+        for (; c + 7 * nsl < nparts; c += 8 * nsl) {      // 8 independent loads in flight, accumulated in order
+            float4 v[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = __ldcg(col + (size_t)(c + i) * part_stride);
+            for (int i = 0; i < 8; i++) v[i] = __ldcg(reinterpret_cast<const float4 *>(col + (size_t)(c + i * nsl) * part_stride));
 #pragma unroll
-            for (int i = 0; i < 8; i++) acc = fmaf(sScale[c + i], v[i], acc);
+            for (int i = 0; i < 8; i++) {
+                const float w = sScale[c + i * nsl];
+                acc.x = fmaf(w, v[i].x, acc.x); acc.y = fmaf(w, v[i].y, acc.y);
+                acc.z = fmaf(w, v[i].z, acc.z); acc.w = fmaf(w, v[i].w, acc.w);
+            }
         }
-        for (; c < nparts; c++) acc = fmaf(sScale[c], __ldcg(col + (size_t)c * part_stride), acc);
-        sN[j] = acc;
+        for (; c < nparts; c += nsl) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(col + (size_t)c * part_stride));
+            const float w = sScale[c];
+            acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+            acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+        }
+        if (nsl > 1) {
+            sScratch[it] = acc;
+        } else {                                           // pad columns of the last quad hold no data
+            const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (4 * c4 + i < TA) sN[4 * c4 + i] = a4[i];
+        }
     }
     __syncthreads();
+    if (nsl > 1) {
+        const float *sc = reinterpret_cast<const float *>(sScratch);
+        for (int j = tid; j < TA; j += blockDim.x) {
+            float acc = 0.f;
+            for (int sl = 0; sl < nsl; sl++) acc += sc[(size_t)sl * 4 * ncol4 + j];
+            sN[j] = acc;
+        }
+        __syncthreads();
+    }
     return Merged{beta, eta};
 }
 
@@ -126,10 +163,11 @@ __device__ void apply_update(const RolloutParams &p, int ctrl, Merged m, float *
 }
 
 // Publish this CTA's partial; the last CTA of the controller merges and finishes the update.
-// sN: CTA sums [TA]; sWork: >= TA floats scratch; sScale: kMaxParts floats; sRed: 32 floats.
+// sN: CTA sums [TA]; sWork: >= TA floats scratch; sScale: kMaxParts floats; sRed: 32 floats;
+// sScratch: scratch_f4 float4 (16-byte aligned) the merge may clobber.
 template <int A, bool PHILOX>
 __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_c, float eta_c, float *sN,
-                                   float *sWork, float *sScale, float *sRed)
+                                   float *sWork, float *sScale, float *sRed, float4 *sScratch, int scratch_f4)
 {
     __shared__ int s_is_last;
     const int TA = p.TA, stride = partial_stride(TA), nparts = gridDim.x;
@@ -151,7 +189,7 @@ __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_
     __threadfence();
     if (threadIdx.x == 0) p.counters[ctrl] = 0u;
     Merged m = merge_parts(p.partials + (size_t)ctrl * nparts * stride, stride, nparts, TA,
-                           p.neg_inv_lambda_log2e, sN, sScale, sRed);
+                           p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
     if (p.world > 1) {
         float *pay = p.payload + (size_t)ctrl * stride;
         if (threadIdx.x == 0) { pay[0] = m.beta; pay[1] = m.eta; pay[2] = 0.f; pay[3] = 0.f; }
