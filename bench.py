@@ -118,6 +118,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic(workload, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload][kernel]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def bytes_alg(K, T, a, n_ctrl=1):
     """eps read once (4*a B per sample-step) + per-sample cost written."""
     return n_ctrl * (4 * a * K * T + 4 * K)
@@ -373,7 +381,9 @@ def main():
             "gpu_launches": args.steps * (2 if exchange else 1),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "rollout_philox_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": measured_traffic(args.workload, "rollout_philox_kernel") if world == 1 and not args.k_override else None,
+                         "peak_source": peak_src,
                          "note": "effective GB/s on the algorithmic bytes 4*a*K*T + 4*K; the Philox kernel moves "
                                  "almost no HBM bytes and is bound by ALU/MUFU issue (see profiles/)"},
         }
@@ -383,12 +393,15 @@ def main():
             line["dtype"] = "bf16"
             line["config"]["mode"] = "philox noise + bf16 tcgen05 MLP rollout (fp32 state and accumulation)"
             line["roofline"] = {"bound": "tensor", "kernel": "rollout_mlp_kernel", "achieved": tf, "peak": tpeak,
-                                "unit": "TFLOP/s", "frac": tf / tpeak, "traffic": None, "peak_source": tsrc,
+                                "unit": "TFLOP/s", "frac": tf / tpeak,
+                                "traffic": measured_traffic(args.workload, "rollout_mlp_kernel") if world == 1 and not args.k_override else None,
+                                "peak_source": tsrc,
                                 "note": "algorithmic flops 2*(9*128+128*128+128*6) = 36608 per sample-step (unpadded)"}
         if inj is not None:
             ia = bytes_alg(K, T, a, n_local) / (inj * 1e-3) / 1e9
             line["roofline_injected"] = {"bound": "hbm", "kernel": "rollout_injected_kernel", "achieved": ia,
-                                         "peak": peak, "unit": "GB/s", "frac": ia / peak, "traffic": None,
+                                         "peak": peak, "unit": "GB/s", "frac": ia / peak,
+                                         "traffic": measured_traffic(args.workload, "rollout_injected_kernel") if not args.k_override else None,
                                          "ms_per_launch": inj,
                                          "inputs": "eps resident in HBM" + (" (larger than L2)" if 4 * n_eps > 126e6 else " (L2 flushed)")}
         if not args.no_cpu_baseline and world == 1 and not is_mlp:
