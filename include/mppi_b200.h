@@ -129,6 +129,17 @@ int mppi_synchronize(mppi_handle *h);
 int mppi_set_goal(mppi_handle *h, const float *goal_host);       /* [s] or [n][s] */
 int mppi_set_lambda(mppi_handle *h, float lambda);
 int mppi_set_sigma(mppi_handle *h, const float *sigma_host);     /* [a][a], must be invertible */
+/* Python-twin extras (/root/reference/scripts/src):
+ *   upsilon scales the sampling, eps = (upsilon sigma) z  (controllers/controller_base.py:348-369);
+ *   MPPI_ACTION_COST_CPP     lambda u^T sigma^-1 eps                        (src/cost_base.cpp:63-68, the default)
+ *   MPPI_ACTION_COST_PYTHON  0.5 [gamma (u^T S^-1 u + 2 u^T S^-1 eps) + lambda (1 - 1/upsilon) eps^T S^-1 eps]
+ *                            (costs/cost_base.py:114-170); u is the un-noised U[t] in both forms.
+ * With injected noise the caller passes the already scaled eps, as the reference's build_noise returns it. */
+typedef enum { MPPI_ACTION_COST_CPP = 0, MPPI_ACTION_COST_PYTHON = 1 } mppi_action_cost_form;
+int mppi_set_action_cost(mppi_handle *h, int form, float gamma, float upsilon);
+/* norm_arg (controllers/controller_base.py:468-474): the exponent becomes -(S - beta) / (lambda max_k(S_k - beta)).
+ * Costs two launches per update (the range must be known before any weight); world == 1 only in this build. */
+int mppi_set_normalize_cost(mppi_handle *h, int on);
 int mppi_set_q(mppi_handle *h, const float *q_host);             /* [s] */
 int mppi_set_mass(mppi_handle *h, float mass);                   /* model mass in B = [dt^2/2; dt] / mass */
 int mppi_set_sequence(mppi_handle *h, const float *U_host);      /* m_U, [n][T][a] */

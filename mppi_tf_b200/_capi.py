@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("MPPI_B200_LIB") or os.path.join(_HERE, "_build", "lib
 MPPI_OK = 0
 MPPI_ERR_BAD_ARG, MPPI_ERR_CUDA, MPPI_ERR_COMM, MPPI_ERR_UNSUPPORTED, MPPI_ERR_STATE = 1, 2, 3, 4, 5
 MPPI_MAX_A = 8
+MPPI_ACTION_COST_CPP, MPPI_ACTION_COST_PYTHON = 0, 1
 
 _fp = C.POINTER(C.c_float)
 
@@ -57,6 +58,8 @@ SYMBOLS = {
     "mppi_set_goal": (_i, [_H, _fp]),
     "mppi_set_lambda": (_i, [_H, _f]),
     "mppi_set_sigma": (_i, [_H, _fp]),
+    "mppi_set_action_cost": (_i, [_H, _i, _f, _f]),
+    "mppi_set_normalize_cost": (_i, [_H, _i]),
     "mppi_set_q": (_i, [_H, _fp]),
     "mppi_set_mass": (_i, [_H, _f]),
     "mppi_set_sequence": (_i, [_H, _fp]),

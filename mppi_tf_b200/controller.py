@@ -126,6 +126,7 @@ class ControllerBase:
         self.k, self.tau, self.dt, self.mass, self.s_dim, self.a_dim = k, tau, dt, mass, s_dim, a_dim
         self.n = n_controllers
         self.device = device
+        self._lam = float(lam)
         cfg = MppiConfig()
         self._lib.mppi_config_default(C.byref(cfg), k, tau, dt, mass, s_dim, a_dim)
         cfg.lambda_ = lam
@@ -224,9 +225,22 @@ class ControllerBase:
 
     def setLambda(self, lam):
         check(self._lib.mppi_set_lambda(self._h, float(lam)), self._h)
+        self._lam = float(lam)
 
     def setSigma(self, sigma):
         check(self._lib.mppi_set_sigma(self._h, _ptr(_f32(sigma))), self._h)
+
+    def setActionCost(self, form="cpp", gamma=None, upsilon=1.0):
+        """Python-twin extras (scripts/src/costs/cost_base.py:114-170, controller_base.py:348-369): `form`
+        "cpp" = lambda u^T S^-1 eps (src/cost_base.cpp:63-68), "python" = the gamma / upsilon form;
+        upsilon also scales the sampling, eps = (upsilon sigma) z.  gamma defaults to lambda."""
+        forms = {"cpp": _capi.MPPI_ACTION_COST_CPP, "python": _capi.MPPI_ACTION_COST_PYTHON}
+        g = self._lam if gamma is None else float(gamma)
+        check(self._lib.mppi_set_action_cost(self._h, forms[form], g, float(upsilon)), self._h)
+
+    def setNormalizeCost(self, on=True):
+        """norm_arg of the Python twin (controller_base.py:468-474): exponent -(S - beta)/(lambda max(S - beta))."""
+        check(self._lib.mppi_set_normalize_cost(self._h, int(bool(on))), self._h)
 
     def setQ(self, q):
         check(self._lib.mppi_set_q(self._h, _ptr(_f32(q))), self._h)

@@ -62,6 +62,12 @@ struct mppi_handle {
     float dt = 0, mass = 1, lambda = 1;
     float sigma[kMaxA * kMaxA], lam_inv_sigma_T[kMaxA * kMaxA], q[kMaxS];
     int sigma_diag = 1, goal_per_ctrl = 0;
+    // Python-twin extras (mppi_set_action_cost / mppi_set_normalize_cost)
+    int cost_form = MPPI_ACTION_COST_CPP;
+    float gamma = 1, upsilon = 1;
+    float inv_sigma[kMaxA * kMaxA];
+    bool normalize = false;
+    float *d_norm = nullptr;
     uint64_t seed = 1;
     uint32_t update_counter = 0, last_update = 0;
     bool have_philox_update = false, last_philox = true, pending_finish = false;
@@ -132,7 +138,10 @@ void derive_sigma(mppi_handle *h)
     for (int i = 0; i < a; i++)
         for (int j = 0; j < a; j++) {
             if (i != j && h->sigma[i * a + j] != 0.f) h->sigma_diag = 0;
-            h->lam_inv_sigma_T[i * a + j] = h->lambda * inv[j * a + i];   // lambda * (Sigma^-1)^T
+            // linear action-cost weight: lambda (src/cost_base.cpp:63-68) or gamma (cost_base.py:141-158)
+            const float lin = h->cost_form == MPPI_ACTION_COST_PYTHON ? h->gamma : h->lambda;
+            h->lam_inv_sigma_T[i * a + j] = lin * inv[j * a + i];   // lin * (Sigma^-1)^T
+            h->inv_sigma[i * a + j] = inv[i * a + j];
         }
 }
 
@@ -154,9 +163,35 @@ RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
     p.neg_inv_lambda_log2e = -kLog2e / h->lambda;
     memcpy(p.q, h->q, sizeof(p.q));
     for (int i = 0; i < kMaxS; i++) p.sqrt_q[i] = sqrtf(h->q[i] > 0.f ? h->q[i] : 0.f);
-    memcpy(p.sigma, h->sigma, sizeof(p.sigma));
+    const int a = h->a;
+    const bool py = h->cost_form == MPPI_ACTION_COST_PYTHON;
+    for (int i = 0; i < a * a; i++) p.sigma[i] = h->upsilon * h->sigma[i];   // sampling scale: eps = (upsilon Sigma) z
     memcpy(p.lam_inv_sigma_T, h->lam_inv_sigma_T, sizeof(p.lam_inv_sigma_T));
+    memcpy(p.inv_sigma, h->inv_sigma, sizeof(p.inv_sigma));
     p.sigma_diag = h->sigma_diag;
+    p.w_scale = (py ? h->gamma : h->lambda) * h->upsilon;    // u^T S^-1 (upsilon S z) = upsilon u^T z
+    p.c0_scale = py ? 0.5f * h->gamma : 0.f;
+    const float kappa = py ? 0.5f * h->lambda * (1.0f - 1.0f / h->upsilon) : 0.f;
+    p.quad = (kappa != 0.f);
+    if (p.quad) {
+        // n = eps (injected): kappa * Sigma^-1 ; n = z (Philox): kappa * (uS)^T Sigma^-1 (uS); symmetrised
+        float M[kMaxA * kMaxA];
+        for (int i = 0; i < a; i++)
+            for (int j = 0; j < a; j++) {
+                if (eps_dev) {
+                    M[i * a + j] = h->inv_sigma[i * a + j];
+                } else {
+                    float acc = 0.f;                       // (S^T S^-1 S)_ij = sum_l S_li (S^-1 S)_lj = S_ji ... kept general
+                    for (int l = 0; l < a; l++)
+                        for (int m = 0; m < a; m++) acc += h->sigma[l * a + i] * h->inv_sigma[l * a + m] * h->sigma[m * a + j];
+                    M[i * a + j] = h->upsilon * h->upsilon * acc;
+                }
+            }
+        for (int i = 0; i < a; i++)
+            for (int j = 0; j < a; j++) p.quadm[i * a + j] = kappa * 0.5f * (M[i * a + j] + M[j * a + i]);
+    }
+    p.norm_mode = 0;
+    p.norm = h->d_norm;
     p.goal_per_ctrl = h->goal_per_ctrl;
     p.key0 = (uint32_t)h->seed;
     p.key1 = (uint32_t)(h->seed >> 32);
@@ -281,6 +316,7 @@ int mppi_create(const mppi_config *cfg, mppi_handle **out)
     CU_TRY_C(cudaMalloc(&h->d_payload, sizeof(float) * (size_t)n_ctrl * h->stride));
     CU_TRY_C(cudaMalloc(&h->d_gather, sizeof(float) * (size_t)world * n_ctrl * h->stride));
     CU_TRY_C(cudaMalloc(&h->d_stats, sizeof(float) * 2 * n_ctrl));
+    CU_TRY_C(cudaMalloc(&h->d_norm, sizeof(float) * 2 * n_ctrl));
     CU_TRY_C(cudaMalloc(&h->d_counters, sizeof(unsigned int) * n_ctrl));
     CU_TRY_C(cudaMemset(h->d_counters, 0, sizeof(unsigned int) * n_ctrl));
     CU_TRY_C(cudaMemset(h->d_U, 0, sizeof(float) * n_ctrl * h->TA));
@@ -308,6 +344,7 @@ int mppi_destroy(mppi_handle *h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     cudaFree(h->d_x); cudaFree(h->d_goal); cudaFree(h->d_U); cudaFree(h->d_Unew); cudaFree(h->d_next);
     cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_counters);
+    cudaFree(h->d_norm);
     cudaFree(h->d_eps_tmp);
     cudaFree(h->d_wblob);
     cudaFree(h->d_fvec);
@@ -352,24 +389,25 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
     CU_TRY(h, cudaSetDevice(h->device));
     RolloutParams p = make_params(h, eps_dev);
     int gx = 0;
-    if (h->mlp) {
-        MlpParams mp{h->d_wblob, h->d_fvec, h->s, h->a};
-        CU_TRY(h, launch_rollout_mlp(p, mp, h->a, eps_dev == nullptr, h->num_sms, h->stream, &gx));
-        h->last_philox = (eps_dev == nullptr);
-        if (!eps_dev) {
-            h->have_philox_update = true;
-            h->last_update = h->update_counter;
-            h->update_counter++;
+    // cost normalisation (controller_base.py:468-474) needs max_k(S_k - beta) before any weight: two launches,
+    // pass 1 = costs + global (min, max), pass 2 = weights and update from the stored costs
+    const int npass = h->normalize ? 2 : 1;
+    for (int pass = 1; pass <= npass; pass++) {
+        p.norm_mode = h->normalize ? pass : 0;
+        if (h->mlp) {
+            MlpParams mp{h->d_wblob, h->d_fvec, h->s, h->a};
+            CU_TRY(h, launch_rollout_mlp(p, mp, h->a, eps_dev == nullptr, h->num_sms, h->stream, &gx));
+        } else if (eps_dev) {
+            cudaError_t e = launch_rollout_injected(p, h->a, h->num_sms, h->smem_optin, h->stream, &gx);
+            if (e == cudaErrorInvalidConfiguration)
+                return fail(h, MPPI_ERR_UNSUPPORTED, "injected-noise mode: one 32-sample tile of tau*a_dim floats does not fit shared memory");
+            CU_TRY(h, e);
+        } else {
+            CU_TRY(h, launch_rollout_philox(p, h->a, h->num_sms, h->stream, &gx));
         }
-    } else if (eps_dev) {
-        cudaError_t e = launch_rollout_injected(p, h->a, h->num_sms, h->smem_optin, h->stream, &gx);
-        if (e == cudaErrorInvalidConfiguration)
-            return fail(h, MPPI_ERR_UNSUPPORTED, "injected-noise mode: one 32-sample tile of tau*a_dim floats does not fit shared memory");
-        CU_TRY(h, e);
-        h->last_philox = false;
-    } else {
-        CU_TRY(h, launch_rollout_philox(p, h->a, h->num_sms, h->stream, &gx));
-        h->last_philox = true;
+    }
+    h->last_philox = (eps_dev == nullptr);
+    if (!eps_dev) {
         h->have_philox_update = true;
         h->last_update = h->update_counter;
         h->update_counter++;
@@ -490,6 +528,25 @@ int mppi_set_lambda(mppi_handle *h, float lambda)
     if (!h || !(lambda > 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "lambda must be > 0");
     h->lambda = lambda;
     derive_sigma(h);
+    return MPPI_OK;
+}
+int mppi_set_action_cost(mppi_handle *h, int form, float gamma, float upsilon)
+{
+    if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
+    if (form != MPPI_ACTION_COST_CPP && form != MPPI_ACTION_COST_PYTHON) return fail(h, MPPI_ERR_BAD_ARG, "unknown action-cost form");
+    if (!(upsilon > 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "upsilon must be > 0");
+    h->cost_form = form;
+    h->gamma = gamma;
+    h->upsilon = upsilon;
+    derive_sigma(h);
+    return MPPI_OK;
+}
+int mppi_set_normalize_cost(mppi_handle *h, int on)
+{
+    if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
+    if (on && h->world > 1)
+        return fail(h, MPPI_ERR_UNSUPPORTED, "cost normalisation needs the global cost range before any weight: not wired for world > 1 yet");
+    h->normalize = on != 0;
     return MPPI_OK;
 }
 int mppi_set_sigma(mppi_handle *h, const float *sigma_host)

@@ -34,6 +34,15 @@ struct RolloutParams {
     float lam_inv_sigma_T[kMaxA * kMaxA];   // v_t = lam_inv_sigma_T * U_t  (injected mode)
     int sigma_diag;
     int goal_per_ctrl;
+    // Python-twin extras (scripts/src/costs/cost_base.py:114-170, controllers/controller_base.py:368,468-474):
+    //   action cost = c0_t + w_t . n + n^T quadm n   per step, n = z (Philox mode) or eps (injected mode)
+    float w_scale;                          // Philox mode: w_t = w_scale * U_t  (lambda*upsilon, or gamma*upsilon)
+    float c0_scale;                         // c0_t = c0_scale * U_t^T Sigma^-1 U_t  (0.5*gamma in the Python form, else 0)
+    float inv_sigma[kMaxA * kMaxA];         // Sigma^-1 (for c0_t)
+    int quad;                               // != 0: the quadratic noise term is present
+    float quadm[kMaxA * kMaxA];             // 0.5*lambda*(1-1/upsilon) * M, M = Sigma^-1 (n = eps) or (uS)^T S^-1 (uS) (n = z)
+    int norm_mode;                          // cost normalisation: 0 off, 1 = cost pass (min/max only), 2 = weight pass
+    float *norm;                            // [n_ctrl][2] beta, max(S - beta) written by pass 1, read by pass 2
     // Philox key / counter words
     uint32_t key0, key1, update;
     uint32_t rk0[10], rk1[10];              // Philox round keys key + r * W (hoisted to the host)

@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
     float *sN = sAcc + NW * TAp;                  // [TAp]
     float *sWork = sN + TAp;                      // [TAp]
     float *sScale = sWork + TAp;                  // [kMaxParts]
-    float *sRed = sScale + kMaxParts;             // [32]
-    float4 *sScratch = reinterpret_cast<float4 *>(sRed + 32);     // [kMlpThreads] merge scratch
+    float *sRed = sScale + kMaxParts;             // [64]
+    float4 *sScratch = reinterpret_cast<float4 *>(sRed + 64);     // [kMlpThreads] merge scratch
     uint64_t *bars = reinterpret_cast<uint64_t *>(sScratch + kMlpThreads);
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + kMlpNumBars);
 
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
     MlpTile t;
     stage_sequence<A, PHILOX>(p, ctrl, sUV);
     mlp_tile_init(t, mp, sW, sF, bars, tslot);    // ends with a CTA barrier: sUV is visible
+    const float C0 = stage_c0<A>(p, ctrl, sWork, sRed);
 
     float *costs = p.costs + (size_t)ctrl * p.K_local;
     const float *eps = PHILOX ? nullptr : p.eps + (size_t)ctrl * p.K_local * TA;
@@ -99,8 +100,10 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
     const uint32_t stream = (uint32_t)ctrl;
 
     // ---- phase 1: rollout + cost -----------------------------------------------------------------
-    float bmin = kInf;
-    if (warp < kMlpRowWarps) {
+    float bmin = kInf, bmax = -kInf;
+    if (p.norm_mode == 2) {
+        // weight pass of a normalised update: costs are in HBM, no rollout
+    } else if (warp < kMlpRowWarps) {
         float g[S], q[S], x0[S];
         {
             const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * S : 0);
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
             float x[S];
 #pragma unroll
             for (int i = 0; i < S; i++) x[i] = x0[i];
-            float Sk = 0.f;
+            float Sk = C0;
             float z[4 * A], zn[4 * A];
 #pragma unroll
             for (int c = 0; c < A; c++) {
@@ -149,6 +152,12 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
                         }
                         u[j] = uv[j] + e;
                         ac = fmaf(uv[H + j], n, ac);
+                    }
+                    if (p.quad) {                         // Python-twin noise cost (grid-uniform branch)
+                        float nn[A];
+#pragma unroll
+                        for (int j = 0; j < A; j++) nn[j] = z[tt * A + j];
+                        ac += quad_cost<A>(p, nn);
                     }
                     mlp_row_begin<S, A>(t, x, u);
                     // in the shadow of layer 1: state cost of the state the step started from (it is
@@ -193,6 +202,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
             if (valid) {
                 costs[k] = Sk;
                 bmin = fminf(bmin, Sk);
+                bmax = fmaxf(bmax, Sk);
             }
         }
     } else {
@@ -200,12 +210,20 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
     }
     mlp_tile_fini(t);
     bmin = warp_min(bmin);
-    if (lane == 0) sRed[warp] = bmin;
+    bmax = -warp_min(-bmax);
+    if (lane == 0) { sRed[warp] = bmin; sRed[32 + warp] = bmax; }
     __syncthreads();
-    float beta_c = sRed[0];
+    float beta_c = sRed[0], max_c = sRed[32];
 #pragma unroll
-    for (int w = 1; w < NW; w++) beta_c = fminf(beta_c, sRed[w]);
+    for (int w = 1; w < NW; w++) { beta_c = fminf(beta_c, sRed[w]); max_c = fmaxf(max_c, sRed[32 + w]); }
     __syncthreads();
+    if (p.norm_mode == 1) {                 // cost pass of a normalised update: publish (min, max) and stop
+        publish_minmax(p, ctrl, beta_c, max_c, sRed);
+        return;
+    }
+    float beta_fixed = 0.f;
+    const float nil = weight_scale(p, ctrl, beta_fixed);
+    if (p.norm_mode == 2) beta_c = beta_fixed;
 
     // ---- phase 2: sum_k e_k n_k (n = z regenerated, or eps re-read); all five warps take samples ----
     const int ncall = (TA + 3) >> 2;
@@ -219,7 +237,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
         for (int k = k_lo + tid; k < k_hi; k += kMlpThreads) {
             const uint32_t kg = (uint32_t)(p.k_offset + k);
             const float *eps_row = PHILOX ? nullptr : eps + (size_t)k * TA;
-            const float e = weight_exp(costs[k], beta_c, p.neg_inv_lambda_log2e);
+            const float e = weight_exp(costs[k], beta_c, nil);
             if (ch == 0) eta += e;
 #pragma unroll
             for (int c8 = 0; c8 < 8; c8++) {
@@ -260,7 +278,7 @@ static size_t mlp_rollout_smem(int A, int T, int TA)
 {
     const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31, NW = kMlpThreads / 32;
     return kWBlobBytes + sizeof(float) * (kFvecFloats + (size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 32) +
-           sizeof(float4) * kMlpThreads + kMlpNumBars * 8 + 16 + 128;
+           sizeof(float) * 32 + sizeof(float4) * kMlpThreads + kMlpNumBars * 8 + 16 + 128;
 }
 
 #define MPPI_DISPATCH_MLP_A(a, ...)              \

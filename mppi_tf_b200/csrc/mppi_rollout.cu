@@ -53,7 +53,7 @@ __device__ __forceinline__ void vec_from(const float *z, Vec<A> &n)
 // One rollout step for one sample (src/controller_base.cpp:251-269):
 //   u = U_t + eps_t ; x <- A x + (B/m) u ; S += q(x) + lambda U_t^T Sigma^-1 eps_t
 // `n` is z_t in Philox mode (eps_t = Sigma z_t formed here) and eps_t in injected mode.
-template <int A, bool PHILOX, bool DIAG>
+template <int A, bool PHILOX, bool DIAG, bool QUAD>
 __device__ __forceinline__ void rollout_step(PointMass<A> &x, CostAcc &S, const float *uv_row, const Vec<A> &n,
                                              const RolloutParams &p, const ModelConsts<A> &mc, const Vec<A> &sigd)
 {
@@ -78,6 +78,12 @@ __device__ __forceinline__ void rollout_step(PointMass<A> &x, CostAcc &S, const 
 #pragma unroll
     for (int i = 0; i < NP; i++) S.a2 = __ffma2_rn(w.pr[i], n.pr[i], S.a2);
     if (ODD) S.a = fmaf(w.sc, n.sc, S.a);
+    if (QUAD) {                                  // Python-twin noise cost (cost_base.py:147-148,160-162)
+        float nn[A];
+#pragma unroll
+        for (int j = 0; j < A; j++) nn[j] = n.get(j);
+        S.a += quad_cost<A>(p, nn);
+    }
     x.step(u, mc);
     x.state_cost(mc, S.a2, S.a);
 }
@@ -102,7 +108,7 @@ __device__ __forceinline__ void thread_consts(const RolloutParams &p, int ctrl, 
 // -------------------------------------------------------------------------------------------------
 // Philox mode
 // -------------------------------------------------------------------------------------------------
-template <int A, bool DIAG>
+template <int A, bool DIAG, bool QUAD>
 __global__ void __launch_bounds__(kPhiloxThreads, kPhiloxCtasPerSm)
 rollout_philox_kernel(const __grid_constant__ RolloutParams p)
 {
@@ -116,8 +122,8 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     float *sN = sAcc + NW * TAp;         // [TAp]
     float *sWork = sN + TAp;             // [TAp]
     float *sScale = sWork + TAp;         // [kMaxParts]
-    float *sRed = sScale + kMaxParts;    // [32]
-    float4 *sScratch = reinterpret_cast<float4 *>(sRed + 32);   // [kPhiloxThreads] merge scratch
+    float *sRed = sScale + kMaxParts;    // [64]
+    float4 *sScratch = reinterpret_cast<float4 *>(sRed + 64);   // [kPhiloxThreads] merge scratch
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     stage_sequence<A, true>(p, ctrl, sUV);
@@ -127,6 +133,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     float x0[2 * A];
     thread_consts<A>(p, ctrl, mc, sigd, x0);
     __syncthreads();
+    const float C0 = stage_c0<A>(p, ctrl, sWork, sRed);
 
     float *costs = p.costs + (size_t)ctrl * p.K_local;
     // contiguous, evenly sized sample range per CTA (32-sample granularity): no whole-iteration
@@ -141,13 +148,14 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     const uint32_t stream = (uint32_t)ctrl;
 
     // ---- phase 1: rollout + cost ---------------------------------------------------------------
-    float bmin = kInf;
-    for (int k = kfirst; k < kend; k += kstride) {
+    float bmin = kInf, bmax = -kInf;
+    for (int k = kfirst; k < kend && p.norm_mode != 2; k += kstride) {   // weight pass of a normalised update: costs are in HBM
         const uint32_t kg = (uint32_t)(p.k_offset + k);
         PointMass<A> x;
         x.init(x0);
         CostAcc S;
         S.zero();
+        S.a = C0;
         const float *uv = sUV;
         uint32_t call = 0;
         for (int tb = 0; tb < nfull; tb++) {       // full blocks of 4 steps = A Philox calls, no guards
@@ -159,7 +167,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
             for (int tt = 0; tt < 4; tt++) {
                 Vec<A> n;
                 vec_from<A>(&z[tt * A], n);
-                rollout_step<A, true, DIAG>(x, S, uv + tt * RS, n, p, mc, sigd);
+                rollout_step<A, true, DIAG, QUAD>(x, S, uv + tt * RS, n, p, mc, sigd);
             }
             uv += 4 * RS;
         }
@@ -172,21 +180,30 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
                 if (tt < trem) {
                     Vec<A> n;
                     vec_from<A>(&z[tt * A], n);
-                    rollout_step<A, true, DIAG>(x, S, uv + tt * RS, n, p, mc, sigd);
+                    rollout_step<A, true, DIAG, QUAD>(x, S, uv + tt * RS, n, p, mc, sigd);
                 }
         }
         x.state_cost(mc, S.a2, S.a);    // terminal cost on top of step T-1's (src/controller_base.cpp:271-272)
         const float Sk = S.total();
         costs[k] = Sk;
         bmin = fminf(bmin, Sk);
+        bmax = fmaxf(bmax, Sk);
     }
     bmin = warp_min(bmin);
-    if (lane == 0) sRed[warp] = bmin;
+    bmax = -warp_min(-bmax);
+    if (lane == 0) { sRed[warp] = bmin; sRed[32 + warp] = bmax; }
     __syncthreads();
-    float beta_c = sRed[0];
+    float beta_c = sRed[0], max_c = sRed[32];
 #pragma unroll
-    for (int w = 1; w < NW; w++) beta_c = fminf(beta_c, sRed[w]);
+    for (int w = 1; w < NW; w++) { beta_c = fminf(beta_c, sRed[w]); max_c = fmaxf(max_c, sRed[32 + w]); }
     __syncthreads();
+    if (p.norm_mode == 1) {                 // cost pass of a normalised update: publish (min, max) and stop
+        publish_minmax(p, ctrl, beta_c, max_c, sRed);
+        return;
+    }
+    float beta_fixed = 0.f;
+    const float nil = weight_scale(p, ctrl, beta_fixed);
+    if (p.norm_mode == 2) beta_c = beta_fixed;
 
     // ---- phase 2: sum_k e_k z_k, regenerating z from the same counters ----------------------------
     const int ncall = (TA + 3) >> 2;
@@ -199,7 +216,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
         const bool full = (ch * 8 + 8 <= ncall);    // warp-uniform: all 8 calls of the chunk exist
         for (int k = kfirst; k < kend; k += kstride) {
             const uint32_t kg = (uint32_t)(p.k_offset + k);
-            const float e = weight_exp(costs[k], beta_c, p.neg_inv_lambda_log2e);
+            const float e = weight_exp(costs[k], beta_c, nil);
             const float2 e2 = make_float2(e, e);
             if (ch == 0) eta += e;
 #pragma unroll
@@ -282,7 +299,7 @@ __device__ __forceinline__ void load_block(const float *row, int tb, int TA, flo
     }
 }
 
-template <int A, bool TMA>
+template <int A, bool TMA, bool QUAD>
 __global__ void __launch_bounds__(512, 1)
 rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedLaunch L)
 {
@@ -338,6 +355,9 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
     Vec<A> sigd;
     float x0[2 * A];
     thread_consts<A>(p, ctrl, mc, sigd, x0);
+    const float C0 = stage_c0<A>(p, ctrl, sWork, sRed);
+    float beta_fixed = 0.f;
+    const float nil = weight_scale(p, ctrl, beta_fixed);
 
     float *costs = p.costs + (size_t)ctrl * p.K_local;
     float *accg = sAccG + grp * TAp;
@@ -350,7 +370,8 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
     const int NB = (TA + 31) >> 5;
     const int nbw = (NB + C - 1) / C;
     const int cb0 = min(NB, cw * nbw), cb1 = min(NB, cb0 + nbw);
-    float beta_g = kInf, eta_lane = 0.f;
+    float beta_g = (p.norm_mode == 2) ? beta_fixed : kInf, eta_lane = 0.f;
+    float gmin = kInf, gmax = -kInf;               // cost pass of a normalised update
 
     // U-part of this chunk's zero-state sums (same for every sample): CU = sum U_t, DU = sum prefix
     Vec<A> CU, DU;
@@ -387,103 +408,119 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
             __syncwarp();
             const float *row = tile + lane * TA;
 
-            PointMass<A> x;
-            if (C > 1) {
-                // ---- pass 1: per-sample part of the chunk's zero-state sums ------------------------
-                Vec<A> Cs, Ds;
-                Cs.fill(0.f);
-                Ds.fill(0.f);
-                for (int tb = tb0; tb < tb1; tb++) {
-                    float e[4 * A];
-                    if (4 * tb + 4 <= p.T) load_block<A, TMA, false>(row, tb, TA, e);
-                    else load_block<A, TMA, true>(row, tb, TA, e);    // zeros past the row end
-#pragma unroll
-                    for (int tt = 0; tt < 4; tt++) {
-                        Vec<A> n;
-                        vec_from<A>(&e[tt * A], n);
-#pragma unroll
-                        for (int i = 0; i < A / 2; i++) {
-                            Ds.pr[i] = __fadd2_rn(Ds.pr[i], Cs.pr[i]);
-                            Cs.pr[i] = __fadd2_rn(Cs.pr[i], n.pr[i]);
-                        }
-                        if (A & 1) { Ds.sc += Cs.sc; Cs.sc += n.sc; }
-                    }
-                }
-                // the guarded tail appends zeros: (4*tb1 - T) extra prefix terms entered D; remove them
-                const int extra = 4 * tb1 - min(p.T, 4 * tb1);
-                float *myb = sB + ((size_t)(grp * C + cw) * 2 * A) * 32 + lane;
-                const float dtcvu = p.dt * p.c_vu;
-#pragma unroll
-                for (int i = 0; i < A; i++) {
-                    const float Ci = Cs.get(i) + CU.get(i);
-                    const float Di = (Ds.get(i) - (float)extra * Cs.get(i)) + DU.get(i);
-                    myb[(2 * i) * 32] = fmaf(p.c_pu, Ci, dtcvu * Di);
-                    myb[(2 * i + 1) * 32] = p.c_vu * Ci;
-                }
-                group_barrier(bar_id, bar_n);
-                // true incoming state: x0 pushed through chunks 0..cw-1 (free response + zero-state response)
-                x.init(x0);
-                for (int cc = 0; cc < cw; cc++) {
-                    const int s0 = 4 * min(nblk, cc * nb), s1 = min(p.T, 4 * min(nblk, cc * nb + nb));
-                    const float ndt = (float)(s1 - s0) * p.dt;
-                    const float *ob = sB + ((size_t)(grp * C + cc) * 2 * A) * 32 + lane;
-#pragma unroll
-                    for (int i = 0; i < A; i++) {
-                        const float vi = x.v.get(i);
-                        x.p.set(i, fmaf(ndt, vi, x.p.get(i)) + ob[(2 * i) * 32]);
-                        x.v.set(i, vi + ob[(2 * i + 1) * 32]);
-                    }
-                }
+            float S;
+            if (p.norm_mode == 2) {                // weight pass of a normalised update: costs are in HBM
+                S = (lane < rows) ? costs[32 * gt + lane] : 0.f;
+                if (TMA && C > 1) group_barrier(bar_id, bar_n);   // the zeroed tail rows are visible to the whole group
             } else {
-                x.init(x0);
-            }
-
-            // ---- pass 2: rollout with costs over this warp's chunk ----------------------------------
-            CostAcc Sa;
-            Sa.zero();
-            for (int tb = tb0; tb < tb1; tb++) {
-                float e[4 * A];
-                if (4 * tb + 4 <= p.T) {
-                    load_block<A, TMA, false>(row, tb, TA, e);
-#pragma unroll
-                    for (int tt = 0; tt < 4; tt++) {
-                        Vec<A> n;
-                        vec_from<A>(&e[tt * A], n);
-                        rollout_step<A, false, false>(x, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
-                    }
-                } else {
-                    load_block<A, TMA, true>(row, tb, TA, e);
-#pragma unroll
-                    for (int tt = 0; tt < 4; tt++)
-                        if (4 * tb + tt < p.T) {
+                PointMass<A> x;
+                if (C > 1) {
+                    // ---- pass 1: per-sample part of the chunk's zero-state sums ------------------------
+                    Vec<A> Cs, Ds;
+                    Cs.fill(0.f);
+                    Ds.fill(0.f);
+                    for (int tb = tb0; tb < tb1; tb++) {
+                        float e[4 * A];
+                        if (4 * tb + 4 <= p.T) load_block<A, TMA, false>(row, tb, TA, e);
+                        else load_block<A, TMA, true>(row, tb, TA, e);    // zeros past the row end
+    #pragma unroll
+                        for (int tt = 0; tt < 4; tt++) {
                             Vec<A> n;
                             vec_from<A>(&e[tt * A], n);
-                            rollout_step<A, false, false>(x, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
+    #pragma unroll
+                            for (int i = 0; i < A / 2; i++) {
+                                Ds.pr[i] = __fadd2_rn(Ds.pr[i], Cs.pr[i]);
+                                Cs.pr[i] = __fadd2_rn(Cs.pr[i], n.pr[i]);
+                            }
+                            if (A & 1) { Ds.sc += Cs.sc; Cs.sc += n.sc; }
                         }
+                    }
+                    // the guarded tail appends zeros: (4*tb1 - T) extra prefix terms entered D; remove them
+                    const int extra = 4 * tb1 - min(p.T, 4 * tb1);
+                    float *myb = sB + ((size_t)(grp * C + cw) * 2 * A) * 32 + lane;
+                    const float dtcvu = p.dt * p.c_vu;
+    #pragma unroll
+                    for (int i = 0; i < A; i++) {
+                        const float Ci = Cs.get(i) + CU.get(i);
+                        const float Di = (Ds.get(i) - (float)extra * Cs.get(i)) + DU.get(i);
+                        myb[(2 * i) * 32] = fmaf(p.c_pu, Ci, dtcvu * Di);
+                        myb[(2 * i + 1) * 32] = p.c_vu * Ci;
+                    }
+                    group_barrier(bar_id, bar_n);
+                    // true incoming state: x0 pushed through chunks 0..cw-1 (free response + zero-state response)
+                    x.init(x0);
+                    for (int cc = 0; cc < cw; cc++) {
+                        const int s0 = 4 * min(nblk, cc * nb), s1 = min(p.T, 4 * min(nblk, cc * nb + nb));
+                        const float ndt = (float)(s1 - s0) * p.dt;
+                        const float *ob = sB + ((size_t)(grp * C + cc) * 2 * A) * 32 + lane;
+    #pragma unroll
+                        for (int i = 0; i < A; i++) {
+                            const float vi = x.v.get(i);
+                            x.p.set(i, fmaf(ndt, vi, x.p.get(i)) + ob[(2 * i) * 32]);
+                            x.v.set(i, vi + ob[(2 * i + 1) * 32]);
+                        }
+                    }
+                } else {
+                    x.init(x0);
+                }
+
+                // ---- pass 2: rollout with costs over this warp's chunk ----------------------------------
+                CostAcc Sa;
+                Sa.zero();
+                if (cw == 0) Sa.a = C0;
+                for (int tb = tb0; tb < tb1; tb++) {
+                    float e[4 * A];
+                    if (4 * tb + 4 <= p.T) {
+                        load_block<A, TMA, false>(row, tb, TA, e);
+    #pragma unroll
+                        for (int tt = 0; tt < 4; tt++) {
+                            Vec<A> n;
+                            vec_from<A>(&e[tt * A], n);
+                            rollout_step<A, false, false, QUAD>(x, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
+                        }
+                    } else {
+                        load_block<A, TMA, true>(row, tb, TA, e);
+    #pragma unroll
+                        for (int tt = 0; tt < 4; tt++)
+                            if (4 * tb + tt < p.T) {
+                                Vec<A> n;
+                                vec_from<A>(&e[tt * A], n);
+                                rollout_step<A, false, false, QUAD>(x, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
+                            }
+                    }
+                }
+                if (tb1 == nblk && tb0 < tb1) x.state_cost(mc, Sa.a2, Sa.a);   // terminal cost (src/controller_base.cpp:271-272)
+                S = Sa.total();
+                if (C > 1) {
+                    sS[(grp * C + cw) * 32 + lane] = S;
+                    group_barrier(bar_id, bar_n);
+                    S = 0.f;
+                    for (int cc = 0; cc < C; cc++) S += sS[(grp * C + cc) * 32 + lane];   // fixed order in every warp
                 }
             }
-            if (tb1 == nblk && tb0 < tb1) x.state_cost(mc, Sa.a2, Sa.a);   // terminal cost (src/controller_base.cpp:271-272)
-            float S = Sa.total();
-            if (C > 1) {
-                sS[(grp * C + cw) * 32 + lane] = S;
-                group_barrier(bar_id, bar_n);
-                S = 0.f;
-                for (int cc = 0; cc < C; cc++) S += sS[(grp * C + cc) * 32 + lane];   // fixed order in every warp
+            if (p.norm_mode != 2 && cw == 0 && lane < rows) costs[32 * gt + lane] = S;
+            if (p.norm_mode == 1) {                // cost pass: track (min, max), no weights yet
+                if (lane < rows) { gmin = fminf(gmin, S); gmax = fmaxf(gmax, S); }
+                if (C > 1) group_barrier(bar_id, bar_n); else __syncwarp();
+                if (TMA && lane == 0 && cw == 0 && seq + ST * NG < nseq) {
+                    fence_proxy_async();
+                    issue(grp, j + ST);
+                }
+                continue;
             }
-            if (cw == 0 && lane < rows) costs[32 * gt + lane] = S;
             if (lane >= rows) S = kInf;
 
             // ---- weighted sum: online max-shifted weights; lane = column of the resident tile ---------
             const float m = warp_min(S);
             if (m < beta_g) {
                 if (beta_g != kInf) {
-                    const float f = weight_exp(beta_g, m, p.neg_inv_lambda_log2e);
+                    const float f = weight_exp(beta_g, m, nil);
                     for (int c = cb0 * 32 + lane; c < min(TA, cb1 * 32); c += 32) accg[c] *= f;
                     eta_lane *= f;
                 }
                 beta_g = m;
             }
-            const float ek = (lane < rows) ? weight_exp(S, beta_g, p.neg_inv_lambda_log2e) : 0.f;
+            const float ek = (lane < rows) ? weight_exp(S, beta_g, nil) : 0.f;
             eta_lane += ek;
             for (int cb = cb0; cb < cb1; cb += 4) {
                 // 4 column blocks per pass: offsets 32*mm are immediates, the row pointer advances by TA.
@@ -510,9 +547,23 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
             }
         }
         eta_lane = warp_sum(eta_lane);
-        if (lane == 0 && cw == 0) { sRed[grp] = beta_g; sRed[32 + grp] = eta_lane; }
+        if (p.norm_mode == 1) {
+            gmin = warp_min(gmin);
+            gmax = -warp_min(-gmax);
+            if (lane == 0 && cw == 0) { sRed[grp] = gmin; sRed[32 + grp] = gmax; }
+        } else if (lane == 0 && cw == 0) {
+            sRed[grp] = beta_g;
+            sRed[32 + grp] = eta_lane;
+        }
     }
     __syncthreads();
+    if (p.norm_mode == 1) {
+        float lo = kInf, hi = -kInf;
+        for (int w = 0; w < NG; w++) { lo = fminf(lo, sRed[w]); hi = fmaxf(hi, sRed[32 + w]); }
+        __syncthreads();
+        publish_minmax(p, ctrl, lo, hi, sRed);
+        return;
+    }
 
     // ---- CTA merge of the per-group running sums ---------------------------------------------------
     float beta_c = kInf;
@@ -520,13 +571,13 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
     float eta_c = 0.f;
     for (int w = 0; w < NG; w++) {
         const float bw = sRed[w];
-        if (bw != kInf) eta_c = fmaf(weight_exp(bw, beta_c, p.neg_inv_lambda_log2e), sRed[32 + w], eta_c);
+        if (bw != kInf) eta_c = fmaf(weight_exp(bw, beta_c, nil), sRed[32 + w], eta_c);
     }
     for (int j = tid; j < TA; j += blockDim.x) {
         float s = 0.f;
         for (int w = 0; w < NG; w++) {
             const float bw = sRed[w];
-            if (bw != kInf) s = fmaf(weight_exp(bw, beta_c, p.neg_inv_lambda_log2e), sAccG[w * TAp + j], s);
+            if (bw != kInf) s = fmaf(weight_exp(bw, beta_c, nil), sAccG[w * TAp + j], s);
         }
         sN[j] = s;
     }
@@ -602,24 +653,25 @@ __global__ void scale_noise_kernel(const __grid_constant__ RolloutParams p, floa
 static size_t philox_smem_bytes(int A, int T, int TA)
 {
     const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31, NW = kPhiloxThreads / 32;
-    return sizeof(float) * ((size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 32) + sizeof(float4) * kPhiloxThreads;
+    return sizeof(float) * ((size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 64) + sizeof(float4) * kPhiloxThreads;
+}
+
+template <int A, bool DIAG, bool QUAD>
+static cudaError_t launch_philox_V(const RolloutParams &p, dim3 grid, size_t smem, cudaStream_t st)
+{
+    cudaError_t err = cudaFuncSetAttribute(rollout_philox_kernel<A, DIAG, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    rollout_philox_kernel<A, DIAG, QUAD><<<grid, kPhiloxThreads, smem, st>>>(p);
+    return cudaGetLastError();
 }
 
 template <int A>
 static cudaError_t launch_philox_A(const RolloutParams &p, dim3 grid, cudaStream_t st)
 {
     const size_t smem = philox_smem_bytes(A, p.T, p.TA);
-    cudaError_t err;
-    if (p.sigma_diag) {
-        err = cudaFuncSetAttribute(rollout_philox_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        rollout_philox_kernel<A, true><<<grid, kPhiloxThreads, smem, st>>>(p);
-    } else {
-        err = cudaFuncSetAttribute(rollout_philox_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        rollout_philox_kernel<A, false><<<grid, kPhiloxThreads, smem, st>>>(p);
-    }
-    return cudaGetLastError();
+    if (p.quad) return launch_philox_V<A, false, true>(p, grid, smem, st);      // noise-quadratic cost: general-Sigma variant
+    if (p.sigma_diag) return launch_philox_V<A, true, false>(p, grid, smem, st);
+    return launch_philox_V<A, false, false>(p, grid, smem, st);
 }
 
 #define MPPI_DISPATCH_A(a, ...)                  \
@@ -703,22 +755,21 @@ bool injected_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sm
     return true;
 }
 
+template <int A, bool TMA, bool QUAD>
+static cudaError_t launch_injected_V(const RolloutParams &p, InjectedLaunch L, dim3 grid, size_t smem, cudaStream_t st)
+{
+    cudaError_t err = cudaFuncSetAttribute(rollout_injected_kernel<A, TMA, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    rollout_injected_kernel<A, TMA, QUAD><<<grid, L.ng * L.c * 32, smem, st>>>(p, L);
+    return cudaGetLastError();
+}
+
 template <int A>
 static cudaError_t launch_injected_A(const RolloutParams &p, InjectedLaunch L, dim3 grid, size_t smem, bool tma,
                                      cudaStream_t st)
 {
-    cudaError_t err;
-    const int threads = L.ng * L.c * 32;
-    if (tma) {
-        err = cudaFuncSetAttribute(rollout_injected_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        rollout_injected_kernel<A, true><<<grid, threads, smem, st>>>(p, L);
-    } else {
-        err = cudaFuncSetAttribute(rollout_injected_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        rollout_injected_kernel<A, false><<<grid, threads, smem, st>>>(p, L);
-    }
-    return cudaGetLastError();
+    if (p.quad) return tma ? launch_injected_V<A, true, true>(p, L, grid, smem, st) : launch_injected_V<A, false, true>(p, L, grid, smem, st);
+    return tma ? launch_injected_V<A, true, false>(p, L, grid, smem, st) : launch_injected_V<A, false, false>(p, L, grid, smem, st);
 }
 
 cudaError_t launch_rollout_injected(RolloutParams p, int a, int num_sms, size_t smem_limit, cudaStream_t st,

@@ -12,7 +12,8 @@ constexpr int kMaxParts = 1024;   // CTA partials (or ranks) one merge can take
 //   [0, A)      U_t   mean action (src/controller_base.cpp:205-208)
 //   [H, H + A)  w_t   action-cost vector: Philox mode lambda*U_t (since eps = Sigma z,
 //                     lambda U^T Sigma^-1 eps = lambda U^T z); injected mode lambda*Sigma^-T U_t
-//                     (src/cost_base.cpp:63-68)
+//                     (src/cost_base.cpp:63-68).  With the Python-twin action cost gamma takes the
+//                     place of lambda and eps = upsilon Sigma z (w_scale / lam_inv_sigma_T, host side)
 // H = A rounded up to even so both halves start on an aligned pair.
 template <int A>
 struct Row {
@@ -33,7 +34,7 @@ __device__ __forceinline__ void stage_sequence(const RolloutParams &p, int ctrl,
         } else if (j >= H && j < H + A) {
             const int r = j - H;
             if (PHILOX) {
-                v = p.lambda * U[t * A + r];
+                v = p.w_scale * U[t * A + r];
             } else {
 #pragma unroll
                 for (int l = 0; l < A; l++) v = fmaf(p.lam_inv_sigma_T[r * A + l], U[t * A + l], v);
@@ -41,6 +42,98 @@ __device__ __forceinline__ void stage_sequence(const RolloutParams &p, int ctrl,
         }
         sUV[i] = v;
     }
+}
+
+// Sample-independent part of the Python-twin action cost, summed over the horizon:
+//   C0 = sum_t c0_scale * U_t^T Sigma^-1 U_t   (0.5*gamma*u^T Sigma^-1 u, cost_base.py:151-155,165-167)
+// Block-uniform result; fixed summation order.  sTmp: >= T floats, sRed: >= 1 float.  Contains CTA barriers.
+template <int A>
+__device__ __forceinline__ float stage_c0(const RolloutParams &p, int ctrl, float *sTmp, float *sRed)
+{
+    if (p.c0_scale == 0.f) return 0.f;             // grid-uniform
+    const float *U = p.U + (size_t)ctrl * p.TA;
+    for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < A; i++) {
+            float r = 0.f;
+#pragma unroll
+            for (int j = 0; j < A; j++) r = fmaf(p.inv_sigma[i * A + j], U[t * A + j], r);
+            acc = fmaf(U[t * A + i], r, acc);
+        }
+        sTmp[t] = p.c0_scale * acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float c = 0.f;
+        for (int t = 0; t < p.T; t++) c += sTmp[t];
+        sRed[0] = c;
+    }
+    __syncthreads();
+    const float c0 = sRed[0];
+    __syncthreads();
+    return c0;
+}
+
+// n^T quadm n for one step (Python-twin noise cost 0.5*lambda*(1-1/upsilon) eps^T Sigma^-1 eps)
+template <int A>
+__device__ __forceinline__ float quad_cost(const RolloutParams &p, const float (&n)[A])
+{
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < A; i++) {
+        float r = 0.f;
+#pragma unroll
+        for (int j = 0; j < A; j++) r = fmaf(p.quadm[i * A + j], n[j], r);
+        acc = fmaf(n[i], r, acc);
+    }
+    return acc;
+}
+
+// Cost normalisation, pass 1 (controller_base.py:468-474 needs max_k(S_k - beta) before any weight):
+// every CTA publishes its (min, max); the last one reduces them into norm[ctrl] = {beta, max - beta}.
+__device__ inline void publish_minmax(const RolloutParams &p, int ctrl, float bmin, float bmax, float *sRed)
+{
+    __shared__ int s_last_mm;
+    const int stride = partial_stride(p.TA), nparts = gridDim.x;
+    float *mine = p.partials + ((size_t)ctrl * nparts + blockIdx.x) * stride;
+    if (threadIdx.x == 0) { mine[0] = bmin; mine[1] = bmax; }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(&p.counters[ctrl], 1u);
+        s_last_mm = (prev == (unsigned)nparts - 1u);
+    }
+    __syncthreads();
+    if (!s_last_mm) return;
+    __threadfence();
+    if (threadIdx.x == 0) p.counters[ctrl] = 0u;
+    const float *parts = p.partials + (size_t)ctrl * nparts * stride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    float lo = kInf, hi = -kInf;
+    for (int c = tid; c < nparts; c += blockDim.x) {
+        lo = fminf(lo, __ldcg(parts + (size_t)c * stride));
+        hi = fmaxf(hi, __ldcg(parts + (size_t)c * stride + 1));
+    }
+    lo = warp_min(lo);
+    hi = -warp_min(-hi);
+    if (lane == 0) { sRed[warp] = lo; sRed[32 + warp] = hi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nw; w++) { lo = fminf(lo, sRed[w]); hi = fmaxf(hi, sRed[32 + w]); }
+        p.norm[2 * ctrl] = lo;
+        p.norm[2 * ctrl + 1] = hi - lo;
+    }
+}
+
+// Weight exponent scale of the update: -log2(e)/lambda, divided by max(S - beta) in the weight pass of a
+// normalised update (all costs equal: every weight is 1, where the reference divides 0 by 0).
+__device__ __forceinline__ float weight_scale(const RolloutParams &p, int ctrl, float &beta_fixed)
+{
+    if (p.norm_mode != 2) return p.neg_inv_lambda_log2e;
+    beta_fixed = p.norm[2 * ctrl];
+    const float r = p.norm[2 * ctrl + 1];
+    return r > 0.f ? p.neg_inv_lambda_log2e / r : 0.f;
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -415,6 +415,98 @@ void FN(orc_mppi_update_mlp)(int k, int T, int s, int a, int H, REAL lambda, con
     free(zero);
 }
 
+/* ---- Python-twin variants ---------------------------------------
+ * CostBase.action_cost of the Python controller — scripts/src/costs/cost_base.py:114-170:
+ *   0.5 * [ gamma * (u^T S^-1 u + 2 u^T S^-1 eps) + lambda * (1 - 1/upsilon) * eps^T S^-1 eps ]
+ * with u the UN-perturbed action and S = sigma (the unscaled covariance factor). */
+void FN(orc_cost_action_py)(int k, int a, REAL lambda, REAL gamma, REAL upsilon, const REAL *sigma,
+                            const REAL *action, const REAL *noise, REAL *out)
+{
+    REAL inv[ORC_MAX_A * ORC_MAX_A], rhsA[ORC_MAX_A];
+    FN(orc_mat_inverse)(sigma, a, inv);
+    FN(orc_bmm_bcast)(inv, a, a, action, 1, rhsA);                      /* rhsAcost :137-138 */
+    REAL aCost = (REAL)0;
+    for (int j = 0; j < a; j++) aCost += action[j] * rhsA[j];           /* :151-152 */
+    aCost = gamma * aCost;                                              /* :154-155 */
+    for (int i = 0; i < k; i++) {
+        REAL rhsN[ORC_MAX_A];
+        FN(orc_bmm_bcast)(inv, a, a, noise + i * a, 1, rhsN);           /* rhsNcost :134-135 */
+        REAL mix = (REAL)0, nC = (REAL)0;
+        for (int j = 0; j < a; j++) {
+            mix += action[j] * rhsN[j];                                 /* :141-142 */
+            nC += noise[i * a + j] * rhsN[j];                           /* :147-148 */
+        }
+        mix = gamma * ((REAL)2 * mix);                                  /* :144,157-158 */
+        nC = (lambda * ((REAL)1 - (REAL)1 / upsilon)) * nC;             /* :160-162 */
+        out[i] = (REAL)0.5 * ((aCost + mix) + nC);                      /* :165-167 */
+    }
+}
+
+/* Python-twin rollout costs — scripts/src/controllers/controller_base.py:371-434 with
+ * PointMassModel (point_mass_model.py:66-151) and StaticCost.state_cost (static_cost.py:40-63):
+ * same loop as orc_rollout_costs with the action cost above; eps is build_noise's output
+ * (upsilon * sigma) z (:348-369). */
+void FN(orc_rollout_costs_py)(int k0, int k1, int T, int s, int a, REAL dt, REAL mass, REAL lambda,
+                              REAL gamma, REAL upsilon, const REAL *sigma, const REAL *goal,
+                              const REAL *q, const REAL *x0, const REAL *U, const REAL *eps, REAL *costs)
+{
+    REAL A[ORC_MAX_S * ORC_MAX_S], B[ORC_MAX_S * ORC_MAX_A];
+    FN(orc_model_matrices)(mass, dt, s, a, A, B);
+    for (int i = k0; i < k1; i++) {
+        REAL x[ORC_MAX_S], xn[ORC_MAX_S], u[ORC_MAX_A], fr[ORC_MAX_S], ac[ORC_MAX_S];
+        REAL S = (REAL)0, c, acst;
+        for (int j = 0; j < s; j++) x[j] = x0[j];
+        for (int t = 0; t < T; t++) {
+            const REAL *e = eps + ((size_t)i * T + t) * a;
+            const REAL *ut = U + t * a;
+            for (int j = 0; j < a; j++) u[j] = ut[j] + e[j];
+            FN(orc_bmm_bcast)(A, s, s, x, 1, fr);
+            FN(orc_bmm_bcast)(B, s, a, u, 1, ac);
+            for (int j = 0; j < s; j++) xn[j] = fr[j] + ac[j];
+            FN(orc_cost_state)(1, s, xn, goal, q, &c);
+            FN(orc_cost_action_py)(1, a, lambda, gamma, upsilon, sigma, ut, e, &acst);
+            S = S + (c + acst);
+            for (int j = 0; j < s; j++) x[j] = xn[j];
+        }
+        FN(orc_cost_state)(1, s, x, goal, q, &c);
+        costs[i] = c + S;                                               /* add_cost(fCost, cost) :428 */
+    }
+}
+
+/* Python-twin update — controller_base.py:436-474: beta = min S; arg = S - beta, divided by its
+ * maximum when `normalize` (norm_arg :468-474); e = exp(-arg/lambda); w = e / sum e;
+ * U' = U + sum_k w_k eps_k; next = U'[0]; shifted = concat(U'[1:], 0) (:547-560). */
+void FN(orc_mppi_update_py)(int k, int T, int s, int a, REAL dt, REAL mass, REAL lambda, REAL gamma,
+                            REAL upsilon, int normalize, const REAL *sigma, const REAL *goal,
+                            const REAL *q, const REAL *x0, const REAL *U, const REAL *eps, REAL *costs,
+                            REAL *U_new, REAL *next, REAL *U_shift)
+{
+    REAL *zero = (REAL *)calloc((size_t)a, sizeof(REAL));
+    REAL *e = (REAL *)malloc(sizeof(REAL) * (size_t)k);
+    FN(orc_rollout_costs_py)(0, k, T, s, a, dt, mass, lambda, gamma, upsilon, sigma, goal, q, x0, U, eps, costs);
+    REAL beta = costs[0];
+    for (int i = 1; i < k; i++) beta = costs[i] < beta ? costs[i] : beta;
+    REAL mx = (REAL)0;
+    for (int i = 0; i < k; i++) mx = (costs[i] - beta) > mx ? (costs[i] - beta) : mx;
+    REAL nabla = (REAL)0;
+    for (int i = 0; i < k; i++) {
+        REAL arg = costs[i] - beta;
+        if (normalize) arg = arg / mx;
+        e[i] = REAL_EXP(((REAL)(-1) / lambda) * arg);
+        nabla += e[i];
+    }
+    for (int j = 0; j < T * a; j++) U_new[j] = (REAL)0;
+    for (int i = 0; i < k; i++) {
+        REAL w = e[i] / nabla;
+        for (int j = 0; j < T * a; j++) U_new[j] += w * eps[(size_t)i * T * a + j];
+    }
+    for (int j = 0; j < T * a; j++) U_new[j] = U[j] + U_new[j];
+    FN(orc_get_new)(T, a, U_new, 1, next);
+    FN(orc_shift)(T, a, U_new, zero, 1, U_shift);
+    free(e);
+    free(zero);
+}
+
 #undef FN
 #undef CAT
 #undef CAT_

@@ -213,6 +213,34 @@ class Oracle:
                                     _p(U_new), _p(nxt), _p(U_shift))
         return dict(costs=costs, U_new=U_new, next=nxt, U_shift=U_shift)
 
+    def cost_action_py(self, lam, gamma, upsilon, sigma, action, noise):
+        """Python-twin action cost (scripts/src/costs/cost_base.py:114-170)."""
+        noise = _c(noise, self.dt)
+        k, a = noise.shape
+        out = np.empty(k, self.dt)
+        self._fn("orc_cost_action_py")(k, a, self.creal(lam), self.creal(gamma), self.creal(upsilon),
+                                       _p(_c(sigma, self.dt)), _p(_c(action, self.dt)), _p(noise), _p(out))
+        return out
+
+    def mppi_update_py(self, cfg, x0, U, eps, gamma=None, upsilon=1.0, normalize=False):
+        """Python-twin update (controller_base.py:371-474): gamma / upsilon action cost, optional cost
+        normalisation.  eps is the already scaled noise (upsilon * sigma) z."""
+        k, T, s, a = cfg["k"], cfg["tau"], cfg["s_dim"], cfg["a_dim"]
+        eps = _c(eps, self.dt)
+        assert eps.shape == (k, T, a)
+        gamma = cfg["lambda"] if gamma is None else gamma
+        costs = np.empty(k, self.dt)
+        U_new = np.empty((T, a), self.dt)
+        nxt = np.empty(a, self.dt)
+        U_shift = np.empty((T, a), self.dt)
+        self._fn("orc_mppi_update_py")(k, T, s, a, self.creal(cfg["dt"]), self.creal(cfg["mass"]),
+                                       self.creal(cfg["lambda"]), self.creal(gamma), self.creal(upsilon),
+                                       int(bool(normalize)), _p(_c(cfg["sigma"], self.dt)),
+                                       _p(_c(cfg["goal"], self.dt)), _p(_c(cfg["q"], self.dt)),
+                                       _p(_c(x0, self.dt)), _p(_c(U, self.dt)), _p(eps), _p(costs),
+                                       _p(U_new), _p(nxt), _p(U_shift))
+        return dict(costs=costs, U_new=U_new, next=nxt, U_shift=U_shift)
+
     def partial(self, lam, costs, eps, k0, k1):
         costs = _c(costs, self.dt)
         eps = _c(eps, self.dt)

@@ -34,6 +34,15 @@ CASES = [
     dict(name="pm1d", k=64, tau=8, s=2, a=1, mass=1.0, dt=0.1, lam=1.0, full_sigma=False),
     dict(name="pm2d", k=96, tau=10, s=4, a=2, mass=2.0, dt=0.05, lam=0.7, full_sigma=True),
     dict(name="pm3d", k=128, tau=12, s=6, a=3, mass=1.5, dt=0.1, lam=2.0, full_sigma=True),
+    # Python-twin extras: gamma != lambda, upsilon != 1, cost normalisation
+    dict(name="tw1d", k=64, tau=8, s=2, a=1, mass=1.0, dt=0.1, lam=1.3, full_sigma=False, gamma=0.4, upsilon=1.7,
+         normalize=False),
+    dict(name="tw2d", k=96, tau=10, s=4, a=2, mass=2.0, dt=0.05, lam=0.7, full_sigma=True, gamma=0.7, upsilon=1.0,
+         normalize=True),
+    dict(name="tw3d", k=128, tau=12, s=6, a=3, mass=1.5, dt=0.1, lam=2.0, full_sigma=True, gamma=0.9, upsilon=2.5,
+         normalize=True),
+    dict(name="tw3e", k=160, tau=9, s=6, a=3, mass=1.0, dt=0.1, lam=0.5, full_sigma=False, gamma=1.5, upsilon=0.6,
+         normalize=False),
 ]
 
 
@@ -49,14 +58,15 @@ def run_case(c, seed):
     x = rng.uniform(-1, 1, (s, 1))
     U = 0.2 * rng.standard_normal((tau, a, 1))
     z = rng.standard_normal((k, tau, a, 1))
-    eps = np.matmul(sigma, z)                                   # build_noise: sigma @ rng (upsilon = 1)
+    gamma, upsilon, normalize = c.get("gamma", c["lam"]), c.get("upsilon", 1.0), c.get("normalize", False)
+    eps = np.matmul(upsilon * sigma, z)                         # build_noise: (upsilon * sigma) @ rng (:368)
 
     model = PointMassModel(None, mass=c["mass"], dt=c["dt"], stateDim=s, actionDim=a)
-    cost = StaticCost(c["lam"], c["lam"], 1.0, sigma, goal, np.diag(q))     # gamma = lambda, upsilon = 1
-    ctrl = ControllerBase(model, cost, k=k, tau=tau, sDim=s, aDim=a, lam=c["lam"], upsilon=1.0, sigma=sigma,
+    cost = StaticCost(c["lam"], gamma, upsilon, sigma, goal, np.diag(q))
+    ctrl = ControllerBase(model, cost, k=k, tau=tau, sDim=s, aDim=a, lam=c["lam"], upsilon=upsilon, sigma=sigma,
                           initSeq=U.copy())
     costs = ctrl.build_model("rollout", k, x, eps, U)           # [k,1,1]
-    update = ctrl.update("update", costs, eps)                  # uses ctrl._actionSeq = U
+    update = ctrl.update("update", costs, eps, normalize=normalize)   # uses ctrl._actionSeq = U
     nxt = ctrl.get_next("next", update, 1)
     shifted = ctrl.shift("shift", update, ctrl.init_zeros("init", 1), 1)
     p = c["name"] + "_"
@@ -64,7 +74,8 @@ def run_case(c, seed):
             p + "eps": eps[..., 0], p + "costs_py": np.asarray(costs).reshape(k),
             p + "U_new": np.asarray(update)[..., 0], p + "next": np.asarray(nxt).reshape(a),
             p + "U_shift": np.asarray(shifted)[..., 0],
-            p + "meta": np.array([k, tau, s, a, c["mass"], c["dt"], c["lam"]], np.float64)}
+            p + "meta": np.array([k, tau, s, a, c["mass"], c["dt"], c["lam"]], np.float64),
+            p + "twin": np.array([gamma, upsilon, float(normalize)], np.float64)}
 
 
 def main():
