@@ -45,6 +45,10 @@ public:
     bool setSigma(const std::vector<float> &sigma);
     bool setQ(const std::vector<float> &q);
     bool setModelMass(float mass);
+    // Python-twin extras (scripts/src/costs/cost_base.py:114-170, controllers/controller_base.py:368,468-474):
+    // python_form = false keeps lambda u^T S^-1 eps (src/cost_base.cpp:63-68); upsilon scales the sampling
+    bool setActionCost(bool python_form, float gamma, float upsilon);
+    bool setNormalizeCost(bool on);
 
     // stage entry points (the reference's m* methods, :123-359) on plain buffers
     float mBeta(const std::vector<float> &cost);                                            // :123

@@ -137,6 +137,14 @@ int mppi_set_sigma(mppi_handle *h, const float *sigma_host);     /* [a][a], must
  * With injected noise the caller passes the already scaled eps, as the reference's build_noise returns it. */
 typedef enum { MPPI_ACTION_COST_CPP = 0, MPPI_ACTION_COST_PYTHON = 1 } mppi_action_cost_form;
 int mppi_set_action_cost(mppi_handle *h, int form, float gamma, float upsilon);
+/* State-cost functor.  ElipseCost.state_cost
+ * (/root/reference/scripts/src/costs/elipse_cost.py:9-79) on the point_mass2d state (x, vx, y, vy):
+ *   m_state |((x-cx)/a)^2 + ((y-cy)/b)^2 - 1| + m_vel (sqrt(vx^2 + vy^2) - speed)^2
+ * replaces (x-g)^T Q (x-g) in the rollout and as terminal cost; needs s_dim = 4, a_dim = 2.
+ * mppi_set_static_cost switches back to the quadratic StaticCost (goal / q are kept). */
+int mppi_set_ellipse_cost(mppi_handle *h, float a, float b, float center_x, float center_y, float speed,
+                          float m_state, float m_vel);
+int mppi_set_static_cost(mppi_handle *h);
 /* norm_arg (controllers/controller_base.py:468-474): the exponent becomes -(S - beta) / (lambda max_k(S_k - beta)).
  * Costs two launches per update (the range must be known before any weight); world == 1 only in this build. */
 int mppi_set_normalize_cost(mppi_handle *h, int on);
@@ -199,6 +207,9 @@ int mppi_model_step(int device, float mass, float dt, int s, int a, int kst, int
                     const float *action, float *out);
 /* CostBase::mStateCost / mBuildFinalStepCostGraph (src/cost_base.cpp:52-61) */
 int mppi_cost_state(int device, int k, int s, const float *state, const float *goal, const float *q, float *out);
+/* ElipseCost.state_cost (scripts/src/costs/elipse_cost.py:46-79): state [k][4] = (x, vx, y, vy) -> out [k] */
+int mppi_cost_state_ellipse(int device, int k, const float *state, float a, float b, float center_x, float center_y,
+                            float speed, float m_state, float m_vel, float *out);
 /* CostBase::mActionCost (src/cost_base.cpp:63-68): lambda * action^T sigma^-1 noise */
 int mppi_cost_action(int device, int k, int a, float lambda, const float *sigma, const float *action,
                      const float *noise, float *out);

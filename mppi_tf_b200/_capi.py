@@ -60,6 +60,9 @@ SYMBOLS = {
     "mppi_set_sigma": (_i, [_H, _fp]),
     "mppi_set_action_cost": (_i, [_H, _i, _f, _f]),
     "mppi_set_normalize_cost": (_i, [_H, _i]),
+    "mppi_set_ellipse_cost": (_i, [_H] + [_f] * 7),
+    "mppi_set_static_cost": (_i, [_H]),
+    "mppi_cost_state_ellipse": (_i, [_i, _i, _fp] + [_f] * 7 + [_fp]),
     "mppi_set_q": (_i, [_H, _fp]),
     "mppi_set_mass": (_i, [_H, _f]),
     "mppi_set_sequence": (_i, [_H, _fp]),

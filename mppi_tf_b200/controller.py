@@ -103,6 +103,16 @@ class CostBase:
         return out
 
 
+def ellipseStateCost(state, a, b, center_x, center_y, speed, m_state, m_vel, device=-1):
+    """ElipseCost.state_cost (scripts/src/costs/elipse_cost.py:46-79) on the GPU: state [k, 4] -> [k]."""
+    lib = _capi.load()
+    st = _f32(np.asarray(state).reshape(-1, 4))
+    out = np.empty(st.shape[0], np.float32)
+    check(lib.mppi_cost_state_ellipse(device, st.shape[0], _ptr(st), *[float(v) for v in (a, b, center_x, center_y, speed, m_state, m_vel)],
+                                      _ptr(out)))
+    return out
+
+
 def blockDiag(block, nb):
     """utile::blockDiag — src/utile.cpp:10-43."""
     lib = _capi.load()
@@ -237,6 +247,14 @@ class ControllerBase:
         forms = {"cpp": _capi.MPPI_ACTION_COST_CPP, "python": _capi.MPPI_ACTION_COST_PYTHON}
         g = self._lam if gamma is None else float(gamma)
         check(self._lib.mppi_set_action_cost(self._h, forms[form], g, float(upsilon)), self._h)
+
+    def setEllipseCost(self, a, b, center_x, center_y, speed, m_state, m_vel):
+        """ElipseCost (scripts/src/costs/elipse_cost.py:9-79) as the state cost; point_mass2d only."""
+        check(self._lib.mppi_set_ellipse_cost(self._h, *[float(v) for v in (a, b, center_x, center_y, speed, m_state, m_vel)]),
+              self._h)
+
+    def setStaticCost(self):
+        check(self._lib.mppi_set_static_cost(self._h), self._h)
 
     def setNormalizeCost(self, on=True):
         """norm_arg of the Python twin (controller_base.py:468-474): exponent -(S - beta)/(lambda max(S - beta))."""

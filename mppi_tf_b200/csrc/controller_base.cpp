@@ -119,6 +119,13 @@ bool ControllerBase::setLambda(float lambda)
     m_lambda = lambda;
     return true;
 }
+bool ControllerBase::setActionCost(bool python_form, float gamma, float upsilon)
+{
+    return mppi_set_action_cost(m_h, python_form ? MPPI_ACTION_COST_PYTHON : MPPI_ACTION_COST_CPP, gamma, upsilon) == MPPI_OK;
+}
+
+bool ControllerBase::setNormalizeCost(bool on) { return mppi_set_normalize_cost(m_h, on ? 1 : 0) == MPPI_OK; }
+
 bool ControllerBase::setSigma(const std::vector<float> &sigma)
 {
     return sigma.size() == (size_t)m_a_dim * m_a_dim && mppi_set_sigma(m_h, sigma.data()) == MPPI_OK;

@@ -68,6 +68,8 @@ struct mppi_handle {
     float inv_sigma[kMaxA * kMaxA];
     bool normalize = false;
     float *d_norm = nullptr;
+    int cost_kind = 0;            // 0 StaticCost, 1 ElipseCost (mppi_set_ellipse_cost)
+    float ell[8] = {0};
     uint64_t seed = 1;
     uint32_t update_counter = 0, last_update = 0;
     bool have_philox_update = false, last_philox = true, pending_finish = false;
@@ -192,6 +194,8 @@ RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
     }
     p.norm_mode = 0;
     p.norm = h->d_norm;
+    p.cost_kind = h->cost_kind;
+    memcpy(p.ell, h->ell, sizeof(p.ell));
     p.goal_per_ctrl = h->goal_per_ctrl;
     p.key0 = (uint32_t)h->seed;
     p.key1 = (uint32_t)(h->seed >> 32);
@@ -541,6 +545,27 @@ int mppi_set_action_cost(mppi_handle *h, int form, float gamma, float upsilon)
     derive_sigma(h);
     return MPPI_OK;
 }
+static bool ellipse_params(float a, float b, float cx, float cy, float speed, float m_state, float m_vel, float *ell)
+{
+    if (!(a != 0.f) || !(b != 0.f)) return false;
+    ell[0] = 1.0f / a; ell[1] = 1.0f / b; ell[2] = cx; ell[3] = cy; ell[4] = speed; ell[5] = m_state; ell[6] = m_vel; ell[7] = 0.f;
+    return true;
+}
+int mppi_set_ellipse_cost(mppi_handle *h, float a, float b, float center_x, float center_y, float speed, float m_state,
+                          float m_vel)
+{
+    if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
+    if (h->s != 4 || h->a != 2) return fail(h, MPPI_ERR_UNSUPPORTED, "ElipseCost is defined on the point_mass2d state (x, vx, y, vy): s_dim = 4, a_dim = 2");
+    if (!ellipse_params(a, b, center_x, center_y, speed, m_state, m_vel, h->ell)) return fail(h, MPPI_ERR_BAD_ARG, "ellipse axes must be non-zero");
+    h->cost_kind = 1;
+    return MPPI_OK;
+}
+int mppi_set_static_cost(mppi_handle *h)
+{
+    if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
+    h->cost_kind = 0;
+    return MPPI_OK;
+}
 int mppi_set_normalize_cost(mppi_handle *h, int on)
 {
     if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
@@ -801,6 +826,22 @@ static int cost_stage(int device, int k, int s, int a, float lambda, const float
 int mppi_cost_state(int device, int k, int s, const float *state, const float *goal, const float *q, float *out)
 {
     return cost_stage(device, k, s, 0, 1.f, nullptr, goal, q, state, nullptr, nullptr, out, 0);
+}
+int mppi_cost_state_ellipse(int device, int k, const float *state, float a, float b, float center_x, float center_y,
+                            float speed, float m_state, float m_vel, float *out)
+{
+    if (!state || !out || k <= 0) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad ellipse-cost argument");
+    float ell[8];
+    if (!ellipse_params(a, b, center_x, center_y, speed, m_state, m_vel, ell)) return fail(nullptr, MPPI_ERR_BAD_ARG, "ellipse axes must be non-zero");
+    int rc = stage_device(device);
+    if (rc) return rc;
+    DevBuf dst, dout;
+    CU_TRY_S(dst.alloc(sizeof(float) * (size_t)k * 4));
+    CU_TRY_S(dout.alloc(sizeof(float) * (size_t)k));
+    CU_TRY_S(cudaMemcpy(dst.p, state, sizeof(float) * (size_t)k * 4, cudaMemcpyHostToDevice));
+    CU_TRY_S(launch_ellipse_cost(k, dst.as<float>(), ell, dout.as<float>(), 0));
+    CU_TRY_S(cudaMemcpy(out, dout.p, sizeof(float) * (size_t)k, cudaMemcpyDeviceToHost));
+    return MPPI_OK;
 }
 int mppi_cost_action(int device, int k, int a, float lambda, const float *sigma, const float *action,
                      const float *noise, float *out)

@@ -41,6 +41,10 @@ struct RolloutParams {
     float inv_sigma[kMaxA * kMaxA];         // Sigma^-1 (for c0_t)
     int quad;                               // != 0: the quadratic noise term is present
     float quadm[kMaxA * kMaxA];             // 0.5*lambda*(1-1/upsilon) * M, M = Sigma^-1 (n = eps) or (uS)^T S^-1 (uS) (n = z)
+    // state-cost functor: 0 = StaticCost (x-g)^T Q (x-g); 1 = ElipseCost (scripts/src/costs/elipse_cost.py:46-79),
+    // point_mass2d only: ell = {1/a, 1/b, cx, cy, speed, m_state, m_vel}
+    int cost_kind;
+    float ell[8];
     int norm_mode;                          // cost normalisation: 0 off, 1 = cost pass (min/max only), 2 = weight pass
     float *norm;                            // [n_ctrl][2] beta, max(S - beta) written by pass 1, read by pass 2
     // Philox key / counter words
@@ -262,6 +266,16 @@ struct PointMass {
     }
 };
 
+// ElipseCost.state_cost (scripts/src/costs/elipse_cost.py:46-79), state (x, vx, y, vy):
+//   m_state |((x-cx)/a)^2 + ((y-cy)/b)^2 - 1| + m_vel (sqrt(vx^2 + vy^2) - speed)^2
+__device__ __forceinline__ float ellipse_cost(const float *ell, float x, float vx, float y, float vy)
+{
+    const float dx = (x - ell[2]) * ell[0], dy = (y - ell[3]) * ell[1];
+    const float d = fabsf(fmaf(dx, dx, dy * dy) - 1.0f);
+    const float dv = __fsqrt_rn(fmaf(vx, vx, vy * vy)) - ell[4];
+    return fmaf(ell[5], d, ell[6] * dv * dv);
+}
+
 // Per-sample cost accumulator: pair lanes + scalar, folded once at the end.
 struct CostAcc {
     float2 a2;
@@ -269,6 +283,17 @@ struct CostAcc {
     __device__ __forceinline__ void zero() { a2 = make_float2(0.f, 0.f); a = 0.f; }
     __device__ __forceinline__ float total() const { return (a2.x + a2.y) + a; }
 };
+
+// q(x) of the selected state-cost functor, added into S
+template <int A, int COST>
+__device__ __forceinline__ void add_state_cost(const PointMass<A> &x, const ModelConsts<A> &mc, const RolloutParams &p, CostAcc &S)
+{
+    if (COST == 1) {
+        S.a += ellipse_cost(p.ell, x.p.get(0), x.v.get(0), x.p.get(A > 1 ? 1 : 0), x.v.get(A > 1 ? 1 : 0));
+    } else {
+        x.state_cost(mc, S.a2, S.a);
+    }
+}
 
 // mbarrier / bulk-copy (TMA) helpers -----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

@@ -64,6 +64,20 @@ __device__ __forceinline__ void noise4(const RolloutParams &p, const float *eps_
     }
 }
 
+// state cost of the selected functor (grid-uniform branch; the MLP step is not bound by the CUDA cores)
+template <int S>
+__device__ __forceinline__ float mlp_state_cost(const RolloutParams &p, const float (&x)[S], const float (&g)[S], const float (&q)[S])
+{
+    if (p.cost_kind == 1 && S == 4) return ellipse_cost(p.ell, x[0], x[1], x[S > 2 ? 2 : 0], x[S > 3 ? 3 : 0]);
+    float c = 0.f;
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+        const float d = x[i] - g[i];
+        c = fmaf(q[i] * d, d, c);
+    }
+    return c;
+}
+
 template <int A, bool PHILOX>
 __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __grid_constant__ RolloutParams p, MlpParams mp)
 {
@@ -163,13 +177,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
                     // in the shadow of layer 1: state cost of the state the step started from (it is
                     // step ts-1's q(x_ts)), and this step's action cost
                     if (ts > 0) {
-                        float c = 0.f;
-#pragma unroll
-                        for (int i = 0; i < S; i++) {
-                            const float d = x[i] - g[i];
-                            c = fmaf(q[i] * d, d, c);
-                        }
-                        Sk += c;
+                        Sk += mlp_state_cost<S>(p, x, g, q);
                     }
                     Sk += ac;
                     mlp_row_layer1(t);
@@ -190,12 +198,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
                 for (int i = 0; i < 4 * A; i++) z[i] = zn[i];
             }
             {
-                float c = 0.f;                       // q(x_T) of step T-1 plus the terminal cost (src/controller_base.cpp:271-272)
-#pragma unroll
-                for (int i = 0; i < S; i++) {
-                    const float d = x[i] - g[i];
-                    c = fmaf(q[i] * d, d, c);
-                }
+                const float c = mlp_state_cost<S>(p, x, g, q);   // q(x_T) of step T-1 plus the terminal cost (src/controller_base.cpp:271-272)
                 Sk += c;
                 Sk += c;
             }

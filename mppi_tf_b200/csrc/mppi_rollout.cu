@@ -53,7 +53,7 @@ __device__ __forceinline__ void vec_from(const float *z, Vec<A> &n)
 // One rollout step for one sample (src/controller_base.cpp:251-269):
 //   u = U_t + eps_t ; x <- A x + (B/m) u ; S += q(x) + lambda U_t^T Sigma^-1 eps_t
 // `n` is z_t in Philox mode (eps_t = Sigma z_t formed here) and eps_t in injected mode.
-template <int A, bool PHILOX, bool DIAG, bool QUAD>
+template <int A, bool PHILOX, bool DIAG, bool QUAD, int COST>
 __device__ __forceinline__ void rollout_step(PointMass<A> &x, CostAcc &S, const float *uv_row, const Vec<A> &n,
                                              const RolloutParams &p, const ModelConsts<A> &mc, const Vec<A> &sigd)
 {
@@ -85,7 +85,7 @@ __device__ __forceinline__ void rollout_step(PointMass<A> &x, CostAcc &S, const 
         S.a += quad_cost<A>(p, nn);
     }
     x.step(u, mc);
-    x.state_cost(mc, S.a2, S.a);
+    add_state_cost<A, COST>(x, mc, p, S);
 }
 
 template <int A>
@@ -108,7 +108,7 @@ __device__ __forceinline__ void thread_consts(const RolloutParams &p, int ctrl, 
 // -------------------------------------------------------------------------------------------------
 // Philox mode
 // -------------------------------------------------------------------------------------------------
-template <int A, bool DIAG, bool QUAD>
+template <int A, bool DIAG, bool QUAD, int COST>
 __global__ void __launch_bounds__(kPhiloxThreads, kPhiloxCtasPerSm)
 rollout_philox_kernel(const __grid_constant__ RolloutParams p)
 {
@@ -167,7 +167,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
             for (int tt = 0; tt < 4; tt++) {
                 Vec<A> n;
                 vec_from<A>(&z[tt * A], n);
-                rollout_step<A, true, DIAG, QUAD>(x, S, uv + tt * RS, n, p, mc, sigd);
+                rollout_step<A, true, DIAG, QUAD, COST>(x, S, uv + tt * RS, n, p, mc, sigd);
             }
             uv += 4 * RS;
         }
@@ -180,10 +180,10 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
                 if (tt < trem) {
                     Vec<A> n;
                     vec_from<A>(&z[tt * A], n);
-                    rollout_step<A, true, DIAG, QUAD>(x, S, uv + tt * RS, n, p, mc, sigd);
+                    rollout_step<A, true, DIAG, QUAD, COST>(x, S, uv + tt * RS, n, p, mc, sigd);
                 }
         }
-        x.state_cost(mc, S.a2, S.a);    // terminal cost on top of step T-1's (src/controller_base.cpp:271-272)
+        add_state_cost<A, COST>(x, mc, p, S);    // terminal cost on top of step T-1's (src/controller_base.cpp:271-272)
         const float Sk = S.total();
         costs[k] = Sk;
         bmin = fminf(bmin, Sk);
@@ -299,7 +299,7 @@ __device__ __forceinline__ void load_block(const float *row, int tb, int TA, flo
     }
 }
 
-template <int A, bool TMA, bool QUAD>
+template <int A, bool TMA, bool QUAD, int COST>
 __global__ void __launch_bounds__(512, 1)
 rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedLaunch L)
 {
@@ -476,7 +476,7 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
                         for (int tt = 0; tt < 4; tt++) {
                             Vec<A> n;
                             vec_from<A>(&e[tt * A], n);
-                            rollout_step<A, false, false, QUAD>(x, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
+                            rollout_step<A, false, false, QUAD, COST>(x, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
                         }
                     } else {
                         load_block<A, TMA, true>(row, tb, TA, e);
@@ -485,11 +485,11 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
                             if (4 * tb + tt < p.T) {
                                 Vec<A> n;
                                 vec_from<A>(&e[tt * A], n);
-                                rollout_step<A, false, false, QUAD>(x, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
+                                rollout_step<A, false, false, QUAD, COST>(x, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
                             }
                     }
                 }
-                if (tb1 == nblk && tb0 < tb1) x.state_cost(mc, Sa.a2, Sa.a);   // terminal cost (src/controller_base.cpp:271-272)
+                if (tb1 == nblk && tb0 < tb1) add_state_cost<A, COST>(x, mc, p, Sa);   // terminal cost (src/controller_base.cpp:271-272)
                 S = Sa.total();
                 if (C > 1) {
                     sS[(grp * C + cw) * 32 + lane] = S;
@@ -656,12 +656,12 @@ static size_t philox_smem_bytes(int A, int T, int TA)
     return sizeof(float) * ((size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 64) + sizeof(float4) * kPhiloxThreads;
 }
 
-template <int A, bool DIAG, bool QUAD>
+template <int A, bool DIAG, bool QUAD, int COST>
 static cudaError_t launch_philox_V(const RolloutParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
-    cudaError_t err = cudaFuncSetAttribute(rollout_philox_kernel<A, DIAG, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(rollout_philox_kernel<A, DIAG, QUAD, COST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    rollout_philox_kernel<A, DIAG, QUAD><<<grid, kPhiloxThreads, smem, st>>>(p);
+    rollout_philox_kernel<A, DIAG, QUAD, COST><<<grid, kPhiloxThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -669,9 +669,16 @@ template <int A>
 static cudaError_t launch_philox_A(const RolloutParams &p, dim3 grid, cudaStream_t st)
 {
     const size_t smem = philox_smem_bytes(A, p.T, p.TA);
-    if (p.quad) return launch_philox_V<A, false, true>(p, grid, smem, st);      // noise-quadratic cost: general-Sigma variant
-    if (p.sigma_diag) return launch_philox_V<A, true, false>(p, grid, smem, st);
-    return launch_philox_V<A, false, false>(p, grid, smem, st);
+    if (p.cost_kind == 1) {                      // ElipseCost: point_mass2d only, general-Sigma variants
+        if constexpr (A == 2) {
+            return p.quad ? launch_philox_V<2, false, true, 1>(p, grid, smem, st) : launch_philox_V<2, false, false, 1>(p, grid, smem, st);
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
+    if (p.quad) return launch_philox_V<A, false, true, 0>(p, grid, smem, st);      // noise-quadratic cost: general-Sigma variant
+    if (p.sigma_diag) return launch_philox_V<A, true, false, 0>(p, grid, smem, st);
+    return launch_philox_V<A, false, false, 0>(p, grid, smem, st);
 }
 
 #define MPPI_DISPATCH_A(a, ...)                  \
@@ -755,12 +762,12 @@ bool injected_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sm
     return true;
 }
 
-template <int A, bool TMA, bool QUAD>
+template <int A, bool TMA, bool QUAD, int COST>
 static cudaError_t launch_injected_V(const RolloutParams &p, InjectedLaunch L, dim3 grid, size_t smem, cudaStream_t st)
 {
-    cudaError_t err = cudaFuncSetAttribute(rollout_injected_kernel<A, TMA, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(rollout_injected_kernel<A, TMA, QUAD, COST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    rollout_injected_kernel<A, TMA, QUAD><<<grid, L.ng * L.c * 32, smem, st>>>(p, L);
+    rollout_injected_kernel<A, TMA, QUAD, COST><<<grid, L.ng * L.c * 32, smem, st>>>(p, L);
     return cudaGetLastError();
 }
 
@@ -768,8 +775,16 @@ template <int A>
 static cudaError_t launch_injected_A(const RolloutParams &p, InjectedLaunch L, dim3 grid, size_t smem, bool tma,
                                      cudaStream_t st)
 {
-    if (p.quad) return tma ? launch_injected_V<A, true, true>(p, L, grid, smem, st) : launch_injected_V<A, false, true>(p, L, grid, smem, st);
-    return tma ? launch_injected_V<A, true, false>(p, L, grid, smem, st) : launch_injected_V<A, false, false>(p, L, grid, smem, st);
+    if (p.cost_kind == 1) {                      // ElipseCost: point_mass2d only
+        if constexpr (A == 2) {
+            if (p.quad) return tma ? launch_injected_V<2, true, true, 1>(p, L, grid, smem, st) : launch_injected_V<2, false, true, 1>(p, L, grid, smem, st);
+            return tma ? launch_injected_V<2, true, false, 1>(p, L, grid, smem, st) : launch_injected_V<2, false, false, 1>(p, L, grid, smem, st);
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
+    if (p.quad) return tma ? launch_injected_V<A, true, true, 0>(p, L, grid, smem, st) : launch_injected_V<A, false, true, 0>(p, L, grid, smem, st);
+    return tma ? launch_injected_V<A, true, false, 0>(p, L, grid, smem, st) : launch_injected_V<A, false, false, 0>(p, L, grid, smem, st);
 }
 
 cudaError_t launch_rollout_injected(RolloutParams p, int a, int num_sms, size_t smem_limit, cudaStream_t st,

@@ -56,6 +56,15 @@ __global__ void cost_kernel(int k, int s, int a, float lambda, const float *inv_
     }
 }
 
+// ElipseCost.state_cost (scripts/src/costs/elipse_cost.py:46-79): state [k][4] = (x, vx, y, vy)
+__global__ void ellipse_cost_kernel(int k, const float *state, float ia, float ib, float cx, float cy, float speed,
+                                    float m_state, float m_vel, float *out)
+{
+    const float ell[8] = {ia, ib, cx, cy, speed, m_state, m_vel, 0.f};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x)
+        out[i] = ellipse_cost(ell, state[4 * i], state[4 * i + 1], state[4 * i + 2], state[4 * i + 3]);
+}
+
 // ControllerBase::mPrepareNoise (src/controller_base.cpp:210-213): noise[:, t] -> [k][a]
 __global__ void prepare_noise_kernel(int k, int T, int a, const float *noise, int t, float *out)
 {
@@ -181,6 +190,12 @@ cudaError_t launch_cost(int k, int s, int a, float lambda, const float *inv_sigm
                         float *out, int mode, cudaStream_t st)
 {
     cost_kernel<<<blocks_for(k, 256), 256, 0, st>>>(k, s, a, lambda, inv_sigma, goal, q, state, action, noise, out, mode);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ellipse_cost(int k, const float *state, const float *ell, float *out, cudaStream_t st)
+{
+    ellipse_cost_kernel<<<blocks_for(k, 256), 256, 0, st>>>(k, state, ell[0], ell[1], ell[2], ell[3], ell[4], ell[5], ell[6], out);
     return cudaGetLastError();
 }
 

@@ -442,13 +442,30 @@ void FN(orc_cost_action_py)(int k, int a, REAL lambda, REAL gamma, REAL upsilon,
     }
 }
 
+/* ElipseCost.state_cost — scripts/src/costs/elipse_cost.py:46-79; state [k][4] = (x, vx, y, vy);
+ * ell = {a, b, cx, cy, speed, m_state, m_vel}:
+ *   v = sqrt(vx^2 + vy^2); d = |((x-cx)/a)^2 + ((y-cy)/b)^2 - 1|; cost = m_state d + m_vel (v - speed)^2 */
+void FN(orc_cost_state_ellipse)(int k, const REAL *state, const REAL *ell, REAL *out)
+{
+    for (int i = 0; i < k; i++) {
+        REAL x = state[4 * i], vx = state[4 * i + 1], y = state[4 * i + 2], vy = state[4 * i + 3];
+        REAL v = (REAL)sqrt((double)(vx * vx + vy * vy));                       /* :68 */
+        REAL diffx = (x - ell[2]) / ell[0], diffy = (y - ell[3]) / ell[1];      /* :69-70 */
+        REAL d = diffx * diffx + diffy * diffy - (REAL)1;                       /* :71 */
+        d = ell[5] * (d < (REAL)0 ? -d : d);                                    /* :71-72 */
+        REAL dv = ell[6] * ((v - ell[4]) * (v - ell[4]));                       /* :73-74 */
+        out[i] = d + dv;                                                        /* :75 */
+    }
+}
+
 /* Python-twin rollout costs — scripts/src/controllers/controller_base.py:371-434 with
  * PointMassModel (point_mass_model.py:66-151) and StaticCost.state_cost (static_cost.py:40-63):
  * same loop as orc_rollout_costs with the action cost above; eps is build_noise's output
  * (upsilon * sigma) z (:348-369). */
 void FN(orc_rollout_costs_py)(int k0, int k1, int T, int s, int a, REAL dt, REAL mass, REAL lambda,
                               REAL gamma, REAL upsilon, const REAL *sigma, const REAL *goal,
-                              const REAL *q, const REAL *x0, const REAL *U, const REAL *eps, REAL *costs)
+                              const REAL *q, const REAL *ell /* NULL: StaticCost; else ElipseCost, s == 4 */,
+                              const REAL *x0, const REAL *U, const REAL *eps, REAL *costs)
 {
     REAL A[ORC_MAX_S * ORC_MAX_S], B[ORC_MAX_S * ORC_MAX_A];
     FN(orc_model_matrices)(mass, dt, s, a, A, B);
@@ -463,12 +480,14 @@ void FN(orc_rollout_costs_py)(int k0, int k1, int T, int s, int a, REAL dt, REAL
             FN(orc_bmm_bcast)(A, s, s, x, 1, fr);
             FN(orc_bmm_bcast)(B, s, a, u, 1, ac);
             for (int j = 0; j < s; j++) xn[j] = fr[j] + ac[j];
-            FN(orc_cost_state)(1, s, xn, goal, q, &c);
+            if (ell) FN(orc_cost_state_ellipse)(1, xn, ell, &c);
+            else FN(orc_cost_state)(1, s, xn, goal, q, &c);
             FN(orc_cost_action_py)(1, a, lambda, gamma, upsilon, sigma, ut, e, &acst);
             S = S + (c + acst);
             for (int j = 0; j < s; j++) x[j] = xn[j];
         }
-        FN(orc_cost_state)(1, s, x, goal, q, &c);
+        if (ell) FN(orc_cost_state_ellipse)(1, x, ell, &c);
+        else FN(orc_cost_state)(1, s, x, goal, q, &c);
         costs[i] = c + S;                                               /* add_cost(fCost, cost) :428 */
     }
 }
@@ -478,12 +497,12 @@ void FN(orc_rollout_costs_py)(int k0, int k1, int T, int s, int a, REAL dt, REAL
  * U' = U + sum_k w_k eps_k; next = U'[0]; shifted = concat(U'[1:], 0) (:547-560). */
 void FN(orc_mppi_update_py)(int k, int T, int s, int a, REAL dt, REAL mass, REAL lambda, REAL gamma,
                             REAL upsilon, int normalize, const REAL *sigma, const REAL *goal,
-                            const REAL *q, const REAL *x0, const REAL *U, const REAL *eps, REAL *costs,
-                            REAL *U_new, REAL *next, REAL *U_shift)
+                            const REAL *q, const REAL *ell, const REAL *x0, const REAL *U, const REAL *eps,
+                            REAL *costs, REAL *U_new, REAL *next, REAL *U_shift)
 {
     REAL *zero = (REAL *)calloc((size_t)a, sizeof(REAL));
     REAL *e = (REAL *)malloc(sizeof(REAL) * (size_t)k);
-    FN(orc_rollout_costs_py)(0, k, T, s, a, dt, mass, lambda, gamma, upsilon, sigma, goal, q, x0, U, eps, costs);
+    FN(orc_rollout_costs_py)(0, k, T, s, a, dt, mass, lambda, gamma, upsilon, sigma, goal, q, ell, x0, U, eps, costs);
     REAL beta = costs[0];
     for (int i = 1; i < k; i++) beta = costs[i] < beta ? costs[i] : beta;
     REAL mx = (REAL)0;

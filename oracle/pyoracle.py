@@ -222,9 +222,17 @@ class Oracle:
                                        _p(_c(sigma, self.dt)), _p(_c(action, self.dt)), _p(noise), _p(out))
         return out
 
-    def mppi_update_py(self, cfg, x0, U, eps, gamma=None, upsilon=1.0, normalize=False):
+    def cost_state_ellipse(self, state, ell):
+        """ElipseCost.state_cost (scripts/src/costs/elipse_cost.py:46-79); ell = (a, b, cx, cy, speed, m_state, m_vel)."""
+        state = _c(np.asarray(state).reshape(-1, 4), self.dt)
+        out = np.empty(state.shape[0], self.dt)
+        self._fn("orc_cost_state_ellipse")(state.shape[0], _p(state), _p(_c(ell, self.dt)), _p(out))
+        return out
+
+    def mppi_update_py(self, cfg, x0, U, eps, gamma=None, upsilon=1.0, normalize=False, ellipse=None):
         """Python-twin update (controller_base.py:371-474): gamma / upsilon action cost, optional cost
-        normalisation.  eps is the already scaled noise (upsilon * sigma) z."""
+        normalisation, optional ElipseCost state cost (ellipse = (a, b, cx, cy, speed, m_state, m_vel)).
+        eps is the already scaled noise (upsilon * sigma) z."""
         k, T, s, a = cfg["k"], cfg["tau"], cfg["s_dim"], cfg["a_dim"]
         eps = _c(eps, self.dt)
         assert eps.shape == (k, T, a)
@@ -237,6 +245,7 @@ class Oracle:
                                        self.creal(cfg["lambda"]), self.creal(gamma), self.creal(upsilon),
                                        int(bool(normalize)), _p(_c(cfg["sigma"], self.dt)),
                                        _p(_c(cfg["goal"], self.dt)), _p(_c(cfg["q"], self.dt)),
+                                       _p(_c(ellipse, self.dt)) if ellipse is not None else None,
                                        _p(_c(x0, self.dt)), _p(_c(U, self.dt)), _p(eps), _p(costs),
                                        _p(U_new), _p(nxt), _p(U_shift))
         return dict(costs=costs, U_new=U_new, next=nxt, U_shift=U_shift)

@@ -28,6 +28,7 @@ from scripts.src.models import model_base as ref_model_base          # noqa: E40
 ref_model_base.ModelBase.add_model_vars = lambda self, name, var: self._modelVars.__setitem__(name, var)
 from scripts.src.models.point_mass_model import PointMassModel       # noqa: E402
 from scripts.src.costs.static_cost import StaticCost                 # noqa: E402
+from scripts.src.costs.elipse_cost import ElipseCost                 # noqa: E402
 from scripts.src.controllers.controller_base import ControllerBase   # noqa: E402
 
 CASES = [
@@ -41,6 +42,11 @@ CASES = [
          normalize=True),
     dict(name="tw3d", k=128, tau=12, s=6, a=3, mass=1.5, dt=0.1, lam=2.0, full_sigma=True, gamma=0.9, upsilon=2.5,
          normalize=True),
+    # ElipseCost as the state cost, point_mass2d
+    dict(name="el2d", k=128, tau=14, s=4, a=2, mass=1.0, dt=0.1, lam=0.6, full_sigma=True, gamma=0.6, upsilon=1.0,
+         normalize=False, ellipse=(1.5, 0.8, 0.2, -0.1, 0.7, 2.0, 0.5)),
+    dict(name="el2n", k=96, tau=11, s=4, a=2, mass=2.0, dt=0.05, lam=1.1, full_sigma=False, gamma=0.3, upsilon=1.4,
+         normalize=True, ellipse=(1.0, 1.0, 0.0, 0.0, 1.0, 1.0, 1.0)),
     dict(name="tw3e", k=160, tau=9, s=6, a=3, mass=1.0, dt=0.1, lam=0.5, full_sigma=False, gamma=1.5, upsilon=0.6,
          normalize=False),
 ]
@@ -62,7 +68,11 @@ def run_case(c, seed):
     eps = np.matmul(upsilon * sigma, z)                         # build_noise: (upsilon * sigma) @ rng (:368)
 
     model = PointMassModel(None, mass=c["mass"], dt=c["dt"], stateDim=s, actionDim=a)
-    cost = StaticCost(c["lam"], gamma, upsilon, sigma, goal, np.diag(q))
+    if "ellipse" in c:
+        ea, eb, ecx, ecy, espeed, ems, emv = c["ellipse"]
+        cost = ElipseCost(c["lam"], gamma, upsilon, sigma, ea, eb, ecx, ecy, espeed, ems, emv)
+    else:
+        cost = StaticCost(c["lam"], gamma, upsilon, sigma, goal, np.diag(q))
     ctrl = ControllerBase(model, cost, k=k, tau=tau, sDim=s, aDim=a, lam=c["lam"], upsilon=upsilon, sigma=sigma,
                           initSeq=U.copy())
     costs = ctrl.build_model("rollout", k, x, eps, U)           # [k,1,1]
@@ -75,7 +85,8 @@ def run_case(c, seed):
             p + "U_new": np.asarray(update)[..., 0], p + "next": np.asarray(nxt).reshape(a),
             p + "U_shift": np.asarray(shifted)[..., 0],
             p + "meta": np.array([k, tau, s, a, c["mass"], c["dt"], c["lam"]], np.float64),
-            p + "twin": np.array([gamma, upsilon, float(normalize)], np.float64)}
+            p + "twin": np.array([gamma, upsilon, float(normalize)], np.float64),
+            p + "ellipse": np.array(c.get("ellipse", ()), np.float64)}
 
 
 def main():

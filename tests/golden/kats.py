@@ -151,6 +151,19 @@ COST_CASES = [
 # which is outside the C++ API (Q = Diag(q), src/cost_base.cpp:40) — listed, not replayed.
 
 # ---------------------------------------------------------------------------------------------
+# ElipseCost (Python twin) — scripts/test.py:1098-1161: a = b = 1, centre (0, 0), speed 1,
+# m_state = m_vel = 1; states (x, vx, y, vy)
+# ---------------------------------------------------------------------------------------------
+ELLIPSE_PARAMS = (1.0, 1.0, 0.0, 0.0, 1.0, 1.0, 1.0)        # a, b, cx, cy, speed, m_state, m_vel (:1102-1109)
+ELLIPSE_CASES = [
+    dict(name="testStepElipseCost_s4_l1_k1",                # :1111-1131
+         state=[[0., 0.5, 1., 0.]], expected=[0.25]),
+    dict(name="testStepElipseCost_s4_l1_k5",                # :1133-1161
+         state=[[0., 0.5, 1., 0.], [0., 2., 0., 0.], [10., 2., 2., 3.], [1., 1., 1., 2.], [3., 4., 5., 6.]],
+         expected=[0.25, 2, 103 + 6.788897449072021, 1 + 1.5278640450004208, 33 + 38.57779489814404]),
+]
+
+# ---------------------------------------------------------------------------------------------
 # ControllerBase — test/test_controller.cpp (k=5, tau=3, a_dim=2, s_dim=4, dt=0.01, lambda=1)
 # ---------------------------------------------------------------------------------------------
 CTRL = dict(

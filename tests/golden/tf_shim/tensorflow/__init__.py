@@ -108,6 +108,18 @@ def clip_by_value(x, lo, hi, name=None):
     return np.clip(_a(x), lo, hi)
 
 
+def sqrt(x, name=None):
+    return np.sqrt(_a(x))
+
+
+def pow(x, y, name=None):                      # noqa: A001  (tf.pow)
+    return np.power(_a(x), y)
+
+
+def abs(x, name=None):                         # noqa: A001  (tf.abs)
+    return np.abs(_a(x))
+
+
 @contextlib.contextmanager
 def name_scope(name):
     yield name

@@ -78,6 +78,14 @@ def test_cost_set_goal_takes_effect():
     assert cost.setGoal([1, 2, 3]) is False             # wrong size, src/controller_base.cpp:127-130
 
 
+@pytest.mark.parametrize("case", kats.ELLIPSE_CASES, ids=lambda c: c["name"])
+def test_ellipse_cost(case):
+    """ElipseCost.state_cost KATs, scripts/test.py:1098-1161 (assertAllClose: rtol 1e-6)."""
+    from mppi_tf_b200 import ellipseStateCost
+    got = ellipseStateCost(case["state"], *kats.ELLIPSE_PARAMS)
+    np.testing.assert_allclose(got, case["expected"], rtol=1e-6, atol=1e-6)
+
+
 def test_data_prep(ctrl):
     for t in range(3):
         np.testing.assert_allclose(ctrl.prepareAction(kats.CTRL["action"], t), f32(kats.CTRL_PREP["a"][t]), **FLOAT_EQ)

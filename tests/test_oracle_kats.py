@@ -78,6 +78,14 @@ def test_cost_action_general_sigma(oracle64):
 
 
 # ---- ControllerBase stages -------------------------------------------------------------------
+@pytest.mark.parametrize("case", kats.ELLIPSE_CASES, ids=lambda c: c["name"])
+def test_ellipse_cost(oracle64, oracle32, case):
+    """scripts/test.py:1098-1161 (assertAllClose: rtol 1e-6)."""
+    for orc in (oracle64, oracle32):
+        got = orc.cost_state_ellipse(case["state"], kats.ELLIPSE_PARAMS)
+        np.testing.assert_allclose(got, case["expected"], rtol=1e-6, atol=1e-6)
+
+
 def test_data_prep(oracle32):
     for t in range(3):
         np.testing.assert_allclose(oracle32.prepare_action(kats.CTRL["action"], t),

@@ -177,3 +177,50 @@ def test_mlp_dynamics_with_twin_cost(oracle64):
     assert rel_err(U_py, U_cpp) < 1e-4
     ref = oracle64.mppi_update_mlp(cfg, mlp, x0, U0, eps)
     assert rel_err(U_cpp, ref["U_new"]) < 2e-2
+
+
+@pytest.mark.parametrize("k,tau,normalize,upsilon", [(4096, 50, False, 1.0), (3000, 27, True, 1.6), (8192, 100, False, 0.8)])
+def test_ellipse_cost_update(oracle64, oracle32, k, tau, normalize, upsilon):
+    """ElipseCost (elipse_cost.py:46-79) as the rollout / terminal state cost, both noise modes."""
+    a, s = 2, 4
+    ell = (1.5, 0.8, 0.2, -0.1, 0.7, 2.0, 0.5)
+    cfg = make_cfg(k, tau, s, a, lam=0.9, sigma=_full_sigma(a, 21))
+    x0, U0, eps = _inputs(cfg, 31, upsilon)
+    c = controller_from_cfg(cfg, seed=3)
+    try:
+        c.setActionCost("python", gamma=0.4, upsilon=upsilon)
+        c.setNormalizeCost(normalize)
+        c.setEllipseCost(*ell)
+        c.setSequence(U0)
+        act = c.nextWithNoise(x0, eps)
+        U_inj, costs_inj = c.getUpdate(), c.getCosts()
+        c.setSequence(U0)
+        c.next(x0)
+        U_phx, costs_phx, eps_phx = c.getUpdate(), c.getCosts(), c.dumpNoise()
+        c.setStaticCost()
+        c.setSequence(U0)
+        c.nextWithNoise(x0, eps)
+        costs_static = c.getCosts()
+    finally:
+        c.close()
+    kw = dict(gamma=0.4, upsilon=upsilon, normalize=normalize, ellipse=ell)
+    ref, ref32 = oracle64.mppi_update_py(cfg, x0, U0, eps, **kw), oracle32.mppi_update_py(cfg, x0, U0, eps, **kw)
+    assert rel_err(costs_inj, ref["costs"]) < 1e-5
+    assert_update_close(U_inj, ref["U_new"], ref32["U_new"], what="U_new injected")
+    assert np.abs(act - ref["next"]).max() <= max(1e-5, 3 * rel_err(ref32["U_new"], ref["U_new"])) * np.abs(ref["U_new"]).max()
+    ref, ref32 = oracle64.mppi_update_py(cfg, x0, U0, eps_phx, **kw), oracle32.mppi_update_py(cfg, x0, U0, eps_phx, **kw)
+    assert rel_err(costs_phx, ref["costs"]) < 1e-5
+    assert_update_close(U_phx, ref["U_new"], ref32["U_new"], what="U_new philox")
+    kw["ellipse"] = None                       # and back to the quadratic cost
+    assert rel_err(costs_static, oracle64.mppi_update_py(cfg, x0, U0, eps, **kw)["costs"]) < 1e-5
+
+
+def test_ellipse_cost_needs_point_mass2d():
+    from mppi_tf_b200 import ControllerBase, MppiError, _capi
+    c = ControllerBase(256, 8, 0.1, 1.0, 6, 3)
+    try:
+        with pytest.raises(MppiError) as e:
+            c.setEllipseCost(1, 1, 0, 0, 1, 1, 1)
+        assert e.value.code == _capi.MPPI_ERR_UNSUPPORTED
+    finally:
+        c.close()
