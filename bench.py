@@ -358,6 +358,10 @@ def main():
         inj = statistics.mean(ims)
         del eps
     clocks = sampler.stop() if sampler else None
+    # fraction of this rank's samples whose fp32 softmin weight is non-zero after the last update: the weighted
+    # noise sum revisits only those (an exact optimisation: 0 * z adds nothing), so the number is part of the workload
+    c_last = np.asarray(ctrl.getCosts(), np.float64).reshape(n_local, -1)
+    nonzero_frac = float(np.mean((c_last - c_last.min(1, keepdims=True)) * 1.4426950408889634 / 1.0 < 126.0))
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -374,7 +378,8 @@ def main():
                        "mode": "philox (fresh noise regenerated in registers every update)",
                        "sharding": f"K/{k_world} samples per rank" if n_ctrl == 1 else f"{n_local} controllers per rank",
                        "exchange": (args.exchange if exchange else "none"),
-                       "l2": "flushed between timed iterations (256 MiB write, untimed)"},
+                       "l2": "flushed between timed iterations (256 MiB write, untimed)",
+                       "nonzero_weight_frac": round(nonzero_frac, 4)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * s * n_local),
                     "d2h_bytes_per_step": int(4 * a * n_local),
                     "latency_ms": {"p10": pct(0.10), "p50": pct(0.50), "p90": pct(0.90)}},

@@ -173,10 +173,14 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane)
     return v[0];
 }
 
-// exp(-(S - beta)/lambda) through ex2 with the max-shift already applied.
+// exp(-(S - beta)/lambda) through one MUFU.EX2 with the max-shift already applied.  Flush-to-zero on
+// purpose: a weight below 2^-126 of the block's best sample is exactly 0.0f, and the kernels skip
+// zero-weight samples in the weighted noise sum (0 * z adds exactly nothing).
 __device__ __forceinline__ float weight_exp(float S, float beta, float neg_inv_lambda_log2e)
 {
-    return exp2f((S - beta) * neg_inv_lambda_log2e);
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((S - beta) * neg_inv_lambda_log2e));
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -22,6 +22,7 @@ namespace mppi {
 
 constexpr int kPhiloxThreads = 512;
 constexpr int kPhiloxCtasPerSm = 2;
+constexpr int kListCap = 256;          // entries of a warp's non-zero-weight list (8 iterations of 32 samples)
 
 template <int A>
 __device__ __forceinline__ void load_uv(const float *uv_row, Vec<A> &U, Vec<A> &w)
@@ -117,7 +118,8 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     extern __shared__ float4 smem_f4[];
     float *smem = reinterpret_cast<float *>(smem_f4);
     const int TA = p.TA, TAp = (TA + 31) & ~31;
-    float *sUV = smem;                   // [T][RS]
+    uint2 *sList = reinterpret_cast<uint2 *>(smem);          // [NW][kListCap] non-zero-weight samples (fixed offset)
+    float *sUV = smem + 2 * NW * kListCap;                   // [T][RS]
     float *sAcc = sUV + p.T * RS;        // [NW][TAp]  per-warp chunk sums
     float *sN = sAcc + NW * TAp;         // [TAp]
     float *sWork = sN + TAp;             // [TAp]
@@ -206,34 +208,92 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     if (p.norm_mode == 2) beta_c = beta_fixed;
 
     // ---- phase 2: sum_k e_k z_k, regenerating z from the same counters ----------------------------
+    // Only samples whose weight is non-zero in fp32 are revisited (with lambda of the order of the cost
+    // spread most weights underflow: e_k = 0 contributes exactly nothing).  Each warp compacts its own
+    // samples, in order, into a private list of (sample, weight) and walks that list with all 32 lanes.
     const int ncall = (TA + 3) >> 2;
     const int nchunk = (ncall + 7) >> 3;
     float eta = 0.f;
-    for (int ch = 0; ch < nchunk; ch++) {
-        float2 acc2[16];
+    // CTA-uniform: can any weight of this CTA underflow at all?  (false also for NaN and for the weight
+    // pass of a normalised update, whose exponents are bounded by 1/lambda)
+    const bool sparse = (max_c - beta_c) * fabsf(nil) > 125.f;
+    if (!sparse) {
+        // dense weights: every thread walks its own samples, chunk by chunk
+        for (int ch = 0; ch < nchunk; ch++) {
+            float2 acc2[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) acc2[i] = make_float2(0.f, 0.f);
-        const bool full = (ch * 8 + 8 <= ncall);    // warp-uniform: all 8 calls of the chunk exist
-        for (int k = kfirst; k < kend; k += kstride) {
-            const uint32_t kg = (uint32_t)(p.k_offset + k);
-            const float e = weight_exp(costs[k], beta_c, nil);
-            const float2 e2 = make_float2(e, e);
-            if (ch == 0) eta += e;
+            for (int i = 0; i < 16; i++) acc2[i] = make_float2(0.f, 0.f);
+            const bool full = (ch * 8 + 8 <= ncall);    // warp-uniform: all 8 calls of the chunk exist
+            for (int k = kfirst; k < kend; k += kstride) {
+                const uint32_t kg = (uint32_t)(p.k_offset + k);
+                const float e = weight_exp(costs[k], beta_c, nil);
+                const float2 e2 = make_float2(e, e);
+                if (ch == 0) eta += e;
 #pragma unroll
-            for (int c8 = 0; c8 < 8; c8++) {
-                if (full || ch * 8 + c8 < ncall) {
-                    float z[4];
-                    normals4((uint32_t)(ch * 8 + c8), kg, stream, p, z);
-                    acc2[2 * c8] = __ffma2_rn(e2, make_float2(z[0], z[1]), acc2[2 * c8]);
-                    acc2[2 * c8 + 1] = __ffma2_rn(e2, make_float2(z[2], z[3]), acc2[2 * c8 + 1]);
+                for (int c8 = 0; c8 < 8; c8++) {
+                    if (full || ch * 8 + c8 < ncall) {
+                        float z[4];
+                        normals4((uint32_t)(ch * 8 + c8), kg, stream, p, z);
+                        acc2[2 * c8] = __ffma2_rn(e2, make_float2(z[0], z[1]), acc2[2 * c8]);
+                        acc2[2 * c8 + 1] = __ffma2_rn(e2, make_float2(z[2], z[3]), acc2[2 * c8 + 1]);
+                    }
                 }
             }
-        }
-        float acc[32];
+            float acc[32];
 #pragma unroll
-        for (int i = 0; i < 16; i++) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
-        const float r = warp_transpose_sum32(acc, lane);
-        sAcc[warp * TAp + ch * 32 + lane] = r;
+            for (int i = 0; i < 16; i++) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
+            const float r = warp_transpose_sum32(acc, lane);
+            sAcc[warp * TAp + ch * 32 + lane] = r;
+        }
+    } else {
+        // sparse weights: each warp compacts its own samples, in order, into a private list of
+        // (global sample index, weight) and walks that list with all 32 lanes
+        uint2 *wlist = sList + warp * kListCap;
+        float *myacc = sAcc + warp * TAp;
+        for (int j = lane; j < TAp; j += 32) myacc[j] = 0.f;
+        for (int kb = kfirst - lane; kb < kend; kb += kstride * (kListCap / 32)) {   // batches of kListCap/32 iterations
+            const int nit = min(kListCap / 32, (kend - kb + kstride - 1) / kstride);   // warp-uniform
+            int cnt = 0;
+#pragma unroll 1
+            for (int it = 0; it < nit; it++) {
+                const int k = kb + it * kstride + lane;
+                float e = 0.f;
+                if (k < kend) e = weight_exp(costs[k], beta_c, nil);
+                eta += e;
+                const unsigned m = __ballot_sync(0xffffffffu, e != 0.f);
+                if (e != 0.f) wlist[cnt + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)(p.k_offset + k), __float_as_uint(e));
+                cnt += __popc(m);
+            }
+            __syncwarp();
+            if (cnt == 0) continue;                                                  // warp-uniform
+            for (int ch = 0; ch < nchunk; ch++) {
+                float2 acc2[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) acc2[i] = make_float2(0.f, 0.f);
+                const bool full = (ch * 8 + 8 <= ncall);
+                for (int i0 = 0; i0 < cnt; i0 += 32) {
+                    const uint2 ent = (i0 + lane < cnt) ? wlist[i0 + lane] : make_uint2(0u, 0u);   // padding lanes: weight 0
+                    const uint32_t kg = ent.x;
+                    const float e = __uint_as_float(ent.y);
+                    const float2 e2 = make_float2(e, e);
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; c8++) {
+                        if (full || ch * 8 + c8 < ncall) {
+                            float z[4];
+                            normals4((uint32_t)(ch * 8 + c8), kg, stream, p, z);
+                            acc2[2 * c8] = __ffma2_rn(e2, make_float2(z[0], z[1]), acc2[2 * c8]);
+                            acc2[2 * c8 + 1] = __ffma2_rn(e2, make_float2(z[2], z[3]), acc2[2 * c8 + 1]);
+                        }
+                    }
+                }
+                float acc[32];
+#pragma unroll
+                for (int i = 0; i < 16; i++) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
+                const float r = warp_transpose_sum32(acc, lane);
+                myacc[ch * 32 + lane] += r;
+            }
+            __syncwarp();                                                            // list reads done before it is rebuilt
+        }
     }
     eta = warp_sum(eta);
     if (lane == 0) sRed[warp] = eta;
@@ -522,17 +582,32 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
             }
             const float ek = (lane < rows) ? weight_exp(S, beta_g, nil) : 0.f;
             eta_lane += ek;
-            for (int cb = cb0; cb < cb1; cb += 4) {
-                // 4 column blocks per pass: offsets 32*mm are immediates, the row pointer advances by TA.
-                // Blocks past cb1 / columns past TA read neighbouring shared memory and are discarded.
-                const float *ptr = tile + cb * 32 + lane;
+            // rows whose weight is exactly zero (fp32 underflow) add nothing: when they are the majority,
+            // visit the others only (bit scan); otherwise the unrolled dense loop is cheaper per row
+            const unsigned nzrows = __ballot_sync(0xffffffffu, ek != 0.f);
+            const bool sparse = __popc(nzrows) <= 12;
+            for (int cb = cb0; cb < cb1 && nzrows != 0u; cb += 4) {
+                // 4 column blocks per pass: offsets 32*mm are immediates.  Blocks past cb1 / columns past TA
+                // read neighbouring shared memory and are discarded.
+                const float *base = tile + cb * 32 + lane;
                 float a4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-                for (int k = 0; k < 32; k++) {
-                    const float w = __shfl_sync(0xffffffffu, ek, k);
+                if (sparse) {
+                    for (unsigned m = nzrows; m != 0u; m &= m - 1u) {
+                        const int k = __ffs((int)m) - 1;
+                        const float w = __shfl_sync(0xffffffffu, ek, k);
+                        const float *ptr = base + k * TA;
 #pragma unroll
-                    for (int mm = 0; mm < 4; mm++) a4[mm] = fmaf(w, ptr[32 * mm], a4[mm]);
-                    ptr += TA;
+                        for (int mm = 0; mm < 4; mm++) a4[mm] = fmaf(w, ptr[32 * mm], a4[mm]);
+                    }
+                } else {
+                    const float *ptr = base;
+#pragma unroll 8
+                    for (int k = 0; k < 32; k++) {
+                        const float w = __shfl_sync(0xffffffffu, ek, k);
+#pragma unroll
+                        for (int mm = 0; mm < 4; mm++) a4[mm] = fmaf(w, ptr[32 * mm], a4[mm]);
+                        ptr += TA;
+                    }
                 }
 #pragma unroll
                 for (int mm = 0; mm < 4; mm++) {
@@ -653,7 +728,8 @@ __global__ void scale_noise_kernel(const __grid_constant__ RolloutParams p, floa
 static size_t philox_smem_bytes(int A, int T, int TA)
 {
     const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31, NW = kPhiloxThreads / 32;
-    return sizeof(float) * ((size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 64) + sizeof(float4) * kPhiloxThreads;
+    return sizeof(float) * ((size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 64) + sizeof(float4) * kPhiloxThreads +
+           sizeof(uint2) * NW * kListCap;
 }
 
 template <int A, bool DIAG, bool QUAD, int COST>
