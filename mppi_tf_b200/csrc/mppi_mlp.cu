@@ -8,6 +8,8 @@
 
 namespace mppi {
 
+constexpr int kMlpListCap = 256;       // entries of a warp's non-zero-weight list
+
 // -------------------------------------------------------------------------------------------------
 // predict: next[k][s] = mlp(state[k|1][s], action[k][a])   (one CTA per 128 samples)
 // -------------------------------------------------------------------------------------------------
@@ -95,7 +97,8 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
     float *sScale = sWork + TAp;                  // [kMaxParts]
     float *sRed = sScale + kMaxParts;             // [64]
     float4 *sScratch = reinterpret_cast<float4 *>(sRed + 64);     // [kMlpThreads] merge scratch
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sScratch + kMlpThreads);
+    uint2 *sList = reinterpret_cast<uint2 *>(sScratch + kMlpThreads);   // [NW][kMlpListCap] non-zero-weight samples
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sList + NW * kMlpListCap);
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + kMlpNumBars);
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -233,27 +236,54 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
     const int nchunk = (ncall + 7) >> 3;
     const int k_lo = t_lo * kMlpRows, k_hi = min(t_hi * kMlpRows, p.K_local);
     float eta = 0.f;
-    for (int ch = 0; ch < nchunk; ch++) {
-        float acc[32];
+    // zero-weight compaction as in rollout_philox_kernel: a weight that underflowed to 0.0f adds exactly
+    // nothing, so only the other samples are revisited (per-warp ordered lists; dense loop when no weight
+    // of the CTA can underflow)
+    const bool sparse = (max_c - beta_c) * fabsf(nil) > 125.f;         // CTA-uniform
+    float *myacc = sAcc + warp * TAp;
+    for (int j = lane; j < TAp; j += 32) myacc[j] = 0.f;
+    uint2 *wlist = sList + warp * kMlpListCap;
+    for (int kb = k_lo + tid - lane; kb < k_hi; kb += kMlpThreads * (kMlpListCap / 32)) {
+        const int nit = min(kMlpListCap / 32, (k_hi - kb + kMlpThreads - 1) / kMlpThreads);   // warp-uniform
+        int cnt = 0;
+#pragma unroll 1
+        for (int it = 0; it < nit; it++) {
+            const int k = kb + it * kMlpThreads + lane;
+            float e = 0.f;
+            if (k < k_hi) e = weight_exp(costs[k], beta_c, nil);
+            eta += e;
+            const bool keep = sparse ? (e != 0.f) : (k < k_hi);
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) wlist[cnt + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)k, __float_as_uint(e));
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        if (cnt == 0) continue;                                          // warp-uniform
+        for (int ch = 0; ch < nchunk; ch++) {
+            float acc[32];
 #pragma unroll
-        for (int i = 0; i < 32; i++) acc[i] = 0.f;
-        for (int k = k_lo + tid; k < k_hi; k += kMlpThreads) {
-            const uint32_t kg = (uint32_t)(p.k_offset + k);
-            const float *eps_row = PHILOX ? nullptr : eps + (size_t)k * TA;
-            const float e = weight_exp(costs[k], beta_c, nil);
-            if (ch == 0) eta += e;
+            for (int i = 0; i < 32; i++) acc[i] = 0.f;
+            for (int i0 = 0; i0 < cnt; i0 += 32) {
+                const bool live = i0 + lane < cnt;
+                const uint2 ent = live ? wlist[i0 + lane] : make_uint2(0u, 0u);     // padding lanes: weight 0
+                const int k = (int)ent.x;
+                const uint32_t kg = (uint32_t)(p.k_offset + k);
+                const float *eps_row = PHILOX ? nullptr : eps + (size_t)k * TA;
+                const float e = __uint_as_float(ent.y);
 #pragma unroll
-            for (int c8 = 0; c8 < 8; c8++) {
-                if (ch * 8 + c8 < ncall) {
-                    float z[4];
-                    noise4<A, PHILOX>(p, eps_row, (uint32_t)(ch * 8 + c8), kg, stream, true, z);
+                for (int c8 = 0; c8 < 8; c8++) {
+                    if (ch * 8 + c8 < ncall) {
+                        float z[4];
+                        noise4<A, PHILOX>(p, eps_row, (uint32_t)(ch * 8 + c8), kg, stream, live, z);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) acc[4 * c8 + j] = fmaf(e, z[j], acc[4 * c8 + j]);
+                        for (int j = 0; j < 4; j++) acc[4 * c8 + j] = fmaf(e, z[j], acc[4 * c8 + j]);
+                    }
                 }
             }
+            const float r = warp_transpose_sum32(acc, lane);
+            myacc[ch * 32 + lane] += r;
         }
-        const float r = warp_transpose_sum32(acc, lane);
-        sAcc[warp * TAp + ch * 32 + lane] = r;
+        __syncwarp();
     }
     eta = warp_sum(eta);
     if (lane == 0) sRed[warp] = eta;
@@ -281,7 +311,7 @@ static size_t mlp_rollout_smem(int A, int T, int TA)
 {
     const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31, NW = kMlpThreads / 32;
     return kWBlobBytes + sizeof(float) * (kFvecFloats + (size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 32) +
-           sizeof(float) * 32 + sizeof(float4) * kMlpThreads + kMlpNumBars * 8 + 16 + 128;
+           sizeof(float) * 32 + sizeof(float4) * kMlpThreads + sizeof(uint2) * NW * kMlpListCap + kMlpNumBars * 8 + 16 + 128;
 }
 
 #define MPPI_DISPATCH_MLP_A(a, ...)              \
