@@ -22,7 +22,7 @@ namespace mppi {
 
 constexpr int kPhiloxThreads = 512;
 constexpr int kPhiloxCtasPerSm = 2;
-constexpr int kListCap = 256;          // entries of a warp's non-zero-weight list (8 iterations of 32 samples)
+constexpr int kListCap = 256;          // list entries per warp: the CTA's non-zero-weight list holds 8 iterations of samples
 
 template <int A>
 __device__ __forceinline__ void load_uv(const float *uv_row, Vec<A> &U, Vec<A> &w)
@@ -118,7 +118,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     extern __shared__ float4 smem_f4[];
     float *smem = reinterpret_cast<float *>(smem_f4);
     const int TA = p.TA, TAp = (TA + 31) & ~31;
-    uint2 *sList = reinterpret_cast<uint2 *>(smem);          // [NW][kListCap] non-zero-weight samples (fixed offset)
+    uint2 *sList = reinterpret_cast<uint2 *>(smem);          // [NW * kListCap] non-zero-weight samples of the CTA (fixed offset)
     float *sUV = smem + 2 * NW * kListCap;                   // [T][RS]
     float *sAcc = sUV + p.T * RS;        // [NW][TAp]  per-warp chunk sums
     float *sN = sAcc + NW * TAp;         // [TAp]
@@ -246,53 +246,76 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
             sAcc[warp * TAp + ch * 32 + lane] = r;
         }
     } else {
-        // sparse weights: each warp compacts its own samples, in order, into a private list of
-        // (global sample index, weight) and walks that list with all 32 lanes
-        uint2 *wlist = sList + warp * kListCap;
+        // sparse weights: the CTA compacts its samples, in order (warp-major, then iteration), into one
+        // shared-memory list of (global sample index, weight); the warps then share the list 32 entries
+        // at a time.  Deterministic: the list order depends only on the data.
         float *myacc = sAcc + warp * TAp;
         for (int j = lane; j < TAp; j += 32) myacc[j] = 0.f;
-        for (int kb = kfirst - lane; kb < kend; kb += kstride * (kListCap / 32)) {   // batches of kListCap/32 iterations
-            const int nit = min(kListCap / 32, (kend - kb + kstride - 1) / kstride);   // warp-uniform
-            int cnt = 0;
+        int *sCnt = reinterpret_cast<int *>(sRed);                                   // [NW] per-warp counts
+        constexpr int BI = kListCap / 32;                                            // iterations per batch
+        const int k_cta = 32 * w_lo;
+        const int n_it_cta = (kend - k_cta + kstride - 1) / kstride;                 // CTA-uniform
+        const unsigned lt = (1u << lane) - 1u;
+        for (int b0 = 0; b0 < n_it_cta; b0 += BI) {
+            const int kb = k_cta + b0 * kstride + 32 * warp;                         // this warp's first sample of the batch
+            const int nit = min(BI, n_it_cta - b0);
+            int cnt_w = 0;
 #pragma unroll 1
             for (int it = 0; it < nit; it++) {
                 const int k = kb + it * kstride + lane;
                 float e = 0.f;
                 if (k < kend) e = weight_exp(costs[k], beta_c, nil);
                 eta += e;
-                const unsigned m = __ballot_sync(0xffffffffu, e != 0.f);
-                if (e != 0.f) wlist[cnt + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)(p.k_offset + k), __float_as_uint(e));
-                cnt += __popc(m);
+                cnt_w += __popc(__ballot_sync(0xffffffffu, e != 0.f));
             }
-            __syncwarp();
-            if (cnt == 0) continue;                                                  // warp-uniform
-            for (int ch = 0; ch < nchunk; ch++) {
-                float2 acc2[16];
+            if (lane == 0) sCnt[warp] = cnt_w;
+            __syncthreads();
+            int off = 0, total = 0;
 #pragma unroll
-                for (int i = 0; i < 16; i++) acc2[i] = make_float2(0.f, 0.f);
-                const bool full = (ch * 8 + 8 <= ncall);
-                for (int i0 = 0; i0 < cnt; i0 += 32) {
-                    const uint2 ent = (i0 + lane < cnt) ? wlist[i0 + lane] : make_uint2(0u, 0u);   // padding lanes: weight 0
-                    const uint32_t kg = ent.x;
-                    const float e = __uint_as_float(ent.y);
-                    const float2 e2 = make_float2(e, e);
+            for (int w = 0; w < NW; w++) {
+                const int c = sCnt[w];
+                if (w < warp) off += c;
+                total += c;
+            }
+#pragma unroll 1
+            for (int it = 0; it < nit; it++) {
+                const int k = kb + it * kstride + lane;
+                float e = 0.f;
+                if (k < kend) e = weight_exp(costs[k], beta_c, nil);
+                const unsigned m = __ballot_sync(0xffffffffu, e != 0.f);
+                if (e != 0.f) sList[off + __popc(m & lt)] = make_uint2((uint32_t)(p.k_offset + k), __float_as_uint(e));
+                off += __popc(m);
+            }
+            __syncthreads();
+            if (32 * warp < total) {                                                  // warp-uniform
+                for (int ch = 0; ch < nchunk; ch++) {
+                    float2 acc2[16];
 #pragma unroll
-                    for (int c8 = 0; c8 < 8; c8++) {
-                        if (full || ch * 8 + c8 < ncall) {
-                            float z[4];
-                            normals4((uint32_t)(ch * 8 + c8), kg, stream, p, z);
-                            acc2[2 * c8] = __ffma2_rn(e2, make_float2(z[0], z[1]), acc2[2 * c8]);
-                            acc2[2 * c8 + 1] = __ffma2_rn(e2, make_float2(z[2], z[3]), acc2[2 * c8 + 1]);
+                    for (int i = 0; i < 16; i++) acc2[i] = make_float2(0.f, 0.f);
+                    const bool full = (ch * 8 + 8 <= ncall);
+                    for (int i0 = 32 * warp; i0 < total; i0 += 32 * NW) {
+                        const uint2 ent = (i0 + lane < total) ? sList[i0 + lane] : make_uint2(0u, 0u);   // padding lanes: weight 0
+                        const uint32_t kg = ent.x;
+                        const float e = __uint_as_float(ent.y);
+                        const float2 e2 = make_float2(e, e);
+#pragma unroll
+                        for (int c8 = 0; c8 < 8; c8++) {
+                            if (full || ch * 8 + c8 < ncall) {
+                                float z[4];
+                                normals4((uint32_t)(ch * 8 + c8), kg, stream, p, z);
+                                acc2[2 * c8] = __ffma2_rn(e2, make_float2(z[0], z[1]), acc2[2 * c8]);
+                                acc2[2 * c8 + 1] = __ffma2_rn(e2, make_float2(z[2], z[3]), acc2[2 * c8 + 1]);
+                            }
                         }
                     }
-                }
-                float acc[32];
+                    float acc[32];
 #pragma unroll
-                for (int i = 0; i < 16; i++) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
-                const float r = warp_transpose_sum32(acc, lane);
-                myacc[ch * 32 + lane] += r;
+                    for (int i = 0; i < 16; i++) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
+                    const float r = warp_transpose_sum32(acc, lane);
+                    myacc[ch * 32 + lane] += r;
+                }
             }
-            __syncwarp();                                                            // list reads done before it is rebuilt
+            __syncthreads();                         // list and counts are reused by the next batch / the reductions below
         }
     }
     eta = warp_sum(eta);
