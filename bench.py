@@ -198,8 +198,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "torch"],
-                    help="N>1: in-library ncclAllGather, or torch.distributed all_gather on external buffers")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch"],
+                    help="N>1: fused in-kernel exchange over peer memory (falls back to nccl if the mailboxes cannot be "
+                         "mapped), in-library ncclAllGather, or torch.distributed all_gather on external buffers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-injected", action="store_true")
     ap.add_argument("--k-override", type=int, default=0, help="developer knob: replace the workload's K (not a bench line)")
@@ -254,8 +255,26 @@ def main():
     if is_mlp:
         ctrl.setMlp(glorot_mlp(s, a))
     exchange = k_world > 1
+    if exchange and args.exchange == "peer":
+        # fused exchange: all-gather the CUDA IPC handles of the mailboxes once, then no collective call at all
+        ok = True
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, ctrl.peerHandle())
+            ctrl.peerAttach(handles)
+        except Exception as e:                      # noqa: BLE001  (IPC not permitted / no peer access)
+            ok = False
+            print(f"[bench] rank {rank}: peer exchange unavailable ({e}); using nccl", file=sys.stderr)
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if ok:
+                raise SystemExit("peer exchange attached on some ranks only")
+            args.exchange = "nccl"
     if exchange:
-        if args.exchange == "nccl":
+        if args.exchange == "peer":
+            pass
+        elif args.exchange == "nccl":
             uid = [comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             ctrl.commInit(uid[0])
@@ -271,7 +290,7 @@ def main():
 
     def one_update(eps_ptr=None):
         ctrl.enqueueUpdate(eps_ptr)
-        if exchange:
+        if exchange and args.exchange != "peer":             # peer: the update kernel exchanges and finishes itself
             if args.exchange == "nccl":
                 ctrl.enqueueExchange()                       # in-library ncclAllGather on the same stream
             else:
@@ -383,7 +402,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * s * n_local),
                     "d2h_bytes_per_step": int(4 * a * n_local),
                     "latency_ms": {"p10": pct(0.10), "p50": pct(0.50), "p90": pct(0.90)}},
-            "gpu_launches": args.steps * (2 if exchange else 1),
+            "gpu_launches": args.steps * (2 if (exchange and args.exchange != "peer") else 1),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "rollout_philox_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,

@@ -45,6 +45,7 @@ typedef enum {
 #define MPPI_MAX_A 8          /* a_dim <= 8, s_dim = 2 a_dim <= 16 */
 #define MPPI_MAX_S 16
 #define MPPI_MAX_TA 4096      /* tau * a_dim */
+#define MPPI_MAX_PEERS 8      /* ranks of one NVLink domain the fused exchange can address */
 
 typedef struct mppi_handle mppi_handle;
 
@@ -179,6 +180,17 @@ int mppi_exchange_set_buffers(mppi_handle *h, void *send_dev, void *recv_dev);
  * ncclUniqueId (mppi_comm_unique_id fills one on the caller that broadcasts it). */
 int mppi_comm_unique_id(void *id128);
 int mppi_comm_init(mppi_handle *h, const void *id128);
+
+/* Fused exchange over peer memory (one box, NVLink / NVSwitch): instead of all-gather + finish, the last CTA
+ * of the update kernel stores its payload into every rank's mailbox, signals, waits for the other ranks'
+ * payloads and finishes the update in the same launch.  Every rank exports the 64-byte CUDA IPC handle of
+ * its mailbox (mppi_peer_handle), the caller all-gathers them (any host channel) and every rank attaches the
+ * world handles in rank order (mppi_peer_attach; world <= MPPI_MAX_PEERS, one process per GPU).  After a
+ * successful attach mppi_next needs no exchange call, and mppi_enqueue_exchange / _finish are no-ops.
+ * A payload that does not arrive within about a second makes mppi_fetch_action return MPPI_ERR_COMM. */
+#define MPPI_PEER_HANDLE_BYTES 64
+int mppi_peer_handle(mppi_handle *h, void *handle64);
+int mppi_peer_attach(mppi_handle *h, const void *handles /* [world][64] */);
 
 /* ---- learned MLP dynamics (learning_base, row A13) ------------------------------------------- */
 /* x' = x + (W3^T relu(W2^T relu(W1^T X + b1) + b2) + b3) * Ystd + Ymean,

@@ -79,6 +79,8 @@ SYMBOLS = {
     "mppi_payload_stride": (_i, [_i]),
     "mppi_exchange_buffers": (_i, [_H, C.POINTER(_vp), C.POINTER(_vp)]),
     "mppi_exchange_set_buffers": (_i, [_H, _vp, _vp]),
+    "mppi_peer_handle": (_i, [_H, _vp]),
+    "mppi_peer_attach": (_i, [_H, _vp]),
     "mppi_comm_unique_id": (_i, [_vp]),
     "mppi_comm_init": (_i, [_H, _vp]),
     "mppi_set_mlp": (_i, [_H, _i] + [_fp] * 10),

@@ -316,6 +316,17 @@ class ControllerBase:
     def setExchangeBuffers(self, send_ptr, recv_ptr):
         check(self._lib.mppi_exchange_set_buffers(self._h, C.c_void_p(send_ptr), C.c_void_p(recv_ptr)), self._h)
 
+    def peerHandle(self):
+        """64-byte CUDA IPC handle of this rank's mailbox (fused exchange over peer memory)."""
+        buf = C.create_string_buffer(64)
+        check(self._lib.mppi_peer_handle(self._h, buf), self._h)
+        return buf.raw
+
+    def peerAttach(self, handles):
+        """handles: the world 64-byte handles in rank order (all-gathered by the caller)."""
+        blob = b"".join(handles)
+        check(self._lib.mppi_peer_attach(self._h, C.create_string_buffer(blob, len(blob))), self._h)
+
     def commInit(self, unique_id_bytes):
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
         check(self._lib.mppi_comm_init(self._h, C.cast(buf, C.c_void_p)), self._h)

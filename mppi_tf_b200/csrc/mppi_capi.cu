@@ -88,6 +88,14 @@ struct mppi_handle {
     float *h_x = nullptr, *h_next = nullptr;
     bool x_staged = false;
     NcclComm comm = nullptr;
+    // fused exchange over peer memory (mppi_peer_handle / mppi_peer_attach)
+    void *d_mailbox = nullptr;            // [2][world][n_ctrl][stride] floats + [2][world][n_ctrl] epochs
+    size_t mail_floats = 0;
+    void *peer_base[kMaxWorld] = {nullptr};
+    bool peer_opened[kMaxWorld] = {false};
+    bool peer_on = false;
+    uint32_t epoch = 0;
+    unsigned int *d_peer_status = nullptr, *h_peer_status = nullptr;
     // learned-MLP dynamics (mppi_set_mlp)
     bool mlp = false;
     void *d_wblob = nullptr;
@@ -217,6 +225,16 @@ RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
     p.stats = h->d_stats;
     p.counters = h->d_counters;
     p.eps = eps_dev;
+    p.peer_on = h->peer_on ? 1 : 0;
+    p.rank = h->rank;
+    p.epoch = h->epoch;
+    if (h->peer_on) {
+        for (int r = 0; r < h->world; r++) {
+            p.peer_mail[r] = static_cast<float *>(h->peer_base[r]);
+            p.peer_flag[r] = reinterpret_cast<uint32_t *>(static_cast<float *>(h->peer_base[r]) + h->mail_floats);
+        }
+        p.peer_status = h->d_peer_status;
+    }
     return p;
 }
 
@@ -346,6 +364,10 @@ int mppi_destroy(mppi_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (int r = 0; r < kMaxWorld; r++)
+        if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    cudaFree(h->d_mailbox); cudaFree(h->d_peer_status);
+    if (h->h_peer_status) cudaFreeHost(h->h_peer_status);
     cudaFree(h->d_x); cudaFree(h->d_goal); cudaFree(h->d_U); cudaFree(h->d_Unew); cudaFree(h->d_next);
     cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_counters);
     cudaFree(h->d_norm);
@@ -391,6 +413,7 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
     if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
     if (!h->x_staged) return fail(h, MPPI_ERR_STATE, "mppi_set_state must precede mppi_enqueue_update");
     CU_TRY(h, cudaSetDevice(h->device));
+    if (h->peer_on) h->epoch++;                     // same count on every rank: one per update
     RolloutParams p = make_params(h, eps_dev);
     int gx = 0;
     // cost normalisation (controller_base.py:468-474) needs max_k(S_k - beta) before any weight: two launches,
@@ -416,14 +439,14 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
         h->last_update = h->update_counter;
         h->update_counter++;
     }
-    h->pending_finish = (h->world > 1);
+    h->pending_finish = (h->world > 1) && !h->peer_on;
     return MPPI_OK;
 }
 
 int mppi_enqueue_finish(mppi_handle *h)
 {
     if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
-    if (h->world <= 1) return MPPI_OK;
+    if (h->world <= 1 || h->peer_on) return MPPI_OK;
     if (!h->pending_finish) return fail(h, MPPI_ERR_STATE, "no update awaiting a finish");
     CU_TRY(h, cudaSetDevice(h->device));
     RolloutParams p = make_params(h, nullptr);
@@ -434,7 +457,7 @@ int mppi_enqueue_finish(mppi_handle *h)
 
 static int exchange(mppi_handle *h)
 {
-    if (h->world <= 1) return MPPI_OK;
+    if (h->world <= 1 || h->peer_on) return MPPI_OK;
     if (!h->comm)
         return fail(h, MPPI_ERR_COMM, "world > 1 needs mppi_comm_init (in-library NCCL) or a caller-side all-gather "
                                       "between mppi_enqueue_update and mppi_enqueue_finish");
@@ -456,8 +479,12 @@ int mppi_fetch_action(mppi_handle *h, float *action_host)
     if (!h || !action_host) return fail(h, MPPI_ERR_BAD_ARG, "null handle/action");
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaMemcpyAsync(h->h_next, h->d_next, sizeof(float) * h->n_ctrl * h->a, cudaMemcpyDeviceToHost, h->stream));
+    if (h->peer_on)
+        CU_TRY(h, cudaMemcpyAsync(h->h_peer_status, h->d_peer_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     memcpy(action_host, h->h_next, sizeof(float) * h->n_ctrl * h->a);
+    if (h->peer_on && *h->h_peer_status != 0u)
+        return fail(h, MPPI_ERR_COMM, "fused exchange: a peer's payload did not arrive in time (is every rank calling the update?)");
     return MPPI_OK;
 }
 
@@ -663,6 +690,59 @@ int mppi_exchange_set_buffers(mppi_handle *h, void *send_dev, void *recv_dev)
     h->d_payload = (float *)send_dev;
     h->d_gather = (float *)recv_dev;
     h->ext_exchange = true;
+    return MPPI_OK;
+}
+static int peer_alloc(mppi_handle *h)
+{
+    if (h->d_mailbox) return MPPI_OK;
+    CU_TRY(h, cudaSetDevice(h->device));
+    h->mail_floats = (size_t)2 * h->world * h->n_ctrl * h->stride;
+    const size_t bytes = sizeof(float) * h->mail_floats + sizeof(uint32_t) * 2 * h->world * h->n_ctrl;
+    CU_TRY(h, cudaMalloc(&h->d_mailbox, bytes));
+    CU_TRY(h, cudaMemset(h->d_mailbox, 0, bytes));
+    CU_TRY(h, cudaMalloc(&h->d_peer_status, sizeof(unsigned int)));
+    CU_TRY(h, cudaMemset(h->d_peer_status, 0, sizeof(unsigned int)));
+    CU_TRY(h, cudaMallocHost(&h->h_peer_status, sizeof(unsigned int)));
+    *h->h_peer_status = 0u;
+    CU_TRY(h, cudaDeviceSynchronize());
+    return MPPI_OK;
+}
+int mppi_peer_handle(mppi_handle *h, void *handle64)
+{
+    if (!h || !handle64) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    if (h->world < 2 || h->world > kMaxWorld) return fail(h, MPPI_ERR_UNSUPPORTED, "fused exchange needs 2 <= world <= MPPI_MAX_PEERS");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MPPI_PEER_HANDLE_BYTES, "IPC handle size");
+    int rc = peer_alloc(h);
+    if (rc) return rc;
+    cudaIpcMemHandle_t ipc;
+    CU_TRY(h, cudaIpcGetMemHandle(&ipc, h->d_mailbox));
+    memcpy(handle64, &ipc, sizeof(ipc));
+    return MPPI_OK;
+}
+int mppi_peer_attach(mppi_handle *h, const void *handles)
+{
+    if (!h || !handles) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    if (h->world < 2 || h->world > kMaxWorld) return fail(h, MPPI_ERR_UNSUPPORTED, "fused exchange needs 2 <= world <= MPPI_MAX_PEERS");
+    if (h->normalize) return fail(h, MPPI_ERR_UNSUPPORTED, "cost normalisation is single-rank only");
+    int rc = peer_alloc(h);
+    if (rc) return rc;
+    CU_TRY(h, cudaSetDevice(h->device));
+    for (int r = 0; r < h->world; r++) {
+        if (r == h->rank) { h->peer_base[r] = h->d_mailbox; continue; }
+        if (h->peer_opened[r]) continue;
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, static_cast<const char *>(handles) + (size_t)r * MPPI_PEER_HANDLE_BYTES, sizeof(ipc));
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(h, MPPI_ERR_COMM, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+        }
+        h->peer_base[r] = ptr;
+        h->peer_opened[r] = true;
+    }
+    h->peer_on = true;
+    h->epoch = 0;
     return MPPI_OK;
 }
 int mppi_comm_unique_id(void *id128)

@@ -8,6 +8,7 @@
 namespace mppi {
 
 constexpr int kMaxA = MPPI_MAX_A;
+constexpr int kMaxWorld = MPPI_MAX_PEERS;
 constexpr int kMaxS = MPPI_MAX_S;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kInf = __builtin_huge_valf();
@@ -65,7 +66,25 @@ struct RolloutParams {
     float *stats;            // [n_ctrl][2]        beta, eta of the last update
     unsigned int *counters;  // [n_ctrl] last-CTA election
     const float *eps;        // injected noise [n_ctrl][K_local][T][a] or nullptr
+    // fused exchange over peer memory (world > 1, mppi_peer_attach): every rank's mailbox
+    //   mail [2][world][n_ctrl][stride] floats, flag [2][world][n_ctrl] epochs, mapped into this process
+    int peer_on, rank;
+    uint32_t epoch;          // exchange epoch of this update (> 0, same on every rank); parity selects the buffer
+    float *peer_mail[kMaxWorld];
+    uint32_t *peer_flag[kMaxWorld];
+    unsigned int *peer_status;   // set != 0 if a peer's payload did not arrive in time
 };
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. SC'11).  Integer contract shared with oracle/mppi_oracle.c.

@@ -283,6 +283,39 @@ __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_
     if (threadIdx.x == 0) p.counters[ctrl] = 0u;
     Merged m = merge_parts(p.partials + (size_t)ctrl * nparts * stride, stride, nparts, TA,
                            p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
+    if (p.world > 1 && p.peer_on) {
+        // Fused exchange: this CTA writes the rank payload straight into every rank's mailbox over NVLink,
+        // raises its flag there, waits for the other ranks' flags in its own mailbox and finishes the update
+        // in the same launch - no collective call, no second kernel.  Buffers alternate with the epoch's
+        // parity, so a rank that races ahead cannot overwrite a payload that is still being read.
+        const int world = p.world, tid = threadIdx.x;
+        const uint32_t par = p.epoch & 1u;
+        const size_t slot = ((size_t)par * world + p.rank) * p.n_ctrl + ctrl;
+        for (int r = 0; r < world; r++) {
+            float *dst = p.peer_mail[r] + slot * stride;
+            if (tid == 0) { dst[0] = m.beta; dst[1] = m.eta; dst[2] = 0.f; dst[3] = 0.f; }
+            for (int j = tid; j < stride - 4; j += blockDim.x) dst[4 + j] = (j < TA) ? sN[j] : 0.f;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < world) st_release_sys(p.peer_flag[tid] + slot, p.epoch);
+        if (tid < world) {
+            const uint32_t *f = p.peer_flag[p.rank] + (((size_t)par * world + tid) * p.n_ctrl + ctrl);
+            const long long t0 = clock64();
+            while (ld_acquire_sys(f) != p.epoch) {
+                if (clock64() - t0 > (1LL << 31)) {            // about a second: a rank is missing, do not hang the GPU
+                    atomicExch(p.peer_status, 1u);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        const float *mail = p.peer_mail[p.rank] + ((size_t)par * world * p.n_ctrl + ctrl) * stride;
+        Merged mw = merge_parts(mail, (size_t)p.n_ctrl * stride, world, TA, p.neg_inv_lambda_log2e, sN, sScale, sRed,
+                                sScratch, scratch_f4);
+        apply_update<A, PHILOX>(p, ctrl, mw, sN, sWork);
+        return;
+    }
     if (p.world > 1) {
         float *pay = p.payload + (size_t)ctrl * stride;
         if (threadIdx.x == 0) { pay[0] = m.beta; pay[1] = m.eta; pay[2] = 0.f; pay[3] = 0.f; }

@@ -1,0 +1,48 @@
+"""Dev (multi-GPU box): the fused peer-memory exchange must give the same sequences as the NCCL path.
+torchrun --nproc-per-node N scripts_dev/peer_check.py"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mppi_tf_b200 import ControllerBase, comm_unique_id
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+K, T, s, a = 65536, 40, 6, 3
+x = np.linspace(-0.5, 0.5, s).astype(np.float32)
+
+
+def make():
+    return ControllerBase(K, T, 0.1, 1.0, s, a, lam=1.0, sigma=0.25 * np.eye(a, dtype=np.float32), seed=3, device=lr,
+                          rank=rank, world=world)
+
+
+c1 = make()
+uid = [comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+c1.commInit(uid[0])
+c2 = make()
+hs = [None] * world
+dist.all_gather_object(hs, c2.peerHandle())
+c2.peerAttach(hs)
+ok = True
+for it in range(5):
+    a1 = c1.next(x)
+    a2 = c2.next(x)
+    u1, u2 = c1.getSequence(), c2.getSequence()
+    same = np.array_equal(u1, u2) and np.array_equal(a1, a2)
+    ok &= same
+    if rank == 0:
+        print(f"update {it}: nccl vs peer identical: {same}; action {a2}", flush=True)
+# all ranks hold the same sequence
+t = torch.tensor(c2.getSequence(), device="cuda")
+g = [torch.empty_like(t) for _ in range(world)]
+dist.all_gather(g, t)
+ok &= all(torch.equal(g[0], gi) for gi in g)
+if rank == 0:
+    print("PEER CHECK", "OK" if ok else "FAILED", flush=True)
+c1.close(); c2.close()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
