@@ -1,5 +1,6 @@
-"""Dev (multi-GPU box): the fused peer-memory exchange must give the same sequences as the NCCL path.
-torchrun --nproc-per-node N scripts_dev/peer_check.py"""
+"""Worker of tests/test_peer_exchange_gpu.py (needs >= 2 GPUs): the fused peer-memory exchange must give the same
+sequences as the NCCL path, on every rank.
+python -m torch.distributed.run --nproc-per-node N tests/peer_check_worker.py"""
 import os, sys
 import numpy as np
 import torch
