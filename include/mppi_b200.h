@@ -206,6 +206,20 @@ int mppi_set_mlp(mppi_handle *h, int hidden, const float *W1, const float *b1, c
  * {1, k}, action [k][a] -> next [k][s].  Requires mppi_set_mlp. */
 int mppi_mlp_predict(mppi_handle *h, int kst, int k, const float *state, const float *action, float *out);
 
+/* Learner side of the MLP model: ONE full-batch Adam step on the mean squared
+ * error of the normalised prediction, as LearnerBase._train_step does
+ * (/root/reference/scripts/src/learners/learner_base.py:469-496 with tf.optimizers.Adam, :325):
+ *   Xn = (concat(x,u) - Xmean)/Xstd, Yn = ((x' - x) - Ymean)/Ystd, loss = mean((net(Xn) - Yn)^2)
+ * over n transitions (state [n][s], action [n][a], next_state [n][s], host).  fp32 master weights and Adam
+ * moments live in the handle; the bf16 copy the rollout uses is refreshed after the step, so the next
+ * mppi_next already plans with the updated model.  *loss_out (may be NULL) is the loss BEFORE the step.
+ * mppi_mlp_set_adam changes (beta1, beta2, epsilon) from the Keras defaults (0.9, 0.999, 1e-7) and resets the
+ * moments and the step count; mppi_set_mlp resets them too. */
+int mppi_mlp_train_step(mppi_handle *h, int n, const float *state, const float *action, const float *next_state,
+                        float learning_rate, float *loss_out);
+int mppi_mlp_set_adam(mppi_handle *h, float beta1, float beta2, float epsilon);
+int mppi_mlp_get_weights(mppi_handle *h, float *W1, float *b1, float *W2, float *b2, float *W3, float *b3);
+
 /* ---- stateless stage entry points (the reference's graph-builder methods on plain buffers) ----
  * All pointers are host memory; each call runs the corresponding CUDA kernel on `device`. */
 /* utile::blockDiag (src/utile.cpp:10-43): in [rows][cols] -> out [nb*rows][nb*cols] */

@@ -85,6 +85,9 @@ SYMBOLS = {
     "mppi_comm_init": (_i, [_H, _vp]),
     "mppi_set_mlp": (_i, [_H, _i] + [_fp] * 10),
     "mppi_mlp_predict": (_i, [_H, _i, _i, _fp, _fp, _fp]),
+    "mppi_mlp_train_step": (_i, [_H, _i, _fp, _fp, _fp, _f, _fp]),
+    "mppi_mlp_set_adam": (_i, [_H, _f, _f, _f]),
+    "mppi_mlp_get_weights": (_i, [_H] + [_fp] * 6),
     "mppi_block_diag": (_i, [_fp, _i, _i, _i, _fp]),
     "mppi_model_free_step": (_i, [_i, _f, _f, _i, _i, _i, _fp, _fp]),
     "mppi_model_action_step": (_i, [_i, _f, _f, _i, _i, _i, _fp, _fp]),

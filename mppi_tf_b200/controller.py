@@ -277,6 +277,25 @@ class ControllerBase:
                                      _ptr(keep["W3"]), _ptr(keep["b3"]), opt("Xmean"), opt("Xstd"), opt("Ymean"),
                                      opt("Ystd")), self._h)
 
+    def mlpTrainStep(self, state, action, next_state, learning_rate):
+        """One full-batch Adam step on the normalised MSE (learner_base.py:469-496); returns the loss before the step."""
+        st, ac, nx = _f32(state).reshape(-1, self.s_dim), _f32(action).reshape(-1, self.a_dim), _f32(next_state).reshape(-1, self.s_dim)
+        assert st.shape[0] == ac.shape[0] == nx.shape[0]
+        loss = C.c_float(0)
+        check(self._lib.mppi_mlp_train_step(self._h, st.shape[0], _ptr(st), _ptr(ac), _ptr(nx), float(learning_rate),
+                                            C.byref(loss)), self._h)
+        return loss.value
+
+    def mlpSetAdam(self, beta1=0.9, beta2=0.999, epsilon=1e-7):
+        check(self._lib.mppi_mlp_set_adam(self._h, float(beta1), float(beta2), float(epsilon)), self._h)
+
+    def mlpGetWeights(self, hidden=128):
+        s, a, H = self.s_dim, self.a_dim, hidden
+        out = dict(W1=np.empty((s + a, H), np.float32), b1=np.empty(H, np.float32), W2=np.empty((H, H), np.float32),
+                   b2=np.empty(H, np.float32), W3=np.empty((H, s), np.float32), b3=np.empty(s, np.float32))
+        check(self._lib.mppi_mlp_get_weights(self._h, *[_ptr(out[k]) for k in ("W1", "b1", "W2", "b2", "W3", "b3")]), self._h)
+        return out
+
     def mlpPredict(self, state, action):
         st = _f32(state).reshape(-1, self.s_dim)
         ac = _f32(action).reshape(-1, self.a_dim)

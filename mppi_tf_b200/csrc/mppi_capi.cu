@@ -100,6 +100,11 @@ struct mppi_handle {
     bool mlp = false;
     void *d_wblob = nullptr;
     float *d_fvec = nullptr;
+    // learner side (mppi_mlp_train_step): fp32 master weights + Adam state, W1 b1 W2 b2 W3 b3 back to back
+    float *d_params = nullptr, *d_adam_m = nullptr, *d_adam_v = nullptr, *d_train_work = nullptr, *d_loss = nullptr;
+    size_t train_work_cap = 0;
+    long long adam_t = 0;
+    float adam_b1 = 0.9f, adam_b2 = 0.999f, adam_eps = 1e-7f;     // tf.optimizers.Adam defaults (learner_base.py:325)
     std::string err;
 };
 
@@ -374,6 +379,7 @@ int mppi_destroy(mppi_handle *h)
     cudaFree(h->d_eps_tmp);
     cudaFree(h->d_wblob);
     cudaFree(h->d_fvec);
+    cudaFree(h->d_params); cudaFree(h->d_adam_m); cudaFree(h->d_adam_v); cudaFree(h->d_train_work); cudaFree(h->d_loss);
     if (!h->ext_exchange) { cudaFree(h->d_payload); cudaFree(h->d_gather); }
     if (h->h_x) cudaFreeHost(h->h_x);
     if (h->h_next) cudaFreeHost(h->h_next);
@@ -797,8 +803,93 @@ int mppi_set_mlp(mppi_handle *h, int hidden, const float *W1, const float *b1, c
     if (!h->d_fvec) CU_TRY(h, cudaMalloc(&h->d_fvec, sizeof(float) * kFvecFloats));
     CU_TRY(h, cudaMemcpyAsync(h->d_wblob, blob.data(), kWBlobBytes, cudaMemcpyHostToDevice, h->stream));
     CU_TRY(h, cudaMemcpyAsync(h->d_fvec, fv.data(), sizeof(float) * kFvecFloats, cudaMemcpyHostToDevice, h->stream));
+    // fp32 master copy for the learner, Adam state reset
+    const size_t np = mlp_param_count(h->s, h->a);
+    std::vector<float> params;
+    params.reserve(np);
+    params.insert(params.end(), W1, W1 + (size_t)in * kMlpH);
+    params.insert(params.end(), b1, b1 + kMlpH);
+    params.insert(params.end(), W2, W2 + (size_t)kMlpH * kMlpH);
+    params.insert(params.end(), b2, b2 + kMlpH);
+    params.insert(params.end(), W3, W3 + (size_t)kMlpH * h->s);
+    params.insert(params.end(), b3, b3 + h->s);
+    if (!h->d_params) {
+        CU_TRY(h, cudaMalloc(&h->d_params, sizeof(float) * np));
+        CU_TRY(h, cudaMalloc(&h->d_adam_m, sizeof(float) * np));
+        CU_TRY(h, cudaMalloc(&h->d_adam_v, sizeof(float) * np));
+        CU_TRY(h, cudaMalloc(&h->d_loss, sizeof(float)));
+    }
+    CU_TRY(h, cudaMemcpyAsync(h->d_params, params.data(), sizeof(float) * np, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->d_adam_m, 0, sizeof(float) * np, h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->d_adam_v, 0, sizeof(float) * np, h->stream));
+    h->adam_t = 0;
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     h->mlp = true;
+    return MPPI_OK;
+}
+
+int mppi_mlp_set_adam(mppi_handle *h, float beta1, float beta2, float epsilon)
+{
+    if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
+    if (!h->mlp) return fail(h, MPPI_ERR_STATE, "mppi_set_mlp has not been called");
+    if (!(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(epsilon > 0.f))
+        return fail(h, MPPI_ERR_BAD_ARG, "Adam needs 0 <= beta < 1 and epsilon > 0");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t np = mlp_param_count(h->s, h->a);
+    h->adam_b1 = beta1; h->adam_b2 = beta2; h->adam_eps = epsilon;
+    h->adam_t = 0;
+    CU_TRY(h, cudaMemsetAsync(h->d_adam_m, 0, sizeof(float) * np, h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->d_adam_v, 0, sizeof(float) * np, h->stream));
+    return MPPI_OK;
+}
+
+int mppi_mlp_train_step(mppi_handle *h, int n, const float *state, const float *action, const float *next_state,
+                        float learning_rate, float *loss_out)
+{
+    if (!h || !state || !action || !next_state || n <= 0) return fail(h, MPPI_ERR_BAD_ARG, "bad train_step argument");
+    if (!h->mlp) return fail(h, MPPI_ERR_STATE, "mppi_set_mlp has not been called");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int s = h->s, a = h->a;
+    const size_t need = train_work_floats(s, a, n) + (size_t)n * (2 * s + a);
+    if (need > h->train_work_cap) {
+        cudaFree(h->d_train_work);
+        h->d_train_work = nullptr;
+        h->train_work_cap = 0;
+        CU_TRY(h, cudaMalloc(&h->d_train_work, sizeof(float) * need));
+        h->train_work_cap = need;
+    }
+    float *dx = h->d_train_work, *du = dx + (size_t)n * s, *dxn = du + (size_t)n * a, *work = dxn + (size_t)n * s;
+    CU_TRY(h, cudaMemcpyAsync(dx, state, sizeof(float) * (size_t)n * s, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(du, action, sizeof(float) * (size_t)n * a, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(dxn, next_state, sizeof(float) * (size_t)n * s, cudaMemcpyHostToDevice, h->stream));
+    h->adam_t++;
+    const double t = (double)h->adam_t;
+    const float lr_t = (float)((double)learning_rate * sqrt(1.0 - pow((double)h->adam_b2, t)) / (1.0 - pow((double)h->adam_b1, t)));
+    CU_TRY(h, launch_train_step(s, a, n, dx, du, dxn, h->d_fvec, h->d_params, h->d_adam_m, h->d_adam_v, lr_t, h->adam_b1,
+                                h->adam_b2, h->adam_eps, work, h->d_loss, h->stream));
+    CU_TRY(h, launch_pack_blob(s, a, h->d_params, h->d_wblob, h->stream));     // the rollout sees the new weights
+    float loss = 0.f;
+    CU_TRY(h, cudaMemcpyAsync(&loss, h->d_loss, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (loss_out) *loss_out = loss;
+    return MPPI_OK;
+}
+
+int mppi_mlp_get_weights(mppi_handle *h, float *W1, float *b1, float *W2, float *b2, float *W3, float *b3)
+{
+    if (!h || !W1 || !b1 || !W2 || !b2 || !W3 || !b3) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    if (!h->mlp) return fail(h, MPPI_ERR_STATE, "mppi_set_mlp has not been called");
+    const int in = h->s + h->a;
+    std::vector<float> params(mlp_param_count(h->s, h->a));
+    int rc = d2h(h, params.data(), h->d_params, params.size());
+    if (rc) return rc;
+    const float *p = params.data();
+    memcpy(W1, p, sizeof(float) * in * kMlpH); p += (size_t)in * kMlpH;
+    memcpy(b1, p, sizeof(float) * kMlpH); p += kMlpH;
+    memcpy(W2, p, sizeof(float) * kMlpH * kMlpH); p += (size_t)kMlpH * kMlpH;
+    memcpy(b2, p, sizeof(float) * kMlpH); p += kMlpH;
+    memcpy(W3, p, sizeof(float) * kMlpH * h->s); p += (size_t)kMlpH * h->s;
+    memcpy(b3, p, sizeof(float) * h->s);
     return MPPI_OK;
 }
 

@@ -27,6 +27,14 @@ cudaError_t launch_rollout_mlp(RolloutParams p, const MlpParams &mp, int a, bool
 void mlp_pack_weights(int s, int a, const float *W1, const float *b1, const float *W2, const float *b2,
                       const float *W3, const float *b3, void *blob_host);
 
+// mppi_train.cu  (device pointers)
+size_t mlp_param_count(int s, int a);
+size_t train_work_floats(int s, int a, int n);
+cudaError_t launch_pack_blob(int s, int a, const float *params, void *blob, cudaStream_t st);
+cudaError_t launch_train_step(int s, int a, int n, const float *x, const float *u, const float *xnext, const float *norm,
+                              float *params, float *adam_m, float *adam_v, float lr_t, float b1, float b2, float eps,
+                              float *work, float *loss_dev, cudaStream_t st);
+
 // mppi_stages.cu  (device pointers)
 cudaError_t launch_model_step(float mass, float dt, int s, int a, int kst, int k, const float *state,
                               const float *action, float *out, int mode, cudaStream_t st);

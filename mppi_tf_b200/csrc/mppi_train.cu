@@ -1,0 +1,227 @@
+// Learner side of the MLP dynamics: one full-batch Adam step on the
+// mean-squared error of the NORMALISED prediction, as LearnerBase._train_step does
+// (/root/reference/scripts/src/learners/learner_base.py:469-496, optimizer tf.optimizers.Adam :325),
+// for the network of mppi_mlp.cuh:   Xn = (concat(x, u) - Xmean)/Xstd,  Yn = ((x' - x) - Ymean)/Ystd,
+//   h1 = relu(Xn W1 + b1), h2 = relu(h1 W2 + b2), out = h2 W3 + b3,  loss = mean((out - Yn)^2).
+// fp32 throughout (the bf16 copy the rollout kernels stage is re-packed from the fp32 master weights after
+// every step).  This is the caller of the hot path, not the hot path: plain shared-memory-tiled kernels,
+// fixed summation order (deterministic).
+#include <cuda_bf16.h>
+
+#include "mppi_internal.h"
+#include "mppi_mlp.cuh"
+
+namespace mppi {
+
+namespace {
+
+constexpr int TS = 32;     // GEMM tile
+
+// C[M][N] = op(A) op(B) (+ bias[N]) (relu), row-major.  TA: A is stored [K][M]; TB: B is stored [N][K].
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(TS * 8) gemm_kernel(int M, int N, int K, const float *A, const float *B, const float *bias,
+                                                      int relu, float *C)
+{
+    __shared__ float sA[TS][TS + 1], sB[TS][TS + 1];
+    const int tx = threadIdx.x & (TS - 1), ty = threadIdx.x / TS;     // 32 x 8 threads, 4 rows each
+    const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < K; k0 += TS) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int i = ty + 8 * r;                     // tile row
+            {   // sA[i][tx] = op(A)[m0 + i][k0 + tx]
+                const int m = m0 + i, k = k0 + tx;
+                sA[i][tx] = (m < M && k < K) ? (TA ? A[(size_t)k * M + m] : A[(size_t)m * K + k]) : 0.f;
+            }
+            {   // sB[i][tx] = op(B)[k0 + i][n0 + tx]
+                const int k = k0 + i, n = n0 + tx;
+                sB[i][tx] = (k < K && n < N) ? (TB ? B[(size_t)n * K + k] : B[(size_t)k * N + n]) : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < TS; kk++) {
+            const float b = sB[kk][tx];
+#pragma unroll
+            for (int r = 0; r < 4; r++) acc[r] = fmaf(sA[ty + 8 * r][kk], b, acc[r]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int m = m0 + ty + 8 * r, n = n0 + tx;
+        if (m < M && n < N) {
+            float v = acc[r] + (bias ? bias[n] : 0.f);
+            if (relu) v = fmaxf(v, 0.f);
+            C[(size_t)m * N + n] = v;
+        }
+    }
+}
+
+template <bool TA, bool TB>
+cudaError_t gemm(int M, int N, int K, const float *A, const float *B, const float *bias, bool relu, float *C, cudaStream_t st)
+{
+    dim3 grid((N + TS - 1) / TS, (M + TS - 1) / TS);
+    gemm_kernel<TA, TB><<<grid, TS * 8, 0, st>>>(M, N, K, A, B, bias, relu ? 1 : 0, C);
+    return cudaGetLastError();
+}
+
+// Xn[n][in] = (concat(x, u) - Xmean) / Xstd ; Yn[n][s] = ((x' - x) - Ymean) / Ystd
+__global__ void prepare_kernel(int n, int s, int a, const float *x, const float *u, const float *xn, const float *norm,
+                               float *Xn, float *Yn)
+{
+    const int in = s + a;
+    const float *xmean = norm, *xinv = norm + 16, *ystd = norm + 32, *ymean = norm + 48;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * in; i += gridDim.x * blockDim.x) {
+        const int r = i / in, c = i - r * in;
+        const float v = c < s ? x[(size_t)r * s + c] : u[(size_t)r * a + (c - s)];
+        Xn[i] = (v - xmean[c]) * xinv[c];
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * s; i += gridDim.x * blockDim.x) {
+        const int c = i % s;
+        Yn[i] = ((xn[i] - x[i]) - ymean[c]) / ystd[c];
+    }
+}
+
+// dOut = 2 (out - Yn) / (n s); per-block partial sums of (out - Yn)^2 in a fixed order
+__global__ void __launch_bounds__(256) loss_kernel(int total, const float *out, const float *Yn, float *dOut, float *partial)
+{
+    __shared__ float sred[256];
+    float acc = 0.f;
+    const float scale = 2.0f / (float)total;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const float d = out[i] - Yn[i];
+        dOut[i] = scale * d;
+        acc = fmaf(d, d, acc);
+    }
+    sred[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sred[threadIdx.x] += sred[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sred[0];
+}
+__global__ void loss_final_kernel(int nblocks, int total, const float *partial, float *loss)
+{
+    float acc = 0.f;
+    for (int i = 0; i < nblocks; i++) acc += partial[i];
+    *loss = acc / (float)total;
+}
+
+// d[i] = act[i] > 0 ? d[i] : 0   (ReLU backward)
+__global__ void relu_mask_kernel(size_t total, const float *act, float *d)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        if (!(act[i] > 0.f)) d[i] = 0.f;
+}
+
+// column sums g[c] = sum_r d[r][c], one thread per column, rows in order
+__global__ void colsum_kernel(int n, int cols, const float *d, float *g)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float acc = 0.f;
+    for (int r = 0; r < n; r++) acc += d[(size_t)r * cols + c];
+    g[c] = acc;
+}
+
+// Keras Adam (non-amsgrad): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; w -= lr_t m / (sqrt(v) + eps),
+// lr_t = lr sqrt(1 - b2^t) / (1 - b1^t)
+__global__ void adam_kernel(int total, float *w, float *m, float *v, const float *g, float lr_t, float b1, float b2, float eps)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+// bf16 canonical blob from the fp32 master weights (device twin of mlp_pack_weights)
+__global__ void pack_blob_kernel(int s, int a, const float *W1, const float *b1, const float *W2, const float *b2,
+                                 const float *W3, const float *b3, uint8_t *blob)
+{
+    const int in = s + a;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kWBlobBytes / 2; i += gridDim.x * blockDim.x)
+        reinterpret_cast<__nv_bfloat16 *>(blob)[i] = __float2bfloat16(0.f);
+    __threadfence();
+    // a single CTA is launched: the zero fill above is complete for this CTA's own later writes after the barrier
+    __syncthreads();
+    auto put = [&](int off, int n, int k, int N, float v) {
+        *reinterpret_cast<__nv_bfloat16 *>(blob + off + canon_offset_bytes(n, k, N)) = __float2bfloat16(v);
+    };
+    for (int i = threadIdx.x; i < kMlpH * (in + 1); i += blockDim.x) {
+        const int n = i / (in + 1), k = i - n * (in + 1);
+        put(0, n, k, kMlpH, k < in ? W1[k * kMlpH + n] : b1[n]);
+    }
+    for (int i = threadIdx.x; i < kMlpH * (kMlpH + 1); i += blockDim.x) {
+        const int n = i / (kMlpH + 1), k = i - n * (kMlpH + 1);
+        put(kW1Bytes, n, k, kMlpH, k < kMlpH ? W2[k * kMlpH + n] : b2[n]);
+    }
+    for (int i = threadIdx.x; i < s * (kMlpH + 1); i += blockDim.x) {
+        const int n = i / (kMlpH + 1), k = i - n * (kMlpH + 1);
+        put(kW1Bytes + kW2Bytes, n, k, kMlpNout, k < kMlpH ? W3[k * s + n] : b3[n]);
+    }
+}
+
+}  // namespace
+
+size_t mlp_param_count(int s, int a) { return (size_t)(s + a) * kMlpH + kMlpH + (size_t)kMlpH * kMlpH + kMlpH + (size_t)kMlpH * s + s; }
+
+cudaError_t launch_pack_blob(int s, int a, const float *params, void *blob, cudaStream_t st)
+{
+    const int in = s + a;
+    const float *W1 = params, *b1 = W1 + in * kMlpH, *W2 = b1 + kMlpH, *b2 = W2 + kMlpH * kMlpH, *W3 = b2 + kMlpH, *b3 = W3 + kMlpH * s;
+    pack_blob_kernel<<<1, 1024, 0, st>>>(s, a, W1, b1, W2, b2, W3, b3, static_cast<uint8_t *>(blob));
+    return cudaGetLastError();
+}
+
+// One Adam step.  params / m / v: the six tensors back to back (W1 b1 W2 b2 W3 b3, Keras layout);
+// work: >= n * (in + 3 s + 4 H) + nparams + 1024 + 1 floats of scratch.  Returns the loss BEFORE the step
+// in *loss_dev.
+cudaError_t launch_train_step(int s, int a, int n, const float *x, const float *u, const float *xnext, const float *norm,
+                              float *params, float *adam_m, float *adam_v, float lr_t, float b1c, float b2c, float eps,
+                              float *work, float *loss_dev, cudaStream_t st)
+{
+    const int in = s + a, H = kMlpH;
+    float *W1 = params, *b1 = W1 + in * H, *W2 = b1 + H, *b2 = W2 + H * H, *W3 = b2 + H, *b3 = W3 + H * s;
+    const size_t np = mlp_param_count(s, a);
+    float *Xn = work, *Yn = Xn + (size_t)n * in, *h1 = Yn + (size_t)n * s, *h2 = h1 + (size_t)n * H, *out = h2 + (size_t)n * H;
+    float *dOut = out + (size_t)n * s, *dh2 = dOut + (size_t)n * s, *dh1 = dh2 + (size_t)n * H, *grad = dh1 + (size_t)n * H;
+    float *partial = grad + np;
+    float *gW1 = grad, *gb1 = gW1 + in * H, *gW2 = gb1 + H, *gb2 = gW2 + H * H, *gW3 = gb2 + H, *gb3 = gW3 + H * s;
+    cudaError_t e;
+    const int eb = 256, eg = 592;
+    prepare_kernel<<<eg, eb, 0, st>>>(n, s, a, x, u, xnext, norm, Xn, Yn);
+    // forward
+    if ((e = gemm<false, false>(n, H, in, Xn, W1, b1, true, h1, st)) != cudaSuccess) return e;
+    if ((e = gemm<false, false>(n, H, H, h1, W2, b2, true, h2, st)) != cudaSuccess) return e;
+    if ((e = gemm<false, false>(n, s, H, h2, W3, b3, false, out, st)) != cudaSuccess) return e;
+    const int nb = 1024;
+    loss_kernel<<<nb, 256, 0, st>>>(n * s, out, Yn, dOut, partial);
+    loss_final_kernel<<<1, 1, 0, st>>>(nb, n * s, partial, loss_dev);
+    // backward
+    if ((e = gemm<true, false>(H, s, n, h2, dOut, nullptr, false, gW3, st)) != cudaSuccess) return e;    // gW3 = h2^T dOut
+    colsum_kernel<<<1, 32, 0, st>>>(n, s, dOut, gb3);
+    if ((e = gemm<false, true>(n, H, s, dOut, W3, nullptr, false, dh2, st)) != cudaSuccess) return e;    // dh2 = dOut W3^T
+    relu_mask_kernel<<<eg, eb, 0, st>>>((size_t)n * H, h2, dh2);
+    if ((e = gemm<true, false>(H, H, n, h1, dh2, nullptr, false, gW2, st)) != cudaSuccess) return e;     // gW2 = h1^T dh2
+    colsum_kernel<<<1, H, 0, st>>>(n, H, dh2, gb2);
+    if ((e = gemm<false, true>(n, H, H, dh2, W2, nullptr, false, dh1, st)) != cudaSuccess) return e;     // dh1 = dh2 W2^T
+    relu_mask_kernel<<<eg, eb, 0, st>>>((size_t)n * H, h1, dh1);
+    if ((e = gemm<true, false>(in, H, n, Xn, dh1, nullptr, false, gW1, st)) != cudaSuccess) return e;    // gW1 = Xn^T dh1
+    colsum_kernel<<<1, H, 0, st>>>(n, H, dh1, gb1);
+    adam_kernel<<<64, 256, 0, st>>>((int)np, params, adam_m, adam_v, grad, lr_t, b1c, b2c, eps);
+    return cudaGetLastError();
+}
+
+size_t train_work_floats(int s, int a, int n)
+{
+    return (size_t)n * ((s + a) + 3 * (size_t)s + 4 * (size_t)kMlpH) + mlp_param_count(s, a) + 1024 + 16;
+}
+
+}  // namespace mppi
