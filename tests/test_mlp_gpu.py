@@ -122,3 +122,29 @@ def test_mlp_unsupported_shapes():
         assert e.value.code == _capi.MPPI_ERR_STATE
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("k,tau,lam", [(400000, 2, 0.05), (4096, 20, 1e4)])
+def test_mlp_weighted_sum_paths(oracle64, k, tau, lam):
+    """Zero-weight compaction in the MLP kernel's phase 2: sparse (several list batches per CTA) and dense weights."""
+    a, s = 3, 6
+    mlp = glorot_mlp(s, a, scale=0.5, bias=True)
+    cfg = make_cfg(k, tau, s, a, lam=lam)
+    rng = np.random.default_rng(k)
+    x0 = rng.uniform(-1, 1, s).astype(np.float32)
+    U0 = (0.2 * rng.standard_normal((tau, a))).astype(np.float32)
+    c = _ctrl(cfg, mlp, seed=5)
+    try:
+        c.setSequence(U0)
+        act = c.next(x0)
+        U_new, costs, eps = c.getUpdate(), c.getCosts(), c.dumpNoise()
+    finally:
+        c.close()
+    ref = oracle64.mppi_update_mlp(cfg, mlp, x0, U0, eps)
+    assert rel_err(costs, ref["costs"]) < TOL               # norm-wise: a large lambda makes the action cost dominate
+    # with a tiny lambda the weights amplify bf16 cost errors: compare the update against the oracle's update
+    # recomputed from the GPU's own costs (the weighted sum itself is exact arithmetic on the same noise)
+    w = np.exp(-(costs.astype(np.float64) - costs.min()) / lam)
+    want = U0 + np.einsum("k,kta->ta", w / w.sum(), eps.astype(np.float64))
+    assert rel_err(U_new, want) < 1e-4
+    assert np.abs(act - want[0]).max() <= 1e-4 * np.abs(want).max()

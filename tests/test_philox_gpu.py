@@ -180,3 +180,38 @@ def test_sample_sharding_is_rank_count_independent(world, philox):
     finally:
         for c in ranks:
             c.close()
+
+
+@pytest.mark.parametrize("k,tau,a,lam,what", [
+    (400000, 9, 3, 0.05, "sparse weights, several samples per thread: CTA-wide compaction"),
+    (400000, 9, 3, 1e3, "dense weights: the direct loop"),
+    (1500000, 4, 1, 2e-4, "more than one compaction batch per CTA (over 4096 samples per CTA)"),
+    (70000, 12, 2, 0.02, "sparse weights, less than one sample per thread"),
+])
+def test_weighted_sum_paths_store_then_replay(oracle32, oracle64, k, tau, a, lam, what):
+    """Phase 2 revisits only the samples whose fp32 weight is non-zero (0 * z adds nothing); which code path runs
+    depends on lambda against the cost spread.  Every path must reproduce the oracle on the dumped noise."""
+    rng = np.random.default_rng(k + tau)
+    cfg = make_cfg(k, tau, 2 * a, a, lam=lam)
+    x0 = rng.uniform(-1, 1, 2 * a).astype(np.float32)
+    U0 = (0.2 * rng.standard_normal((tau, a))).astype(np.float32)
+    ctrl = controller_from_cfg(cfg, seed=9)
+    try:
+        ctrl.setSequence(U0)
+        act = ctrl.next(x0)
+        U_new, costs, eps = ctrl.getUpdate(), ctrl.getCosts(), ctrl.dumpNoise()
+        beta, eta = ctrl.getWeightStats()
+    finally:
+        ctrl.close()
+    d = (costs.astype(np.float64) - costs.min()) / lam * 1.4426950408889634
+    frac_nonzero = np.mean(d < 126)
+    if lam < 1:
+        assert frac_nonzero < 0.9, (what, frac_nonzero)          # the case really exercises the sparse path
+    else:
+        assert frac_nonzero == 1.0
+    r64 = oracle64.mppi_update(cfg, x0, U0, eps)
+    r32 = oracle32.mppi_update(cfg, x0, U0, eps)
+    assert rel_err(costs, r64["costs"]) < 1e-5            # norm-wise: with lambda = 1e3 the action cost dominates
+    assert_update_close(U_new, r64["U_new"], r32["U_new"], what="U_new: " + what)
+    assert_update_close(act, r64["next"], r32["next"], what="next: " + what)
+    assert abs(float(np.ravel(beta)[0]) - r64["costs"].min()) <= 2e-5 * abs(r64["costs"].min()) + 2e-5
