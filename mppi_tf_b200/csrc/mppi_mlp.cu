@@ -32,13 +32,15 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_predict_kernel(MlpParams mp, 
 #pragma unroll
         for (int i = 0; i < A; i++) u[i] = (r < k) ? action[(size_t)r * A + i] : 0.f;
         mlp_row_begin<S, A>(t, x, u);
-        mlp_row_layer1(t);
-        mlp_row_layer2(t);
+        mlp_row_layer1(t, 0);
+        mlp_row_layer2(t, 0);
         mlp_row_finish<S>(t, x);
         if (r < k) {
 #pragma unroll
             for (int i = 0; i < S; i++) out[(size_t)r * S + i] = x[i];
         }
+    } else if (threadIdx.x < 32 * kMlpEpiWarps) {
+        mlp_helper_loop(t, 1);
     } else {
         mlp_mma_loop(t, 1);
     }
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
     if (p.norm_mode == 2) {
         // weight pass of a normalised update: costs are in HBM, no rollout
     } else if (warp < kMlpRowWarps) {
+        reg_inc<kMlpRegsRow>();
         float g[S], q[S], x0[S];
         {
             const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * S : 0);
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
                         Sk += mlp_state_cost<S>(p, x, g, q);
                     }
                     Sk += ac;
-                    mlp_row_layer1(t);
+                    mlp_row_layer1(t, 0);
                     // in the shadow of layer 2 (the long MMA): this step's share of the next block's noise
                     if (more) {
 #pragma unroll
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
                             for (int j = 0; j < 4; j++) zn[4 * c + j] = z4[j];
                         }
                     }
-                    mlp_row_layer2(t);
+                    mlp_row_layer2(t, 0);
                     mlp_row_finish<S>(t, x);
                 }
 #pragma unroll
@@ -211,8 +214,15 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
                 bmax = fmaxf(bmax, Sk);
             }
         }
+        reg_dec<kMlpRegsLaunch>();
+    } else if (warp < kMlpEpiWarps) {
+        reg_dec<kMlpRegsHelper>();
+        mlp_helper_loop(t, (t_hi - t_lo) * p.T);
+        reg_inc<kMlpRegsLaunch>();
     } else {
+        reg_dec<kMlpRegsMma>();
         mlp_mma_loop(t, (t_hi - t_lo) * p.T);
+        reg_inc<kMlpRegsLaunch>();
     }
     mlp_tile_fini(t);
     bmin = warp_min(bmin);

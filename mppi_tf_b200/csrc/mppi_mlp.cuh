@@ -33,8 +33,11 @@ constexpr int kMlpRows = 128;     // samples per tile = TMEM lanes
 #define MPPI_MLP_SPLIT_N 1
 #endif
 constexpr bool kMlpSplitN = MPPI_MLP_SPLIT_N != 0;   // layer 2 as two N = 64 halves (1) or one N = 128 MMA per K step (0)
-constexpr int kMlpRowWarps = 4;    // one per TMEM lane quadrant
-constexpr int kMlpThreads = 160;  // 4 row warps + 1 MMA warp
+constexpr int kMlpRowWarps = 4;    // one per TMEM lane quadrant: thread = sample row (state, noise, cost)
+constexpr int kMlpEpiWarps = 8;    // warps 0-3 (rows) and 4-7 (helpers): two threads per row share every conversion,
+                                   // each taking 32 of the 64 accumulator columns of an N half
+constexpr int kMlpMmaWarp = kMlpEpiWarps;
+constexpr int kMlpThreads = 32 * (kMlpEpiWarps + 1);
 
 // shared-memory weight blob (bytes), canonical K-major no-swizzle core-matrix layout:
 //   element (n, k) of B[N x K] at ((k/8)*(N/8) + n/8)*128 + (n%8)*16 + (k%8)*2
@@ -193,6 +196,14 @@ __device__ int g_mlp_trace_n[2];
 #define MLP_TRACE(who, ev)
 #endif
 
+// Register re-partitioning between the roles (setmaxnreg, warp-group granularity): the kernel launches with 96
+// registers per thread; during the rollout the row warps take what the helper and MMA warps do not need.
+constexpr int kMlpRegsLaunch = 96, kMlpRegsRow = 136, kMlpRegsHelper = 56, kMlpRegsMma = 40;
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // mbarriers of one CTA tile
 enum MlpBar : int {
     kBarW = 0,     // weights landed (TMA complete_tx)
@@ -313,24 +324,20 @@ __device__ __forceinline__ void mlp_mma_loop(MlpTile &t, int nsteps)
 }
 
 // ---- row warps ------------------------------------------------------------------------------------
-// accumulator N half `h` -> 32 packed bf16x2 words, ReLU folded into the conversion (the bias already
-// sits in the accumulator: K-augmented GEMM)
-__device__ __forceinline__ void mlp_load_pack(const MlpTile &t, int h, uint32_t (&o)[32])
+// this thread's 32 columns (`part` 0 / 1) of accumulator N half `h` -> 16 packed bf16x2 words, ReLU folded
+// into the conversion (the bias already sits in the accumulator: K-augmented GEMM)
+__device__ __forceinline__ void mlp_load_pack(const MlpTile &t, int h, int part, uint32_t (&o)[16])
 {
-    uint32_t v0[32], v1[32];
-    const uint32_t d = t.lane_addr + kColD + 64u * h;
-    tmem_ld32(d, v0);
-    tmem_ld32(d + 32u, v1);
+    uint32_t v[32];
+    tmem_ld32(t.lane_addr + kColD + 64u * h + 32u * part, v);
     tc_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 16; i++) o[i] = pack_relu_bf16x2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
-#pragma unroll
-    for (int i = 0; i < 16; i++) o[16 + i] = pack_relu_bf16x2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+    for (int i = 0; i < 16; i++) o[i] = pack_relu_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
 }
-// store K half `h` of the next A operand and hand it to the MMA warp
-__device__ __forceinline__ void mlp_store_signal(const MlpTile &t, int h, const uint32_t (&o)[32])
+// store this thread's 16 columns of K half `h` of the next A operand and hand them to the MMA warp
+__device__ __forceinline__ void mlp_store_signal(const MlpTile &t, int h, int part, const uint32_t (&o)[16])
 {
-    tmem_st32(t.lane_addr + kColA + 32u * h, o);
+    tmem_st16(t.lane_addr + kColA + 32u * h + 16u * part, o);
     tc_wait_st();
     tc_fence_before();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&t.bars[h ? kBarA1 : kBarA0]);
@@ -360,45 +367,54 @@ __device__ __forceinline__ void mlp_row_begin(MlpTile &t, const float (&x)[S], c
     MLP_TRACE(0, 1);
 }
 // Step part 2: layer-1 epilogue (the A region is dead here: the previous output layer has completed).
-__device__ __forceinline__ void mlp_row_layer1(MlpTile &t)
+// Called by the row thread (part 0) and by its helper (part 1).
+__device__ __forceinline__ void mlp_row_layer1(MlpTile &t, int part)
 {
-    uint32_t o[32];
+    uint32_t o[16];
     MLP_TRACE(0, 2);
     mbar_wait(&t.bars[kBarD0], t.ph_d);
     MLP_TRACE(0, 3);
     tc_fence_after();
-    mlp_load_pack(t, 0, o);
+    mlp_load_pack(t, 0, part, o);
     MLP_TRACE(0, 4);
-    mlp_store_signal(t, 0, o);
+    mlp_store_signal(t, 0, part, o);
     MLP_TRACE(0, 5);
     mbar_wait(&t.bars[kBarD1], t.ph_d);
     MLP_TRACE(0, 6);
     tc_fence_after();
-    mlp_load_pack(t, 1, o);
-    mlp_store_signal(t, 1, o);
+    mlp_load_pack(t, 1, part, o);
+    mlp_store_signal(t, 1, part, o);
     MLP_TRACE(0, 7);
     t.ph_d ^= 1;
 }
 // Step part 3: layer-2 epilogue.  Half 0 is converted while the tensor pipe produces half 1, but it
 // is stored only after half 1 has completed: until then the MMAs still read A1 from the same columns.
-__device__ __forceinline__ void mlp_row_layer2(MlpTile &t)
+__device__ __forceinline__ void mlp_row_layer2(MlpTile &t, int part)
 {
-    uint32_t o[32];
+    uint32_t o[16];
     MLP_TRACE(0, 8);
     mbar_wait(&t.bars[kBarD0], t.ph_d);
     MLP_TRACE(0, 9);
     tc_fence_after();
-    mlp_load_pack(t, 0, o);
+    mlp_load_pack(t, 0, part, o);
     MLP_TRACE(0, 10);
     mbar_wait(&t.bars[kBarD1], t.ph_d);
     MLP_TRACE(0, 11);
     tc_fence_after();
-    mlp_store_signal(t, 0, o);
+    mlp_store_signal(t, 0, part, o);
     MLP_TRACE(0, 12);
-    mlp_load_pack(t, 1, o);
-    mlp_store_signal(t, 1, o);
+    mlp_load_pack(t, 1, part, o);
+    mlp_store_signal(t, 1, part, o);
     MLP_TRACE(0, 13);
     t.ph_d ^= 1;
+}
+// The helper thread of a row: its share of every conversion of `nsteps` network evaluations.
+__device__ __forceinline__ void mlp_helper_loop(MlpTile &t, int nsteps)
+{
+    for (int s = 0; s < nsteps; s++) {
+        mlp_row_layer1(t, 1);
+        mlp_row_layer2(t, 1);
+    }
 }
 // Step part 4: x' = x + d * Ystd + Ymean
 template <int S>
@@ -426,15 +442,15 @@ __device__ __forceinline__ void mlp_tile_init(MlpTile &t, const MlpParams &mp, u
     if (threadIdx.x == 0) {
         mbar_init(&bars[kBarW], 1);
         mbar_init(&bars[kBarX], kMlpRowWarps);
-        mbar_init(&bars[kBarA0], kMlpRowWarps);
-        mbar_init(&bars[kBarA1], kMlpRowWarps);
+        mbar_init(&bars[kBarA0], kMlpEpiWarps);
+        mbar_init(&bars[kBarA1], kMlpEpiWarps);
         mbar_init(&bars[kBarD0], 1);
         mbar_init(&bars[kBarD1], 1);
         mbar_init(&bars[kBarD3], 1);
         fence_mbar_init();
     }
     for (int i = threadIdx.x; i < kFvecFloats; i += blockDim.x) smem_f[i] = mp.fvec[i];
-    if (warp == kMlpRowWarps) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == kMlpMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -451,7 +467,7 @@ __device__ __forceinline__ void mlp_tile_init(MlpTile &t, const MlpParams &mp, u
     t.ph_d3 = 0;
 #ifdef MPPI_MLP_TRACE
     t.tr_n = 0;
-    t.tr_on = blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (warp == 0 || warp == 4);
+    t.tr_on = blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (warp == 0 || warp == kMlpMmaWarp);
 #endif
     if (warp < kMlpRowWarps) {   // K-augmentation columns of the activation operand: k = 128 is the constant 1, k = 129..143 are 0
         uint32_t one[8] = {pack_bf16x2(1.0f, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -469,7 +485,7 @@ __device__ __forceinline__ void mlp_tile_fini(MlpTile &t)
 {
     tc_fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == kMlpRowWarps) tmem_dealloc(t.tmem, kTmemCols);
+    if ((threadIdx.x >> 5) == kMlpMmaWarp) tmem_dealloc(t.tmem, kTmemCols);
 }
 
 }  // namespace mppi
