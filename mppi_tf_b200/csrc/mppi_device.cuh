@@ -150,13 +150,30 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float &z0, 
     z1 = r * sn;
 }
 
-// Four standard normals z[4c .. 4c+3] of sample `k` (global index).
+// Four standard normals z[4c .. 4c+3] of sample `k` (global index): Box-Muller on (x0,x1) and (x2,x3), the
+// two pairs processed together with packed fp32 instructions (FFMA2 / FMUL2) wherever both need the same op.
 __device__ __forceinline__ void normals4(uint32_t call, uint32_t k, uint32_t stream, const RolloutParams &p,
                                          float z[4])
 {
     const uint4 x = philox4x32_10_rk(call, k, p.update, stream, p.rk0, p.rk1);
-    box_muller(x.x, x.y, z[0], z[1]);
-    box_muller(x.z, x.w, z[2], z[3]);
+    const float2 fa = make_float2(bits_to_1_2(x.x), bits_to_1_2(x.z));           // radius uniforms of both pairs
+    const float2 fb = make_float2(bits_to_1_2(x.y), bits_to_1_2(x.w));           // angle uniforms of both pairs
+    const float2 u1 = __ffma2_rn(fa, make_float2(-1.f, -1.f), make_float2(2.f, 2.f));                       // (0, 1]
+    const float2 th = __ffma2_rn(fb, make_float2(6.2831853071795865f, 6.2831853071795865f),
+                                 make_float2(-6.2831853071795865f, -6.2831853071795865f));                  // [0, 2pi)
+    float2 l2;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2.x) : "f"(u1.x));                   // u1 is never denormal
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2.y) : "f"(u1.y));
+    const float2 a2 = __fmul2_rn(l2, make_float2(-1.3862943611198906f, -1.3862943611198906f));             // -2 ln u1
+    float2 r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(a2.x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(a2.y));
+    float2 csA, csB;                                                              // (cos, sin) of each pair
+    __sincosf(th.x, &csA.y, &csA.x);
+    __sincosf(th.y, &csB.y, &csB.x);
+    const float2 zA = __fmul2_rn(make_float2(r.x, r.x), csA);
+    const float2 zB = __fmul2_rn(make_float2(r.y, r.y), csB);
+    z[0] = zA.x; z[1] = zA.y; z[2] = zB.x; z[3] = zB.y;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ cudaError_t launch_finish(RolloutParams p, int a, bool philox, const float *gath
 cudaError_t launch_dump_noise(RolloutParams p, int a, float *out_dev, cudaStream_t st);
 int max_grid_x(int K_local, int n_ctrl, int num_sms);
 bool injected_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sms, size_t smem_limit,
-                       int *ng_out, int *c_out, int *stages_out, int *grid_x_out, size_t *smem_out);
+                       int *ng_out, int *c_out, int *nbuf_out, int *grid_x_out, size_t *smem_out);
 
 // mppi_mlp.cu
 struct MlpParams;

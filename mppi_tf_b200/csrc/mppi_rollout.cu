@@ -353,7 +353,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
 struct InjectedLaunch {
     int ng;      // tile groups per CTA
     int c;       // warps per group (time chunks)
-    int stages;  // tile buffers per group (private ring per group)
+    int nbuf;    // tile buffers of the CTA: a shared pool, tile sequence number seq lives in buffer seq % nbuf
 };
 
 __device__ __forceinline__ void group_barrier(int id, int nthreads)
@@ -390,7 +390,7 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
     extern __shared__ float4 smem_f4[];
     float *smem = reinterpret_cast<float *>(smem_f4);
     const int TA = p.TA, TAp = (TA + 31) & ~31;
-    const int NG = L.ng, C = L.c, ST = L.stages, NBUF = NG * ST;
+    const int NG = L.ng, C = L.c, NBUF = L.nbuf;
     const int tile_words = 32 * TA;                // multiple of 32 words: every tile 128-B aligned
     float *sTiles = smem;                          // [NBUF][32][TA]
     float *sUV = sTiles + (size_t)NBUF * tile_words;   // [T][RS]
@@ -402,6 +402,7 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
     float *sB = sRed + 64;                         // [NG][C][2A][32] zero-state chunk responses
     float *sS = sB + NG * C * 2 * A * 32;          // [NG][C][32] chunk costs
     uint64_t *bars = reinterpret_cast<uint64_t *>(sS + NG * C * 32);   // [NBUF]
+    volatile int *sIssued = reinterpret_cast<volatile int *>(bars + 64);   // [NBUF] tile sequence number last issued into a buffer
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = warp / C, cw = warp - grp * C;
@@ -409,29 +410,31 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
     const int nseq = (n_tiles > (int)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const float *eps = p.eps + (size_t)ctrl * p.K_local * TA;
 
-    // Group g consumes tile sequence numbers seq = g + j*NG (j = 0,1,..) of this CTA; its j-th tile
-    // lands in its private buffer g*ST + j%ST and completes phase j/ST of that buffer's mbarrier.
-    auto issue = [&](int g, int j) {   // one elected lane; TMA bulk copy of a whole tile
-        const int b = g * ST + (j % ST);
-        const int seq = g + j * NG;
+    // Tile sequence number seq (0, 1, .. of this CTA) is consumed by group seq % NG and lives in buffer
+    // seq % NBUF, completing phase seq / NBUF of that buffer's mbarrier.  The group that finishes tile seq
+    // refills its buffer with tile seq + NBUF at once - a tile another group will consume - so with
+    // NBUF > NG every group finds its next tile already in flight (config 3: 4 groups, 5 buffers).
+    auto issue = [&](int seq) {   // one elected lane; TMA bulk copy of a whole tile
+        const int b = seq % NBUF;
         const int gt = seq * gridDim.x + blockIdx.x;
         const int rows = min(32, p.K_local - 32 * gt);
         const uint32_t bytes = (uint32_t)rows * TA * 4u;
+        sIssued[b] = seq;
         mbar_expect_tx(&bars[b], bytes);
         bulk_g2s(sTiles + (size_t)b * tile_words, eps + (size_t)gt * tile_words, bytes, &bars[b]);
     };
 
     if (TMA) {
         if (tid == 0) {
-            for (int b = 0; b < NBUF; b++) mbar_init(&bars[b], 1);
+            for (int b = 0; b < NBUF; b++) { mbar_init(&bars[b], 1); sIssued[b] = -1; }
             fence_mbar_init();
         }
     }
     stage_sequence<A, false>(p, ctrl, sUV);
     for (int i = tid; i < NG * TAp; i += blockDim.x) sAccG[i] = 0.f;
     __syncthreads();
-    if (TMA && lane == 0 && cw == 0 && grp < NG) {
-        for (int j = 0; j < ST && grp + j * NG < nseq; j++) issue(grp, j);
+    if (TMA && tid == 0) {
+        for (int seq = 0; seq < NBUF && seq < nseq; seq++) issue(seq);
     }
 
     ModelConsts<A> mc;
@@ -472,13 +475,17 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
     }
 
     if (grp < NG) {
-        for (int j = 0, seq = grp; seq < nseq; j++, seq += NG) {
-            const int b = grp * ST + (j % ST);
+        for (int seq = grp; seq < nseq; seq += NG) {
+            const int b = TMA ? seq % NBUF : grp;          // cooperative-load fallback: a private buffer per group
             const int gt = seq * gridDim.x + blockIdx.x;
             const int rows = min(32, p.K_local - 32 * gt);
             float *tile = sTiles + (size_t)b * tile_words;
             if (TMA) {
-                mbar_wait(&bars[b], (uint32_t)((j / ST) & 1));
+                // A parity wait cannot tell phase n from phase n - 2: with a shared pool a group may get here before
+                // the load of ITS tile has even been issued (the buffer's previous user, another group, is still
+                // busy), so first wait until the buffer has been handed to this tile, then for the bytes.
+                while (sIssued[b] != seq) __nanosleep(32);
+                mbar_wait(&bars[b], (uint32_t)((seq / NBUF) & 1));
                 if (rows < 32 && cw == 0) {   // zero the rows the copy did not write (e = 0 must not meet NaN garbage)
                     for (int i = rows * TA + lane; i < tile_words; i += 32) tile[i] = 0.f;
                 }
@@ -585,9 +592,9 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
             if (p.norm_mode == 1) {                // cost pass: track (min, max), no weights yet
                 if (lane < rows) { gmin = fminf(gmin, S); gmax = fmaxf(gmax, S); }
                 if (C > 1) group_barrier(bar_id, bar_n); else __syncwarp();
-                if (TMA && lane == 0 && cw == 0 && seq + ST * NG < nseq) {
+                if (TMA && lane == 0 && cw == 0 && seq + NBUF < nseq) {
                     fence_proxy_async();
-                    issue(grp, j + ST);
+                    issue(seq + NBUF);
                 }
                 continue;
             }
@@ -639,9 +646,9 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
                 }
             }
             if (C > 1) group_barrier(bar_id, bar_n); else __syncwarp();   // everyone is done with the tile
-            if (TMA && lane == 0 && cw == 0 && seq + ST * NG < nseq) {
+            if (TMA && lane == 0 && cw == 0 && seq + NBUF < nseq) {
                 fence_proxy_async();
-                issue(grp, j + ST);
+                issue(seq + NBUF);
             }
         }
         eta_lane = warp_sum(eta_lane);
@@ -816,9 +823,9 @@ cudaError_t launch_rollout_philox(RolloutParams p, int a, int num_sms, cudaStrea
     return cudaSuccess;
 }
 
-// Injected mode geometry: tile groups / warps per group / stages that fit in shared memory.
+// Injected mode geometry: tile groups / warps per group / tile buffers that fit in shared memory.
 bool injected_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sms, size_t smem_limit,
-                       int *ng_out, int *c_out, int *stages_out, int *grid_x_out, size_t *smem_out)
+                       int *ng_out, int *c_out, int *nbuf_out, int *grid_x_out, size_t *smem_out)
 {
     const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31;
     const size_t tile_b = (size_t)128 * TA;
@@ -829,21 +836,25 @@ bool injected_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sm
     if (n_ctrl >= 2 * num_sms) ctas_per_sm = 4;
     const int max_warps = 16 / ctas_per_sm;         // 512 threads per SM: <= 128 registers per thread
     const size_t budget = smem_limit / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
-    const size_t fixed = sizeof(float) * ((size_t)T * RS + 2 * TAp + kMaxParts + 64) + 8 * 64 + 64;
+    const size_t fixed = sizeof(float) * ((size_t)T * RS + 2 * TAp + kMaxParts + 64) + 8 * 64 + 4 * 64 + 64;
     // per group: running sums + chunk responses/costs for up to 4 warps
     const size_t per_group = sizeof(float) * ((size_t)TAp + 4 * (2 * A + 1) * 32);
     if (fixed + per_group + tile_b > budget) return false;
-    int ng = (int)((budget - fixed) / (per_group + tile_b));
+    int fit = (int)((budget - fixed) / (per_group + tile_b));      // tiles that fit if every tile had its own group
+    int ng = fit;
     if (ng > max_warps) ng = max_warps;
     if (ng > n_tiles) ng = n_tiles > 0 ? n_tiles : 1;
+    // few large tiles (config 3: five of 38 KB): give one buffer up as a prefetch slot - every group then finds
+    // its next tile in flight - and spend the warps on splitting the horizon instead
+    if (ng == fit && ng >= 3 && ng < max_warps && n_tiles > ng) ng -= 1;
     int c = max_warps / ng;
     if (c > 4) c = 4;
     if (c > nblk / 6) c = nblk / 6;                 // at least 24 steps per time chunk
     if (c < 1) c = 1;
     if (c > 1 && ng > 15) c = 1;                    // named barriers 1..15
-    int st = (int)((budget - fixed - ng * per_group) / (ng * tile_b));
-    if (st > 3) st = 3;
-    if (st < 1) st = 1;
+    int nbuf = (int)((budget - fixed - ng * per_group) / tile_b);
+    if (nbuf > 3 * ng) nbuf = 3 * ng;
+    if (nbuf < ng) nbuf = ng;
     int gx;
     const int need = (n_tiles + ng - 1) / ng;
     if (n_ctrl == 1) gx = num_sms * ctas_per_sm;
@@ -851,13 +862,13 @@ bool injected_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sm
     if (gx > need) gx = need;
     if (gx < 1) gx = 1;
     if (gx > kMaxParts) gx = kMaxParts;
-    const int tiles_per_group = (n_tiles + gx * ng - 1) / (gx * ng);
-    if (st > tiles_per_group) st = tiles_per_group > 0 ? tiles_per_group : 1;
+    const int tiles_per_cta = (n_tiles + gx - 1) / gx;
+    if (nbuf > tiles_per_cta) nbuf = tiles_per_cta > ng ? tiles_per_cta : ng;
     *ng_out = ng;
     *c_out = c;
-    *stages_out = st;
+    *nbuf_out = nbuf;
     *grid_x_out = gx;
-    *smem_out = fixed + ng * per_group + (size_t)ng * st * tile_b;
+    *smem_out = fixed + ng * per_group + (size_t)nbuf * tile_b;
     return true;
 }
 
@@ -892,7 +903,7 @@ cudaError_t launch_rollout_injected(RolloutParams p, int a, int num_sms, size_t 
     InjectedLaunch L;
     int gx = 1;
     size_t smem = 0;
-    if (!injected_geometry(a, p.T, p.TA, p.K_local, p.n_ctrl, num_sms, smem_limit, &L.ng, &L.c, &L.stages, &gx, &smem))
+    if (!injected_geometry(a, p.T, p.TA, p.K_local, p.n_ctrl, num_sms, smem_limit, &L.ng, &L.c, &L.nbuf, &gx, &smem))
         return cudaErrorInvalidConfiguration;
     if (grid_x_out) *grid_x_out = gx;
     // TMA path needs 16-byte aligned tiles and rows: T*a % 4 == 0 and an aligned base pointer.
