@@ -14,6 +14,9 @@
 //
 // Reference maths: /root/reference/src/controller_base.cpp:166-329, src/model_base.cpp:53-82,
 // src/cost_base.cpp:37-68 (restated in the CPU checker that tests compare against).
+#include <cstdio>
+#include <cstdlib>
+
 #include "mppi_device.cuh"
 #include "mppi_internal.h"
 #include "mppi_update.cuh"
@@ -905,6 +908,14 @@ cudaError_t launch_rollout_injected(RolloutParams p, int a, int num_sms, size_t 
     size_t smem = 0;
     if (!injected_geometry(a, p.T, p.TA, p.K_local, p.n_ctrl, num_sms, smem_limit, &L.ng, &L.c, &L.nbuf, &gx, &smem))
         return cudaErrorInvalidConfiguration;
+    if (const char *ov = getenv("MPPI_INJ_GEOM")) {      // developer knob: "ng,c,nbuf" (no validation beyond the smem size)
+        int ng = 0, c = 0, nb = 0;
+        if (sscanf(ov, "%d,%d,%d", &ng, &c, &nb) == 3 && ng >= 1 && c >= 1 && nb >= ng && ng * c <= 16) {
+            const size_t tile_b = (size_t)128 * p.TA;
+            const size_t grown = smem - (size_t)L.nbuf * tile_b + (size_t)nb * tile_b + 4096;
+            if (grown <= smem_limit) { L.ng = ng; L.c = c; L.nbuf = nb; smem = grown; }
+        }
+    }
     if (grid_x_out) *grid_x_out = gx;
     // TMA path needs 16-byte aligned tiles and rows: T*a % 4 == 0 and an aligned base pointer.
     const bool tma = (p.TA % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.eps) & 15u) == 0);
