@@ -3,6 +3,7 @@
 // parameter block and launches the kernels of mppi_rollout.cu / mppi_stages.cu.
 #include <dlfcn.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -86,6 +87,10 @@ struct mppi_handle {
     bool ext_exchange = false;
     // pinned host staging
     float *h_x = nullptr, *h_next = nullptr;
+    // zero-copy result path (n_ctrl == 1): mapped pinned [a floats | pad | completion word]
+    float *h_zc = nullptr, *d_zc = nullptr;
+    unsigned int zc_epoch = 0;
+    bool zc_armed = false, zc_request = false;   // requested by the synchronous next(): async callers do not pay the host write
     bool x_staged = false;
     NcclComm comm = nullptr;
     // fused exchange over peer memory (mppi_peer_handle / mppi_peer_attach)
@@ -230,6 +235,11 @@ RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
     p.stats = h->d_stats;
     p.counters = h->d_counters;
     p.eps = eps_dev;
+    if (h->d_zc && h->zc_request) {
+        p.next_host = h->d_zc;
+        p.done_host = reinterpret_cast<unsigned int *>(h->d_zc + 16);
+        p.done_epoch = h->zc_epoch;
+    }
     p.peer_on = h->peer_on ? 1 : 0;
     p.rank = h->rank;
     p.epoch = h->epoch;
@@ -352,6 +362,17 @@ int mppi_create(const mppi_config *cfg, mppi_handle **out)
     CU_TRY_C(cudaMemset(h->d_x, 0, sizeof(float) * n_ctrl * s));
     CU_TRY_C(cudaMallocHost(&h->h_x, sizeof(float) * n_ctrl * s));
     CU_TRY_C(cudaMallocHost(&h->h_next, sizeof(float) * n_ctrl * a));
+    if (n_ctrl == 1) {
+        if (cudaHostAlloc(&h->h_zc, 128, cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer(&h->d_zc, h->h_zc, 0) == cudaSuccess) {
+            memset(h->h_zc, 0, 128);
+        } else {
+            (void)cudaGetLastError();
+            if (h->h_zc) cudaFreeHost(h->h_zc);
+            h->h_zc = nullptr;
+            h->d_zc = nullptr;
+        }
+    }
     memset(h->h_x, 0, sizeof(float) * n_ctrl * s);
 
     std::vector<float> goal(n_goal);
@@ -383,6 +404,7 @@ int mppi_destroy(mppi_handle *h)
     if (!h->ext_exchange) { cudaFree(h->d_payload); cudaFree(h->d_gather); }
     if (h->h_x) cudaFreeHost(h->h_x);
     if (h->h_next) cudaFreeHost(h->h_next);
+    if (h->h_zc) cudaFreeHost(h->h_zc);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MPPI_OK;
@@ -420,6 +442,7 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
     if (!h->x_staged) return fail(h, MPPI_ERR_STATE, "mppi_set_state must precede mppi_enqueue_update");
     CU_TRY(h, cudaSetDevice(h->device));
     if (h->peer_on) h->epoch++;                     // same count on every rank: one per update
+    if (h->d_zc && h->zc_request) { h->zc_epoch++; h->zc_armed = true; }
     RolloutParams p = make_params(h, eps_dev);
     int gx = 0;
     // cost normalisation (controller_base.py:468-474) needs max_k(S_k - beta) before any weight: two launches,
@@ -484,6 +507,31 @@ int mppi_fetch_action(mppi_handle *h, float *action_host)
 {
     if (!h || !action_host) return fail(h, MPPI_ERR_BAD_ARG, "null handle/action");
     CU_TRY(h, cudaSetDevice(h->device));
+    // zero-copy fast path: the kernel that applies the update has stored the action and then the update's epoch
+    // into mapped pinned memory; wait for the word instead of copying and synchronising the stream
+    const bool finish_in_kernel = (h->world <= 1) || h->peer_on;
+    if (h->zc_armed && h->h_zc && finish_in_kernel && !h->pending_finish) {
+        volatile unsigned int *done = reinterpret_cast<volatile unsigned int *>(h->h_zc + 16);
+        bool seen = false;
+        for (long long spin = 0; spin < (1LL << 34); spin++) {
+            if (*done == h->zc_epoch) { seen = true; break; }
+            if ((spin & 0xfffff) == 0xfffff && cudaStreamQuery(h->stream) != cudaErrorNotReady) break;   // finished or failed
+        }
+        h->zc_armed = false;
+        if (seen || *done == h->zc_epoch) {
+            std::atomic_thread_fence(std::memory_order_acquire);
+            memcpy(action_host, h->h_zc, sizeof(float) * h->a);
+            if (h->peer_on) {
+                CU_TRY(h, cudaMemcpyAsync(h->h_peer_status, h->d_peer_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+                CU_TRY(h, cudaStreamSynchronize(h->stream));
+                if (*h->h_peer_status != 0u)
+                    return fail(h, MPPI_ERR_COMM, "fused exchange: a peer's payload did not arrive in time (is every rank calling the update?)");
+            }
+            return MPPI_OK;
+        }
+        CU_TRY(h, cudaStreamSynchronize(h->stream));    // surfaces the launch failure, if any; else fall through
+    }
+    h->zc_armed = false;
     CU_TRY(h, cudaMemcpyAsync(h->h_next, h->d_next, sizeof(float) * h->n_ctrl * h->a, cudaMemcpyDeviceToHost, h->stream));
     if (h->peer_on)
         CU_TRY(h, cudaMemcpyAsync(h->h_peer_status, h->d_peer_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
@@ -506,7 +554,9 @@ static int next_common(mppi_handle *h, const float *x_host, const float *eps_dev
 {
     int rc = mppi_set_state(h, x_host);
     if (rc) return rc;
+    h->zc_request = true;            // the caller waits for the action: let the kernel hand it over through mapped memory
     rc = mppi_enqueue_update(h, eps_dev);
+    h->zc_request = false;
     if (rc) return rc;
     if (h->world > 1) {
         rc = exchange(h);

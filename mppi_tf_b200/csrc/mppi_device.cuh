@@ -73,6 +73,11 @@ struct RolloutParams {
     float *peer_mail[kMaxWorld];
     uint32_t *peer_flag[kMaxWorld];
     unsigned int *peer_status;   // set != 0 if a peer's payload did not arrive in time
+    // zero-copy result (single controller): the finishing CTA also stores the action into mapped pinned host
+    // memory and publishes `done_epoch`, so the synchronous next() needs neither a D2H copy nor a stream sync
+    float *next_host;            // device alias of the mapped host buffer [a], or nullptr
+    unsigned int *done_host;     // device alias of the mapped completion word
+    unsigned int done_epoch;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)

@@ -27,6 +27,22 @@ cudaError_t launch_rollout_mlp(RolloutParams p, const MlpParams &mp, int a, bool
 void mlp_pack_weights(int s, int a, const float *W1, const float *b1, const float *W2, const float *b2,
                       const float *W3, const float *b3, void *blob_host);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs a microsecond or two per call: remember, per kernel
+// instantiation and device, the largest size already granted and only raise it.
+template <auto kernel>
+inline cudaError_t ensure_dyn_smem(size_t smem)
+{
+    static size_t granted[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem <= granted[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) granted[dev] = smem;
+    return e;
+}
+
 // mppi_train.cu  (device pointers)
 size_t mlp_param_count(int s, int a);
 size_t train_work_floats(int s, int a, int n);

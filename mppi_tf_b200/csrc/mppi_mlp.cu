@@ -340,7 +340,7 @@ cudaError_t launch_mlp_predict(const MlpParams &mp, int kst, int k, const float 
     const size_t smem = mlp_predict_smem();
     const int grid = (k + kMlpRows - 1) / kMlpRows;
     MPPI_DISPATCH_MLP_A(mp.a, {
-        cudaError_t err = cudaFuncSetAttribute(mlp_predict_kernel<2 * A_, A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t err = ensure_dyn_smem<mlp_predict_kernel<2 * A_, A_>>(smem);
         if (err != cudaSuccess) return err;
         mlp_predict_kernel<2 * A_, A_><<<grid, kMlpThreads, smem, st>>>(mp, kst, k, state, action, out);
     });
@@ -367,11 +367,11 @@ cudaError_t launch_rollout_mlp(RolloutParams p, const MlpParams &mp, int a, bool
     MPPI_DISPATCH_MLP_A(a, {
         cudaError_t err;
         if (philox) {
-            err = cudaFuncSetAttribute(rollout_mlp_kernel<A_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            err = ensure_dyn_smem<rollout_mlp_kernel<A_, true>>(smem);
             if (err != cudaSuccess) return err;
             rollout_mlp_kernel<A_, true><<<grid, kMlpThreads, smem, st>>>(p, mp);
         } else {
-            err = cudaFuncSetAttribute(rollout_mlp_kernel<A_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            err = ensure_dyn_smem<rollout_mlp_kernel<A_, false>>(smem);
             if (err != cudaSuccess) return err;
             rollout_mlp_kernel<A_, false><<<grid, kMlpThreads, smem, st>>>(p, mp);
         }

@@ -768,7 +768,7 @@ static size_t philox_smem_bytes(int A, int T, int TA)
 template <int A, bool DIAG, bool QUAD, int COST>
 static cudaError_t launch_philox_V(const RolloutParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
-    cudaError_t err = cudaFuncSetAttribute(rollout_philox_kernel<A, DIAG, QUAD, COST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = ensure_dyn_smem<rollout_philox_kernel<A, DIAG, QUAD, COST>>(smem);
     if (err != cudaSuccess) return err;
     rollout_philox_kernel<A, DIAG, QUAD, COST><<<grid, kPhiloxThreads, smem, st>>>(p);
     return cudaGetLastError();
@@ -878,7 +878,7 @@ bool injected_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sm
 template <int A, bool TMA, bool QUAD, int COST>
 static cudaError_t launch_injected_V(const RolloutParams &p, InjectedLaunch L, dim3 grid, size_t smem, cudaStream_t st)
 {
-    cudaError_t err = cudaFuncSetAttribute(rollout_injected_kernel<A, TMA, QUAD, COST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = ensure_dyn_smem<rollout_injected_kernel<A, TMA, QUAD, COST>>(smem);
     if (err != cudaSuccess) return err;
     rollout_injected_kernel<A, TMA, QUAD, COST><<<grid, L.ng * L.c * 32, smem, st>>>(p, L);
     return cudaGetLastError();

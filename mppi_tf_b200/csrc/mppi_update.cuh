@@ -253,6 +253,15 @@ __device__ void apply_update(const RolloutParams &p, int ctrl, Merged m, float *
         p.stats[2 * ctrl] = m.beta;
         p.stats[2 * ctrl + 1] = m.eta;
     }
+    if (p.next_host != nullptr) {              // zero-copy result for the host (grid-uniform; n_ctrl == 1)
+        if (threadIdx.x < A) p.next_host[threadIdx.x] = sOut[threadIdx.x];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int *>(p.done_host) = p.done_epoch;
+        }
+    }
 }
 
 // Publish this CTA's partial; the last CTA of the controller merges and finishes the update.
