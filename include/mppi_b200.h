@@ -147,7 +147,8 @@ int mppi_set_ellipse_cost(mppi_handle *h, float a, float b, float center_x, floa
                           float m_state, float m_vel);
 int mppi_set_static_cost(mppi_handle *h);
 /* norm_arg (controllers/controller_base.py:468-474): the exponent becomes -(S - beta) / (lambda max_k(S_k - beta)).
- * Costs two launches per update (the range must be known before any weight); world == 1 only in this build. */
+ * Costs two launches per update (the range must be known before any weight).  With world > 1 the range is
+ * exchanged through the fused peer-memory mailboxes: call mppi_peer_attach first (MPPI_ERR_UNSUPPORTED otherwise). */
 int mppi_set_normalize_cost(mppi_handle *h, int on);
 int mppi_set_q(mppi_handle *h, const float *q_host);             /* [s] */
 int mppi_set_mass(mppi_handle *h, float mass);                   /* model mass in B = [dt^2/2; dt] / mass */

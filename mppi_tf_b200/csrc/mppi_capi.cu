@@ -441,7 +441,6 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
     if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
     if (!h->x_staged) return fail(h, MPPI_ERR_STATE, "mppi_set_state must precede mppi_enqueue_update");
     CU_TRY(h, cudaSetDevice(h->device));
-    if (h->peer_on) h->epoch++;                     // same count on every rank: one per update
     if (h->d_zc && h->zc_request) { h->zc_epoch++; h->zc_armed = true; }
     RolloutParams p = make_params(h, eps_dev);
     int gx = 0;
@@ -450,6 +449,7 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
     const int npass = h->normalize ? 2 : 1;
     for (int pass = 1; pass <= npass; pass++) {
         p.norm_mode = h->normalize ? pass : 0;
+        if (h->peer_on) p.epoch = ++h->epoch;       // one exchange per launch; the same count on every rank
         if (h->mlp) {
             MlpParams mp{h->d_wblob, h->d_fvec, h->s, h->a};
             CU_TRY(h, launch_rollout_mlp(p, mp, h->a, eps_dev == nullptr, h->num_sms, h->stream, &gx));
@@ -652,8 +652,9 @@ int mppi_set_static_cost(mppi_handle *h)
 int mppi_set_normalize_cost(mppi_handle *h, int on)
 {
     if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
-    if (on && h->world > 1)
-        return fail(h, MPPI_ERR_UNSUPPORTED, "cost normalisation needs the global cost range before any weight: not wired for world > 1 yet");
+    if (on && h->world > 1 && !h->peer_on)
+        return fail(h, MPPI_ERR_UNSUPPORTED, "cost normalisation needs the global cost range before any weight: with world > 1 it "
+                                              "runs over the fused peer-memory exchange only (mppi_peer_attach first)");
     h->normalize = on != 0;
     return MPPI_OK;
 }
@@ -779,7 +780,6 @@ int mppi_peer_attach(mppi_handle *h, const void *handles)
 {
     if (!h || !handles) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
     if (h->world < 2 || h->world > kMaxWorld) return fail(h, MPPI_ERR_UNSUPPORTED, "fused exchange needs 2 <= world <= MPPI_MAX_PEERS");
-    if (h->normalize) return fail(h, MPPI_ERR_UNSUPPORTED, "cost normalisation is single-rank only");
     int rc = peer_alloc(h);
     if (rc) return rc;
     CU_TRY(h, cudaSetDevice(h->device));

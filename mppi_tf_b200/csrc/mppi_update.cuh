@@ -121,6 +121,48 @@ __device__ inline void publish_minmax(const RolloutParams &p, int ctrl, float bm
     __syncthreads();
     if (tid == 0) {
         for (int w = 1; w < nw; w++) { lo = fminf(lo, sRed[w]); hi = fmaxf(hi, sRed[32 + w]); }
+        sRed[0] = lo;
+        sRed[32] = hi;
+    }
+    __syncthreads();
+    lo = sRed[0];
+    hi = sRed[32];
+    if (p.world > 1) {
+        // sharded samples: the range must be global before any rank forms a weight.  Same mailbox hand-over as
+        // the payload exchange (publish_and_finish), with the (min, max) pair in the first two payload words.
+        const int world = p.world;
+        const uint32_t par = p.epoch & 1u;
+        const size_t slot = ((size_t)par * world + p.rank) * p.n_ctrl + ctrl;
+        if (tid < world) {
+            float *dst = p.peer_mail[tid] + slot * stride;
+            dst[0] = lo;
+            dst[1] = hi;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < world) st_release_sys(p.peer_flag[tid] + slot, p.epoch);
+        if (tid < world) {
+            const size_t src = ((size_t)par * world + tid) * p.n_ctrl + ctrl;
+            const uint32_t *f = p.peer_flag[p.rank] + src;
+            const long long t0 = clock64();
+            while (ld_acquire_sys(f) != p.epoch) {
+                if (clock64() - t0 > (1LL << 31)) {
+                    atomicExch(p.peer_status, 1u);
+                    break;
+                }
+            }
+            const float *m = p.peer_mail[p.rank] + src * stride;
+            sRed[tid] = __ldcg(m);
+            sRed[32 + tid] = __ldcg(m + 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            lo = sRed[0];
+            hi = sRed[32];
+            for (int r = 1; r < world; r++) { lo = fminf(lo, sRed[r]); hi = fmaxf(hi, sRed[32 + r]); }
+        }
+    }
+    if (tid == 0) {
         p.norm[2 * ctrl] = lo;
         p.norm[2 * ctrl + 1] = hi - lo;
     }

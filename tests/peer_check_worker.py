@@ -42,6 +42,34 @@ t = torch.tensor(c2.getSequence(), device="cuda")
 g = [torch.empty_like(t) for _ in range(world)]
 dist.all_gather(g, t)
 ok &= all(torch.equal(g[0], gi) for gi in g)
+# cost normalisation over the mailboxes (two exchanges per update): the sharded result must agree with an
+# unsharded controller on the same seed (Philox noise does not depend on the rank count)
+c3 = make()
+hs = [None] * world
+dist.all_gather_object(hs, c3.peerHandle())
+c3.peerAttach(hs)
+c3.setActionCost("python", gamma=0.5, upsilon=1.2)
+c3.setNormalizeCost(True)
+c0 = None
+if rank == 0:
+    c0 = ControllerBase(K, T, 0.1, 1.0, s, a, lam=1.0, sigma=0.25 * np.eye(a, dtype=np.float32), seed=3, device=lr)
+    c0.setActionCost("python", gamma=0.5, upsilon=1.2)
+    c0.setNormalizeCost(True)
+for it in range(3):
+    a3 = c3.next(x)
+    if rank == 0:
+        a0 = c0.next(x)
+        u3, u0 = c3.getSequence(), c0.getSequence()
+        err = np.abs(u3 - u0).max() / max(np.abs(u0).max(), 1e-30)
+        same = err < 5e-5 and np.abs(a3 - a0).max() <= 5e-5 * max(np.abs(u0).max(), 1e-30)
+        ok &= bool(same)
+        print(f"normalised update {it}: sharded vs unsharded rel err {err:.2e}", flush=True)
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.broadcast(flag, src=0)
+ok = bool(flag.item())
+c3.close()
+if c0 is not None:
+    c0.close()
 if rank == 0:
     print("PEER CHECK", "OK" if ok else "FAILED", flush=True)
 c1.close(); c2.close()

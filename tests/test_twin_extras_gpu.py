@@ -139,7 +139,9 @@ def test_normalised_update_batched_controllers(oracle64):
         assert rel_err(U_new[i], ref["U_new"]) < 1e-5
 
 
-def test_normalise_rejected_when_sharded():
+def test_normalise_rejected_when_sharded_without_peer_exchange():
+    """With world > 1 the cost range travels through the fused peer-memory mailboxes (tests/peer_check_worker.py
+    covers that on two GPUs); without them it is refused."""
     from mppi_tf_b200 import ControllerBase, MppiError, _capi
     c = ControllerBase(1024, 8, 0.1, 1.0, 2, 1, rank=0, world=2)
     try:
