@@ -234,6 +234,10 @@ int mppi_model_step(int device, float mass, float dt, int s, int a, int kst, int
                     const float *action, float *out);
 /* CostBase::mStateCost / mBuildFinalStepCostGraph (src/cost_base.cpp:52-61) */
 int mppi_cost_state(int device, int k, int s, const float *state, const float *goal, const float *q, float *out);
+/* CostBase.action_cost of the Python twin (scripts/src/costs/cost_base.py:114-170), a <= MPPI_MAX_A:
+ * 0.5 [gamma (u^T S^-1 u + 2 u^T S^-1 eps) + lambda (1 - 1/upsilon) eps^T S^-1 eps] */
+int mppi_cost_action_py(int device, int k, int a, float lambda, float gamma, float upsilon, const float *sigma,
+                        const float *action, const float *noise, float *out);
 /* ElipseCost.state_cost (scripts/src/costs/elipse_cost.py:46-79): state [k][4] = (x, vx, y, vy) -> out [k] */
 int mppi_cost_state_ellipse(int device, int k, const float *state, float a, float b, float center_x, float center_y,
                             float speed, float m_state, float m_vel, float *out);

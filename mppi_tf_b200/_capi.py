@@ -62,6 +62,7 @@ SYMBOLS = {
     "mppi_set_normalize_cost": (_i, [_H, _i]),
     "mppi_set_ellipse_cost": (_i, [_H] + [_f] * 7),
     "mppi_set_static_cost": (_i, [_H]),
+    "mppi_cost_action_py": (_i, [_i, _i, _i, _f, _f, _f, _fp, _fp, _fp, _fp]),
     "mppi_cost_state_ellipse": (_i, [_i, _i, _fp] + [_f] * 7 + [_fp]),
     "mppi_set_q": (_i, [_H, _fp]),
     "mppi_set_mass": (_i, [_H, _f]),

@@ -103,6 +103,17 @@ class CostBase:
         return out
 
 
+def actionCostPython(lam, gamma, upsilon, sigma, action, noise, device=-1):
+    """CostBase.action_cost of the Python twin (scripts/src/costs/cost_base.py:114-170) on the GPU: noise [k, a] -> [k]."""
+    lib = _capi.load()
+    ac = _f32(action).ravel()
+    nz = _f32(np.asarray(noise).reshape(-1, ac.size))
+    out = np.empty(nz.shape[0], np.float32)
+    check(lib.mppi_cost_action_py(device, nz.shape[0], ac.size, float(lam), float(gamma), float(upsilon), _ptr(_f32(sigma)),
+                                  _ptr(ac), _ptr(nz), _ptr(out)))
+    return out
+
+
 def ellipseStateCost(state, a, b, center_x, center_y, speed, m_state, m_vel, device=-1):
     """ElipseCost.state_cost (scripts/src/costs/elipse_cost.py:46-79) on the GPU: state [k, 4] -> [k]."""
     lib = _capi.load()

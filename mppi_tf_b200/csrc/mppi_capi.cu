@@ -1048,6 +1048,28 @@ int mppi_cost_state(int device, int k, int s, const float *state, const float *g
 {
     return cost_stage(device, k, s, 0, 1.f, nullptr, goal, q, state, nullptr, nullptr, out, 0);
 }
+int mppi_cost_action_py(int device, int k, int a, float lambda, float gamma, float upsilon, const float *sigma,
+                        const float *action, const float *noise, float *out)
+{
+    if (!sigma || !action || !noise || !out || k <= 0 || a <= 0 || a > MPPI_MAX_A || !(upsilon > 0.f))
+        return fail(nullptr, MPPI_ERR_BAD_ARG, "bad action-cost argument");
+    int rc = stage_device(device);
+    if (rc) return rc;
+    float inv[kMaxA * kMaxA] = {0};
+    if (!invert_matrix(sigma, a, inv)) return fail(nullptr, MPPI_ERR_BAD_ARG, "sigma is singular");
+    DevBuf dinv, dac, dn, dout;
+    CU_TRY_S(dinv.alloc(sizeof(inv)));
+    CU_TRY_S(dac.alloc(sizeof(float) * a));
+    CU_TRY_S(dn.alloc(sizeof(float) * (size_t)k * a));
+    CU_TRY_S(dout.alloc(sizeof(float) * (size_t)k));
+    CU_TRY_S(cudaMemcpy(dinv.p, inv, sizeof(inv), cudaMemcpyHostToDevice));
+    CU_TRY_S(cudaMemcpy(dac.p, action, sizeof(float) * a, cudaMemcpyHostToDevice));
+    CU_TRY_S(cudaMemcpy(dn.p, noise, sizeof(float) * (size_t)k * a, cudaMemcpyHostToDevice));
+    CU_TRY_S(launch_action_cost_py(k, a, lambda, gamma, upsilon, dinv.as<float>(), dac.as<float>(), dn.as<float>(),
+                                   dout.as<float>(), 0));
+    CU_TRY_S(cudaMemcpy(out, dout.p, sizeof(float) * (size_t)k, cudaMemcpyDeviceToHost));
+    return MPPI_OK;
+}
 int mppi_cost_state_ellipse(int device, int k, const float *state, float a, float b, float center_x, float center_y,
                             float speed, float m_state, float m_vel, float *out)
 {

@@ -57,6 +57,8 @@ cudaError_t launch_model_step(float mass, float dt, int s, int a, int kst, int k
 cudaError_t launch_cost(int k, int s, int a, float lambda, const float *inv_sigma, const float *goal,
                         const float *q, const float *state, const float *action, const float *noise,
                         float *out, int mode, cudaStream_t st);
+cudaError_t launch_action_cost_py(int k, int a, float lambda, float gamma, float upsilon, const float *inv_sigma,
+                                  const float *action, const float *noise, float *out, cudaStream_t st);
 cudaError_t launch_ellipse_cost(int k, const float *state, const float *ell /*[7] host*/, float *out, cudaStream_t st);
 cudaError_t launch_prepare_noise(int k, int T, int a, const float *noise, int t, float *out, cudaStream_t st);
 cudaError_t launch_update_stages(int k, int T, int a, float lambda, const float *cost, const float *noise,

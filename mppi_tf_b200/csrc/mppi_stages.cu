@@ -56,6 +56,27 @@ __global__ void cost_kernel(int k, int s, int a, float lambda, const float *inv_
     }
 }
 
+// CostBase.action_cost of the Python twin (scripts/src/costs/cost_base.py:114-170):
+//   0.5 [gamma (u^T S^-1 u + 2 u^T S^-1 eps) + lambda (1 - 1/upsilon) eps^T S^-1 eps]
+__global__ void action_cost_py_kernel(int k, int a, float lambda, float gamma, float upsilon, const float *inv_sigma,
+                                      const float *action, const float *noise, float *out)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+        float uu = 0.f, ue = 0.f, ee = 0.f;
+        for (int r = 0; r < a; r++) {
+            float su = 0.f, se = 0.f;
+            for (int l = 0; l < a; l++) {
+                su = fmaf(inv_sigma[r * a + l], action[l], su);
+                se = fmaf(inv_sigma[r * a + l], noise[(size_t)i * a + l], se);
+            }
+            uu = fmaf(action[r], su, uu);
+            ue = fmaf(action[r], se, ue);
+            ee = fmaf(noise[(size_t)i * a + r], se, ee);
+        }
+        out[i] = 0.5f * (gamma * (uu + 2.0f * ue) + lambda * (1.0f - 1.0f / upsilon) * ee);
+    }
+}
+
 // ElipseCost.state_cost (scripts/src/costs/elipse_cost.py:46-79): state [k][4] = (x, vx, y, vy)
 __global__ void ellipse_cost_kernel(int k, const float *state, float ia, float ib, float cx, float cy, float speed,
                                     float m_state, float m_vel, float *out)
@@ -190,6 +211,13 @@ cudaError_t launch_cost(int k, int s, int a, float lambda, const float *inv_sigm
                         float *out, int mode, cudaStream_t st)
 {
     cost_kernel<<<blocks_for(k, 256), 256, 0, st>>>(k, s, a, lambda, inv_sigma, goal, q, state, action, noise, out, mode);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_action_cost_py(int k, int a, float lambda, float gamma, float upsilon, const float *inv_sigma,
+                                  const float *action, const float *noise, float *out, cudaStream_t st)
+{
+    action_cost_py_kernel<<<blocks_for(k, 256), 256, 0, st>>>(k, a, lambda, gamma, upsilon, inv_sigma, action, noise, out);
     return cudaGetLastError();
 }
 

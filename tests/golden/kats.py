@@ -151,6 +151,46 @@ COST_CASES = [
 # which is outside the C++ API (Q = Diag(q), src/cost_base.cpp:40) — listed, not replayed.
 
 # ---------------------------------------------------------------------------------------------
+# Python-twin action cost — scripts/test.py:685-838 (CostBase.action_cost, Sigma = I):
+#   0.5 * (gamma * (u.u + 2 u.eps) + lambda * (1 - 1/upsilon) * eps.eps), u = action (a), eps = noise [k][a]
+# The expected values are transcribed as the reference writes them (its literals for u.u, u.eps, eps.eps).
+# ---------------------------------------------------------------------------------------------
+_PY_ACTION3 = [0.5, 2.0, 0.25]
+_PY_NOISE3 = [[0.5, 1., 2.], [0.5, 2., 0.25], [-2, -0.2, -1], [0., 0., 0.], [1., 0.5, 3.]]
+_PY_TERMS3 = [(4.3125, 2.75, 5.25), (4.3125, 4.3125, 4.3125), (4.3125, -1.65, 5.04), (4.3125, 0.0, 0.0), (4.3125, 2.25, 10.25)]
+
+
+def _py_ac(lam, gamma, upsilon, terms):
+    return [0.5 * (gamma * (uu + 2. * ue) + lam * (1 - 1. / upsilon) * ee) for uu, ue, ee in terms]
+
+
+PY_ACTION_COST_CASES = [
+    dict(name="testStepCost_s2_a2_l1", lam=1., gamma=1., upsilon=1., action=[1., 1.], noise=[[1., 1.]],        # :689-708
+         expected=_py_ac(1., 1., 1., [(2., 2., 0.)])),
+    dict(name="testStepCost_s4_a2_l1", lam=1., gamma=1., upsilon=1., action=[0.5, 2.], noise=[[0.5, 1.]],      # :710-730
+         expected=_py_ac(1., 1., 1., [(4.25, 2.25, 1.25)])),
+    dict(name="testStepCost_s4_a3_l1", lam=1., gamma=1., upsilon=1., action=_PY_ACTION3, noise=_PY_NOISE3,     # :732-766
+         expected=_py_ac(1., 1., 1., _PY_TERMS3)),
+    dict(name="testStepCost_s4_a3_l10_g2_u3", lam=10., gamma=2., upsilon=3., action=_PY_ACTION3,               # :768-802
+         noise=_PY_NOISE3, expected=_py_ac(10., 2., 3., _PY_TERMS3)),
+    dict(name="testStepCost_s4_a3_l15_g20_u30", lam=15., gamma=20., upsilon=30., action=_PY_ACTION3,           # :804-838
+         noise=_PY_NOISE3, expected=_py_ac(15., 20., 30., _PY_TERMS3)),
+]
+
+# StaticCost on the 13-dimensional AUV state with a = 6 — scripts/test.py:944-1095.  Q is diagonal there
+# (1 on pose, 10 on velocities), so the case replays through the diagonal-Q state cost and the a = 6 action cost.
+PY_STATIC13 = dict(
+    state=[[0., 0.5, 2., 0., 0., 0., 1., 1., 2., 3., 4., 5., 6.], [0., 2., 0., 0., 0.5, 0.5, 0., 4., 5., 6., 1., 2., 3.]],
+    goal=[1., 1., 2., 0., 0., 0., 1., 0., 0., 0., 0., 0., 0.],
+    q=[1.] * 7 + [10.] * 6,
+    action=[0.5, 2., 0.25, 4., 1., 1.5],
+    noise=[[0.5, 1., 2., 3., 4., 5.], [0.5, 2., 0.25, 1.25, 2.5, 0.75]],
+    lam=1., gamma=1., upsilon=1.,
+    expected_action=_py_ac(1., 1., 1., [(23.5625, 26.25, 55.25), (23.5625, 12.9375, 12.6875)]),   # :1073-1080
+    expected_state=[911.25, 917.5],                                                               # :1082-1089
+)
+
+# ---------------------------------------------------------------------------------------------
 # ElipseCost (Python twin) — scripts/test.py:1098-1161: a = b = 1, centre (0, 0), speed 1,
 # m_state = m_vel = 1; states (x, vx, y, vy)
 # ---------------------------------------------------------------------------------------------

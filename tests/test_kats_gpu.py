@@ -78,6 +78,25 @@ def test_cost_set_goal_takes_effect():
     assert cost.setGoal([1, 2, 3]) is False             # wrong size, src/controller_base.cpp:127-130
 
 
+@pytest.mark.parametrize("case", kats.PY_ACTION_COST_CASES, ids=lambda c: c["name"])
+def test_python_action_cost(case):
+    """gamma / upsilon action cost KATs of the Python twin, scripts/test.py:685-838."""
+    from mppi_tf_b200 import actionCostPython
+    a = len(case["action"])
+    got = actionCostPython(case["lam"], case["gamma"], case["upsilon"], np.eye(a), case["action"], case["noise"])
+    np.testing.assert_allclose(got, case["expected"], rtol=1e-6, atol=1e-6)
+
+
+def test_python_static_cost_s13():
+    """scripts/test.py:944-1095 (13-dimensional state, a = 6, diagonal Q) on the GPU stages."""
+    from mppi_tf_b200 import CostBase, actionCostPython
+    c = kats.PY_STATIC13
+    cost = CostBase(c["lam"], np.eye(6), c["goal"], c["q"])
+    np.testing.assert_allclose(cost.stateCost(np.asarray(c["state"])), c["expected_state"], rtol=1e-6)
+    got = actionCostPython(c["lam"], c["gamma"], c["upsilon"], np.eye(6), c["action"], c["noise"])
+    np.testing.assert_allclose(got, c["expected_action"], rtol=1e-6)
+
+
 @pytest.mark.parametrize("case", kats.ELLIPSE_CASES, ids=lambda c: c["name"])
 def test_ellipse_cost(case):
     """ElipseCost.state_cost KATs, scripts/test.py:1098-1161 (assertAllClose: rtol 1e-6)."""

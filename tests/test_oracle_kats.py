@@ -78,6 +78,23 @@ def test_cost_action_general_sigma(oracle64):
 
 
 # ---- ControllerBase stages -------------------------------------------------------------------
+@pytest.mark.parametrize("case", kats.PY_ACTION_COST_CASES, ids=lambda c: c["name"])
+def test_python_action_cost(oracle64, case):
+    """The gamma / upsilon action cost against the reference's own known answers (scripts/test.py:685-838)."""
+    a = len(case["action"])
+    got = oracle64.cost_action_py(case["lam"], case["gamma"], case["upsilon"], np.eye(a), case["action"], case["noise"])
+    np.testing.assert_allclose(got, case["expected"], rtol=1e-6, atol=1e-6)
+
+
+def test_python_static_cost_s13(oracle64):
+    """scripts/test.py:944-1095: 13-dimensional state, a = 6, diagonal Q; step cost = state + action cost."""
+    c = kats.PY_STATIC13
+    sc = oracle64.cost_state(c["state"], c["goal"], c["q"])
+    ac = oracle64.cost_action_py(c["lam"], c["gamma"], c["upsilon"], np.eye(6), c["action"], c["noise"])
+    np.testing.assert_allclose(sc, c["expected_state"], rtol=1e-6)
+    np.testing.assert_allclose(ac, c["expected_action"], rtol=1e-6)
+
+
 @pytest.mark.parametrize("case", kats.ELLIPSE_CASES, ids=lambda c: c["name"])
 def test_ellipse_cost(oracle64, oracle32, case):
     """scripts/test.py:1098-1161 (assertAllClose: rtol 1e-6)."""
