@@ -297,6 +297,8 @@ __device__ void apply_update(const RolloutParams &p, int ctrl, Merged m, float *
     }
     if (p.next_host != nullptr) {              // zero-copy result for the host (grid-uniform; n_ctrl == 1)
         if (threadIdx.x < A) p.next_host[threadIdx.x] = sOut[threadIdx.x];
+        if (threadIdx.x == A)                   // the exchange status travels with the action (word 8 of the block)
+            reinterpret_cast<unsigned int *>(p.next_host)[8] = p.peer_on ? *reinterpret_cast<volatile unsigned int *>(p.peer_status) : 0u;
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
