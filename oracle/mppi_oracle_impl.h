@@ -526,6 +526,128 @@ void FN(orc_mppi_update_py)(int k, int T, int s, int a, REAL dt, REAL mass, REAL
     free(zero);
 }
 
+/* ---- AUV (Fossen) dynamics — scripts/src/models/auv_model.py ------------
+ * prm (primitive parameters, 127 values): mass, volume, density, cog[3], cob[3], Ma[36], inertia {ixx, iyy,
+ * izz, ixy, ixz, iyz}, linear_damping[36], quad_damping[6], linear_damping_forward_speed[36].
+ * State x = (p[3], q = (qx, qy, qz, qw), nu[6]); action u[6] = generalised force. */
+#define ORC_AUV_NPRM 127
+static void FN(orc_auv_mass)(const REAL *prm, REAL *Mtot /*36*/, REAL *invM /*36*/)
+{
+    const REAL m = prm[0];
+    const REAL *cog = prm + 3, *Ma = prm + 9, *in = prm + 45;
+    /* tf_skew_op (:23-40) concatenates its three rows along axis 1, i.e. as COLUMNS: it returns the transposed
+     * skew matrix.  Restated as written (it only matters for an off-centre centre of gravity). */
+    REAL S[9] = {0, cog[2], -cog[1], -cog[2], 0, cog[0], cog[1], -cog[0], 0};
+    REAL I[9] = {in[0], in[3], in[4], in[3], in[1], in[5], in[4], in[5], in[2]};      /* get_inertial :265-280 */
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {                                                 /* rigid_body_mass :257-260 */
+            Mtot[r * 6 + c] = (r == c) ? m : (REAL)0;
+            Mtot[r * 6 + 3 + c] = -(m * S[r * 3 + c]);
+            Mtot[(3 + r) * 6 + c] = m * S[r * 3 + c];
+            Mtot[(3 + r) * 6 + 3 + c] = I[r * 3 + c];
+        }
+    for (int i = 0; i < 36; i++) Mtot[i] = Mtot[i] + Ma[i];                           /* total_mass :262-263 */
+    FN(orc_mat_inverse)(Mtot, 6, invM);                                               /* :238 */
+}
+
+/* state_dot — auv_model.py:308-333 with body2inertial_transform :353-398, get_jacobian :335-351,
+ * damping_matrix :478-506, coriolis_matrix :508-542, restoring_forces :450-476, acc :544-559 */
+static void FN(orc_auv_state_dot)(const REAL *prm, const REAL *Mtot, const REAL *invM, const REAL *x, const REAL *u,
+                                  REAL *xd /*13*/)
+{
+    const REAL m = prm[0], vol = prm[1], rho = prm[2], g = (REAL)9.81;
+    const REAL *cog = prm + 3, *cob = prm + 6, *Dl = prm + 51, *dq = prm + 87, *Dlf = prm + 93;
+    const REAL qx = x[3], qy = x[4], qz = x[5], qw = x[6];
+    const REAL *nu = x + 7;
+    REAL R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw),
+                 2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
+                 2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)};
+    REAL T[12] = {qw, -qz, qy, qz, qw, -qx, -qy, qx, qw, -qx, -qy, -qz};             /* rows x, y, z, w; times 0.5 */
+    for (int r = 0; r < 3; r++) xd[r] = R[r * 3] * nu[0] + R[r * 3 + 1] * nu[1] + R[r * 3 + 2] * nu[2];
+    for (int r = 0; r < 4; r++)
+        xd[3 + r] = (REAL)0.5 * T[r * 3] * nu[3] + (REAL)0.5 * T[r * 3 + 1] * nu[4] + (REAL)0.5 * T[r * 3 + 2] * nu[5];
+    /* D nu */
+    REAL Dv[6], Cv[6], gv[6], rhs[6];
+    for (int r = 0; r < 6; r++) {
+        REAL acc = (REAL)0;
+        for (int c = 0; c < 6; c++) {
+            REAL d = -Dl[r * 6 + c] - nu[0] * Dlf[r * 6 + c];
+            if (r == c) d = d + (-(dq[r] * (nu[r] < 0 ? -nu[r] : nu[r])));
+            acc += d * nu[c];
+        }
+        Dv[r] = acc;
+    }
+    /* C nu: C = [[0, S12], [S12, S22]], S12 = -skew(M11 nu1 + M12 nu2), S22 = -skew(M21 nu1 + M22 nu2) */
+    REAL a1[3], a2[3];
+    for (int r = 0; r < 3; r++) {
+        a1[r] = (Mtot[r * 6] * nu[0] + Mtot[r * 6 + 1] * nu[1] + Mtot[r * 6 + 2] * nu[2]) +
+                (Mtot[r * 6 + 3] * nu[3] + Mtot[r * 6 + 4] * nu[4] + Mtot[r * 6 + 5] * nu[5]);
+        a2[r] = (Mtot[(3 + r) * 6] * nu[0] + Mtot[(3 + r) * 6 + 1] * nu[1] + Mtot[(3 + r) * 6 + 2] * nu[2]) +
+                (Mtot[(3 + r) * 6 + 3] * nu[3] + Mtot[(3 + r) * 6 + 4] * nu[4] + Mtot[(3 + r) * 6 + 5] * nu[5]);
+    }
+    REAL S12[9] = {0, a1[2], -a1[1], -a1[2], 0, a1[0], a1[1], -a1[0], 0};             /* -skew(a1) */
+    REAL S22[9] = {0, a2[2], -a2[1], -a2[2], 0, a2[0], a2[1], -a2[0], 0};
+    for (int r = 0; r < 3; r++) {
+        Cv[r] = S12[r * 3] * nu[3] + S12[r * 3 + 1] * nu[4] + S12[r * 3 + 2] * nu[5];
+        Cv[3 + r] = (S12[r * 3] * nu[0] + S12[r * 3 + 1] * nu[1] + S12[r * 3 + 2] * nu[2]) +
+                    (S22[r * 3] * nu[3] + S22[r * 3 + 1] * nu[4] + S22[r * 3 + 2] * nu[5]);
+    }
+    /* restoring: fbg = R^T (0,0,-m g), fbb = R^T (0,0,V rho g); g = -[fbg + fbb; cog x fbg + cob x fbb] */
+    REAL fng = -(m * g), fnb = vol * rho * g, fbg[3], fbb[3];
+    for (int r = 0; r < 3; r++) { fbg[r] = R[6 + r] * fng; fbb[r] = R[6 + r] * fnb; }
+    REAL mbg[3] = {cog[1] * fbg[2] - cog[2] * fbg[1], cog[2] * fbg[0] - cog[0] * fbg[2], cog[0] * fbg[1] - cog[1] * fbg[0]};
+    REAL mbb[3] = {cob[1] * fbb[2] - cob[2] * fbb[1], cob[2] * fbb[0] - cob[0] * fbb[2], cob[0] * fbb[1] - cob[1] * fbb[0]};
+    for (int r = 0; r < 3; r++) { gv[r] = -(fbg[r] + fbb[r]); gv[3 + r] = -(mbg[r] + mbb[r]); }
+    for (int r = 0; r < 6; r++) rhs[r] = ((u[r] - Cv[r]) - Dv[r]) - gv[r];           /* :555 */
+    for (int r = 0; r < 6; r++) {
+        REAL acc = (REAL)0;
+        for (int c = 0; c < 6; c++) acc += invM[r * 6 + c] * rhs[c];
+        xd[7 + r] = acc;
+    }
+}
+
+/* AUVModel.step — :285-306 (rk = 1, 2; the rk = 4 branch of the reference multiplies k4 by dt twice and is
+ * restated as written) followed by normalize_quat :426-448 (tf.math.l2_normalize, epsilon 1e-12). */
+void FN(orc_auv_step)(int k, const REAL *prm, REAL dt, int rk, const REAL *state, const REAL *action, REAL *out)
+{
+    REAL Mtot[36], invM[36];
+    FN(orc_auv_mass)(prm, Mtot, invM);
+    for (int i = 0; i < k; i++) {
+        const REAL *x = state + 13 * i, *u = action + 6 * i;
+        REAL k1[13], k2[13], k3[13], k4[13], tmp[13], xs[13];
+        FN(orc_auv_state_dot)(prm, Mtot, invM, x, u, k1);
+        if (rk == 2) {
+            for (int j = 0; j < 13; j++) xs[j] = x[j] + dt * k1[j];
+            FN(orc_auv_state_dot)(prm, Mtot, invM, xs, u, k2);
+            for (int j = 0; j < 13; j++) tmp[j] = dt / (REAL)2 * (k1[j] + k2[j]);
+        } else if (rk == 4) {
+            for (int j = 0; j < 13; j++) xs[j] = x[j] + dt * k1[j] / (REAL)2;
+            FN(orc_auv_state_dot)(prm, Mtot, invM, xs, u, k2);
+            for (int j = 0; j < 13; j++) xs[j] = x[j] + dt * k2[j] / (REAL)2;
+            FN(orc_auv_state_dot)(prm, Mtot, invM, xs, u, k3);
+            for (int j = 0; j < 13; j++) xs[j] = x[j] + dt * k3[j];
+            FN(orc_auv_state_dot)(prm, Mtot, invM, xs, u, k4);
+            for (int j = 0; j < 13; j++)
+                tmp[j] = (REAL)(1. / 6.) * ((k1[j] + (REAL)2 * k2[j]) + ((REAL)2 * k3[j] + k4[j] * dt)) * dt;
+        } else {
+            for (int j = 0; j < 13; j++) tmp[j] = k1[j] * dt;
+        }
+        REAL *o = out + 13 * i;
+        for (int j = 0; j < 13; j++) o[j] = x[j] + tmp[j];
+        REAL n2 = o[3] * o[3] + o[4] * o[4] + o[5] * o[5] + o[6] * o[6];
+        REAL inv = (REAL)1 / (REAL)sqrt((double)(n2 > (REAL)1e-12 ? n2 : (REAL)1e-12));
+        for (int j = 3; j < 7; j++) o[j] = o[j] * inv;
+    }
+}
+
+/* the state derivative alone, for the component fixtures (rotation / damping / Coriolis / restoring enter it) */
+void FN(orc_auv_state_dot_k)(int k, const REAL *prm, const REAL *state, const REAL *action, REAL *out)
+{
+    REAL Mtot[36], invM[36];
+    FN(orc_auv_mass)(prm, Mtot, invM);
+    for (int i = 0; i < k; i++) FN(orc_auv_state_dot)(prm, Mtot, invM, state + 13 * i, action + 6 * i, out + 13 * i);
+}
+
 #undef FN
 #undef CAT
 #undef CAT_

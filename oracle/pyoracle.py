@@ -250,6 +250,30 @@ class Oracle:
                                        _p(U_new), _p(nxt), _p(U_shift))
         return dict(costs=costs, U_new=U_new, next=nxt, U_shift=U_shift)
 
+    @staticmethod
+    def auv_pack(prm):
+        """Flat primitive-parameter vector of the AUV model (oracle/mppi_oracle_impl.h, ORC_AUV_NPRM = 127)."""
+        sq = lambda v: (np.diag(v) if np.ndim(v) == 1 else np.asarray(v, np.float64)).ravel()
+        i = prm["inertial"]
+        return np.concatenate([[prm["mass"], prm["volume"], prm["density"]], prm["cog"], prm["cob"],
+                               np.asarray(prm["Ma"], np.float64).ravel(),
+                               [i["ixx"], i["iyy"], i["izz"], i["ixy"], i["ixz"], i["iyz"]],
+                               sq(np.asarray(prm["linear_damping"], np.float64)), np.asarray(prm["quad_damping"], np.float64),
+                               sq(np.asarray(prm["linear_damping_forward_speed"], np.float64))]).astype(np.float64)
+
+    def auv_step(self, prm, dt, rk, state, action):
+        """AUVModel.step (scripts/src/models/auv_model.py:285-306): state [k,13], action [k,6] -> [k,13]."""
+        st, ac = _c(np.asarray(state).reshape(-1, 13), self.dt), _c(np.asarray(action).reshape(-1, 6), self.dt)
+        out = np.empty_like(st)
+        self._fn("orc_auv_step")(st.shape[0], _p(_c(self.auv_pack(prm), self.dt)), self.creal(dt), int(rk), _p(st), _p(ac), _p(out))
+        return out
+
+    def auv_state_dot(self, prm, state, action):
+        st, ac = _c(np.asarray(state).reshape(-1, 13), self.dt), _c(np.asarray(action).reshape(-1, 6), self.dt)
+        out = np.empty_like(st)
+        self._fn("orc_auv_state_dot_k")(st.shape[0], _p(_c(self.auv_pack(prm), self.dt)), _p(st), _p(ac), _p(out))
+        return out
+
     def partial(self, lam, costs, eps, k0, k1):
         costs = _c(costs, self.dt)
         eps = _c(eps, self.dt)

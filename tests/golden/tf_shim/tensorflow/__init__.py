@@ -89,7 +89,9 @@ def slice(x, begin, size, name=None):          # noqa: A001  (tf.slice)
 
 
 def concat(values, axis, name=None):
-    return np.concatenate([_a(v) for v in values], axis=axis)
+    # rank-0 operands are taken as one-element vectors: AUVModel.get_inertial concatenates scalar Variables
+    # (auv_model.py:274-276), which only makes sense as building the rows of the inertia matrix
+    return np.concatenate([np.atleast_1d(_a(v)) for v in values], axis=axis)
 
 
 def reduce_min(x, axis=None, name=None):
@@ -106,6 +108,26 @@ def reduce_sum(x, axis=None, name=None):
 
 def clip_by_value(x, lo, hi, name=None):
     return np.clip(_a(x), lo, hi)
+
+
+def eye(n, dtype=float64, name=None):
+    return np.eye(n, dtype=dtype)
+
+
+def multiply(a, b, name=None):
+    return _a(a) * _a(b)
+
+
+def subtract(a, b, name=None):
+    return _a(a) - _a(b)
+
+
+def matmul(a, b, transpose_a=False, transpose_b=False, name=None):
+    return _matmul(a, b, transpose_a, transpose_b)
+
+
+def transpose(x, perm=None, name=None):
+    return np.transpose(_a(x), perm)
 
 
 def sqrt(x, name=None):
@@ -138,12 +160,29 @@ def _matmul(a, b, transpose_a=False, transpose_b=False, name=None):
     return np.matmul(a, b)
 
 
-linalg = types.SimpleNamespace(matmul=_matmul, inv=lambda m, name=None: np.linalg.inv(_a(m)),
-                               diag=lambda v, name=None: np.diag(_a(v)))
+def _diag(v, name=None):
+    v = _a(v)
+    if v.ndim == 1:
+        return np.diag(v)
+    out = np.zeros(v.shape + (v.shape[-1],), v.dtype)           # batched: [..., n] -> [..., n, n]
+    idx = np.arange(v.shape[-1])
+    out[..., idx, idx] = v
+    return out
+
+
+def _l2_normalize(x, axis=None, epsilon=1e-12, name=None):
+    x = _a(x)
+    return x / np.sqrt(np.maximum(np.sum(x * x, axis=axis, keepdims=True), epsilon))
+
+
+linalg = types.SimpleNamespace(matmul=_matmul, inv=lambda m, name=None: np.linalg.inv(_a(m)), diag=_diag,
+                               cross=lambda a, b, name=None: np.cross(_a(a), _a(b)),
+                               norm=lambda x, axis=None, keepdims=False, name=None: np.linalg.norm(_a(x), axis=axis, keepdims=keepdims))
 math = types.SimpleNamespace(
     subtract=lambda a, b, name=None: _a(a) - _a(b), multiply=lambda a, b, name=None: _a(a) * _a(b),
     add=add, exp=lambda x, name=None: np.exp(_a(x)), reduce_sum=reduce_sum, reduce_min=reduce_min,
-    reduce_max=reduce_max, divide=divide)
+    reduce_max=reduce_max, divide=divide, l2_normalize=_l2_normalize, acos=lambda x, name=None: np.arccos(_a(x)),
+    abs=lambda x, name=None: np.abs(_a(x)))
 
 
 def _normal(shape, mean=0.0, stddev=1.0, dtype=float32, seed=None, name=None):
