@@ -495,14 +495,11 @@ void FN(orc_rollout_costs_py)(int k0, int k1, int T, int s, int a, REAL dt, REAL
 /* Python-twin update — controller_base.py:436-474: beta = min S; arg = S - beta, divided by its
  * maximum when `normalize` (norm_arg :468-474); e = exp(-arg/lambda); w = e / sum e;
  * U' = U + sum_k w_k eps_k; next = U'[0]; shifted = concat(U'[1:], 0) (:547-560). */
-void FN(orc_mppi_update_py)(int k, int T, int s, int a, REAL dt, REAL mass, REAL lambda, REAL gamma,
-                            REAL upsilon, int normalize, const REAL *sigma, const REAL *goal,
-                            const REAL *q, const REAL *ell, const REAL *x0, const REAL *U, const REAL *eps,
-                            REAL *costs, REAL *U_new, REAL *next, REAL *U_shift)
+static void FN(orc_update_tail_py)(int k, int T, int a, REAL lambda, int normalize, const REAL *costs, const REAL *U,
+                                   const REAL *eps, REAL *U_new, REAL *next, REAL *U_shift)
 {
     REAL *zero = (REAL *)calloc((size_t)a, sizeof(REAL));
     REAL *e = (REAL *)malloc(sizeof(REAL) * (size_t)k);
-    FN(orc_rollout_costs_py)(0, k, T, s, a, dt, mass, lambda, gamma, upsilon, sigma, goal, q, ell, x0, U, eps, costs);
     REAL beta = costs[0];
     for (int i = 1; i < k; i++) beta = costs[i] < beta ? costs[i] : beta;
     REAL mx = (REAL)0;
@@ -524,6 +521,15 @@ void FN(orc_mppi_update_py)(int k, int T, int s, int a, REAL dt, REAL mass, REAL
     FN(orc_shift)(T, a, U_new, zero, 1, U_shift);
     free(e);
     free(zero);
+}
+
+void FN(orc_mppi_update_py)(int k, int T, int s, int a, REAL dt, REAL mass, REAL lambda, REAL gamma,
+                            REAL upsilon, int normalize, const REAL *sigma, const REAL *goal,
+                            const REAL *q, const REAL *ell, const REAL *x0, const REAL *U, const REAL *eps,
+                            REAL *costs, REAL *U_new, REAL *next, REAL *U_shift)
+{
+    FN(orc_rollout_costs_py)(0, k, T, s, a, dt, mass, lambda, gamma, upsilon, sigma, goal, q, ell, x0, U, eps, costs);
+    FN(orc_update_tail_py)(k, T, a, lambda, normalize, costs, U, eps, U_new, next, U_shift);
 }
 
 /* ---- AUV (Fossen) dynamics — scripts/src/models/auv_model.py ------------
@@ -647,6 +653,75 @@ void FN(orc_auv_state_dot_k)(int k, const REAL *prm, const REAL *state, const RE
     FN(orc_auv_mass)(prm, Mtot, invM);
     for (int i = 0; i < k; i++) FN(orc_auv_state_dot)(prm, Mtot, invM, state + 13 * i, action + 6 * i, out + 13 * i);
 }
+
+/* StaticQuatCost.state_cost — scripts/src/costs/static_cost.py:116-159: d = (p - g_p, 2 acos(q . g_q), nu - g_nu),
+ * cost = d^T Q d with Q [10][10] (full, as the reference multiplies it). */
+void FN(orc_cost_state_quat)(int k, const REAL *state, const REAL *goal, const REAL *Q, REAL *out)
+{
+    for (int i = 0; i < k; i++) {
+        const REAL *x = state + 13 * i;
+        REAL d[10], r[10];
+        REAL dot = ((x[3] * goal[3] + x[4] * goal[4]) + x[5] * goal[5]) + x[6] * goal[6];     /* tensordot :148 */
+        for (int j = 0; j < 3; j++) d[j] = x[j] - goal[j];
+        d[3] = (REAL)2 * (REAL)acos((double)dot);
+        for (int j = 0; j < 6; j++) d[4 + j] = x[7 + j] - goal[7 + j];
+        for (int a = 0; a < 10; a++) {
+            r[a] = (REAL)0;
+            for (int b = 0; b < 10; b++) r[a] += Q[a * 10 + b] * d[b];
+        }
+        REAL c = (REAL)0;
+        for (int a = 0; a < 10; a++) c += d[a] * r[a];
+        out[i] = c;
+    }
+}
+
+/* Python controller rollout with the AUV model — controller_base.py:371-434 with AUVModel.build_step_graph
+ * (auv_model.py:285-306) and StaticCost (quat_cost = 0: Q = diag(q[13])) or StaticQuatCost (quat_cost = 1:
+ * Q [10][10]); action cost cost_base.py:114-170; eps = (upsilon * sigma) z. */
+void FN(orc_rollout_costs_auv)(int k0, int k1, int T, const REAL *prm, REAL dt, int rk, REAL lambda, REAL gamma,
+                               REAL upsilon, const REAL *sigma, const REAL *goal, const REAL *Q, int quat_cost,
+                               const REAL *x0, const REAL *U, const REAL *eps, REAL *costs)
+{
+    const int s = 13, a = 6;
+    for (int i = k0; i < k1; i++) {
+        REAL x[13], xn[13], u[6];
+        REAL S = (REAL)0, c, acst;
+        for (int j = 0; j < s; j++) x[j] = x0[j];
+        for (int t = 0; t < T; t++) {
+            const REAL *e = eps + ((size_t)i * T + t) * a;
+            const REAL *ut = U + t * a;
+            for (int j = 0; j < a; j++) u[j] = ut[j] + e[j];
+            FN(orc_auv_step)(1, prm, dt, rk, x, u, xn);
+            if (quat_cost) FN(orc_cost_state_quat)(1, xn, goal, Q, &c);
+            else FN(orc_cost_state)(1, s, xn, goal, Q, &c);
+            FN(orc_cost_action_py)(1, a, lambda, gamma, upsilon, sigma, ut, e, &acst);
+            S = S + (c + acst);
+            for (int j = 0; j < s; j++) x[j] = xn[j];
+        }
+        if (quat_cost) FN(orc_cost_state_quat)(1, x, goal, Q, &c);
+        else FN(orc_cost_state)(1, s, x, goal, Q, &c);
+        costs[i] = c + S;
+    }
+}
+
+void FN(orc_mppi_update_auv)(int k, int T, const REAL *prm, REAL dt, int rk, REAL lambda, REAL gamma, REAL upsilon,
+                             int normalize, const REAL *sigma, const REAL *goal, const REAL *Q, int quat_cost,
+                             const REAL *x0, const REAL *U, const REAL *eps, REAL *costs, REAL *U_new, REAL *next,
+                             REAL *U_shift)
+{
+#pragma omp parallel
+    {
+        int nt = 1, id = 0;
+#ifdef _OPENMP
+        nt = omp_get_num_threads();
+        id = omp_get_thread_num();
+#endif
+        int lo = (int)((long long)k * id / nt), hi = (int)((long long)k * (id + 1) / nt);
+        FN(orc_rollout_costs_auv)(lo, hi, T, prm, dt, rk, lambda, gamma, upsilon, sigma, goal, Q, quat_cost, x0, U, eps, costs);
+    }
+    FN(orc_update_tail_py)(k, T, 6, lambda, normalize, costs, U, eps, U_new, next, U_shift);
+}
+
 
 #undef FN
 #undef CAT

@@ -274,6 +274,35 @@ class Oracle:
         self._fn("orc_auv_state_dot_k")(st.shape[0], _p(_c(self.auv_pack(prm), self.dt)), _p(st), _p(ac), _p(out))
         return out
 
+    def cost_state_quat(self, state, goal, Q):
+        """StaticQuatCost.state_cost (scripts/src/costs/static_cost.py:116-159); Q [10][10] or its diagonal [10]."""
+        st = _c(np.asarray(state).reshape(-1, 13), self.dt)
+        Q = np.asarray(Q, np.float64)
+        Q = np.diag(Q) if Q.ndim == 1 else Q
+        out = np.empty(st.shape[0], self.dt)
+        self._fn("orc_cost_state_quat")(st.shape[0], _p(st), _p(_c(np.asarray(goal).ravel(), self.dt)), _p(_c(Q, self.dt)), _p(out))
+        return out
+
+    def mppi_update_auv(self, prm, dt, rk, lam, sigma, goal, q, x0, U, eps, gamma=None, upsilon=1.0, normalize=False,
+                        quat_cost=False):
+        """Python-controller update with the AUV model (controller_base.py:371-474, auv_model.py:285-306) and
+        StaticCost (q [13]) or StaticQuatCost (q [10], quat_cost=True).  eps = (upsilon * sigma) z, [k][T][6]."""
+        eps = _c(eps, self.dt)
+        k, T, a = eps.shape
+        assert a == 6
+        gamma = lam if gamma is None else gamma
+        Q = _c(np.diag(np.asarray(q, np.float64)) if quat_cost else np.asarray(q, np.float64), self.dt)
+        costs = np.empty(k, self.dt)
+        U_new = np.empty((T, a), self.dt)
+        nxt = np.empty(a, self.dt)
+        U_shift = np.empty((T, a), self.dt)
+        self._fn("orc_mppi_update_auv")(k, T, _p(_c(self.auv_pack(prm), self.dt)), self.creal(dt), int(rk), self.creal(lam),
+                                        self.creal(gamma), self.creal(upsilon), int(bool(normalize)),
+                                        _p(_c(sigma, self.dt)), _p(_c(np.asarray(goal).ravel(), self.dt)), _p(Q),
+                                        int(bool(quat_cost)), _p(_c(x0, self.dt)), _p(_c(U, self.dt)), _p(eps), _p(costs),
+                                        _p(U_new), _p(nxt), _p(U_shift))
+        return dict(costs=costs, U_new=U_new, next=nxt, U_shift=U_shift)
+
     def partial(self, lam, costs, eps, k0, k1):
         costs = _c(costs, self.dt)
         eps = _c(eps, self.dt)

@@ -94,6 +94,10 @@ def concat(values, axis, name=None):
     return np.concatenate([np.atleast_1d(_a(v)) for v in values], axis=axis)
 
 
+def tensordot(a, b, axes, name=None):
+    return np.tensordot(_a(a), _a(b), axes)
+
+
 def reduce_min(x, axis=None, name=None):
     return np.min(_a(x), axis=axis)
 
