@@ -50,7 +50,7 @@ typedef enum {
 typedef struct mppi_handle mppi_handle;
 
 /* Dynamics model selector (ModelBase vs the learning_base MLP). */
-typedef enum { MPPI_MODEL_POINT_MASS = 0, MPPI_MODEL_MLP = 1 } mppi_model_kind;
+typedef enum { MPPI_MODEL_POINT_MASS = 0, MPPI_MODEL_MLP = 1, MPPI_MODEL_AUV = 2 } mppi_model_kind;
 
 /*
  * Construction parameters.  Mirrors ControllerBase(k, tau, dt, mass, s_dim, a_dim)
@@ -62,7 +62,7 @@ typedef enum { MPPI_MODEL_POINT_MASS = 0, MPPI_MODEL_MLP = 1 } mppi_model_kind;
 typedef struct {
     int k;                 /* samples per controller, summed over all ranks */
     int tau;               /* horizon T */
-    int s_dim;             /* must equal 2 * a_dim for the point-mass model */
+    int s_dim;             /* must equal 2 * a_dim for the point-mass model; 13 for MPPI_MODEL_AUV */
     int a_dim;
     float dt;
     float mass;            /* model mass used in B = [dt^2/2; dt] / mass */
@@ -77,6 +77,9 @@ typedef struct {
     int n_controllers;     /* independent controllers batched in one handle (>= 1) */
     int goal_per_controller;
     void *stream;          /* cudaStream_t to launch on; NULL = library-owned stream */
+    int model;             /* mppi_model_kind at construction: MPPI_MODEL_POINT_MASS (0, default) or MPPI_MODEL_AUV
+                            * (s_dim = 13, a_dim = 6; mppi_set_auv_model must follow).  MPPI_MODEL_MLP is selected
+                            * later, by mppi_set_mlp on a point-mass handle. */
 } mppi_config;
 
 /* Fill *cfg with the reference constructor's defaults for the given sizes. */
@@ -220,6 +223,32 @@ int mppi_mlp_train_step(mppi_handle *h, int n, const float *state, const float *
                         float learning_rate, float *loss_out);
 int mppi_mlp_set_adam(mppi_handle *h, float beta1, float beta2, float epsilon);
 int mppi_mlp_get_weights(mppi_handle *h, float *W1, float *b1, float *W2, float *b2, float *W3, float *b3);
+
+/* ---- AUV (Fossen) dynamics and the quaternion goal cost -------------- */
+/* Parameters of AUVModel (/root/reference/scripts/src/models/auv_model.py:146-255); matrices row-major [6][6].
+ * State x = (position[3], quaternion (qx, qy, qz, qw), body velocity nu[6]); action = generalised force [6]. */
+typedef struct {
+    float mass, volume, density;
+    float cog[3], cob[3];
+    float added_mass[36];                     /* "Ma" */
+    float inertia[6];                         /* ixx, iyy, izz, ixy, ixz, iyz */
+    float linear_damping[36];                 /* a diagonal parameter list is expanded by the caller */
+    float quad_damping[6];
+    float linear_damping_forward_speed[36];
+    int rk;                                   /* integrator of AUVModel.step (:285-306): 1, 2 or 4 */
+} mppi_auv_params;
+
+/* Installs the Fossen model on a handle created with cfg.model = MPPI_MODEL_AUV: x' = normalize_quat(x + rk(x, u)),
+ * acc = M^-1 (u - C(nu) nu - D(nu) nu - g(q)) (auv_model.py:285-333,450-559).  The rigid-body mass matrix uses the
+ * reference's transposed skew of cog (tf_skew_op, :23-40) and its rk = 4 branch is reproduced as written. */
+int mppi_set_auv_model(mppi_handle *h, const mppi_auv_params *prm);
+/* AUVModel.build_step_graph on a batch (the model's predict): state [kst][13], kst in {1, k}; action [k][6]. */
+int mppi_auv_predict(mppi_handle *h, int kst, int k, const float *state, const float *action, float *out);
+/* StaticQuatCost (scripts/src/costs/static_cost.py:73-159) as the state cost of an AUV handle:
+ * d = (p - g_p, 2 acos(q . g_q), nu - g_nu), cost = sum_i q10_i d_i^2 (diagonal Q; the dot product is clamped to
+ * [-1, 1], where the reference would return NaN).  mppi_set_static_cost returns to StaticCost (diag q [13]). */
+int mppi_set_quat_cost(mppi_handle *h, const float *q10);
+int mppi_cost_state_quat(int device, int k, const float *state, const float *goal, const float *q10, float *out);
 
 /* ---- stateless stage entry points (the reference's graph-builder methods on plain buffers) ----
  * All pointers are host memory; each call runs the corresponding CUDA kernel on `device`. */

@@ -28,6 +28,22 @@ class MppiConfig(C.Structure):
         ("device", C.c_int), ("rank", C.c_int), ("world", C.c_int),
         ("n_controllers", C.c_int), ("goal_per_controller", C.c_int),
         ("stream", C.c_void_p),
+        ("model", C.c_int),
+    ]
+
+
+MODEL_POINT_MASS, MODEL_MLP, MODEL_AUV = 0, 1, 2
+
+
+class MppiAuvParams(C.Structure):
+    """struct mppi_auv_params, field for field."""
+    _fields_ = [
+        ("mass", C.c_float), ("volume", C.c_float), ("density", C.c_float),
+        ("cog", C.c_float * 3), ("cob", C.c_float * 3),
+        ("added_mass", C.c_float * 36), ("inertia", C.c_float * 6),
+        ("linear_damping", C.c_float * 36), ("quad_damping", C.c_float * 6),
+        ("linear_damping_forward_speed", C.c_float * 36),
+        ("rk", C.c_int),
     ]
 
 
@@ -89,6 +105,10 @@ SYMBOLS = {
     "mppi_mlp_train_step": (_i, [_H, _i, _fp, _fp, _fp, _f, _fp]),
     "mppi_mlp_set_adam": (_i, [_H, _f, _f, _f]),
     "mppi_mlp_get_weights": (_i, [_H] + [_fp] * 6),
+    "mppi_set_auv_model": (_i, [_H, C.POINTER(MppiAuvParams)]),
+    "mppi_auv_predict": (_i, [_H, _i, _i, _fp, _fp, _fp]),
+    "mppi_set_quat_cost": (_i, [_H, _fp]),
+    "mppi_cost_state_quat": (_i, [_i, _i, _fp, _fp, _fp, _fp]),
     "mppi_block_diag": (_i, [_fp, _i, _i, _i, _fp]),
     "mppi_model_free_step": (_i, [_i, _f, _f, _i, _i, _i, _fp, _fp]),
     "mppi_model_action_step": (_i, [_i, _f, _f, _i, _i, _i, _fp, _fp]),

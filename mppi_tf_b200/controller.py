@@ -124,6 +124,15 @@ def ellipseStateCost(state, a, b, center_x, center_y, speed, m_state, m_vel, dev
     return out
 
 
+def quatStateCost(state, goal, q10, device=-1):
+    """StaticQuatCost.state_cost on a batch: state [k, 13], goal [13], q10 [10] -> [k]."""
+    st = _f32(state).reshape(-1, 13)
+    out = np.empty(st.shape[0], np.float32)
+    check(_capi.load().mppi_cost_state_quat(device, st.shape[0], _ptr(st), _ptr(_f32(goal).ravel()), _ptr(_f32(q10).ravel()),
+                                            _ptr(out)))
+    return out
+
+
 def blockDiag(block, nb):
     """utile::blockDiag — src/utile.cpp:10-43."""
     lib = _capi.load()
@@ -142,7 +151,7 @@ class ControllerBase:
     """
 
     def __init__(self, k, tau, dt, mass, s_dim, a_dim, lam=1.0, sigma=None, goal=None, Q=None, seed=1,
-                 device=-1, rank=0, world=1, n_controllers=1, goal_per_controller=False, stream=None):
+                 device=-1, rank=0, world=1, n_controllers=1, goal_per_controller=False, stream=None, model="point_mass"):
         self._lib = _capi.load()
         self.k, self.tau, self.dt, self.mass, self.s_dim, self.a_dim = k, tau, dt, mass, s_dim, a_dim
         self.n = n_controllers
@@ -163,6 +172,7 @@ class ControllerBase:
         cfg.n_controllers = n_controllers
         cfg.goal_per_controller = 1 if goal_per_controller else 0
         cfg.stream = stream
+        cfg.model = {"point_mass": _capi.MODEL_POINT_MASS, "auv": _capi.MODEL_AUV}[model]
         self._h = C.c_void_p()
         check(self._lib.mppi_create(C.byref(cfg), C.byref(self._h)))
         self.k_local = self._lib.mppi_k_local(self._h)
@@ -313,6 +323,39 @@ class ControllerBase:
         out = np.empty((ac.shape[0], self.s_dim), np.float32)
         check(self._lib.mppi_mlp_predict(self._h, st.shape[0], ac.shape[0], _ptr(st), _ptr(ac), _ptr(out)), self._h)
         return out
+
+    # ---- AUV (Fossen) dynamics and StaticQuatCost (rows N3 / N4) -------------------------------------
+    def setAuvModel(self, parameters, rk=None):
+        """AUVModel parameters as the reference's dict (scripts/src/models/auv_model.py:146-255): mass, volume,
+        density, cog, cob, Ma, inertial{ixx..iyz}, linear_damping, quad_damping, linear_damping_forward_speed
+        (damping lists of 6 are diagonals), rk.  Needs a controller created with model="auv"."""
+        sq = lambda v: (np.diag(np.asarray(v, np.float64)) if np.ndim(v) == 1 else np.asarray(v, np.float64)).ravel()
+        p = _capi.MppiAuvParams()
+        p.mass, p.volume, p.density = float(parameters["mass"]), float(parameters["volume"]), float(parameters["density"])
+        p.cog[:] = [float(v) for v in parameters["cog"]]
+        p.cob[:] = [float(v) for v in parameters["cob"]]
+        p.added_mass[:] = [float(v) for v in np.asarray(parameters["Ma"], np.float64).ravel()]
+        i = parameters["inertial"]
+        p.inertia[:] = [float(i[k]) for k in ("ixx", "iyy", "izz", "ixy", "ixz", "iyz")]
+        p.linear_damping[:] = [float(v) for v in sq(parameters["linear_damping"])]
+        p.quad_damping[:] = [float(v) for v in parameters["quad_damping"]]
+        p.linear_damping_forward_speed[:] = [float(v) for v in sq(parameters["linear_damping_forward_speed"])]
+        p.rk = int(parameters.get("rk", 1) if rk is None else rk)
+        check(self._lib.mppi_set_auv_model(self._h, C.byref(p)), self._h)
+
+    def auvPredict(self, state, action):
+        """AUVModel.build_step_graph (auv_model.py:285-306): state [k|1, 13], action [k, 6] -> [k, 13]."""
+        st = _f32(state).reshape(-1, 13)
+        ac = _f32(action).reshape(-1, 6)
+        out = np.empty((ac.shape[0], 13), np.float32)
+        check(self._lib.mppi_auv_predict(self._h, st.shape[0], ac.shape[0], _ptr(st), _ptr(ac), _ptr(out)), self._h)
+        return out
+
+    def setQuatCost(self, q10):
+        """StaticQuatCost (scripts/src/costs/static_cost.py:73-159) with Q = diag(q10) as the state cost."""
+        q = _f32(q10).ravel()
+        assert q.size == 10
+        check(self._lib.mppi_set_quat_cost(self._h, _ptr(q)), self._h)
 
     # ---- asynchronous halves (bench / multi-rank) ---------------------------------------------------
     def setState(self, x):

@@ -1,0 +1,320 @@
+// Fused MPPI update with the AUV (Fossen) dynamics model (sm_100a) — SURVEY.md section 8f, row N4.
+//
+//   rollout_auv_kernel<PHILOX>   one launch per update, same structure as the point-mass kernels: phase 1 rolls
+//                                every sample of the CTA through the horizon (explicit Euler / Heun / the
+//                                reference's rk-4 variant of the 13-state rigid-body model, quaternion
+//                                renormalised every step) and keeps only its cost; phase 2 forms the
+//                                max-shifted weights and the weighted noise sums (Philox mode: the noise is
+//                                regenerated from the same counters; injected mode: eps is re-read, lane =
+//                                column); the last CTA merges the CTA partials, applies the update and shifts.
+//   auv_predict_kernel           AUVModel.build_step_graph on a batch (the model's `predict`).
+//   quat_cost_kernel             StaticQuatCost.state_cost on a batch.
+//
+// A sample-step is ~0.5 (rk1) to ~2 (rk4) kFLOP of dependent fp32 arithmetic against 24 bytes of noise: the
+// kernel is bound by the FMA pipe, not by HBM; model parameters (160 words) ride in the kernel parameter block
+// and are read as constant-bank operands.
+//
+// Reference maths: /root/reference/scripts/src/models/auv_model.py:285-559,
+// scripts/src/controllers/controller_base.py:371-474, scripts/src/costs/static_cost.py:40-63,116-159,
+// scripts/src/costs/cost_base.py:114-170 (restated in the CPU checker that tests compare against).
+#include "mppi_auv.cuh"
+#include "mppi_internal.h"
+#include "mppi_update.cuh"
+
+namespace mppi {
+
+constexpr int kAuvThreads = 256;
+constexpr int kAuvCtasPerSm = 2;
+
+// n = z (Philox mode: eps = sigma z formed here) or eps (injected mode)
+template <bool PHILOX>
+__device__ __forceinline__ void auv_rollout_step(const RolloutParams &p, const AuvParams &P, const float *uv_row,
+                                                 const float (&n)[kAuvA], const float (&g)[kAuvS], float (&x)[kAuvS], float &S)
+{
+    constexpr int A = kAuvA, H = Row<A>::H;
+    float u[A];
+#pragma unroll
+    for (int j = 0; j < A; j++) {
+        float e;
+        if (PHILOX) {
+            e = 0.f;
+#pragma unroll
+            for (int l = 0; l < A; l++) e = fmaf(p.sigma[j * A + l], n[l], e);
+        } else {
+            e = n[j];
+        }
+        u[j] = uv_row[j] + e;
+    }
+    float ac = 0.f;
+#pragma unroll
+    for (int j = 0; j < A; j++) ac = fmaf(uv_row[H + j], n[j], ac);
+    if (p.quad) ac += quad_cost<A>(p, n);                   // grid-uniform
+    auv_step(P, x, u);
+    S += auv_state_cost(p.cost_kind, p.q, g, x) + ac;
+}
+
+template <bool PHILOX>
+__global__ void __launch_bounds__(kAuvThreads, kAuvCtasPerSm)
+rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constant__ AuvParams P)
+{
+    constexpr int A = kAuvA, RS = Row<A>::RS, NW = kAuvThreads / 32;
+    extern __shared__ float4 smem_f4[];
+    float *smem = reinterpret_cast<float *>(smem_f4);
+    const int TA = p.TA, TAp = (TA + 31) & ~31;
+    float *sUV = smem;                    // [T][RS]
+    float *sAcc = sUV + p.T * RS;         // [NW][TAp]
+    float *sN = sAcc + NW * TAp;          // [TAp]
+    float *sWork = sN + TAp;              // [TAp]
+    float *sScale = sWork + TAp;          // [kMaxParts]
+    float *sRed = sScale + kMaxParts;     // [64]
+    float4 *sScratch = reinterpret_cast<float4 *>(sRed + 64);   // [kAuvThreads]
+
+    const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    stage_sequence<A, PHILOX>(p, ctrl, sUV);
+    float g[kAuvS], x0[kAuvS];
+    {
+        const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * kAuvS : 0);
+        const float *xp = p.x + (size_t)ctrl * kAuvS;
+#pragma unroll
+        for (int i = 0; i < kAuvS; i++) {
+            g[i] = gp[i];
+            x0[i] = p.x_inline ? p.x0[i] : xp[i];
+        }
+    }
+    __syncthreads();
+    const float C0 = stage_c0<A>(p, ctrl, sWork, sRed);
+
+    float *costs = p.costs + (size_t)ctrl * p.K_local;
+    const float *eps = PHILOX ? nullptr : p.eps + (size_t)ctrl * p.K_local * TA;
+    // contiguous sample range per CTA at 32-sample granularity; every warp walks whole 32-sample groups so the
+    // loop trip counts are warp-uniform
+    const int n_w = (p.K_local + 31) >> 5;
+    const int w_lo = (int)((long long)n_w * blockIdx.x / gridDim.x);
+    const int w_hi = (int)((long long)n_w * (blockIdx.x + 1) / gridDim.x);
+    const uint32_t stream = (uint32_t)ctrl;
+
+    // ---- phase 1: rollout + cost -----------------------------------------------------------------------
+    float bmin = kInf, bmax = -kInf;
+    for (int wg = w_lo + warp; wg < w_hi && p.norm_mode != 2; wg += NW) {
+        const int k = 32 * wg + lane;
+        if (k >= p.K_local) continue;
+        const uint32_t kg = (uint32_t)(p.k_offset + k);
+        float x[kAuvS];
+#pragma unroll
+        for (int i = 0; i < kAuvS; i++) x[i] = x0[i];
+        float S = C0;
+        if (PHILOX) {
+            // flattened [T][6] row: call c yields normals 4c .. 4c+3; two steps = three calls
+            uint32_t call = 0;
+            int t = 0;
+            for (; t + 2 <= p.T; t += 2) {
+                float z[12];
+#pragma unroll
+                for (int c = 0; c < 3; c++) normals4(call + c, kg, stream, p, &z[4 * c]);
+                call += 3;
+#pragma unroll
+                for (int tt = 0; tt < 2; tt++) {
+                    float n[A];
+#pragma unroll
+                    for (int j = 0; j < A; j++) n[j] = z[tt * A + j];
+                    auv_rollout_step<true>(p, P, sUV + (t + tt) * RS, n, g, x, S);
+                }
+            }
+            if (t < p.T) {
+                float z[8];
+                normals4(call, kg, stream, p, &z[0]);
+                normals4(call + 1, kg, stream, p, &z[4]);
+                float n[A];
+#pragma unroll
+                for (int j = 0; j < A; j++) n[j] = z[j];
+                auv_rollout_step<true>(p, P, sUV + t * RS, n, g, x, S);
+            }
+        } else {
+            const float2 *row = reinterpret_cast<const float2 *>(eps + (size_t)k * TA);   // TA = 6 T: 8-byte aligned rows
+            for (int t = 0; t < p.T; t++) {
+                float n[A];
+#pragma unroll
+                for (int j = 0; j < A / 2; j++) {
+                    const float2 v = __ldg(row + t * (A / 2) + j);
+                    n[2 * j] = v.x;
+                    n[2 * j + 1] = v.y;
+                }
+                auv_rollout_step<false>(p, P, sUV + t * RS, n, g, x, S);
+            }
+        }
+        S += auv_state_cost(p.cost_kind, p.q, g, x);          // terminal cost on top of step T-1's
+        costs[k] = S;
+        bmin = fminf(bmin, S);
+        bmax = fmaxf(bmax, S);
+    }
+    bmin = warp_min(bmin);
+    bmax = -warp_min(-bmax);
+    if (lane == 0) { sRed[warp] = bmin; sRed[32 + warp] = bmax; }
+    __syncthreads();
+    float beta_c = sRed[0], max_c = sRed[32];
+#pragma unroll
+    for (int w = 1; w < NW; w++) { beta_c = fminf(beta_c, sRed[w]); max_c = fmaxf(max_c, sRed[32 + w]); }
+    __syncthreads();
+    if (p.norm_mode == 1) {
+        publish_minmax(p, ctrl, beta_c, max_c, sRed);
+        return;
+    }
+    float beta_fixed = 0.f;
+    const float nil = weight_scale(p, ctrl, beta_fixed);
+    if (p.norm_mode == 2) beta_c = beta_fixed;
+
+    // ---- phase 2: eta and the weighted noise sums ----------------------------------------------------------
+    float eta = 0.f;
+    float *myacc = sAcc + warp * TAp;
+    for (int j = lane; j < TAp; j += 32) myacc[j] = 0.f;
+    __syncwarp();
+    if (PHILOX) {
+        const int ncall = (TA + 3) >> 2, nchunk = (ncall + 7) >> 3;
+        for (int ch = 0; ch < nchunk; ch++) {
+            float acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) acc[i] = 0.f;
+            for (int wg = w_lo + warp; wg < w_hi; wg += NW) {
+                const int k = 32 * wg + lane;
+                const float e = (k < p.K_local) ? weight_exp(costs[k], beta_c, nil) : 0.f;
+                if (ch == 0) eta += e;
+                if (__ballot_sync(0xffffffffu, e != 0.f) == 0u) continue;        // the whole group underflowed
+                const uint32_t kg = (uint32_t)(p.k_offset + k);
+#pragma unroll
+                for (int c8 = 0; c8 < 8; c8++) {
+                    if (ch * 8 + c8 < ncall) {
+                        float z[4];
+                        normals4((uint32_t)(ch * 8 + c8), kg, stream, p, z);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) acc[4 * c8 + i] = fmaf(e, z[i], acc[4 * c8 + i]);
+                    }
+                }
+            }
+            const float r = warp_transpose_sum32(acc, lane);
+            myacc[ch * 32 + lane] = r;
+        }
+    } else {
+        // lane = column: 256 columns per pass, the group's non-zero weights broadcast one by one
+        for (int cb = 0; cb < TA; cb += 256) {
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = 0.f;
+            for (int wg = w_lo + warp; wg < w_hi; wg += NW) {
+                const int k = 32 * wg + lane;
+                const float e = (k < p.K_local) ? weight_exp(costs[k], beta_c, nil) : 0.f;
+                if (cb == 0) eta += e;
+                unsigned live = __ballot_sync(0xffffffffu, e != 0.f);
+                while (live) {
+                    const int j = __ffs(live) - 1;
+                    live &= live - 1;
+                    const float ej = __shfl_sync(0xffffffffu, e, j);
+                    const float *row = eps + (size_t)(32 * wg + j) * TA + cb;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int col = 32 * i + lane;
+                        if (cb + col < TA) acc[i] = fmaf(ej, __ldg(row + col), acc[i]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (cb + 32 * i + lane < TAp) myacc[cb + 32 * i + lane] = acc[i];
+        }
+    }
+    eta = warp_sum(eta);
+    if (lane == 0) sRed[warp] = eta;
+    __syncthreads();
+    float eta_c = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; w++) eta_c += sRed[w];
+    for (int j = tid; j < TA; j += kAuvThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) s += sAcc[w * TAp + j];
+        sN[j] = s;
+    }
+    __syncthreads();
+    publish_and_finish<A, PHILOX>(p, ctrl, beta_c, eta_c, sN, sWork, sScale, sRed, sScratch, kAuvThreads);
+}
+
+// AUVModel.build_step_graph on a batch: state [kst][13] (kst in {1, k}), action [k][6] -> next [k][13]
+__global__ void __launch_bounds__(256) auv_predict_kernel(const __grid_constant__ AuvParams P, int kst, int k,
+                                                          const float *state, const float *action, float *out)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+        float x[kAuvS], u[kAuvA];
+        const float *xs = state + (size_t)(kst == 1 ? 0 : i) * kAuvS;
+#pragma unroll
+        for (int j = 0; j < kAuvS; j++) x[j] = xs[j];
+#pragma unroll
+        for (int j = 0; j < kAuvA; j++) u[j] = action[(size_t)i * kAuvA + j];
+        auv_step(P, x, u);
+#pragma unroll
+        for (int j = 0; j < kAuvS; j++) out[(size_t)i * kAuvS + j] = x[j];
+    }
+}
+
+struct QuatCostArgs { float q[kAuvS]; float g[kAuvS]; int kind; };
+
+__global__ void __launch_bounds__(256) auv_cost_kernel(const __grid_constant__ QuatCostArgs a, int k, const float *state, float *out)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+        float x[kAuvS], g[kAuvS];
+#pragma unroll
+        for (int j = 0; j < kAuvS; j++) { x[j] = state[(size_t)i * kAuvS + j]; g[j] = a.g[j]; }
+        out[i] = auv_state_cost(a.kind, a.q, g, x);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Host launchers
+// -------------------------------------------------------------------------------------------------
+int auv_grid_x(int K_local, int n_ctrl, int num_sms)
+{
+    int per_ctrl = num_sms * kAuvCtasPerSm / (n_ctrl > 0 ? n_ctrl : 1);
+    if (per_ctrl < 1) per_ctrl = 1;
+    const int need = (K_local + 63) / 64;          // at least two warps of samples per CTA
+    int gx = need < per_ctrl ? need : per_ctrl;
+    if (gx > kMaxParts) gx = kMaxParts;
+    return gx < 1 ? 1 : gx;
+}
+
+cudaError_t launch_rollout_auv(RolloutParams p, const AuvParams &P, bool philox, int num_sms, cudaStream_t st, int *grid_x_out)
+{
+    constexpr int RS = Row<kAuvA>::RS, NW = kAuvThreads / 32;
+    const int TAp = (p.TA + 31) & ~31;
+    const size_t smem = sizeof(float) * ((size_t)p.T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 64) + sizeof(float4) * kAuvThreads;
+    const int gx = auv_grid_x(p.K_local, p.n_ctrl, num_sms);
+    if (grid_x_out) *grid_x_out = gx;
+    dim3 grid(gx, p.n_ctrl);
+    cudaError_t err;
+    if (philox) {
+        if ((err = ensure_dyn_smem<rollout_auv_kernel<true>>(smem)) != cudaSuccess) return err;
+        rollout_auv_kernel<true><<<grid, kAuvThreads, smem, st>>>(p, P);
+    } else {
+        if ((err = ensure_dyn_smem<rollout_auv_kernel<false>>(smem)) != cudaSuccess) return err;
+        rollout_auv_kernel<false><<<grid, kAuvThreads, smem, st>>>(p, P);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_auv_predict(const AuvParams &P, int kst, int k, const float *state, const float *action, float *out, cudaStream_t st)
+{
+    int blocks = (k + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    auv_predict_kernel<<<blocks, 256, 0, st>>>(P, kst, k, state, action, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_auv_cost(int kind, int k, const float *q, const float *goal, const float *state, float *out, cudaStream_t st)
+{
+    QuatCostArgs a;
+    for (int i = 0; i < kAuvS; i++) { a.q[i] = q[i]; a.g[i] = goal[i]; }
+    a.kind = kind;
+    int blocks = (k + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    auv_cost_kernel<<<blocks, 256, 0, st>>>(a, k, state, out);
+    return cudaGetLastError();
+}
+
+}  // namespace mppi

@@ -13,6 +13,7 @@
 
 #include "mppi_device.cuh"
 #include "mppi_internal.h"
+#include "mppi_auv.cuh"
 #include "mppi_mlp.cuh"
 
 using namespace mppi;
@@ -101,6 +102,9 @@ struct mppi_handle {
     bool peer_on = false;
     uint32_t epoch = 0;
     unsigned int *d_peer_status = nullptr, *h_peer_status = nullptr;
+    // AUV (Fossen) dynamics (cfg.model = MPPI_MODEL_AUV + mppi_set_auv_model)
+    bool auv = false, auv_ready = false;
+    AuvParams auv_prm;
     // learned-MLP dynamics (mppi_set_mlp)
     bool mlp = false;
     void *d_wblob = nullptr;
@@ -288,7 +292,12 @@ int mppi_create(const mppi_config *cfg, mppi_handle **out)
     const int world = cfg->world > 0 ? cfg->world : 1;
     if (cfg->k <= 0 || cfg->tau <= 0 || cfg->a_dim <= 0 || cfg->s_dim <= 0)
         return fail(nullptr, MPPI_ERR_BAD_ARG, "k, tau, s_dim, a_dim must be positive");
-    if (cfg->s_dim != 2 * cfg->a_dim)
+    if (cfg->model != MPPI_MODEL_POINT_MASS && cfg->model != MPPI_MODEL_AUV)
+        return fail(nullptr, MPPI_ERR_BAD_ARG, "cfg.model must be MPPI_MODEL_POINT_MASS or MPPI_MODEL_AUV (the MLP is selected by mppi_set_mlp)");
+    const bool auv = cfg->model == MPPI_MODEL_AUV;
+    if (auv && (cfg->s_dim != kAuvS || cfg->a_dim != kAuvA))
+        return fail(nullptr, MPPI_ERR_BAD_ARG, "AUV model needs s_dim == 13, a_dim == 6");
+    if (!auv && cfg->s_dim != 2 * cfg->a_dim)
         return fail(nullptr, MPPI_ERR_BAD_ARG, "point-mass model needs s_dim == 2 * a_dim");
     if (cfg->a_dim > MPPI_MAX_A) return fail(nullptr, MPPI_ERR_UNSUPPORTED, "a_dim > MPPI_MAX_A");
     if ((long long)cfg->tau * cfg->a_dim > MPPI_MAX_TA) return fail(nullptr, MPPI_ERR_UNSUPPORTED, "tau*a_dim > MPPI_MAX_TA");
@@ -312,6 +321,8 @@ int mppi_create(const mppi_config *cfg, mppi_handle **out)
     // rank r owns samples [r*k/world, (r+1)*k/world)  
     mppi_shard_range(cfg->k, cfg->rank, world, &h->k_offset, &h->K_local);
     h->goal_per_ctrl = cfg->goal_per_controller ? 1 : 0;
+    h->auv = auv;
+    memset(&h->auv_prm, 0, sizeof(h->auv_prm));
 
     const int a = h->a, s = h->s;
     memset(h->sigma, 0, sizeof(h->sigma));
@@ -377,7 +388,9 @@ int mppi_create(const mppi_config *cfg, mppi_handle **out)
 
     std::vector<float> goal(n_goal);
     for (size_t i = 0; i < n_goal; i++)
-        goal[i] = cfg->goal ? cfg->goal[i] : ((i % s) % 2 == 0 ? 1.f : 0.f);   // (1,0,1,0,..), :43-46
+        goal[i] = cfg->goal ? cfg->goal[i]
+                  : auv     ? ((i % s) == 6 ? 1.f : 0.f)                         // origin, identity attitude, at rest
+                            : ((i % s) % 2 == 0 ? 1.f : 0.f);                    // (1,0,1,0,..), :43-46
     CU_TRY_C(cudaMemcpy(h->d_goal, goal.data(), sizeof(float) * n_goal, cudaMemcpyHostToDevice));
 #undef CU_TRY_C
     *out = h;
@@ -440,6 +453,7 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
 {
     if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
     if (!h->x_staged) return fail(h, MPPI_ERR_STATE, "mppi_set_state must precede mppi_enqueue_update");
+    if (h->auv && !h->auv_ready) return fail(h, MPPI_ERR_STATE, "AUV handle: mppi_set_auv_model has not been called");
     CU_TRY(h, cudaSetDevice(h->device));
     if (h->d_zc && h->zc_request) { h->zc_epoch++; h->zc_armed = true; }
     RolloutParams p = make_params(h, eps_dev);
@@ -450,7 +464,9 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
     for (int pass = 1; pass <= npass; pass++) {
         p.norm_mode = h->normalize ? pass : 0;
         if (h->peer_on) p.epoch = ++h->epoch;       // one exchange per launch; the same count on every rank
-        if (h->mlp) {
+        if (h->auv) {
+            CU_TRY(h, launch_rollout_auv(p, h->auv_prm, eps_dev == nullptr, h->num_sms, h->stream, &gx));
+        } else if (h->mlp) {
             MlpParams mp{h->d_wblob, h->d_fvec, h->s, h->a};
             CU_TRY(h, launch_rollout_mlp(p, mp, h->a, eps_dev == nullptr, h->num_sms, h->stream, &gx));
         } else if (eps_dev) {
@@ -666,6 +682,7 @@ int mppi_set_sigma(mppi_handle *h, const float *sigma_host)
 int mppi_set_q(mppi_handle *h, const float *q_host)
 {
     if (!h || !q_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    if (h->cost_kind == 2) return fail(h, MPPI_ERR_STATE, "StaticQuatCost is active: its weights are set by mppi_set_quat_cost");
     for (int i = 0; i < h->s; i++)
         if (!(q_host[i] >= 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "q must be non-negative (diag of a PSD Q)");
     memcpy(h->q, q_host, sizeof(float) * h->s);
@@ -822,11 +839,129 @@ int mppi_comm_init(mppi_handle *h, const void *id128)
     return MPPI_OK;
 }
 
+// ---- AUV (Fossen) model and quaternion cost (rows N3 / N4) ------------------------------------------
+static bool invert6(const double *m, double *inv)
+{
+    double w[6][12];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) { w[i][j] = m[i * 6 + j]; w[i][6 + j] = (i == j) ? 1.0 : 0.0; }
+    for (int c = 0; c < 6; c++) {
+        int piv = c;
+        for (int r = c + 1; r < 6; r++)
+            if (fabs(w[r][c]) > fabs(w[piv][c])) piv = r;
+        if (w[piv][c] == 0.0) return false;
+        if (piv != c)
+            for (int j = 0; j < 12; j++) { const double t = w[c][j]; w[c][j] = w[piv][j]; w[piv][j] = t; }
+        const double d = w[c][c];
+        for (int j = 0; j < 12; j++) w[c][j] /= d;
+        for (int r = 0; r < 6; r++) {
+            if (r == c) continue;
+            const double f = w[r][c];
+            for (int j = 0; j < 12; j++) w[r][j] -= f * w[c][j];
+        }
+    }
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) inv[i * 6 + j] = w[i][6 + j];
+    return true;
+}
+
+// Derived constants of AUVModel.__init__ (auv_model.py:146-283), in double, rounded once to fp32.
+static bool derive_auv(const mppi_auv_params *prm, float dt, AuvParams *out)
+{
+    const double m = prm->mass, g = 9.81;
+    const float *cog = prm->cog, *in = prm->inertia;
+    // tf_skew_op (:23-40) stacks its rows as columns: the TRANSPOSED skew matrix of cog, kept as the reference has it
+    const double S[9] = {0, cog[2], -cog[1], -cog[2], 0, cog[0], cog[1], -cog[0], 0};
+    const double I[9] = {in[0], in[3], in[4], in[3], in[1], in[5], in[4], in[5], in[2]};
+    double M[36], Minv[36];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+            M[r * 6 + c] = (r == c) ? m : 0.0;
+            M[r * 6 + 3 + c] = -(m * S[r * 3 + c]);
+            M[(3 + r) * 6 + c] = m * S[r * 3 + c];
+            M[(3 + r) * 6 + 3 + c] = I[r * 3 + c];
+        }
+    for (int i = 0; i < 36; i++) M[i] += prm->added_mass[i];
+    if (!invert6(M, Minv)) return false;
+    memset(out, 0, sizeof(*out));
+    out->fng = (float)(-(m * g));
+    out->fnb = (float)((double)prm->volume * (double)prm->density * g);
+    for (int i = 0; i < 3; i++) { out->cog[i] = prm->cog[i]; out->cob[i] = prm->cob[i]; }
+    for (int i = 0; i < 36; i++) {
+        out->Mtot[i] = (float)M[i];
+        out->invM[i] = (float)Minv[i];
+        out->Dl[i] = prm->linear_damping[i];
+        out->Dlf[i] = prm->linear_damping_forward_speed[i];
+    }
+    for (int i = 0; i < 6; i++) out->dq[i] = prm->quad_damping[i];
+    out->dt = dt;
+    out->rk = prm->rk;
+    return true;
+}
+
+int mppi_set_auv_model(mppi_handle *h, const mppi_auv_params *prm)
+{
+    if (!h || !prm) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    if (!h->auv) return fail(h, MPPI_ERR_STATE, "handle was not created with cfg.model = MPPI_MODEL_AUV");
+    if (prm->rk != 1 && prm->rk != 2 && prm->rk != 4) return fail(h, MPPI_ERR_BAD_ARG, "rk must be 1, 2 or 4");
+    if (!derive_auv(prm, h->dt, &h->auv_prm)) return fail(h, MPPI_ERR_BAD_ARG, "total mass matrix is singular");
+    h->auv_ready = true;
+    return MPPI_OK;
+}
+
+int mppi_auv_predict(mppi_handle *h, int kst, int k, const float *state, const float *action, float *out)
+{
+    if (!h || !state || !action || !out || k <= 0 || (kst != 1 && kst != k)) return fail(h, MPPI_ERR_BAD_ARG, "bad auv_predict argument");
+    if (!h->auv || !h->auv_ready) return fail(h, MPPI_ERR_STATE, "mppi_set_auv_model has not been called");
+    CU_TRY(h, cudaSetDevice(h->device));
+    DevBuf ds, da, dout;
+    CU_TRY(h, ds.alloc(sizeof(float) * (size_t)kst * kAuvS));
+    CU_TRY(h, da.alloc(sizeof(float) * (size_t)k * kAuvA));
+    CU_TRY(h, dout.alloc(sizeof(float) * (size_t)k * kAuvS));
+    CU_TRY(h, cudaMemcpyAsync(ds.p, state, sizeof(float) * (size_t)kst * kAuvS, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(da.p, action, sizeof(float) * (size_t)k * kAuvA, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, launch_auv_predict(h->auv_prm, kst, k, ds.as<float>(), da.as<float>(), dout.as<float>(), h->stream));
+    CU_TRY(h, cudaMemcpyAsync(out, dout.p, sizeof(float) * (size_t)k * kAuvS, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_set_quat_cost(mppi_handle *h, const float *q10)
+{
+    if (!h || !q10) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    if (!h->auv) return fail(h, MPPI_ERR_UNSUPPORTED, "StaticQuatCost is defined on the 13-dimensional AUV state");
+    for (int i = 0; i < 10; i++)
+        if (!(q10[i] >= 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "q must be non-negative (diag of a PSD Q)");
+    memset(h->q, 0, sizeof(h->q));
+    memcpy(h->q, q10, sizeof(float) * 10);
+    h->cost_kind = 2;
+    return MPPI_OK;
+}
+
+int mppi_cost_state_quat(int device, int k, const float *state, const float *goal, const float *q10, float *out)
+{
+    if (k <= 0 || !state || !goal || !q10 || !out) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad cost_state_quat argument");
+    cudaDeviceProp prop;
+    int dev = 0;
+    int rc = select_device(nullptr, device, &dev, &prop);
+    if (rc != MPPI_OK) return rc;
+    float q[kAuvS] = {0};
+    memcpy(q, q10, sizeof(float) * 10);
+    DevBuf ds, dout;
+    CU_TRY(nullptr, ds.alloc(sizeof(float) * (size_t)k * kAuvS));
+    CU_TRY(nullptr, dout.alloc(sizeof(float) * (size_t)k));
+    CU_TRY(nullptr, cudaMemcpy(ds.p, state, sizeof(float) * (size_t)k * kAuvS, cudaMemcpyHostToDevice));
+    CU_TRY(nullptr, launch_auv_cost(2, k, q, goal, ds.as<float>(), dout.as<float>(), nullptr));
+    CU_TRY(nullptr, cudaMemcpy(out, dout.p, sizeof(float) * (size_t)k, cudaMemcpyDeviceToHost));
+    return MPPI_OK;
+}
+
 int mppi_set_mlp(mppi_handle *h, int hidden, const float *W1, const float *b1, const float *W2, const float *b2,
                  const float *W3, const float *b3, const float *Xmean, const float *Xstd, const float *Ymean,
                  const float *Ystd)
 {
     if (!h || !W1 || !b1 || !W2 || !b2 || !W3 || !b3) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    if (h->auv) return fail(h, MPPI_ERR_UNSUPPORTED, "mppi_set_mlp needs a point-mass handle (s_dim = 2 a_dim)");
     if (hidden != kMlpH) return fail(h, MPPI_ERR_UNSUPPORTED, "this build supports hidden = 128 only");
     if (h->s + h->a + 1 > kMlpKin || h->a > 5) return fail(h, MPPI_ERR_UNSUPPORTED, "MLP path needs s + a <= 15 (a <= 5)");
     CU_TRY(h, cudaSetDevice(h->device));

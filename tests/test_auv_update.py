@@ -38,3 +38,119 @@ def test_oracle_quat_cost(oracle64, name):
     _, _, g = load(name)
     got = oracle64.cost_state_quat(g("qc_state"), g("goal"), g("q"))
     np.testing.assert_allclose(got, g("qc_cost"), rtol=1e-12, atol=1e-12)
+
+
+# ---- CUDA path (through the C-ABI) ----------------------------------------------------------------------
+def _auv_controller(prm, m, g, k=None, tau=None, **kw):
+    from mppi_tf_b200 import ControllerBase
+    q = g("q")
+    ctrl = ControllerBase(k or m["k"], tau or m["tau"], 0.1, 1.0, 13, 6, lam=m["lam"], sigma=g("sigma"), goal=g("goal"),
+                          Q=(np.ones(13) if m["quat"] else q), model="auv", **kw)
+    ctrl.setAuvModel(prm, rk=m["rk"])
+    if m["quat"]:
+        ctrl.setQuatCost(q)
+    ctrl.setActionCost("python", gamma=m["gamma"], upsilon=m["upsilon"])
+    ctrl.setNormalizeCost(m["normalize"])
+    return ctrl
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["test", "full"])
+@pytest.mark.parametrize("rk", [1, 2, 4])
+def test_cuda_auv_predict_matches_reference_model(which, rk):
+    """mppi_auv_predict against the reference AUVModel's own outputs (tests/golden/auv_fixtures.npz)."""
+    from mppi_tf_b200 import ControllerBase
+    from tests.util import rel_err
+    d = np.load(os.path.join(os.path.dirname(FIX), "auv_fixtures.npz"))
+    prm = json.loads(bytes(d["params_json"]).decode())[which]
+    ctrl = ControllerBase(64, 4, 0.1, 1.0, 13, 6, model="auv")
+    try:
+        ctrl.setAuvModel(prm, rk=rk)
+        st, ac, want = d[f"{which}_state"], d[f"{which}_action"], d[f"{which}_next_rk{rk}"]
+        got = ctrl.auvPredict(st, ac)
+        assert rel_err(got, want) < 1e-5
+        np.testing.assert_allclose(np.linalg.norm(got[:, 3:7], axis=1), 1.0, rtol=1e-6)
+        one = ctrl.auvPredict(st[:1], ac)                                    # broadcast state (kst = 1)
+        np.testing.assert_allclose(one[0], got[0], rtol=1e-6, atol=1e-7)
+    finally:
+        ctrl.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["auv_quat", "auv_quatn"])
+def test_cuda_quat_cost(name):
+    from mppi_tf_b200 import quatStateCost
+    _, _, g = load(name)
+    got = quatStateCost(g("qc_state"), g("goal"), g("q"))
+    np.testing.assert_allclose(got, g("qc_cost"), rtol=2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_matches_reference_controller(oracle32, name):
+    """Full update with injected noise against the reference controller's own output."""
+    from tests.util import assert_update_close, rel_err
+    prm, m, g = load(name)
+    r32 = oracle32.mppi_update_auv(prm, 0.1, m["rk"], m["lam"], g("sigma"), g("goal"), g("q"), g("x"), g("U"), g("eps"),
+                                   gamma=m["gamma"], upsilon=m["upsilon"], normalize=m["normalize"], quat_cost=m["quat"])
+    ctrl = _auv_controller(prm, m, g)
+    try:
+        ctrl.setSequence(g("U"))
+        act = ctrl.nextWithNoise(g("x"), g("eps"))
+        assert rel_err(ctrl.getCosts(), g("costs_py")) < 1e-5
+        assert_update_close(ctrl.getUpdate(), g("U_new"), r32["U_new"], what=name + " U_new")
+        assert_update_close(ctrl.getSequence(), g("U_shift"), r32["U_shift"], what=name + " U_shift")
+        assert np.abs(act - g("next")).max() <= max(1e-5, 3 * rel_err(r32["U_new"], g("U_new"))) * np.abs(g("U_new")).max()
+    finally:
+        ctrl.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,k,tau", [("auv_rk2", 20000, 15), ("auv_quat", 4133, 12), ("auv_quatn", 9000, 7)])
+def test_cuda_philox_store_then_replay(oracle64, oracle32, name, k, tau):
+    """Philox mode at multi-CTA sizes (ragged K, odd horizon): run the update, dump the noise it generated and feed
+    exactly that tensor to the checker; then the injected-noise kernel on the same tensor."""
+    from tests.util import assert_update_close, rel_err
+    prm, m, g = load(name)
+    rng = np.random.default_rng(7)
+    U = (20.0 * rng.standard_normal((tau, 6))).astype(np.float32)
+    x = g("x").astype(np.float32)
+    ctrl = _auv_controller(prm, m, g, k=k, tau=tau)
+    try:
+        ctrl.setSequence(U)
+        act = ctrl.next(x)
+        eps = ctrl.dumpNoise().reshape(k, tau, 6)
+        kw = dict(gamma=m["gamma"], upsilon=m["upsilon"], normalize=m["normalize"], quat_cost=m["quat"])
+        r64 = oracle64.mppi_update_auv(prm, 0.1, m["rk"], m["lam"], g("sigma"), g("goal"), g("q"), x, U, eps, **kw)
+        r32 = oracle32.mppi_update_auv(prm, 0.1, m["rk"], m["lam"], g("sigma"), g("goal"), g("q"), x, U, eps, **kw)
+        assert rel_err(ctrl.getCosts(), r64["costs"]) < 1e-5
+        assert_update_close(ctrl.getUpdate(), r64["U_new"], r32["U_new"], what=name + " philox U_new")
+        assert_update_close(act, r64["next"], r32["next"], what=name + " philox next")
+        ctrl.setSequence(U)
+        ctrl.nextWithNoise(x, eps)
+        assert rel_err(ctrl.getCosts(), r64["costs"]) < 1e-5
+        assert_update_close(ctrl.getUpdate(), r64["U_new"], r32["U_new"], what=name + " injected U_new")
+    finally:
+        ctrl.close()
+
+
+@pytest.mark.gpu
+def test_cuda_auv_errors():
+    from mppi_tf_b200 import ControllerBase, MppiError, _capi
+    with pytest.raises(MppiError) as e:
+        ControllerBase(64, 4, 0.1, 1.0, 12, 6, model="auv")
+    assert e.value.code == _capi.MPPI_ERR_BAD_ARG
+    ctrl = ControllerBase(64, 4, 0.1, 1.0, 13, 6, model="auv")
+    try:
+        with pytest.raises(MppiError) as e:
+            ctrl.next(np.zeros(13))
+        assert e.value.code == _capi.MPPI_ERR_STATE                     # model parameters not installed yet
+    finally:
+        ctrl.close()
+    pm = ControllerBase(64, 4, 0.1, 1.0, 4, 2)
+    try:
+        with pytest.raises(MppiError) as e:
+            pm.setQuatCost(np.ones(10))
+        assert e.value.code == _capi.MPPI_ERR_UNSUPPORTED
+    finally:
+        pm.close()
