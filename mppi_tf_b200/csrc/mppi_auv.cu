@@ -17,19 +17,21 @@
 // Reference maths: /root/reference/scripts/src/models/auv_model.py:285-559,
 // scripts/src/controllers/controller_base.py:371-474, scripts/src/costs/static_cost.py:40-63,116-159,
 // scripts/src/costs/cost_base.py:114-170 (restated in the CPU checker that tests compare against).
+#include <cstdlib>
+
 #include "mppi_auv.cuh"
 #include "mppi_internal.h"
 #include "mppi_update.cuh"
 
 namespace mppi {
 
-constexpr int kAuvThreads = 256;
-constexpr int kAuvCtasPerSm = 2;
+// CTA shape: THREADS x CTAS-per-SM is a template parameter pair so that the register budget (65536 / resident
+// threads) can be chosen per integrator; see auv_geometry().
 
 // n = z (Philox mode: eps = sigma z formed here) or eps (injected mode)
-template <bool PHILOX>
+template <bool PHILOX, int RK>
 __device__ __forceinline__ void auv_rollout_step(const RolloutParams &p, const AuvParams &P, const float *uv_row,
-                                                 const float (&n)[kAuvA], const float (&g)[kAuvS], float (&x)[kAuvS], float &S)
+                                                 const float (&n)[kAuvA], const float *g, float (&x)[kAuvS], float &S)
 {
     constexpr int A = kAuvA, H = Row<A>::H;
     float u[A];
@@ -49,11 +51,11 @@ __device__ __forceinline__ void auv_rollout_step(const RolloutParams &p, const A
 #pragma unroll
     for (int j = 0; j < A; j++) ac = fmaf(uv_row[H + j], n[j], ac);
     if (p.quad) ac += quad_cost<A>(p, n);                   // grid-uniform
-    auv_step(P, x, u);
+    auv_step<RK>(P, x, u);
     S += auv_state_cost(p.cost_kind, p.q, g, x) + ac;
 }
 
-template <bool PHILOX>
+template <bool PHILOX, int RK, int kAuvThreads, int kAuvCtasPerSm>
 __global__ void __launch_bounds__(kAuvThreads, kAuvCtasPerSm)
 rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constant__ AuvParams P)
 {
@@ -67,20 +69,16 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
     float *sWork = sN + TAp;              // [TAp]
     float *sScale = sWork + TAp;          // [kMaxParts]
     float *sRed = sScale + kMaxParts;     // [64]
-    float4 *sScratch = reinterpret_cast<float4 *>(sRed + 64);   // [kAuvThreads]
+    float *sGX = sRed + 64;               // [32] goal at 0, initial state at 16 (broadcast reads instead of 26 registers)
+    float4 *sScratch = reinterpret_cast<float4 *>(sGX + 32);    // [kAuvThreads]
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     stage_sequence<A, PHILOX>(p, ctrl, sUV);
-    float g[kAuvS], x0[kAuvS];
-    {
-        const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * kAuvS : 0);
-        const float *xp = p.x + (size_t)ctrl * kAuvS;
-#pragma unroll
-        for (int i = 0; i < kAuvS; i++) {
-            g[i] = gp[i];
-            x0[i] = p.x_inline ? p.x0[i] : xp[i];
-        }
+    if (tid < kAuvS) {
+        sGX[tid] = p.goal[(p.goal_per_ctrl ? (size_t)ctrl * kAuvS : 0) + tid];
+        sGX[16 + tid] = p.x_inline ? p.x0[tid] : p.x[(size_t)ctrl * kAuvS + tid];
     }
+    const float *g = sGX, *x0 = sGX + 16;
     __syncthreads();
     const float C0 = stage_c0<A>(p, ctrl, sWork, sRed);
 
@@ -117,7 +115,7 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
                     float n[A];
 #pragma unroll
                     for (int j = 0; j < A; j++) n[j] = z[tt * A + j];
-                    auv_rollout_step<true>(p, P, sUV + (t + tt) * RS, n, g, x, S);
+                    auv_rollout_step<true, RK>(p, P, sUV + (t + tt) * RS, n, g, x, S);
                 }
             }
             if (t < p.T) {
@@ -127,7 +125,7 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
                 float n[A];
 #pragma unroll
                 for (int j = 0; j < A; j++) n[j] = z[j];
-                auv_rollout_step<true>(p, P, sUV + t * RS, n, g, x, S);
+                auv_rollout_step<true, RK>(p, P, sUV + t * RS, n, g, x, S);
             }
         } else {
             const float2 *row = reinterpret_cast<const float2 *>(eps + (size_t)k * TA);   // TA = 6 T: 8-byte aligned rows
@@ -139,7 +137,7 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
                     n[2 * j] = v.x;
                     n[2 * j + 1] = v.y;
                 }
-                auv_rollout_step<false>(p, P, sUV + t * RS, n, g, x, S);
+                auv_rollout_step<false, RK>(p, P, sUV + t * RS, n, g, x, S);
             }
         }
         S += auv_state_cost(p.cost_kind, p.q, g, x);          // terminal cost on top of step T-1's
@@ -248,7 +246,9 @@ __global__ void __launch_bounds__(256) auv_predict_kernel(const __grid_constant_
         for (int j = 0; j < kAuvS; j++) x[j] = xs[j];
 #pragma unroll
         for (int j = 0; j < kAuvA; j++) u[j] = action[(size_t)i * kAuvA + j];
-        auv_step(P, x, u);
+        if (P.rk == 2) auv_step<2>(P, x, u);
+        else if (P.rk == 4) auv_step<4>(P, x, u);
+        else auv_step<1>(P, x, u);
 #pragma unroll
         for (int j = 0; j < kAuvS; j++) out[(size_t)i * kAuvS + j] = x[j];
     }
@@ -269,33 +269,62 @@ __global__ void __launch_bounds__(256) auv_cost_kernel(const __grid_constant__ Q
 // -------------------------------------------------------------------------------------------------
 // Host launchers
 // -------------------------------------------------------------------------------------------------
-int auv_grid_x(int K_local, int n_ctrl, int num_sms)
+template <bool PHILOX, int RK, int THREADS, int CTAS>
+static cudaError_t launch_auv_V(const RolloutParams &p, const AuvParams &P, int num_sms, cudaStream_t st, int *grid_x_out)
 {
-    int per_ctrl = num_sms * kAuvCtasPerSm / (n_ctrl > 0 ? n_ctrl : 1);
+    constexpr int RS = Row<kAuvA>::RS, NW = THREADS / 32;
+    const int TAp = (p.TA + 31) & ~31;
+    const size_t smem = sizeof(float) * ((size_t)p.T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 64 + 32) + sizeof(float4) * THREADS;
+    int per_ctrl = num_sms * CTAS / (p.n_ctrl > 0 ? p.n_ctrl : 1);
     if (per_ctrl < 1) per_ctrl = 1;
-    const int need = (K_local + 63) / 64;          // at least two warps of samples per CTA
+    const int need = (p.K_local + 63) / 64;        // at least two warps of samples per CTA
     int gx = need < per_ctrl ? need : per_ctrl;
     if (gx > kMaxParts) gx = kMaxParts;
-    return gx < 1 ? 1 : gx;
+    if (gx < 1) gx = 1;
+    if (grid_x_out) *grid_x_out = gx;
+    cudaError_t err = ensure_dyn_smem<rollout_auv_kernel<PHILOX, RK, THREADS, CTAS>>(smem);
+    if (err != cudaSuccess) return err;
+    rollout_auv_kernel<PHILOX, RK, THREADS, CTAS><<<dim3(gx, p.n_ctrl), THREADS, smem, st>>>(p, P);
+    return cudaGetLastError();
+}
+
+// CTA shapes: 0 = 256 x 2 (128 registers), 1 = 128 x 3 (168), 2 = 256 x 1 (255).  MPPI_AUV_GEOM overrides the
+// measured default (developer knob).
+static int auv_geometry(bool philox, int rk)
+{
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("MPPI_AUV_GEOM");
+        forced = e ? atoi(e) : -1;
+    }
+    if (forced >= 0 && forced <= 2) return forced;
+    // measured at K = 262144, T = 50 (scripts_dev/auv_bench.py): the Philox variants want ~240 registers (0.30 / 0.42 /
+    // 0.79 ms for rk 1 / 2 / 4 against 0.37 / 0.68 / 2.15 ms at 128); the injected-noise variants fit 128 up to rk 2
+    if (philox) return 2;
+    return rk == 4 ? 1 : 0;
+}
+
+template <bool PHILOX, int RK>
+static cudaError_t launch_auv_G(const RolloutParams &p, const AuvParams &P, int num_sms, cudaStream_t st, int *grid_x_out)
+{
+    switch (auv_geometry(PHILOX, RK)) {
+        case 1: return launch_auv_V<PHILOX, RK, 128, 3>(p, P, num_sms, st, grid_x_out);
+        case 2: return launch_auv_V<PHILOX, RK, 256, 1>(p, P, num_sms, st, grid_x_out);
+        default: return launch_auv_V<PHILOX, RK, 256, 2>(p, P, num_sms, st, grid_x_out);
+    }
+}
+
+template <bool PHILOX>
+static cudaError_t launch_auv_R(const RolloutParams &p, const AuvParams &P, int num_sms, cudaStream_t st, int *grid_x_out)
+{
+    if (P.rk == 2) return launch_auv_G<PHILOX, 2>(p, P, num_sms, st, grid_x_out);
+    if (P.rk == 4) return launch_auv_G<PHILOX, 4>(p, P, num_sms, st, grid_x_out);
+    return launch_auv_G<PHILOX, 1>(p, P, num_sms, st, grid_x_out);
 }
 
 cudaError_t launch_rollout_auv(RolloutParams p, const AuvParams &P, bool philox, int num_sms, cudaStream_t st, int *grid_x_out)
 {
-    constexpr int RS = Row<kAuvA>::RS, NW = kAuvThreads / 32;
-    const int TAp = (p.TA + 31) & ~31;
-    const size_t smem = sizeof(float) * ((size_t)p.T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 64) + sizeof(float4) * kAuvThreads;
-    const int gx = auv_grid_x(p.K_local, p.n_ctrl, num_sms);
-    if (grid_x_out) *grid_x_out = gx;
-    dim3 grid(gx, p.n_ctrl);
-    cudaError_t err;
-    if (philox) {
-        if ((err = ensure_dyn_smem<rollout_auv_kernel<true>>(smem)) != cudaSuccess) return err;
-        rollout_auv_kernel<true><<<grid, kAuvThreads, smem, st>>>(p, P);
-    } else {
-        if ((err = ensure_dyn_smem<rollout_auv_kernel<false>>(smem)) != cudaSuccess) return err;
-        rollout_auv_kernel<false><<<grid, kAuvThreads, smem, st>>>(p, P);
-    }
-    return cudaGetLastError();
+    return philox ? launch_auv_R<true>(p, P, num_sms, st, grid_x_out) : launch_auv_R<false>(p, P, num_sms, st, grid_x_out);
 }
 
 cudaError_t launch_auv_predict(const AuvParams &P, int kst, int k, const float *state, const float *action, float *out, cudaStream_t st)

@@ -83,20 +83,22 @@ __device__ __forceinline__ void auv_state_dot(const AuvParams &P, const float (&
     }
 }
 
-// x <- step(x, u): explicit Euler / Heun / the reference's rk-4 variant, then quaternion normalisation
+// x <- step(x, u): explicit Euler / Heun / the reference's rk-4 variant, then quaternion normalisation.
+// RK is a template parameter: the register budget of the rollout kernel is set by the integrator.
+template <int RK>
 __device__ __forceinline__ void auv_step(const AuvParams &P, float (&x)[kAuvS], const float (&u)[kAuvA])
 {
     float k1[kAuvS], xs[kAuvS], acc[kAuvS];
     const float dt = P.dt;
     auv_state_dot(P, x, u, k1);
-    if (P.rk == 2) {                               // grid-uniform
+    if (RK == 2) {
         float k2[kAuvS];
 #pragma unroll
         for (int j = 0; j < kAuvS; j++) xs[j] = fmaf(dt, k1[j], x[j]);
         auv_state_dot(P, xs, u, k2);
 #pragma unroll
         for (int j = 0; j < kAuvS; j++) acc[j] = 0.5f * dt * (k1[j] + k2[j]);
-    } else if (P.rk == 4) {
+    } else if (RK == 4) {
         float kk[kAuvS];
 #pragma unroll
         for (int j = 0; j < kAuvS; j++) { xs[j] = fmaf(0.5f * dt, k1[j], x[j]); acc[j] = k1[j]; }
