@@ -249,6 +249,15 @@ int mppi_auv_predict(mppi_handle *h, int kst, int k, const float *state, const f
  * [-1, 1], where the reference would return NaN).  mppi_set_static_cost returns to StaticCost (diag q [13]). */
 int mppi_set_quat_cost(mppi_handle *h, const float *q10);
 int mppi_cost_state_quat(int device, int k, const float *state, const float *goal, const float *q10, float *out);
+/* ElipseCost3D (scripts/src/costs/elipse_cost.py:99-246) as the state cost of an AUV handle: the ellipse with half-axes
+ * axis = (a, b) lies in the plane with unit `normal` whose first axis is `a_vec` (all [3]); cost of one sample =
+ * m_state (|(p'x/a)^2 + (p'y/b)^2 + p'z^2 - 1| + angle between the attitude and the ellipse tangent) + m_vel | |v|^2 -
+ * speed^2 |, p' and the attitude expressed in the plane frame.  `center` is accepted and ignored, as the reference's
+ * state_cost ignores it; the per-sample sum is the reference's k = 1 result (for k > 1 its own sum mis-broadcasts). */
+int mppi_set_ellipse3d_cost(mppi_handle *h, const float *normal, const float *a_vec, const float *axis, const float *center,
+                            float speed, float m_state, float m_vel);
+int mppi_cost_state_ellipse3d(int device, int k, const float *state, const float *normal, const float *a_vec, const float *axis,
+                              const float *center, float speed, float m_state, float m_vel, float *out);
 
 /* ---- stateless stage entry points (the reference's graph-builder methods on plain buffers) ----
  * All pointers are host memory; each call runs the corresponding CUDA kernel on `device`. */

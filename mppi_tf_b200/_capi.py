@@ -109,6 +109,8 @@ SYMBOLS = {
     "mppi_auv_predict": (_i, [_H, _i, _i, _fp, _fp, _fp]),
     "mppi_set_quat_cost": (_i, [_H, _fp]),
     "mppi_cost_state_quat": (_i, [_i, _i, _fp, _fp, _fp, _fp]),
+    "mppi_set_ellipse3d_cost": (_i, [_H, _fp, _fp, _fp, _fp, _f, _f, _f]),
+    "mppi_cost_state_ellipse3d": (_i, [_i, _i, _fp, _fp, _fp, _fp, _fp, _f, _f, _f, _fp]),
     "mppi_block_diag": (_i, [_fp, _i, _i, _i, _fp]),
     "mppi_model_free_step": (_i, [_i, _f, _f, _i, _i, _i, _fp, _fp]),
     "mppi_model_action_step": (_i, [_i, _f, _f, _i, _i, _i, _fp, _fp]),

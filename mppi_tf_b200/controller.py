@@ -133,6 +133,16 @@ def quatStateCost(state, goal, q10, device=-1):
     return out
 
 
+def ellipse3dStateCost(state, normal, a_vec, axis, center, speed, m_state, m_vel, device=-1):
+    """ElipseCost3D.state_cost on a batch: state [k, 13] -> [k]."""
+    st = _f32(state).reshape(-1, 13)
+    out = np.empty(st.shape[0], np.float32)
+    check(_capi.load().mppi_cost_state_ellipse3d(device, st.shape[0], _ptr(st), _ptr(_f32(normal).ravel()), _ptr(_f32(a_vec).ravel()),
+                                                 _ptr(_f32(axis).ravel()), _ptr(_f32(center).ravel()), float(speed), float(m_state),
+                                                 float(m_vel), _ptr(out)))
+    return out
+
+
 def blockDiag(block, nb):
     """utile::blockDiag — src/utile.cpp:10-43."""
     lib = _capi.load()
@@ -356,6 +366,11 @@ class ControllerBase:
         q = _f32(q10).ravel()
         assert q.size == 10
         check(self._lib.mppi_set_quat_cost(self._h, _ptr(q)), self._h)
+
+    def setEllipse3dCost(self, normal, a_vec, axis, center, speed, m_state, m_vel):
+        """ElipseCost3D (scripts/src/costs/elipse_cost.py:99-246) as the state cost of an AUV controller."""
+        check(self._lib.mppi_set_ellipse3d_cost(self._h, _ptr(_f32(normal).ravel()), _ptr(_f32(a_vec).ravel()), _ptr(_f32(axis).ravel()),
+                                                _ptr(_f32(center).ravel()), float(speed), float(m_state), float(m_vel)), self._h)
 
     # ---- asynchronous halves (bench / multi-rank) ---------------------------------------------------
     def setState(self, x):

@@ -52,7 +52,7 @@ __device__ __forceinline__ void auv_rollout_step(const RolloutParams &p, const A
     for (int j = 0; j < A; j++) ac = fmaf(uv_row[H + j], n[j], ac);
     if (p.quad) ac += quad_cost<A>(p, n);                   // grid-uniform
     auv_step<RK>(P, x, u);
-    S += auv_state_cost(p.cost_kind, p.q, g, x) + ac;
+    S += auv_state_cost(p.cost_kind, p.q, g, p.ell, x) + ac;
 }
 
 template <bool PHILOX, int RK, int kAuvThreads, int kAuvCtasPerSm>
@@ -140,7 +140,7 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
                 auv_rollout_step<false, RK>(p, P, sUV + t * RS, n, g, x, S);
             }
         }
-        S += auv_state_cost(p.cost_kind, p.q, g, x);          // terminal cost on top of step T-1's
+        S += auv_state_cost(p.cost_kind, p.q, g, p.ell, x);          // terminal cost on top of step T-1's
         costs[k] = S;
         bmin = fminf(bmin, S);
         bmax = fmaxf(bmax, S);
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256) auv_predict_kernel(const __grid_constant_
     }
 }
 
-struct QuatCostArgs { float q[kAuvS]; float g[kAuvS]; int kind; };
+struct QuatCostArgs { float q[kAuvS]; float g[kAuvS]; float ell[12]; int kind; };
 
 __global__ void __launch_bounds__(256) auv_cost_kernel(const __grid_constant__ QuatCostArgs a, int k, const float *state, float *out)
 {
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) auv_cost_kernel(const __grid_constant__ Q
         float x[kAuvS], g[kAuvS];
 #pragma unroll
         for (int j = 0; j < kAuvS; j++) { x[j] = state[(size_t)i * kAuvS + j]; g[j] = a.g[j]; }
-        out[i] = auv_state_cost(a.kind, a.q, g, x);
+        out[i] = auv_state_cost(a.kind, a.q, g, a.ell, x);
     }
 }
 
@@ -335,10 +335,12 @@ cudaError_t launch_auv_predict(const AuvParams &P, int kst, int k, const float *
     return cudaGetLastError();
 }
 
-cudaError_t launch_auv_cost(int kind, int k, const float *q, const float *goal, const float *state, float *out, cudaStream_t st)
+cudaError_t launch_auv_cost(int kind, int k, const float *q, const float *goal, const float *ell, const float *state, float *out,
+                            cudaStream_t st)
 {
     QuatCostArgs a;
-    for (int i = 0; i < kAuvS; i++) { a.q[i] = q[i]; a.g[i] = goal[i]; }
+    for (int i = 0; i < kAuvS; i++) { a.q[i] = q ? q[i] : 0.f; a.g[i] = goal ? goal[i] : 0.f; }
+    for (int i = 0; i < 12; i++) a.ell[i] = ell ? ell[i] : 0.f;
     a.kind = kind;
     int blocks = (k + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;

@@ -123,17 +123,55 @@ __device__ __forceinline__ void auv_step(const AuvParams &P, float (&x)[kAuvS], 
     for (int j = 3; j < 7; j++) x[j] *= inv;
 }
 
+// Hamilton product of quaternions stored (x, y, z, w)
+__device__ __forceinline__ void quat_mul(const float *a, const float *b, float *o)
+{
+    o[0] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+    o[1] = -a[0] * b[2] + a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+    o[2] = a[0] * b[1] - a[1] * b[0] + a[2] * b[3] + a[3] * b[2];
+    o[3] = -a[0] * b[0] - a[1] * b[1] - a[2] * b[2] + a[3] * b[3];
+}
+
+// ElipseCost3D.state_cost of one sample (scripts/src/costs/elipse_cost.py:156-246):
+//   p' = q p q*, q' = q quat;  m_state (| (p'x/a)^2 + (p'y/b)^2 + p'z^2 - 1 | + angle(q_t, q')) + m_vel | |v|^2 - speed^2 |
+// with q_t the shortest rotation from (1,0,0) to the ellipse tangent (-a/b p'y, b/a p'x, 0) and angle = 2 acos|q_t . q'|.
+__device__ __forceinline__ float ellipse3d_cost(const float *ell, const float (&x)[kAuvS])
+{
+    const float q[4] = {ell[0], ell[1], ell[2], ell[3]}, qc[4] = {-ell[0], -ell[1], -ell[2], ell[3]};
+    const float p4[4] = {x[0], x[1], x[2], 0.f}, xq[4] = {x[3], x[4], x[5], x[6]};
+    float t[4], pf[4], qpf[4];
+    quat_mul(q, p4, t);
+    quat_mul(t, qc, pf);
+    quat_mul(q, xq, qpf);
+    const float dx = pf[0] * ell[4], dy = pf[1] * ell[5];
+    const float pos = fabsf(fmaf(dx, dx, fmaf(dy, dy, pf[2] * pf[2])) - 1.0f);
+    float tx = pf[1] * ell[6], ty = pf[0] * ell[7];
+    const float inv = rsqrtf(fmaxf(fmaf(tx, tx, ty * ty), 1e-24f));
+    tx *= inv;
+    ty *= inv;
+    // between_two_vectors_3d((1,0,0), (tx, ty, 0)) = normalise(0, 0, ty, 1 + tx); antiparallel: (0, 0, 1, 0)
+    float rz = ty, rw = 1.0f + tx;
+    if (rw < 1e-6f) { rz = 1.0f; rw = 0.f; }
+    const float ir = rsqrtf(fmaxf(fmaf(rz, rz, rw * rw), 1e-12f));
+    const float dot = fminf(fabsf(fmaf(rz * ir, qpf[2], (rw * ir) * qpf[3])), 1.0f);
+    const float ori = 2.0f * acosf(dot);
+    const float dv = fabsf(fmaf(x[7], x[7], fmaf(x[8], x[8], x[9] * x[9])) - ell[8]);
+    return fmaf(ell[9], pos + ori, ell[10] * dv);
+}
+
 // State costs on the 13-dimensional state.
 //   kind 0  StaticCost      sum_i q_i (x_i - g_i)^2                                   (static_cost.py:40-63, diagonal Q)
 //   kind 2  StaticQuatCost  d = (p - g_p, 2 acos(q . g_q), nu - g_nu), sum_i q_i d_i^2  (static_cost.py:116-159, diagonal Q[10])
-__device__ __forceinline__ float auv_state_cost(int kind, const float *q, const float *g, const float (&x)[kAuvS])
+//   kind 3  ElipseCost3D    (above)
+__device__ __forceinline__ float auv_state_cost(int kind, const float *q, const float *g, const float *ell, const float (&x)[kAuvS])
 {
     float c = 0.f;
+    if (kind == 3) return ellipse3d_cost(ell, x);
     if (kind == 2) {
 #pragma unroll
         for (int i = 0; i < 3; i++) { const float d = x[i] - g[i]; c = fmaf(q[i] * d, d, c); }
         const float dot = fmaf(x[3], g[3], fmaf(x[4], g[4], fmaf(x[5], g[5], x[6] * g[6])));
-        const float th = 2.0f * acosf(dot);
+        const float th = 2.0f * acosf(fminf(fmaxf(dot, -1.0f), 1.0f));
         c = fmaf(q[3] * th, th, c);
 #pragma unroll
         for (int i = 0; i < 6; i++) { const float d = x[7 + i] - g[7 + i]; c = fmaf(q[4 + i] * d, d, c); }

@@ -71,7 +71,7 @@ struct mppi_handle {
     bool normalize = false;
     float *d_norm = nullptr;
     int cost_kind = 0;            // 0 StaticCost, 1 ElipseCost (mppi_set_ellipse_cost)
-    float ell[8] = {0};
+    float ell[12] = {0};
     uint64_t seed = 1;
     uint32_t update_counter = 0, last_update = 0;
     bool have_philox_update = false, last_philox = true, pending_finish = false;
@@ -951,7 +951,83 @@ int mppi_cost_state_quat(int device, int k, const float *state, const float *goa
     CU_TRY(nullptr, ds.alloc(sizeof(float) * (size_t)k * kAuvS));
     CU_TRY(nullptr, dout.alloc(sizeof(float) * (size_t)k));
     CU_TRY(nullptr, cudaMemcpy(ds.p, state, sizeof(float) * (size_t)k * kAuvS, cudaMemcpyHostToDevice));
-    CU_TRY(nullptr, launch_auv_cost(2, k, q, goal, ds.as<float>(), dout.as<float>(), nullptr));
+    CU_TRY(nullptr, launch_auv_cost(2, k, q, goal, nullptr, ds.as<float>(), dout.as<float>(), nullptr));
+    CU_TRY(nullptr, cudaMemcpy(out, dout.p, sizeof(float) * (size_t)k, cudaMemcpyDeviceToHost));
+    return MPPI_OK;
+}
+
+// ElipseCost3D.prepare_consts (elipse_cost.py:137-154) on the host: N = [aVec, normal x aVec, normal] (columns),
+// R = inv(N)^T, q = from_rotation_matrix(R) (tensorflow_graphics' four-branch trace method), then the kernel constants.
+static bool ellipse3d_params(const float *normal, const float *a_vec, const float *axis, float speed, float m_state, float m_vel,
+                             float *ell)
+{
+    if (!(axis[0] != 0.f) || !(axis[1] != 0.f)) return false;
+    const double n[3] = {normal[0], normal[1], normal[2]}, a[3] = {a_vec[0], a_vec[1], a_vec[2]};
+    const double b[3] = {n[1] * a[2] - n[2] * a[1], n[2] * a[0] - n[0] * a[2], n[0] * a[1] - n[1] * a[0]};
+    const double N[9] = {a[0], b[0], n[0], a[1], b[1], n[1], a[2], b[2], n[2]};
+    const double det = N[0] * (N[4] * N[8] - N[5] * N[7]) - N[1] * (N[3] * N[8] - N[5] * N[6]) + N[2] * (N[3] * N[7] - N[4] * N[6]);
+    if (det == 0.0) return false;
+    double inv[9];
+    inv[0] = (N[4] * N[8] - N[5] * N[7]) / det; inv[1] = (N[2] * N[7] - N[1] * N[8]) / det; inv[2] = (N[1] * N[5] - N[2] * N[4]) / det;
+    inv[3] = (N[5] * N[6] - N[3] * N[8]) / det; inv[4] = (N[0] * N[8] - N[2] * N[6]) / det; inv[5] = (N[2] * N[3] - N[0] * N[5]) / det;
+    inv[6] = (N[3] * N[7] - N[4] * N[6]) / det; inv[7] = (N[1] * N[6] - N[0] * N[7]) / det; inv[8] = (N[0] * N[4] - N[1] * N[3]) / det;
+    double R[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) R[r * 3 + c] = inv[c * 3 + r];
+    double q[4], sq;
+    const double tr = R[0] + R[4] + R[8];
+    if (tr > 0.0) {
+        sq = sqrt(tr + 1.0) * 2.0;
+        q[0] = (R[7] - R[5]) / sq; q[1] = (R[2] - R[6]) / sq; q[2] = (R[3] - R[1]) / sq; q[3] = 0.25 * sq;
+    } else if (R[0] > R[4] && R[0] > R[8]) {
+        sq = sqrt(1.0 + R[0] - R[4] - R[8]) * 2.0;
+        q[0] = 0.25 * sq; q[1] = (R[1] + R[3]) / sq; q[2] = (R[2] + R[6]) / sq; q[3] = (R[7] - R[5]) / sq;
+    } else if (R[4] > R[8]) {
+        sq = sqrt(1.0 + R[4] - R[0] - R[8]) * 2.0;
+        q[0] = (R[1] + R[3]) / sq; q[1] = 0.25 * sq; q[2] = (R[5] + R[7]) / sq; q[3] = (R[2] - R[6]) / sq;
+    } else {
+        sq = sqrt(1.0 + R[8] - R[0] - R[4]) * 2.0;
+        q[0] = (R[2] + R[6]) / sq; q[1] = (R[5] + R[7]) / sq; q[2] = 0.25 * sq; q[3] = (R[3] - R[1]) / sq;
+    }
+    for (int i = 0; i < 4; i++) {
+        if (!(q[i] == q[i])) return false;
+        ell[i] = (float)q[i];
+    }
+    const double ea = axis[0], eb = axis[1];
+    ell[4] = (float)(1.0 / ea); ell[5] = (float)(1.0 / eb); ell[6] = (float)(-ea / eb); ell[7] = (float)(eb / ea);
+    ell[8] = (float)((double)speed * speed); ell[9] = m_state; ell[10] = m_vel; ell[11] = 0.f;
+    return true;
+}
+
+int mppi_set_ellipse3d_cost(mppi_handle *h, const float *normal, const float *a_vec, const float *axis, const float *center,
+                            float speed, float m_state, float m_vel)
+{
+    if (!h || !normal || !a_vec || !axis) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    (void)center;                 // stored by the reference (self.t) and never used by its state_cost
+    if (!h->auv) return fail(h, MPPI_ERR_UNSUPPORTED, "ElipseCost3D is defined on the 13-dimensional AUV state");
+    if (!ellipse3d_params(normal, a_vec, axis, speed, m_state, m_vel, h->ell))
+        return fail(h, MPPI_ERR_BAD_ARG, "ellipse axes must be non-zero and (aVec, normal x aVec, normal) must be a basis");
+    h->cost_kind = 3;
+    return MPPI_OK;
+}
+
+int mppi_cost_state_ellipse3d(int device, int k, const float *state, const float *normal, const float *a_vec, const float *axis,
+                              const float *center, float speed, float m_state, float m_vel, float *out)
+{
+    if (k <= 0 || !state || !normal || !a_vec || !axis || !out) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad cost_state_ellipse3d argument");
+    (void)center;
+    float ell[12];
+    if (!ellipse3d_params(normal, a_vec, axis, speed, m_state, m_vel, ell))
+        return fail(nullptr, MPPI_ERR_BAD_ARG, "ellipse axes must be non-zero and (aVec, normal x aVec, normal) must be a basis");
+    cudaDeviceProp prop;
+    int dev = 0;
+    int rc = select_device(nullptr, device, &dev, &prop);
+    if (rc != MPPI_OK) return rc;
+    DevBuf ds, dout;
+    CU_TRY(nullptr, ds.alloc(sizeof(float) * (size_t)k * kAuvS));
+    CU_TRY(nullptr, dout.alloc(sizeof(float) * (size_t)k));
+    CU_TRY(nullptr, cudaMemcpy(ds.p, state, sizeof(float) * (size_t)k * kAuvS, cudaMemcpyHostToDevice));
+    CU_TRY(nullptr, launch_auv_cost(3, k, nullptr, nullptr, ell, ds.as<float>(), dout.as<float>(), nullptr));
     CU_TRY(nullptr, cudaMemcpy(out, dout.p, sizeof(float) * (size_t)k, cudaMemcpyDeviceToHost));
     return MPPI_OK;
 }

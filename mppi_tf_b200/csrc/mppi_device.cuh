@@ -43,9 +43,10 @@ struct RolloutParams {
     int quad;                               // != 0: the quadratic noise term is present
     float quadm[kMaxA * kMaxA];             // 0.5*lambda*(1-1/upsilon) * M, M = Sigma^-1 (n = eps) or (uS)^T S^-1 (uS) (n = z)
     // state-cost functor: 0 = StaticCost (x-g)^T Q (x-g); 1 = ElipseCost (scripts/src/costs/elipse_cost.py:46-79),
-    // point_mass2d only: ell = {1/a, 1/b, cx, cy, speed, m_state, m_vel}
+    // point_mass2d only: ell = {1/a, 1/b, cx, cy, speed, m_state, m_vel}; AUV state: 2 = StaticQuatCost (q[10]),
+    // 3 = ElipseCost3D (elipse_cost.py:99-246): ell = {plane quaternion (x,y,z,w), 1/a, 1/b, -a/b, b/a, speed^2, m_state, m_vel}
     int cost_kind;
-    float ell[8];
+    float ell[12];
     int norm_mode;                          // cost normalisation: 0 off, 1 = cost pass (min/max only), 2 = weight pass
     float *norm;                            // [n_ctrl][2] beta, max(S - beta) written by pass 1, read by pass 2
     // Philox key / counter words

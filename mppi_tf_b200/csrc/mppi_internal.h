@@ -32,8 +32,8 @@ struct AuvParams;
 cudaError_t launch_rollout_auv(RolloutParams p, const AuvParams &P, bool philox, int num_sms, cudaStream_t st, int *grid_x_out);
 cudaError_t launch_auv_predict(const AuvParams &P, int kst, int k, const float *state, const float *action, float *out,
                                cudaStream_t st);
-cudaError_t launch_auv_cost(int kind, int k, const float *q /*[13] host*/, const float *goal /*[13] host*/, const float *state,
-                            float *out, cudaStream_t st);
+cudaError_t launch_auv_cost(int kind, int k, const float *q /*[13] host*/, const float *goal /*[13] host*/,
+                            const float *ell /*[12] host*/, const float *state, float *out, cudaStream_t st);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs a microsecond or two per call: remember, per kernel
 // instantiation and device, the largest size already granted and only raise it.

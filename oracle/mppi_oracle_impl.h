@@ -675,9 +675,88 @@ void FN(orc_cost_state_quat)(int k, const REAL *state, const REAL *goal, const R
     }
 }
 
+/* ElipseCost3D — scripts/src/costs/elipse_cost.py:99-246.  tensorflow_graphics (un-vendored, unpinned; imported at
+ * elipse_cost.py:3) supplies the quaternion algebra; its published algorithms are restated here, quaternions (x, y, z, w):
+ * multiply = Hamilton product, rotate(p, q) = q (p, 0) q*, from_rotation_matrix = the four-branch trace method,
+ * between_two_vectors_3d(v1, v2) = normalise(cross(v1, v2), 1 + v1.v2) with the antiparallel fallback,
+ * relative_angle = 2 acos(|q1.q2|).  Pinned by the reference's known-answer tests (scripts/test.py:1183-1359) through
+ * tests/golden/gen_ellipse3d_fixtures.py.
+ * prepare_consts (:150-154): N = [aVec, normal x aVec, normal] (columns), R = inv(N)^T, q = from_rotation_matrix(R). */
+static void FN(orc_quat_mul)(const REAL *a, const REAL *b, REAL *o)
+{
+    o[0] = ((a[0] * b[3] + a[1] * b[2]) - a[2] * b[1]) + a[3] * b[0];
+    o[1] = ((-a[0] * b[2] + a[1] * b[3]) + a[2] * b[0]) + a[3] * b[1];
+    o[2] = ((a[0] * b[1] - a[1] * b[0]) + a[2] * b[3]) + a[3] * b[2];
+    o[3] = ((-a[0] * b[0] - a[1] * b[1]) - a[2] * b[2]) + a[3] * b[3];
+}
+
+void FN(orc_ellipse3d_prep)(const REAL *normal, const REAL *aVec, REAL *R /*9*/, REAL *q /*4*/)
+{
+    REAL b[3] = {normal[1] * aVec[2] - normal[2] * aVec[1], normal[2] * aVec[0] - normal[0] * aVec[2],
+                 normal[0] * aVec[1] - normal[1] * aVec[0]};                                /* bVec = normal x aVec :137-142 */
+    REAL N[9] = {aVec[0], b[0], normal[0], aVec[1], b[1], normal[1], aVec[2], b[2], normal[2]}, inv[9];
+    FN(orc_mat_inverse)(N, 3, inv);
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) R[r * 3 + c] = inv[c * 3 + r];                          /* transpose :152 */
+    REAL tr = R[0] + R[4] + R[8], sq;
+    if (tr > (REAL)0) {
+        sq = (REAL)sqrt((double)(tr + (REAL)1)) * (REAL)2;
+        q[0] = (R[7] - R[5]) / sq; q[1] = (R[2] - R[6]) / sq; q[2] = (R[3] - R[1]) / sq; q[3] = (REAL)0.25 * sq;
+    } else if (R[0] > R[4] && R[0] > R[8]) {
+        sq = (REAL)sqrt((double)((REAL)1 + R[0] - R[4] - R[8])) * (REAL)2;
+        q[0] = (REAL)0.25 * sq; q[1] = (R[1] + R[3]) / sq; q[2] = (R[2] + R[6]) / sq; q[3] = (R[7] - R[5]) / sq;
+    } else if (R[4] > R[8]) {
+        sq = (REAL)sqrt((double)((REAL)1 + R[4] - R[0] - R[8])) * (REAL)2;
+        q[0] = (R[1] + R[3]) / sq; q[1] = (REAL)0.25 * sq; q[2] = (R[5] + R[7]) / sq; q[3] = (R[2] - R[6]) / sq;
+    } else {
+        sq = (REAL)sqrt((double)((REAL)1 + R[8] - R[0] - R[4])) * (REAL)2;
+        q[0] = (R[2] + R[6]) / sq; q[1] = (R[5] + R[7]) / sq; q[2] = (REAL)0.25 * sq; q[3] = (R[3] - R[1]) / sq;
+    }
+}
+
+/* state_cost (:156-170) of ONE state at a time (for k > 1 the reference's sum broadcasts [k,1,1] + [k] to [k,1,k]; the
+ * per-sample meaning is the k = 1 call).  e3 = {q[4], a, b, speed, mS, mV}.  `center` never enters state_cost in the
+ * reference (self.t is stored and not used) and does not here. */
+void FN(orc_cost_state_ellipse3d)(int k, const REAL *state, const REAL *e3, REAL *out)
+{
+    const REAL *q = e3, a = e3[4], b = e3[5], gv = e3[6], mS = e3[7], mV = e3[8];
+    for (int i = 0; i < k; i++) {
+        const REAL *x = state + 13 * i;
+        REAL p4[4] = {x[0], x[1], x[2], (REAL)0}, qc[4] = {-q[0], -q[1], -q[2], q[3]}, t[4], pf[4], qpf[4];
+        FN(orc_quat_mul)(q, p4, t);                                                         /* rotate :160 */
+        FN(orc_quat_mul)(t, qc, pf);
+        FN(orc_quat_mul)(q, x + 3, qpf);                                                    /* :162 */
+        REAL d = (pf[0] / a) * (pf[0] / a) + (pf[1] / b) * (pf[1] / b) + (pf[2] / (REAL)1) * (pf[2] / (REAL)1);   /* :188-190 */
+        d = d - (REAL)1;
+        REAL pos = d < (REAL)0 ? -d : d;
+        /* orientation_error :193-219: tangent (-a/b y, b/a x, 0), normalised; q_t = between((1,0,0), tangent) */
+        REAL tg[3] = {pf[1] * (-a / b), pf[0] * (b / a), (REAL)0};
+        REAL nrm = (REAL)sqrt((double)(tg[0] * tg[0] + tg[1] * tg[1] + tg[2] * tg[2]));
+        for (int j = 0; j < 3; j++) tg[j] = tg[j] / nrm;
+        REAL n2 = tg[0] * tg[0] + tg[1] * tg[1] + tg[2] * tg[2];
+        REAL in = (REAL)1 / (REAL)sqrt((double)(n2 > (REAL)1e-12 ? n2 : (REAL)1e-12));      /* l2_normalize of both inputs */
+        for (int j = 0; j < 3; j++) tg[j] = tg[j] * in;
+        REAL real = (REAL)1 + tg[0];                                                        /* 1 + x . tg */
+        REAL rot[4] = {(REAL)0, -tg[2], tg[1], real};                                       /* cross((1,0,0), tg) */
+        if (real < (REAL)1e-6) { rot[0] = (REAL)0; rot[1] = (REAL)0; rot[2] = (REAL)1; rot[3] = (REAL)0; }   /* |x| > |y|: (-z, 0, x) of (1,0,0) */
+        REAL r2 = rot[0] * rot[0] + rot[1] * rot[1] + rot[2] * rot[2] + rot[3] * rot[3];
+        REAL ir = (REAL)1 / (REAL)sqrt((double)(r2 > (REAL)1e-12 ? r2 : (REAL)1e-12));
+        REAL dot = (REAL)0;
+        for (int j = 0; j < 4; j++) dot += (rot[j] * ir) * qpf[j];
+        dot = dot < (REAL)0 ? -dot : dot;
+        if (dot > (REAL)1) dot = (REAL)1;
+        REAL ori = (REAL)2 * (REAL)acos((double)dot);                                       /* relative_angle */
+        REAL v2 = x[7] * x[7] + x[8] * x[8] + x[9] * x[9];                                  /* :236-238: | |v|^2 - gv^2 | */
+        REAL vn = (REAL)sqrt((double)v2);
+        REAL dv = vn * vn - gv * gv;
+        dv = dv < (REAL)0 ? -dv : dv;
+        out[i] = (mS * pos + mS * ori) + mV * dv;                                           /* :168 */
+    }
+}
+
 /* Python controller rollout with the AUV model — controller_base.py:371-434 with AUVModel.build_step_graph
- * (auv_model.py:285-306) and StaticCost (quat_cost = 0: Q = diag(q[13])) or StaticQuatCost (quat_cost = 1:
- * Q [10][10]); action cost cost_base.py:114-170; eps = (upsilon * sigma) z. */
+ * (auv_model.py:285-306) and StaticCost (quat_cost = 0: Q = diag(q[13])), StaticQuatCost (quat_cost = 1:
+ * Q [10][10]) or ElipseCost3D (quat_cost = 2: Q = e3[9]); action cost cost_base.py:114-170; eps = (upsilon * sigma) z. */
 void FN(orc_rollout_costs_auv)(int k0, int k1, int T, const REAL *prm, REAL dt, int rk, REAL lambda, REAL gamma,
                                REAL upsilon, const REAL *sigma, const REAL *goal, const REAL *Q, int quat_cost,
                                const REAL *x0, const REAL *U, const REAL *eps, REAL *costs)
@@ -692,13 +771,15 @@ void FN(orc_rollout_costs_auv)(int k0, int k1, int T, const REAL *prm, REAL dt, 
             const REAL *ut = U + t * a;
             for (int j = 0; j < a; j++) u[j] = ut[j] + e[j];
             FN(orc_auv_step)(1, prm, dt, rk, x, u, xn);
-            if (quat_cost) FN(orc_cost_state_quat)(1, xn, goal, Q, &c);
+            if (quat_cost == 2) FN(orc_cost_state_ellipse3d)(1, xn, Q, &c);
+            else if (quat_cost) FN(orc_cost_state_quat)(1, xn, goal, Q, &c);
             else FN(orc_cost_state)(1, s, xn, goal, Q, &c);
             FN(orc_cost_action_py)(1, a, lambda, gamma, upsilon, sigma, ut, e, &acst);
             S = S + (c + acst);
             for (int j = 0; j < s; j++) x[j] = xn[j];
         }
-        if (quat_cost) FN(orc_cost_state_quat)(1, x, goal, Q, &c);
+        if (quat_cost == 2) FN(orc_cost_state_ellipse3d)(1, x, Q, &c);
+        else if (quat_cost) FN(orc_cost_state_quat)(1, x, goal, Q, &c);
         else FN(orc_cost_state)(1, s, x, goal, Q, &c);
         costs[i] = c + S;
     }

@@ -283,8 +283,25 @@ class Oracle:
         self._fn("orc_cost_state_quat")(st.shape[0], _p(st), _p(_c(np.asarray(goal).ravel(), self.dt)), _p(_c(Q, self.dt)), _p(out))
         return out
 
+    def ellipse3d_prep(self, normal, aVec):
+        """ElipseCost3D.prepare_consts (elipse_cost.py:150-154): returns (R [3,3], q [4] as (x, y, z, w))."""
+        R, q = np.empty((3, 3), self.dt), np.empty(4, self.dt)
+        self._fn("orc_ellipse3d_prep")(_p(_c(np.asarray(normal).ravel(), self.dt)), _p(_c(np.asarray(aVec).ravel(), self.dt)), _p(R), _p(q))
+        return R, q
+
+    def ellipse3d_pack(self, normal, aVec, axis, speed, m_state, m_vel):
+        _, q = self.ellipse3d_prep(normal, aVec)
+        return np.concatenate([q, np.asarray(axis, np.float64).ravel(), [speed, m_state, m_vel]])
+
+    def cost_state_ellipse3d(self, state, e3):
+        """ElipseCost3D.state_cost, one state at a time (elipse_cost.py:156-170); e3 from ellipse3d_pack."""
+        st = _c(np.asarray(state).reshape(-1, 13), self.dt)
+        out = np.empty(st.shape[0], self.dt)
+        self._fn("orc_cost_state_ellipse3d")(st.shape[0], _p(st), _p(_c(e3, self.dt)), _p(out))
+        return out
+
     def mppi_update_auv(self, prm, dt, rk, lam, sigma, goal, q, x0, U, eps, gamma=None, upsilon=1.0, normalize=False,
-                        quat_cost=False):
+                        quat_cost=False, ellipse3d=None):
         """Python-controller update with the AUV model (controller_base.py:371-474, auv_model.py:285-306) and
         StaticCost (q [13]) or StaticQuatCost (q [10], quat_cost=True).  eps = (upsilon * sigma) z, [k][T][6]."""
         eps = _c(eps, self.dt)
@@ -292,6 +309,9 @@ class Oracle:
         assert a == 6
         gamma = lam if gamma is None else gamma
         Q = _c(np.diag(np.asarray(q, np.float64)) if quat_cost else np.asarray(q, np.float64), self.dt)
+        kind = int(bool(quat_cost))
+        if ellipse3d is not None:                       # ElipseCost3D parameters from ellipse3d_pack replace goal / q
+            Q, kind = _c(ellipse3d, self.dt), 2
         costs = np.empty(k, self.dt)
         U_new = np.empty((T, a), self.dt)
         nxt = np.empty(a, self.dt)
@@ -299,7 +319,7 @@ class Oracle:
         self._fn("orc_mppi_update_auv")(k, T, _p(_c(self.auv_pack(prm), self.dt)), self.creal(dt), int(rk), self.creal(lam),
                                         self.creal(gamma), self.creal(upsilon), int(bool(normalize)),
                                         _p(_c(sigma, self.dt)), _p(_c(np.asarray(goal).ravel(), self.dt)), _p(Q),
-                                        int(bool(quat_cost)), _p(_c(x0, self.dt)), _p(_c(U, self.dt)), _p(eps), _p(costs),
+                                        kind, _p(_c(x0, self.dt)), _p(_c(U, self.dt)), _p(eps), _p(costs),
                                         _p(U_new), _p(nxt), _p(U_shift))
         return dict(costs=costs, U_new=U_new, next=nxt, U_shift=U_shift)
 

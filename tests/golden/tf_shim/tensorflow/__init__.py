@@ -98,6 +98,14 @@ def tensordot(a, b, axes, name=None):
     return np.tensordot(_a(a), _a(b), axes)
 
 
+def gather(params, indices, axis=0, name=None):
+    return np.take(_a(params), indices, axis=axis)
+
+
+def norm(x, ord="euclidean", axis=None, keepdims=False, name=None):     # noqa: A002
+    return np.linalg.norm(_a(x), axis=axis, keepdims=keepdims)
+
+
 def reduce_min(x, axis=None, name=None):
     return np.min(_a(x), axis=axis)
 
@@ -181,7 +189,10 @@ def _l2_normalize(x, axis=None, epsilon=1e-12, name=None):
 
 linalg = types.SimpleNamespace(matmul=_matmul, inv=lambda m, name=None: np.linalg.inv(_a(m)), diag=_diag,
                                cross=lambda a, b, name=None: np.cross(_a(a), _a(b)),
-                               norm=lambda x, axis=None, keepdims=False, name=None: np.linalg.norm(_a(x), axis=axis, keepdims=keepdims))
+                               norm=lambda x, axis=None, keepdims=False, name=None: np.linalg.norm(_a(x), axis=axis, keepdims=keepdims),
+                               normalize=lambda x, ord="euclidean", axis=None, name=None: (
+                                   _a(x) / np.linalg.norm(_a(x), axis=axis, keepdims=True),
+                                   np.linalg.norm(_a(x), axis=axis, keepdims=True)))
 math = types.SimpleNamespace(
     subtract=lambda a, b, name=None: _a(a) - _a(b), multiply=lambda a, b, name=None: _a(a) * _a(b),
     add=add, exp=lambda x, name=None: np.exp(_a(x)), reduce_sum=reduce_sum, reduce_min=reduce_min,
