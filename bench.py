@@ -174,7 +174,7 @@ def run_reference(args, rank, world):
         return
     desc, K, T, s, a, n_ctrl = WORKLOADS[args.workload]
     steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 2))
+    warm = 3                                   # W >= 3 warm-up steps, each a bounded CPU sample
     r = cpu_port_throughput(K, T, s, a, steps, warm, budget_s=60.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
