@@ -154,3 +154,62 @@ def test_cuda_auv_errors():
         assert e.value.code == _capi.MPPI_ERR_UNSUPPORTED
     finally:
         pm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("philox", [True, False])
+def test_cuda_auv_sample_sharding(world, philox):
+    """The AUV kernel on sharded samples (ranks emulated as handles on one GPU, the all-gather done by a device copy):
+    global Philox sample index and exact (beta, eta, N) merge give the unsharded result, as for the point-mass kernels."""
+    import torch
+    from tests.util import rel_err
+    prm, m, g = load("auv_rk2")
+    k, tau = 5000, 11
+    rng = np.random.default_rng(3)
+    U = (20.0 * rng.standard_normal((tau, 6))).astype(np.float32)
+    x = g("x").astype(np.float32)
+    single = _auv_controller(prm, m, g, k=k, tau=tau, seed=5)
+    try:
+        single.setSequence(U)
+        a_ref = single.next(x)
+        eps_full = single.dumpNoise().reshape(k, tau, 6)
+        if not philox:
+            single.setSequence(U)
+            a_ref = single.nextWithNoise(x, eps_full)
+        u_ref, c_ref = single.getUpdate(), single.getCosts()
+    finally:
+        single.close()
+    ranks = [_auv_controller(prm, m, g, k=k, tau=tau, seed=5, rank=r, world=world) for r in range(world)]
+    try:
+        stride = ranks[0].exchangeStride()
+        gathered = torch.zeros(world, stride, device="cuda")
+        sends = [torch.zeros(stride, device="cuda") for _ in range(world)]
+        keep = []
+        for r, c in enumerate(ranks):
+            c.setExchangeBuffers(sends[r].data_ptr(), gathered.data_ptr())
+            c.setSequence(U)
+            c.setState(x)
+            if philox:
+                c.enqueueUpdate()
+            else:
+                e = torch.from_numpy(np.ascontiguousarray(eps_full[c.k_offset:c.k_offset + c.k_local])).cuda()
+                keep.append(e)
+                c.enqueueUpdate(e.data_ptr())
+            c.synchronize()
+        for r in range(world):
+            gathered[r].copy_(sends[r])
+        torch.cuda.synchronize()
+        costs = []
+        for c in ranks:
+            c.enqueueFinish()
+            assert rel_err(c.fetchAction(), a_ref) < 1e-5
+            assert rel_err(c.getUpdate(), u_ref) < 1e-5
+            costs.append(c.getCosts())
+        np.testing.assert_array_equal(np.concatenate(costs), c_ref)
+        seqs = [c.getSequence() for c in ranks]
+        for s in seqs[1:]:
+            np.testing.assert_array_equal(s, seqs[0])
+    finally:
+        for c in ranks:
+            c.close()
