@@ -85,7 +85,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -307,11 +307,12 @@ def main():
     ctrl.setState(x)
 
     # ---- device-timed loop: value ------------------------------------------------------------------
+    if sampler:
+        sampler.start()                    # runs through warm-up and both timed regions (short regions at N = 8)
+        time.sleep(0.15)                   # nvidia-smi needs a moment before its first row
     for _ in range(args.warmup):
         one_update()
     barrier()
-    if sampler:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
         flush.zero_()                      # L2 flush between timed iterations (untimed)
