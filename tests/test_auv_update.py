@@ -213,3 +213,43 @@ def test_cuda_auv_sample_sharding(world, philox):
     finally:
         for c in ranks:
             c.close()
+
+
+@pytest.mark.gpu
+def test_cuda_auv_batched_controllers(oracle64, oracle32):
+    """Independent AUV controllers (own state, goal, sequence) batched in one handle, injected noise and Philox replay."""
+    from mppi_tf_b200 import ControllerBase
+    from tests.util import assert_update_close, rel_err
+    prm, m, g = load("auv_quat")
+    n, k, tau = 5, 700, 9
+    rng = np.random.default_rng(21)
+    goals = rng.uniform(-1, 1, (n, 13))
+    goals[:, 3:7] /= np.linalg.norm(goals[:, 3:7], axis=1, keepdims=True)
+    xs = goals + 0.3 * rng.standard_normal((n, 13))
+    xs[:, 3:7] /= np.linalg.norm(xs[:, 3:7], axis=1, keepdims=True)
+    goals, xs = goals.astype(np.float32), xs.astype(np.float32)
+    U0 = (20.0 * rng.standard_normal((n, tau, 6))).astype(np.float32)
+    sigma, q = g("sigma").astype(np.float32), g("q").astype(np.float32)
+    ctrl = ControllerBase(k, tau, 0.1, 1.0, 13, 6, lam=m["lam"], sigma=sigma, goal=goals, model="auv", n_controllers=n,
+                          goal_per_controller=True)
+    try:
+        ctrl.setAuvModel(prm, rk=m["rk"])
+        ctrl.setQuatCost(q)
+        ctrl.setActionCost("python", gamma=m["gamma"], upsilon=m["upsilon"])
+        ctrl.setSequence(U0)
+        ctrl.next(xs)
+        eps = ctrl.dumpNoise().reshape(n, k, tau, 6)
+        Un_p, c_p = ctrl.getUpdate(), ctrl.getCosts()
+        ctrl.setSequence(U0)
+        ctrl.nextWithNoise(xs, eps)
+        Un_i, c_i = ctrl.getUpdate(), ctrl.getCosts()
+    finally:
+        ctrl.close()
+    assert not np.array_equal(eps[0], eps[1])                 # every controller has its own noise stream
+    for c in range(n):
+        kw = dict(gamma=m["gamma"], upsilon=m["upsilon"], quat_cost=True)
+        r64 = oracle64.mppi_update_auv(prm, 0.1, m["rk"], m["lam"], sigma, goals[c], q, xs[c], U0[c], eps[c], **kw)
+        r32 = oracle32.mppi_update_auv(prm, 0.1, m["rk"], m["lam"], sigma, goals[c], q, xs[c], U0[c], eps[c], **kw)
+        for Un, cs, what in ((Un_p, c_p, "philox"), (Un_i, c_i, "injected")):
+            assert rel_err(cs.reshape(n, k)[c], r64["costs"]) < 1e-5, (what, c)
+            assert_update_close(Un.reshape(n, tau, 6)[c], r64["U_new"], r32["U_new"], what=f"{what} U_new[{c}]")
