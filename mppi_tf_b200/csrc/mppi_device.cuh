@@ -156,12 +156,10 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float &z0, 
     z1 = r * sn;
 }
 
-// Four standard normals z[4c .. 4c+3] of sample `k` (global index): Box-Muller on (x0,x1) and (x2,x3), the
-// two pairs processed together with packed fp32 instructions (FFMA2 / FMUL2) wherever both need the same op.
-__device__ __forceinline__ void normals4(uint32_t call, uint32_t k, uint32_t stream, const RolloutParams &p,
-                                         float z[4])
+// Box-Muller on the four words of one Philox call: (x0,x1) and (x2,x3), the two pairs processed together with packed
+// fp32 instructions (FFMA2 / FMUL2) wherever both need the same op.
+__device__ __forceinline__ void normals_from_words(const uint4 x, float z[4])
 {
-    const uint4 x = philox4x32_10_rk(call, k, p.update, stream, p.rk0, p.rk1);
     const float2 fa = make_float2(bits_to_1_2(x.x), bits_to_1_2(x.z));           // radius uniforms of both pairs
     const float2 fb = make_float2(bits_to_1_2(x.y), bits_to_1_2(x.w));           // angle uniforms of both pairs
     const float2 u1 = __ffma2_rn(fa, make_float2(-1.f, -1.f), make_float2(2.f, 2.f));                       // (0, 1]
@@ -180,6 +178,81 @@ __device__ __forceinline__ void normals4(uint32_t call, uint32_t k, uint32_t str
     const float2 zA = __fmul2_rn(make_float2(r.x, r.x), csA);
     const float2 zB = __fmul2_rn(make_float2(r.y, r.y), csB);
     z[0] = zA.x; z[1] = zA.y; z[2] = zB.x; z[3] = zB.y;
+}
+
+// Four standard normals z[4c .. 4c+3] of sample `k` (global index).
+__device__ __forceinline__ void normals4(uint32_t call, uint32_t k, uint32_t stream, const RolloutParams &p,
+                                         float z[4])
+{
+    normals_from_words(philox4x32_10_rk(call, k, p.update, stream, p.rk0, p.rk1), z);
+}
+
+// ------------------------------------------------------------------------------------------
+// The same Philox4x32-10 words with the warp-uniform part of the first rounds taken out of the per-sample stream.
+// The counter is (call, sample, update, stream): only the second word differs between samples, so
+//   round 1  both products are uniform; the only per-sample value is c0' = A ^ sample, A = hi(M1 update) ^ key0_0
+//   round 2  M0 c0' depends on the sample alone: computed ONCE PER SAMPLE (PhiloxSample), not per call;
+//            M1 c2' is uniform per call
+//   round 3  M0 c0'' is uniform per call;  round 4  one XOR operand is uniform per call
+// A per-call table {E, B, C, D} (philox_call_table, staged in shared memory once per CTA) folds the uniform words and
+// round keys; per call and sample 15 IMAD.WIDE + 17 LOP3 remain of 20 + 20.  Bit-identical to philox4x32_10_rk
+// (checked against the generic generator by every store-then-replay test: mppi_dump_noise uses the generic one).
+// ------------------------------------------------------------------------------------------
+struct PhiloxSample { uint32_t h0, l0; };
+
+__device__ __forceinline__ uint32_t philox_uniform_A(const RolloutParams &p)
+{
+    return (uint32_t)(((uint64_t)kPhiloxM1 * p.update) >> 32) ^ p.rk0[0];
+}
+__device__ __forceinline__ PhiloxSample philox_sample(uint32_t A, uint32_t k)
+{
+    const uint64_t p0 = (uint64_t)kPhiloxM0 * (A ^ k);
+    return PhiloxSample{(uint32_t)(p0 >> 32), (uint32_t)p0};
+}
+__device__ __forceinline__ uint4 philox_call_table(uint32_t call, uint32_t stream, const RolloutParams &p)
+{
+    const uint64_t p0 = (uint64_t)kPhiloxM0 * call;                                   // round 1
+    const uint32_t c2p = (uint32_t)(p0 >> 32) ^ stream ^ p.rk1[0], c3p = (uint32_t)p0;
+    const uint32_t c1p = (uint32_t)((uint64_t)kPhiloxM1 * p.update);
+    const uint64_t p1 = (uint64_t)kPhiloxM1 * c2p;                                    // round 2, uniform half
+    const uint32_t T0 = (uint32_t)(p1 >> 32) ^ c1p ^ p.rk0[1];
+    const uint64_t q0 = (uint64_t)kPhiloxM0 * T0;                                     // round 3, uniform half
+    return make_uint4(c3p ^ p.rk1[1], (uint32_t)p1 ^ p.rk0[2], (uint32_t)(q0 >> 32) ^ p.rk1[2], (uint32_t)q0 ^ p.rk1[3]);
+}
+__device__ __forceinline__ uint4 philox4x32_10_tab(const uint4 t, const PhiloxSample s, const RolloutParams &p)
+{
+    uint32_t c0, c1, c2, c3;
+    c2 = s.h0 ^ t.x;                                                                  // end of round 2
+    {                                                                                 // round 3
+        const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+        c0 = (uint32_t)(p1 >> 32) ^ t.y;
+        c2 = s.l0 ^ t.z;
+        c1 = (uint32_t)p1;
+    }
+    {                                                                                 // round 4
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+        const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ p.rk0[3];
+        c2 = (uint32_t)(p0 >> 32) ^ t.w;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+    }
+#pragma unroll
+    for (int r = 4; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+        const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ p.rk0[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ p.rk1[r];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ void normals4_tab(const uint4 *tab, uint32_t call, const PhiloxSample s, const RolloutParams &p, float z[4])
+{
+    normals_from_words(philox4x32_10_tab(tab[call], s, p), z);
 }
 
 // ------------------------------------------------------------------------------------------

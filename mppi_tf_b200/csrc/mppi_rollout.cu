@@ -129,9 +129,12 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     float *sScale = sWork + TAp;         // [kMaxParts]
     float *sRed = sScale + kMaxParts;    // [64]
     float4 *sScratch = reinterpret_cast<float4 *>(sRed + 64);   // [kPhiloxThreads] merge scratch
+    uint4 *sTab = reinterpret_cast<uint4 *>(sScratch + kPhiloxThreads);   // [ceil(TA/4)] per-call uniform Philox words
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     stage_sequence<A, true>(p, ctrl, sUV);
+    for (int c = tid; c < ((TA + 3) >> 2); c += kPhiloxThreads) sTab[c] = philox_call_table((uint32_t)c, (uint32_t)ctrl, p);
+    const uint32_t phA = philox_uniform_A(p);
 
     ModelConsts<A> mc;
     Vec<A> sigd;
@@ -150,12 +153,11 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     const int kend = min(p.K_local, 32 * w_hi);
     constexpr int kstride = kPhiloxThreads;
     const int nfull = p.T >> 2, trem = p.T & 3;
-    const uint32_t stream = (uint32_t)ctrl;
 
     // ---- phase 1: rollout + cost ---------------------------------------------------------------
     float bmin = kInf, bmax = -kInf;
     for (int k = kfirst; k < kend && p.norm_mode != 2; k += kstride) {   // weight pass of a normalised update: costs are in HBM
-        const uint32_t kg = (uint32_t)(p.k_offset + k);
+        const PhiloxSample ps = philox_sample(phA, (uint32_t)(p.k_offset + k));
         PointMass<A> x;
         x.init(x0);
         CostAcc S;
@@ -166,7 +168,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
         for (int tb = 0; tb < nfull; tb++) {       // full blocks of 4 steps = A Philox calls, no guards
             float z[4 * A];
 #pragma unroll
-            for (int c = 0; c < A; c++) normals4(call + c, kg, stream, p, &z[4 * c]);
+            for (int c = 0; c < A; c++) normals4_tab(sTab, call + c, ps, p, &z[4 * c]);
             call += A;
 #pragma unroll
             for (int tt = 0; tt < 4; tt++) {
@@ -176,10 +178,11 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
             }
             uv += 4 * RS;
         }
-        if (trem) {                                 // tail: T % 4 steps
+        if (trem) {                                 // tail: T % 4 steps (calls past the row end read table entries that exist: ceil)
             float z[4 * A];
 #pragma unroll
-            for (int c = 0; c < A; c++) normals4(call + c, kg, stream, p, &z[4 * c]);
+            for (int c = 0; c < A; c++)
+                if ((int)(call + c) < ((TA + 3) >> 2)) normals4_tab(sTab, call + c, ps, p, &z[4 * c]);
 #pragma unroll
             for (int tt = 0; tt < 3; tt++)
                 if (tt < trem) {
@@ -228,7 +231,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
             for (int i = 0; i < 16; i++) acc2[i] = make_float2(0.f, 0.f);
             const bool full = (ch * 8 + 8 <= ncall);    // warp-uniform: all 8 calls of the chunk exist
             for (int k = kfirst; k < kend; k += kstride) {
-                const uint32_t kg = (uint32_t)(p.k_offset + k);
+                const PhiloxSample ps = philox_sample(phA, (uint32_t)(p.k_offset + k));
                 const float e = weight_exp(costs[k], beta_c, nil);
                 const float2 e2 = make_float2(e, e);
                 if (ch == 0) eta += e;
@@ -236,7 +239,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
                 for (int c8 = 0; c8 < 8; c8++) {
                     if (full || ch * 8 + c8 < ncall) {
                         float z[4];
-                        normals4((uint32_t)(ch * 8 + c8), kg, stream, p, z);
+                        normals4_tab(sTab, (uint32_t)(ch * 8 + c8), ps, p, z);
                         acc2[2 * c8] = __ffma2_rn(e2, make_float2(z[0], z[1]), acc2[2 * c8]);
                         acc2[2 * c8 + 1] = __ffma2_rn(e2, make_float2(z[2], z[3]), acc2[2 * c8 + 1]);
                     }
@@ -298,14 +301,14 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
                     const bool full = (ch * 8 + 8 <= ncall);
                     for (int i0 = 32 * warp; i0 < total; i0 += 32 * NW) {
                         const uint2 ent = (i0 + lane < total) ? sList[i0 + lane] : make_uint2(0u, 0u);   // padding lanes: weight 0
-                        const uint32_t kg = ent.x;
+                        const PhiloxSample ps = philox_sample(phA, ent.x);
                         const float e = __uint_as_float(ent.y);
                         const float2 e2 = make_float2(e, e);
 #pragma unroll
                         for (int c8 = 0; c8 < 8; c8++) {
                             if (full || ch * 8 + c8 < ncall) {
                                 float z[4];
-                                normals4((uint32_t)(ch * 8 + c8), kg, stream, p, z);
+                                normals4_tab(sTab, (uint32_t)(ch * 8 + c8), ps, p, z);
                                 acc2[2 * c8] = __ffma2_rn(e2, make_float2(z[0], z[1]), acc2[2 * c8]);
                                 acc2[2 * c8 + 1] = __ffma2_rn(e2, make_float2(z[2], z[3]), acc2[2 * c8 + 1]);
                             }
@@ -762,7 +765,7 @@ static size_t philox_smem_bytes(int A, int T, int TA)
 {
     const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31, NW = kPhiloxThreads / 32;
     return sizeof(float) * ((size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 64) + sizeof(float4) * kPhiloxThreads +
-           sizeof(uint2) * NW * kListCap;
+           sizeof(uint2) * NW * kListCap + sizeof(uint4) * (size_t)((TA + 3) >> 2);
 }
 
 template <int A, bool DIAG, bool QUAD, int COST>
