@@ -410,7 +410,7 @@ def main():
                          "traffic": measured_traffic(args.workload, "rollout_philox_kernel") if world == 1 and not args.k_override else None,
                          "peak_source": peak_src,
                          "note": "effective GB/s on the algorithmic bytes 4*a*K*T + 4*K; the Philox kernel moves "
-                                 "almost no HBM bytes and is bound by ALU/MUFU issue (see profiles/)"},
+                                 "almost no HBM bytes and runs at the scheduler-dispatch bound of its instruction mix (DESIGN.md 3.1, profiles/)"},
         }
         if is_mlp:
             tpeak, tsrc = measured_tensor_peak()
