@@ -46,6 +46,37 @@ __device__ __forceinline__ void load_uv(const float *uv_row, Vec<A> &U, Vec<A> &
     w.sc = uv[H + A - 1];
 }
 
+// Philox mode: the action-cost vector is w_t = w_scale * U_t with a uniform scale, so only U_t is staged (one LDS.128 per
+// step at a <= 4) and the dot products U_t . z_t are summed on their own and scaled once per sample.
+template <int A>
+struct RowU { static constexpr int RS = (A + 3) & ~3; };
+
+template <int A>
+__device__ __forceinline__ void load_u(const float *u_row, Vec<A> &U)
+{
+    constexpr int RS = RowU<A>::RS, NP = A / 2;
+    float uv[RS];
+#pragma unroll
+    for (int i = 0; i < RS / 4; i++) {
+        const float4 v = reinterpret_cast<const float4 *>(u_row)[i];
+        uv[4 * i] = v.x; uv[4 * i + 1] = v.y; uv[4 * i + 2] = v.z; uv[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < NP; i++) U.pr[i] = make_float2(uv[2 * i], uv[2 * i + 1]);
+    U.sc = uv[A - 1];
+}
+
+template <int A>
+__device__ __forceinline__ void stage_u(const RolloutParams &p, int ctrl, float *sU)
+{
+    constexpr int RS = RowU<A>::RS;
+    const float *U = p.U + (size_t)ctrl * p.TA;
+    for (int i = threadIdx.x; i < p.T * RS; i += blockDim.x) {
+        const int t = i / RS, j = i - t * RS;
+        sU[i] = (j < A) ? U[t * A + j] : 0.f;
+    }
+}
+
 template <int A>
 __device__ __forceinline__ void vec_from(const float *z, Vec<A> &n)
 {
@@ -58,13 +89,14 @@ __device__ __forceinline__ void vec_from(const float *z, Vec<A> &n)
 //   u = U_t + eps_t ; x <- A x + (B/m) u ; S += q(x) + lambda U_t^T Sigma^-1 eps_t
 // `n` is z_t in Philox mode (eps_t = Sigma z_t formed here) and eps_t in injected mode.
 template <int A, bool PHILOX, bool DIAG, bool QUAD, int COST>
-__device__ __forceinline__ void rollout_step(PointMass<A> &x, CostAcc &S, const float *uv_row, const Vec<A> &n,
+__device__ __forceinline__ void rollout_step(PointMass<A> &x, CostAcc &S, CostAcc &Sw, const float *uv_row, const Vec<A> &n,
                                              const RolloutParams &p, const ModelConsts<A> &mc, const Vec<A> &sigd)
 {
     constexpr int NP = A / 2;
     constexpr bool ODD = (A & 1) != 0;
     Vec<A> U, w, u;
-    load_uv<A>(uv_row, U, w);
+    if (PHILOX) load_u<A>(uv_row, U);            // Sw collects U_t . z_t, scaled by w_scale once per sample
+    else load_uv<A>(uv_row, U, w);
     if (PHILOX && !DIAG) {
 #pragma unroll
         for (int j = 0; j < A; j++) {
@@ -79,9 +111,15 @@ __device__ __forceinline__ void rollout_step(PointMass<A> &x, CostAcc &S, const 
             u.pr[i] = PHILOX ? __ffma2_rn(sigd.pr[i], n.pr[i], U.pr[i]) : __fadd2_rn(U.pr[i], n.pr[i]);
         if (ODD) u.sc = PHILOX ? fmaf(sigd.sc, n.sc, U.sc) : U.sc + n.sc;
     }
+    if (PHILOX) {
 #pragma unroll
-    for (int i = 0; i < NP; i++) S.a2 = __ffma2_rn(w.pr[i], n.pr[i], S.a2);
-    if (ODD) S.a = fmaf(w.sc, n.sc, S.a);
+        for (int i = 0; i < NP; i++) Sw.a2 = __ffma2_rn(U.pr[i], n.pr[i], Sw.a2);
+        if (ODD) Sw.a = fmaf(U.sc, n.sc, Sw.a);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) S.a2 = __ffma2_rn(w.pr[i], n.pr[i], S.a2);
+        if (ODD) S.a = fmaf(w.sc, n.sc, S.a);
+    }
     if (QUAD) {                                  // Python-twin noise cost (cost_base.py:147-148,160-162)
         float nn[A];
 #pragma unroll
@@ -116,7 +154,7 @@ template <int A, bool DIAG, bool QUAD, int COST>
 __global__ void __launch_bounds__(kPhiloxThreads, kPhiloxCtasPerSm)
 rollout_philox_kernel(const __grid_constant__ RolloutParams p)
 {
-    constexpr int RS = Row<A>::RS;
+    constexpr int RS = RowU<A>::RS;
     constexpr int NW = kPhiloxThreads / 32;
     extern __shared__ float4 smem_f4[];
     float *smem = reinterpret_cast<float *>(smem_f4);
@@ -132,7 +170,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     uint4 *sTab = reinterpret_cast<uint4 *>(sScratch + kPhiloxThreads);   // [ceil(TA/4)] per-call uniform Philox words
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    stage_sequence<A, true>(p, ctrl, sUV);
+    stage_u<A>(p, ctrl, sUV);
     for (int c = tid; c < ((TA + 3) >> 2); c += kPhiloxThreads) sTab[c] = philox_call_table((uint32_t)c, (uint32_t)ctrl, p);
     const uint32_t phA = philox_uniform_A(p);
 
@@ -160,8 +198,9 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
         const PhiloxSample ps = philox_sample(phA, (uint32_t)(p.k_offset + k));
         PointMass<A> x;
         x.init(x0);
-        CostAcc S;
+        CostAcc S, Sw;
         S.zero();
+        Sw.zero();
         S.a = C0;
         const float *uv = sUV;
         uint32_t call = 0;
@@ -174,7 +213,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
             for (int tt = 0; tt < 4; tt++) {
                 Vec<A> n;
                 vec_from<A>(&z[tt * A], n);
-                rollout_step<A, true, DIAG, QUAD, COST>(x, S, uv + tt * RS, n, p, mc, sigd);
+                rollout_step<A, true, DIAG, QUAD, COST>(x, S, Sw, uv + tt * RS, n, p, mc, sigd);
             }
             uv += 4 * RS;
         }
@@ -188,11 +227,11 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
                 if (tt < trem) {
                     Vec<A> n;
                     vec_from<A>(&z[tt * A], n);
-                    rollout_step<A, true, DIAG, QUAD, COST>(x, S, uv + tt * RS, n, p, mc, sigd);
+                    rollout_step<A, true, DIAG, QUAD, COST>(x, S, Sw, uv + tt * RS, n, p, mc, sigd);
                 }
         }
         add_state_cost<A, COST>(x, mc, p, S);    // terminal cost on top of step T-1's (src/controller_base.cpp:271-272)
-        const float Sk = S.total();
+        const float Sk = fmaf(p.w_scale, Sw.total(), S.total());
         costs[k] = Sk;
         bmin = fminf(bmin, Sk);
         bmax = fmaxf(bmax, Sk);
@@ -572,7 +611,7 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
                         for (int tt = 0; tt < 4; tt++) {
                             Vec<A> n;
                             vec_from<A>(&e[tt * A], n);
-                            rollout_step<A, false, false, QUAD, COST>(x, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
+                            rollout_step<A, false, false, QUAD, COST>(x, Sa, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
                         }
                     } else {
                         load_block<A, TMA, true>(row, tb, TA, e);
@@ -581,7 +620,7 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
                             if (4 * tb + tt < p.T) {
                                 Vec<A> n;
                                 vec_from<A>(&e[tt * A], n);
-                                rollout_step<A, false, false, QUAD, COST>(x, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
+                                rollout_step<A, false, false, QUAD, COST>(x, Sa, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
                             }
                     }
                 }
@@ -763,7 +802,7 @@ __global__ void scale_noise_kernel(const __grid_constant__ RolloutParams p, floa
 // -------------------------------------------------------------------------------------------------
 static size_t philox_smem_bytes(int A, int T, int TA)
 {
-    const int H = (A + 1) & ~1, RS = (2 * H + 3) & ~3, TAp = (TA + 31) & ~31, NW = kPhiloxThreads / 32;
+    const int RS = (A + 3) & ~3, TAp = (TA + 31) & ~31, NW = kPhiloxThreads / 32;
     return sizeof(float) * ((size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 64) + sizeof(float4) * kPhiloxThreads +
            sizeof(uint2) * NW * kListCap + sizeof(uint4) * (size_t)((TA + 3) >> 2);
 }
