@@ -44,7 +44,9 @@ typedef enum {
 
 #define MPPI_MAX_A 8          /* a_dim <= 8, s_dim = 2 a_dim <= 16 */
 #define MPPI_MAX_S 16
-#define MPPI_MAX_TA 4096      /* tau * a_dim */
+#define MPPI_MAX_TA 4096      /* tau * a_dim accepted by mppi_create; the update kernels keep per-warp rows of tau * a_dim
+                               * partial sums in shared memory, so an update with tau * a_dim above about 2400 (Philox mode) or
+                               * 1700 (injected noise) returns MPPI_ERR_UNSUPPORTED on a 227 KB part */
 #define MPPI_MAX_PEERS 8      /* ranks of one NVLink domain the fused exchange can address */
 
 typedef struct mppi_handle mppi_handle;

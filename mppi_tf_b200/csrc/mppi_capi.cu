@@ -475,7 +475,10 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
                 return fail(h, MPPI_ERR_UNSUPPORTED, "injected-noise mode: one 32-sample tile of tau*a_dim floats does not fit shared memory");
             CU_TRY(h, e);
         } else {
-            CU_TRY(h, launch_rollout_philox(p, h->a, h->num_sms, h->stream, &gx));
+            cudaError_t e = launch_rollout_philox(p, h->a, h->num_sms, h->smem_optin, h->stream, &gx);
+            if (e == cudaErrorInvalidConfiguration)
+                return fail(h, MPPI_ERR_UNSUPPORTED, "tau*a_dim is too large for the per-CTA shared-memory tables of the update kernel (about 2400 floats on this device)");
+            CU_TRY(h, e);
         }
     }
     h->last_philox = (eps_dev == nullptr);

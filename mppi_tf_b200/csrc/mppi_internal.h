@@ -9,7 +9,7 @@ namespace mppi {
 struct RolloutParams;
 
 // mppi_rollout.cu
-cudaError_t launch_rollout_philox(RolloutParams p, int a, int num_sms, cudaStream_t st, int *grid_x_out);
+cudaError_t launch_rollout_philox(RolloutParams p, int a, int num_sms, size_t smem_limit, cudaStream_t st, int *grid_x_out);
 cudaError_t launch_rollout_injected(RolloutParams p, int a, int num_sms, size_t smem_limit, cudaStream_t st,
                                     int *grid_x_out);
 cudaError_t launch_finish(RolloutParams p, int a, bool philox, const float *gathered, cudaStream_t st);

@@ -858,8 +858,11 @@ int philox_grid_x(int K_local, int n_ctrl, int num_sms)
     return gx;
 }
 
-cudaError_t launch_rollout_philox(RolloutParams p, int a, int num_sms, cudaStream_t st, int *grid_x_out)
+cudaError_t launch_rollout_philox(RolloutParams p, int a, int num_sms, size_t smem_limit, cudaStream_t st, int *grid_x_out)
 {
+    // 16 per-warp rows of T*a partial sums + the sequence and call tables must fit one CTA's shared memory
+    // (T*a up to about 2400 on a 227 KB part)
+    if (philox_smem_bytes(a, p.T, p.TA) > smem_limit) return cudaErrorInvalidConfiguration;
     const int gx = philox_grid_x(p.K_local, p.n_ctrl, num_sms);
     p.n_iter = (p.K_local + gx * kPhiloxThreads - 1) / (gx * kPhiloxThreads);
     if (grid_x_out) *grid_x_out = gx;

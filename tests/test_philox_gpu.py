@@ -215,3 +215,32 @@ def test_weighted_sum_paths_store_then_replay(oracle32, oracle64, k, tau, a, lam
     assert_update_close(U_new, r64["U_new"], r32["U_new"], what="U_new: " + what)
     assert_update_close(act, r64["next"], r32["next"], what="next: " + what)
     assert abs(float(np.ravel(beta)[0]) - r64["costs"].min()) <= 2e-5 * abs(r64["costs"].min()) + 2e-5
+
+
+def test_long_rows_and_the_shared_memory_limit(oracle64, oracle32):
+    """tau * a_dim = 1800 still runs in Philox mode (store-then-replay against the checker); a row of 4000 floats does
+    not fit the per-CTA tables and must fail with MPPI_ERR_UNSUPPORTED, not with a launch error."""
+    from mppi_tf_b200 import MppiError, _capi
+    k, tau, a = 256, 600, 3
+    cfg = make_cfg(k, tau, 6, a, lam=5.0)
+    rng = np.random.default_rng(8)
+    x0 = rng.uniform(-1, 1, 6).astype(np.float32)
+    U0 = (0.05 * rng.standard_normal((tau, a))).astype(np.float32)
+    ctrl = controller_from_cfg(cfg, seed=3)
+    try:
+        ctrl.setSequence(U0)
+        ctrl.next(x0)
+        eps = ctrl.dumpNoise()
+        ref = oracle64.mppi_update(cfg, x0, U0, eps)
+        r32 = oracle32.mppi_update(cfg, x0, U0, eps)
+        from tests.util import assert_update_close
+        assert_update_close(ctrl.getUpdate(), ref["U_new"], r32["U_new"], what="T*a = 1800")
+    finally:
+        ctrl.close()
+    big = controller_from_cfg(make_cfg(64, 1000, 8, 4))
+    try:
+        with pytest.raises(MppiError) as e:
+            big.next(np.zeros(8, np.float32))
+        assert e.value.code == _capi.MPPI_ERR_UNSUPPORTED
+    finally:
+        big.close()
