@@ -36,8 +36,43 @@ WORKLOADS = {
     "cfg5": ("4096 x point_mass2d K=1024 T=30 (BASELINE config 5)", 1024, 30, 4, 2, 4096),
     "cfg4": ("learned MLP 9->128->128->6 on point_mass3d state, K=262144 T=50, bf16 tcgen05 (BASELINE config 4)",
              262144, 50, 6, 3, 1),
+    # not a BASELINE config: the AUV (Fossen) model of SURVEY.md section 8f row N4, Heun integrator, StaticCost, Python-twin
+    # action cost; parameters = the "full" set of tests/golden/auv_fixtures.npz
+    "auv": ("AUV Fossen model rk2 (s=13, a=6) K=262144 T=50 [next-row workload, not a BASELINE config]", 262144, 50, 13, 6, 1),
 }
 MLP_WORKLOADS = {"cfg4"}
+AUV_WORKLOADS = {"auv"}
+
+
+def auv_params():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "auv_fixtures.npz"))
+    return json.loads(bytes(d["params_json"]).decode())["full"]
+
+
+def cpu_auv_throughput(K_full, T, budget_s=15.0):
+    """CPU arm of the AUV workload: the OpenMP C restatement (oracle/, kind "port") on a bounded sample of K."""
+    from oracle import Oracle, pyoracle                     # bench.py's cpu_baseline leg may use oracle/
+    orc = Oracle("f32")
+    prm = auv_params()
+    rng = np.random.default_rng(1)
+    sigma = 80.0 * np.eye(6)
+    x = np.zeros(13); x[6] = 1.0
+    U = np.zeros((T, 6))
+    k = 4096
+    eps = (80.0 * rng.standard_normal((k, T, 6))).astype(np.float32)
+    t0 = time.perf_counter()
+    orc.mppi_update_auv(prm, 0.1, 2, 1.0, sigma, x, np.ones(13), x, U, eps)
+    per = (time.perf_counter() - t0) / k
+    k = int(max(4096, min(K_full, budget_s / 4 / max(per, 1e-9))))
+    eps = (80.0 * rng.standard_normal((k, T, 6))).astype(np.float32)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        orc.mppi_update_auv(prm, 0.1, 2, 1.0, sigma, x, np.ones(13), x, U, eps)
+        times.append(time.perf_counter() - t0)
+    return dict(value=k * T * 3 / sum(times), threads=pyoracle.num_threads(),
+                sample=f"K={k} of {K_full} samples per update (T={T}), 3 updates, OpenMP C restatement of the Python controller "
+                       f"with AUVModel rk2 (noise generation not included)")
 MLP_FLOPS_PER_SAMPLE_STEP = 2 * (9 * 128 + 128 * 128 + 128 * 6)      # 36 608 (SURVEY.md section 8d)
 METRIC = "mppi_sample_steps_per_sec"
 UNIT = "sample-steps/s"
@@ -175,7 +210,11 @@ def run_reference(args, rank, world):
     desc, K, T, s, a, n_ctrl = WORKLOADS[args.workload]
     steps = max(1, min(args.steps, 5))
     warm = 3                                   # W >= 3 warm-up steps, each a bounded CPU sample
-    r = cpu_port_throughput(K, T, s, a, steps, warm, budget_s=60.0)
+    if args.workload in AUV_WORKLOADS:
+        r = cpu_auv_throughput(K, T, budget_s=60.0)
+        r["ms_per_step"] = None
+    else:
+        r = cpu_port_throughput(K, T, s, a, steps, warm, budget_s=60.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -238,7 +277,8 @@ def main():
     else:
         n_local = 1
         k_rank, k_world, k_rankid = K, world, rank
-    sigma = 0.25 * np.eye(a, dtype=np.float32)
+    is_auv = args.workload in AUV_WORKLOADS
+    sigma = (80.0 if is_auv else 0.25) * np.eye(a, dtype=np.float32)
     rng = np.random.default_rng(5)
     goal = None
     if n_ctrl > 1:
@@ -250,7 +290,10 @@ def main():
     assert stream != 0
     ctrl = ControllerBase(k_rank, T, 0.1, 1.0, s, a, lam=1.0, sigma=sigma, goal=goal, seed=1, device=local_rank,
                           rank=k_rankid, world=k_world, n_controllers=n_local,
-                          goal_per_controller=(n_ctrl > 1), stream=stream)
+                          goal_per_controller=(n_ctrl > 1), stream=stream, model=("auv" if is_auv else "point_mass"))
+    if is_auv:
+        ctrl.setAuvModel(auv_params(), rk=2)
+        ctrl.setActionCost("python", gamma=1.0, upsilon=1.0)
     is_mlp = args.workload in MLP_WORKLOADS
     if is_mlp:
         ctrl.setMlp(glorot_mlp(s, a))
@@ -286,6 +329,9 @@ def main():
 
     x = np.zeros((n_local, s), np.float32) if n_ctrl == 1 else \
         rng.uniform(-1, 1, (n_ctrl, s)).astype(np.float32)[rank * n_local:(rank + 1) * n_local]
+    if is_auv:
+        x[:, 6] = 1.0                               # identity attitude (a zero quaternion is not a state)
+        x[:, 0] = 1.0
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def one_update(eps_ptr=None):
@@ -362,7 +408,7 @@ def main():
     if world == 1 and not args.no_injected and not is_mlp:
         n_eps = n_local * K * T * a
         g = torch.Generator(device=dev).manual_seed(1234)
-        eps = torch.randn(n_eps, device=dev, generator=g) * 0.25
+        eps = torch.randn(n_eps, device=dev, generator=g) * (80.0 if is_auv else 0.25)
         isteps = max(10, min(args.steps, 50))
         for _ in range(3):
             one_update(eps.data_ptr())
@@ -412,6 +458,12 @@ def main():
                          "note": "effective GB/s on the algorithmic bytes 4*a*K*T + 4*K; the Philox kernel moves "
                                  "almost no HBM bytes and runs at the scheduler-dispatch bound of its instruction mix (DESIGN.md 3.1, profiles/)"},
         }
+        if is_auv:
+            line["config"]["mode"] = "philox noise + Fossen dynamics (Heun), fp32"
+            line["roofline"]["kernel"] = "rollout_auv_kernel"
+            line["roofline"]["traffic"] = None
+            line["roofline"]["note"] = ("effective GB/s on the algorithmic bytes 4*a*K*T + 4*K; the kernel is bound by its fp32 FFMA "
+                                        "chains (DESIGN.md 3.5: 70 % issue-active, 45 % of the FFMA peak)")
         if is_mlp:
             tpeak, tsrc = measured_tensor_peak()
             tf = MLP_FLOPS_PER_SAMPLE_STEP * (K // k_world) * T / (kernel_ms * 1e-3) / 1e12
@@ -424,12 +476,15 @@ def main():
                                 "note": "algorithmic flops 2*(9*128+128*128+128*6) = 36608 per sample-step (unpadded)"}
         if inj is not None:
             ia = bytes_alg(K, T, a, n_local) / (inj * 1e-3) / 1e9
-            line["roofline_injected"] = {"bound": "hbm", "kernel": "rollout_injected_kernel", "achieved": ia,
+            line["roofline_injected"] = {"bound": "hbm", "kernel": "rollout_auv_kernel<injected>" if is_auv else "rollout_injected_kernel", "achieved": ia,
                                          "peak": peak, "unit": "GB/s", "frac": ia / peak,
                                          "traffic": measured_traffic(args.workload, "rollout_injected_kernel") if not args.k_override else None,
                                          "ms_per_launch": inj,
                                          "inputs": "eps resident in HBM" + (" (larger than L2)" if 4 * n_eps > 126e6 else " (L2 flushed)")}
-        if not args.no_cpu_baseline and world == 1 and not is_mlp:
+        if not args.no_cpu_baseline and world == 1 and is_auv:
+            r = cpu_auv_throughput(K, T)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"]}
+        elif not args.no_cpu_baseline and world == 1 and not is_mlp:
             r = cpu_port_throughput(K, T, s, a, steps=3, warmup=1, budget_s=15.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                                     "sample": r["sample"]}
