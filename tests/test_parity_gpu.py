@@ -1,7 +1,7 @@
 """Parity of the fused CUDA update (through the C-ABI) against the CPU oracle on the same state
 and the same injected noise tensor.  Bar (BASELINE.json): control sequence and per-sample costs
 within 1e-5 relative in fp32 — measured norm-wise against the exact (fp64) oracle, see
-tests/util.py:assert_update_close."""
+tests/util.py:assert_update_close (flat bar; the lambda = 0.05 case alone may use three times the fp32 oracle's own distance)."""
 import numpy as np
 import pytest
 
@@ -10,7 +10,7 @@ from tests.util import (CFG1, CFG2, assert_update_close, controller_from_cfg, ma
 pytestmark = pytest.mark.gpu
 
 
-def _run_injected(cfg, x0, U0, eps, oracle32, oracle64, check_costs=True):
+def _run_injected(cfg, x0, U0, eps, oracle32, oracle64, check_costs=True, allow_fp32_distance=False):
     ctrl = controller_from_cfg(cfg)
     try:
         ctrl.setSequence(U0)
@@ -22,7 +22,7 @@ def _run_injected(cfg, x0, U0, eps, oracle32, oracle64, check_costs=True):
     r32 = oracle32.mppi_update(cfg, x0, U0, eps)
     errs = {}
     for key in ("U_new", "next", "U_shift"):
-        errs[key] = assert_update_close(got[key], r64[key], r32[key], what=key)
+        errs[key] = assert_update_close(got[key], r64[key], r32[key], what=key, allow_fp32_distance=allow_fp32_distance)
     if check_costs:
         # per-sample costs: element-wise relative 1e-5 (plus the fp32 oracle's own distance)
         np.testing.assert_allclose(got["costs"], r64["costs"], rtol=1e-5,
@@ -92,7 +92,8 @@ def test_lambda_extremes(oracle32, oracle64, lam):
     """Small lambda: eta dominated by a few samples (the fp32-reproducibility hard part)."""
     cfg = make_cfg(8192, 20, 4, 2, lam=lam)
     x0, U0, eps = _inputs(cfg, seed=2)
-    _run_injected(cfg, x0, U0, eps, oracle32, oracle64)
+    # lambda = 0.05 is the one case that may use the fp32-distance allowance (tests/util.py); every other test is flat 1e-5
+    _run_injected(cfg, x0, U0, eps, oracle32, oracle64, allow_fp32_distance=(lam < 0.1))
 
 
 def test_consecutive_updates_keep_state(oracle64):
@@ -194,8 +195,7 @@ def test_batched_controllers(oracle32, oracle64):
         ref = oracle64.mppi_update(cc, xs[c], U0[c], eps[c])
         r32 = oracle32.mppi_update(cc, xs[c], U0[c], eps[c])
         assert_update_close(Ush[c], ref["U_shift"], r32["U_shift"], what=f"U_shift[{c}]")
-        assert np.abs(act[c] - ref["next"]).max() <= max(1e-5, 3 * rel_err(r32["U_shift"], ref["U_shift"])) * \
-            np.abs(ref["U_new"]).max(), c
+        assert np.abs(act[c] - ref["next"]).max() <= 1e-5 * np.abs(ref["U_new"]).max(), c
         np.testing.assert_allclose(costs[c], ref["costs"], rtol=1e-5, atol=1e-6)
 
 

@@ -57,7 +57,7 @@ def test_injected_noise_matches_twin_oracle(oracle64, oracle32, k, tau, a, full,
     assert rel_err(costs, ref["costs"]) < 1e-5
     assert_update_close(U_new, ref["U_new"], ref32["U_new"], what="U_new")
     assert_update_close(U_shift, ref["U_shift"], ref32["U_shift"], what="U_shift")
-    assert np.abs(act - ref["next"]).max() <= max(1e-5, 3 * rel_err(ref32["U_new"], ref["U_new"])) * np.abs(ref["U_new"]).max()
+    assert np.abs(act - ref["next"]).max() <= 1e-5 * np.abs(ref["U_new"]).max()
     np.testing.assert_array_equal(U_shift[:-1], U_new[1:])
 
 
@@ -85,7 +85,7 @@ def test_philox_store_then_replay_matches_twin_oracle(oracle64, oracle32, k, tau
     ref32 = oracle32.mppi_update_py(cfg, x0, U0, eps, **kw)
     assert rel_err(costs, ref["costs"]) < 1e-5
     assert_update_close(U_new, ref["U_new"], ref32["U_new"], what="U_new")
-    assert np.abs(act - ref["next"]).max() <= max(1e-5, 3 * rel_err(ref32["U_new"], ref["U_new"])) * np.abs(ref["U_new"]).max()
+    assert np.abs(act - ref["next"]).max() <= 1e-5 * np.abs(ref["U_new"]).max()
 
 
 def test_upsilon_with_cpp_action_cost(oracle64):
@@ -209,7 +209,7 @@ def test_ellipse_cost_update(oracle64, oracle32, k, tau, normalize, upsilon):
     ref, ref32 = oracle64.mppi_update_py(cfg, x0, U0, eps, **kw), oracle32.mppi_update_py(cfg, x0, U0, eps, **kw)
     assert rel_err(costs_inj, ref["costs"]) < 1e-5
     assert_update_close(U_inj, ref["U_new"], ref32["U_new"], what="U_new injected")
-    assert np.abs(act - ref["next"]).max() <= max(1e-5, 3 * rel_err(ref32["U_new"], ref["U_new"])) * np.abs(ref["U_new"]).max()
+    assert np.abs(act - ref["next"]).max() <= 1e-5 * np.abs(ref["U_new"]).max()
     ref, ref32 = oracle64.mppi_update_py(cfg, x0, U0, eps_phx, **kw), oracle32.mppi_update_py(cfg, x0, U0, eps_phx, **kw)
     assert rel_err(costs_phx, ref["costs"]) < 1e-5
     assert_update_close(U_phx, ref["U_new"], ref32["U_new"], what="U_new philox")

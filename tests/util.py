@@ -47,15 +47,35 @@ def rel_err(got, want):
     return np.abs(got - want).max() / (scale if scale > 0 else 1.0)
 
 
-def assert_update_close(got, ref64, ref32=None, tol=1e-5, what=""):
-    """The parity bar of BASELINE.json: 1e-5 relative (norm-wise) against the exact (fp64) oracle.
-    Where the reference's own fp32 arithmetic (the op-for-op fp32 oracle) is itself further than
-    that from fp64 — ill-conditioned softmin: costs of ~50 carry an fp32 ulp of 4e-6 straight into
-    the exponent — two fp32 implementations with different rounding orders cannot agree better
-    than a small multiple of that distance, so allow three times the fp32 oracle's own error."""
+def _note_allowance(what, err, bar):
+    """Every comparison that needed more than the flat bar is listed in gpurun_out/parity_allowance_r2.json."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "gpurun_out", "parity_allowance_r2.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        try:
+            data = json.load(open(path))
+        except (OSError, ValueError):
+            data = []
+        data.append({"what": what, "test": os.environ.get("PYTEST_CURRENT_TEST", ""), "err": float(err), "bar": float(bar)})
+        json.dump(data, open(path, "w"), indent=1)
+    except OSError:
+        pass
+
+
+def assert_update_close(got, ref64, ref32=None, tol=1e-5, what="", allow_fp32_distance=False):
+    """The parity bar of BASELINE.json: 1e-5 relative (norm-wise) against the exact (fp64) oracle, flat.
+    `allow_fp32_distance=True` (the ill-conditioned softmin cases only: lambda = 0.05, where costs of ~50 carry an
+    fp32 ulp of 4e-6 straight into an exponent scaled by 1/lambda) widens the bar to three times the distance of the
+    reference's own fp32 arithmetic (the op-for-op fp32 oracle) from fp64 — two fp32 implementations with different
+    rounding orders cannot agree better than a small multiple of that distance."""
     err = rel_err(got, ref64)
     bar = tol
-    if ref32 is not None:
+    if allow_fp32_distance and ref32 is not None:
         bar = max(bar, 3.0 * rel_err(ref32, ref64))
+    if err > tol:
+        _note_allowance(what, err, bar)
     assert err <= bar, f"{what}: rel err {err:.3e} > {bar:.3e}"
     return err
