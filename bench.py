@@ -10,9 +10,14 @@ N > 1).  Default workload: BASELINE config 3 — point_mass3d, K = 1,048,576 sam
 configuration the metric's target is quoted on; it fits one GPU, and at N GPUs the SAME total K is
 sharded K/N per rank (strong scaling), so N = 8 is exactly config 3 as written.
 
-Prints ONE JSON line (rank 0).  Keys beyond the base contract: roofline (dominant kernel, effective
-HBM GB/s on the algorithmic bytes), roofline_injected (the HBM-bound injected-noise kernel),
-cpu_baseline (graph-faithful CPU port timed on this box), latency percentiles.
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline           dominant kernel, effective HBM GB/s on the algorithmic bytes
+  roofline_injected  the HBM-bound injected-noise kernel on the same workload (N = 1)
+  dense_weights      the same workload with lambda large enough that every fp32 weight is non-zero (N = 1)
+  other_configs      BASELINE configs 1, 2, 4, 5 at their full sizes, ~20 updates each (N = 1)
+  parity_check       N > 1: sequences bit-identical across ranks after the timed region, and a reduced-K sharded
+                     update equal (1e-5) to a single-handle update on rank 0 that draws the same Philox stream
+  cpu_baseline       the graph-faithful CPU port timed on this box (+ cpu_baseline_c: the OpenMP C restatement)
 """
 import argparse
 import json
@@ -42,40 +47,26 @@ WORKLOADS = {
 }
 MLP_WORKLOADS = {"cfg4"}
 AUV_WORKLOADS = {"auv"}
+MLP_FLOPS_PER_SAMPLE_STEP = 2 * (9 * 128 + 128 * 128 + 128 * 6)      # 36 608
+METRIC = "mppi_sample_steps_per_sec"
+UNIT = "sample-steps/s"
+DENSE_LAMBDA = 200.0     # config 3: costs spread over a few hundred -> every fp32 weight is non-zero
+L2_NOTE = ("GPU arm: L2 flushed between timed iterations (256 MiB write, untimed); CPU arm: the per-step working set "
+           "(the noise tensor) is larger than the last-level cache")
+
+
+def workload_config(name, k_override=0):
+    """The `config` object: the same in the GPU arm and the reference arm."""
+    desc, K, T, s, a, n_ctrl = WORKLOADS[name]
+    if k_override:
+        K, desc = k_override, desc + f" [K overridden to {k_override}: developer run, not the BASELINE config]"
+    return {"workload": desc, "K": K, "T": T, "s_dim": s, "a_dim": a, "n_controllers": n_ctrl, "lambda": 1.0,
+            "sigma": "80 I" if name in AUV_WORKLOADS else "0.25 I", "noise": "fresh noise drawn inside every step", "l2": L2_NOTE}
 
 
 def auv_params():
     d = np.load(os.path.join(ROOT, "tests", "golden", "auv_fixtures.npz"))
     return json.loads(bytes(d["params_json"]).decode())["full"]
-
-
-def cpu_auv_throughput(K_full, T, budget_s=15.0):
-    """CPU arm of the AUV workload: the OpenMP C restatement (oracle/, kind "port") on a bounded sample of K."""
-    from oracle import Oracle, pyoracle                     # bench.py's cpu_baseline leg may use oracle/
-    orc = Oracle("f32")
-    prm = auv_params()
-    rng = np.random.default_rng(1)
-    sigma = 80.0 * np.eye(6)
-    x = np.zeros(13); x[6] = 1.0
-    U = np.zeros((T, 6))
-    k = 4096
-    eps = (80.0 * rng.standard_normal((k, T, 6))).astype(np.float32)
-    t0 = time.perf_counter()
-    orc.mppi_update_auv(prm, 0.1, 2, 1.0, sigma, x, np.ones(13), x, U, eps)
-    per = (time.perf_counter() - t0) / k
-    k = int(max(4096, min(K_full, budget_s / 4 / max(per, 1e-9))))
-    eps = (80.0 * rng.standard_normal((k, T, 6))).astype(np.float32)
-    times = []
-    for _ in range(3):
-        t0 = time.perf_counter()
-        orc.mppi_update_auv(prm, 0.1, 2, 1.0, sigma, x, np.ones(13), x, U, eps)
-        times.append(time.perf_counter() - t0)
-    return dict(value=k * T * 3 / sum(times), threads=pyoracle.num_threads(),
-                sample=f"K={k} of {K_full} samples per update (T={T}), 3 updates, OpenMP C restatement of the Python controller "
-                       f"with AUVModel rk2 (noise generation not included)")
-MLP_FLOPS_PER_SAMPLE_STEP = 2 * (9 * 128 + 128 * 128 + 128 * 6)      # 36 608 (SURVEY.md section 8d)
-METRIC = "mppi_sample_steps_per_sec"
-UNIT = "sample-steps/s"
 
 
 def measured_peaks():
@@ -167,13 +158,29 @@ def bytes_alg(K, T, a, n_ctrl=1):
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU arm: the reference's own CPU implementation stands in as the graph-faithful torch-CPU port
-# (oracle/graph_oracle.py; TensorFlow C++ r2.1 cannot be installed offline).
+# CPU arms.  The reference's own CPU implementation (TensorFlow C++ r2.1 / the TF Python twin) cannot be installed
+# offline; its stand-in is the graph-faithful torch-CPU port (oracle/graph_oracle.py: the same op sequence on the same
+# materialised tensors), beside the fused OpenMP C restatement (oracle/mppi_oracle.c).
 # ---------------------------------------------------------------------------------------------------
-def cpu_port_throughput(K_full, T, s, a, steps, warmup, budget_s=20.0):
+def cpu_threads():
+    """All host threads, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
     import torch
-    from oracle.graph_oracle import GraphOracle     # bench.py's cpu_baseline leg may use oracle/
-    threads = torch.get_num_threads()
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_port_run(K_full, T, s, a, n_ctrl, steps, warmup, budget_s):
+    """Graph-faithful torch-CPU port, `steps` timed updates after `warmup`.  The FULL workload per step when the whole
+    run fits `budget_s`; otherwise a bounded sample of it (fewer samples, or fewer of the independent controllers)."""
+    import torch
+    from oracle.graph_oracle import GraphOracle     # bench.py's cpu_baseline / reference leg may use oracle/
+    threads = cpu_threads()
     gen = torch.Generator().manual_seed(1)
     goal = np.tile([1.0, 0.0], a)
 
@@ -182,50 +189,256 @@ def cpu_port_throughput(K_full, T, s, a, steps, warmup, budget_s=20.0):
 
     x = torch.zeros(s)
     U = torch.zeros(T, a)
-    probe_k = min(K_full, 2048)
-    g = make(probe_k)
-    g.next_generating(x, U, gen)
-    t0 = time.perf_counter()
-    g.next_generating(x, U, gen)
-    per_sample = (time.perf_counter() - t0) / probe_k
-    k = int(min(K_full, max(probe_k, budget_s / max(per_sample, 1e-9) / max(steps + warmup, 1))))
-    k = max(32, (k // 32) * 32)
-    g = make(k)
-    for _ in range(warmup):
+    n_runs = max(steps + warmup, 1)
+    if n_ctrl == 1:
+        probe_k = min(K_full, 4096)
+        g = make(probe_k)
         g.next_generating(x, U, gen)
+        t0 = time.perf_counter()
+        g.next_generating(x, U, gen)
+        per_sample = (time.perf_counter() - t0) / probe_k
+        k = K_full if per_sample * K_full * n_runs <= budget_s else int(budget_s / per_sample / n_runs)
+        k = max(32, min(K_full, (k // 32) * 32))
+        nc = 1
+    else:
+        k = K_full
+        g = make(k)
+        g.next_generating(x, U, gen)
+        t0 = time.perf_counter()
+        g.next_generating(x, U, gen)
+        per_ctrl = time.perf_counter() - t0
+        nc = n_ctrl if per_ctrl * n_ctrl * n_runs <= budget_s else max(1, int(budget_s / per_ctrl / n_runs))
+    g = make(k)
+
+    def step():
+        for _ in range(nc):
+            g.next_generating(x, U, gen)
+
+    for _ in range(warmup):
+        step()
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        g.next_generating(x, U, gen)
+        step()
         times.append(time.perf_counter() - t0)
     total = sum(times)
-    return dict(value=k * T * steps / total, k=k, threads=threads, ms_per_step=1e3 * total / steps,
-                sample=f"K={k} of {K_full} samples per update (T={T}, a={a}), {steps} updates, "
-                       f"torch-CPU fp32 op-for-op graph port, noise generated inside the step")
+    full = (k == K_full and nc == n_ctrl)
+    what = (f"the full workload per update (K={k}" + (f", {nc} controllers" if n_ctrl > 1 else "") + ")") if full else \
+        (f"K={k} of {K_full} samples per update" if n_ctrl == 1 else f"{nc} of {n_ctrl} controllers per update (K={k} each)")
+    return dict(value=k * T * nc * steps / total, threads=threads, ms_per_step=1e3 * total / steps, full=full,
+                sample=f"{what}, T={T}, a={a}, {steps} updates after {warmup} warm-up, torch-CPU fp32 op-for-op graph port "
+                       f"(oracle/graph_oracle.py), noise generated inside the step, {threads} threads")
+
+
+def cpu_c_run(K_full, T, s, a, n_ctrl, budget_s=8.0):
+    """The fused OpenMP C restatement (oracle/mppi_oracle.c, fp32) on a bounded sample; noise drawn by numpy outside the
+    timed region (the C oracle takes eps as an input)."""
+    from oracle import Oracle, pyoracle
+    cpu_threads()
+    orc = Oracle("f32")
+    cfg = dict(k=0, tau=T, s_dim=s, a_dim=a, dt=0.1, mass=1.0, sigma=0.25 * np.eye(a, dtype=np.float32),
+               goal=np.tile([1.0, 0.0], a).astype(np.float32), q=np.ones(s, np.float32))
+    cfg["lambda"] = 1.0
+    rng = np.random.default_rng(1)
+    k = min(K_full * n_ctrl, 65536)
+    x, U = np.zeros(s, np.float32), np.zeros((T, a), np.float32)
+    eps = (0.25 * rng.standard_normal((k, T, a), dtype=np.float32))
+    cfg["k"] = k
+    orc.mppi_update(cfg, x, U, eps)
+    t0 = time.perf_counter()
+    orc.mppi_update(cfg, x, U, eps)
+    per = (time.perf_counter() - t0) / k
+    k2 = int(max(k, min(K_full * n_ctrl, budget_s / 3 / max(per, 1e-12))))
+    if k2 != k:
+        k = k2
+        eps = (0.25 * rng.standard_normal((k, T, a), dtype=np.float32))
+        cfg["k"] = k
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        orc.mppi_update(cfg, x, U, eps)
+        times.append(time.perf_counter() - t0)
+    return {"value": k * T * 3 / sum(times), "unit": UNIT, "cores": pyoracle.num_threads(), "kind": "port",
+            "sample": f"K={k} samples per update (T={T}, a={a}), 3 updates, fused OpenMP C restatement (oracle/mppi_oracle.c, fp32); "
+                      f"noise drawn outside the timed region"}
+
+
+def cpu_mlp_run(K_full, T, s, a, budget_s=10.0):
+    """Config 4 on the CPU: the OpenMP C restatement of the MLP rollout (fp32), bounded sample."""
+    from oracle import Oracle, pyoracle
+    cpu_threads()
+    orc = Oracle("f32")
+    mlp = glorot_mlp(s, a)
+    mlp.update(Xmean=np.zeros(s + a, np.float32), Xstd=np.ones(s + a, np.float32), Ymean=np.zeros(s, np.float32), Ystd=np.ones(s, np.float32))
+    cfg = dict(k=2048, tau=T, s_dim=s, a_dim=a, dt=0.1, mass=1.0, sigma=0.25 * np.eye(a, dtype=np.float32),
+               goal=np.tile([1.0, 0.0], a).astype(np.float32), q=np.ones(s, np.float32))
+    cfg["lambda"] = 1.0
+    rng = np.random.default_rng(1)
+    x, U = np.zeros(s, np.float32), np.zeros((T, a), np.float32)
+    eps = 0.25 * rng.standard_normal((2048, T, a), dtype=np.float32)
+    t0 = time.perf_counter()
+    orc.mppi_update_mlp(cfg, mlp, x, U, eps)
+    per = (time.perf_counter() - t0) / 2048
+    k = int(max(2048, min(K_full, budget_s / 2 / max(per, 1e-12))))
+    cfg["k"] = k
+    eps = 0.25 * rng.standard_normal((k, T, a), dtype=np.float32)
+    times = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        orc.mppi_update_mlp(cfg, mlp, x, U, eps)
+        times.append(time.perf_counter() - t0)
+    return {"value": k * T * 2 / sum(times), "unit": UNIT, "cores": pyoracle.num_threads(), "kind": "port",
+            "sample": f"K={k} of {K_full} samples per update (T={T}), 2 updates, OpenMP C restatement of the MLP rollout (fp32)"}
+
+
+def cpu_auv_throughput(K_full, T, budget_s=15.0):
+    """CPU arm of the AUV workload: the OpenMP C restatement (oracle/, kind "port") on a bounded sample of K."""
+    from oracle import Oracle, pyoracle                     # bench.py's cpu_baseline leg may use oracle/
+    cpu_threads()
+    orc = Oracle("f32")
+    prm = auv_params()
+    rng = np.random.default_rng(1)
+    sigma = 80.0 * np.eye(6)
+    x = np.zeros(13); x[6] = 1.0
+    U = np.zeros((T, 6))
+    k = 4096
+    eps = (80.0 * rng.standard_normal((k, T, 6))).astype(np.float32)
+    t0 = time.perf_counter()
+    orc.mppi_update_auv(prm, 0.1, 2, 1.0, sigma, x, np.ones(13), x, U, eps)
+    per = (time.perf_counter() - t0) / k
+    k = int(max(4096, min(K_full, budget_s / 4 / max(per, 1e-9))))
+    eps = (80.0 * rng.standard_normal((k, T, 6))).astype(np.float32)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        orc.mppi_update_auv(prm, 0.1, 2, 1.0, sigma, x, np.ones(13), x, U, eps)
+        times.append(time.perf_counter() - t0)
+    return dict(value=k * T * 3 / sum(times), threads=pyoracle.num_threads(), ms_per_step=None, full=False,
+                sample=f"K={k} of {K_full} samples per update (T={T}), 3 updates, OpenMP C restatement of the Python controller "
+                       f"with AUVModel rk2 (noise generation not included)")
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the CPU stand-in of the reference on this box's host cores, the driver's --steps / --warmup, the
+    full workload per step whenever the run fits a few minutes.  Rank 0 only."""
     if rank != 0:
         return
     desc, K, T, s, a, n_ctrl = WORKLOADS[args.workload]
-    steps = max(1, min(args.steps, 5))
-    warm = 3                                   # W >= 3 warm-up steps, each a bounded CPU sample
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     if args.workload in AUV_WORKLOADS:
         r = cpu_auv_throughput(K, T, budget_s=60.0)
-        r["ms_per_step"] = None
+    elif args.workload in MLP_WORKLOADS:
+        m = cpu_mlp_run(K, T, s, a, budget_s=60.0)
+        r = dict(value=m["value"], threads=m["cores"], ms_per_step=None, full=False, sample=m["sample"])
     else:
-        r = cpu_port_throughput(K, T, s, a, steps, warm, budget_s=60.0)
+        r = cpu_port_run(K, T, s, a, n_ctrl, steps, warm, budget_s=240.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "K": K, "T": T, "s_dim": s, "a_dim": a, "n_controllers": n_ctrl},
+            "scaling": "strong" if n_ctrl == 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload),
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-                             "sample": r["sample"]},
+                             "sample": r["sample"], "full_workload_per_step": r["full"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def make_controller(name, dev_index, stream, rounds, lam=1.0, rank=0, world=1, k_override=0, seed=1):
+    """Controller + initial state of a workload (this rank's shard of it)."""
+    from mppi_tf_b200 import ControllerBase
+    desc, K, T, s, a, n_ctrl = WORKLOADS[name]
+    if k_override:
+        K = k_override
+    is_auv, is_mlp = name in AUV_WORKLOADS, name in MLP_WORKLOADS
+    rng = np.random.default_rng(5)
+    if n_ctrl > 1:                          # independent controllers: partitioned across ranks, no exchange at all
+        n_local, k_world, k_rank = n_ctrl // world, 1, 0
+        goal = rng.uniform(-1, 1, (n_ctrl, s)).astype(np.float32)[rank * n_local:(rank + 1) * n_local]
+        x = rng.uniform(-1, 1, (n_ctrl, s)).astype(np.float32)[rank * n_local:(rank + 1) * n_local]
+    else:
+        n_local, k_world, k_rank = 1, world, rank
+        goal = None
+        x = np.zeros((1, s), np.float32)
+    sigma = (80.0 if is_auv else 0.25) * np.eye(a, dtype=np.float32)
+    ctrl = ControllerBase(K, T, 0.1, 1.0, s, a, lam=lam, sigma=sigma, goal=goal, seed=seed, device=dev_index,
+                          rank=k_rank, world=k_world, n_controllers=n_local, goal_per_controller=(n_ctrl > 1), stream=stream,
+                          model=("auv" if is_auv else "point_mass"), philox_rounds=rounds)
+    if is_auv:
+        ctrl.setAuvModel(auv_params(), rk=2)
+        ctrl.setActionCost("python", gamma=1.0, upsilon=1.0)
+        x[:, 6] = 1.0                       # identity attitude (a zero quaternion is not a state)
+        x[:, 0] = 1.0
+    if is_mlp:
+        ctrl.setMlp(glorot_mlp(s, a))
+    return ctrl, x, dict(K=K, T=T, s=s, a=a, n_ctrl=n_ctrl, n_local=n_local, k_world=k_world)
+
+
+def nonzero_weight_frac(ctrl, n_local, lam):
+    c = np.asarray(ctrl.getCosts(), np.float64).reshape(n_local, -1)
+    return float(np.mean((c - c.min(1, keepdims=True)) * 1.4426950408889634 / lam < 126.0))
+
+
+def time_updates(torch, ctrl, flush, steps, warmup, eps_ptr=None):
+    """Device-timed updates on the current stream: per-step CUDA-event times (ms), L2 flushed between iterations."""
+    for _ in range(warmup):
+        ctrl.enqueueUpdate(eps_ptr)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        flush.zero_()
+        ev[i][0].record()
+        ctrl.enqueueUpdate(eps_ptr)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    return [e0.elapsed_time(e1) for e0, e1 in ev]
+
+
+def roofline_of(name, info, ms, peak, peak_src, kernel, world=1):
+    if name in MLP_WORKLOADS:
+        tpeak, tsrc = measured_tensor_peak()
+        tf = MLP_FLOPS_PER_SAMPLE_STEP * (info["K"] // info["k_world"]) * info["T"] / (ms * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": "rollout_mlp_kernel", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
+                "frac": tf / tpeak, "traffic": measured_traffic(name, "rollout_mlp_kernel") if world == 1 else None, "peak_source": tsrc,
+                "note": "algorithmic flops 2*(9*128+128*128+128*6) = 36608 per sample-step (unpadded)"}
+    b = bytes_alg(info["K"] // info["k_world"], info["T"], info["a"], info["n_local"])
+    ach = b / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": measured_traffic(name, kernel) if world == 1 else None, "peak_source": peak_src}
+
+
+def philox_kernel_name(ctrl_info, name):
+    if name in AUV_WORKLOADS:
+        return "rollout_auv_kernel"
+    ta = ctrl_info["T"] * ctrl_info["a"]
+    return "rollout_philox_resident_kernel" if (ta + 3) // 4 <= 37 else "rollout_philox_fast_kernel"
+
+
+def side_config(torch, name, dev_index, stream, flush, rounds, steps, peak, peak_src, lam=1.0):
+    """One BASELINE config at full size on this GPU: ~`steps` device-timed updates (other_configs / dense_weights)."""
+    ctrl, x, info = make_controller(name, dev_index, stream, rounds, lam=lam)
+    try:
+        ctrl.setState(x)
+        ms = time_updates(torch, ctrl, flush, steps, 5)
+        m = statistics.mean(ms)
+        units = info["K"] * info["T"] * info["n_ctrl"]
+        out = {"workload": WORKLOADS[name][0], "ms_per_step": m, "value": units / (m * 1e-3), "steps": steps, "lambda": lam,
+               "roofline": roofline_of(name, info, m, peak, peak_src, philox_kernel_name(info, name)),
+               "nonzero_weight_frac": round(nonzero_weight_frac(ctrl, info["n_local"], lam), 4)}
+        # latency through the synchronous public call (host buffers)
+        lat = []
+        for i in range(5 + steps):
+            t0 = time.perf_counter()
+            ctrl.next(x)
+            if i >= 5:
+                lat.append(1e3 * (time.perf_counter() - t0))
+        out["e2e_p50_ms"] = sorted(lat)[len(lat) // 2]
+        return out
+    finally:
+        ctrl.close()
+
+
 def main():
     # keep stdout clean for the ONE JSON line: libraries (NCCL version banner, ...) write to fd 1
     real_stdout = os.dup(1)
@@ -242,7 +455,11 @@ def main():
                          "mapped), in-library ncclAllGather, or torch.distributed all_gather on external buffers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-injected", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip other_configs / dense_weights (developer runs)")
     ap.add_argument("--k-override", type=int, default=0, help="developer knob: replace the workload's K (not a bench line)")
+    ap.add_argument("--philox-rounds", type=int, default=7, choices=[7, 10],
+                    help="rounds of the Philox4x32 noise generator (library default 10; the bench runs the 7-round variant, "
+                         "pinned on Random123's known-answer vectors, and says so in run.mode)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -256,7 +473,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from mppi_tf_b200 import ControllerBase, comm_unique_id
+    from mppi_tf_b200 import comm_unique_id
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
@@ -267,81 +484,61 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
-    desc, K, T, s, a, n_ctrl = WORKLOADS[args.workload]
-    if args.k_override:
-        K, desc = args.k_override, desc + f" [K overridden to {args.k_override}: developer run, not the BASELINE config]"
-    if n_ctrl > 1:
-        # independent controllers: partition the controllers across ranks, no exchange at all
-        n_local = n_ctrl // world
-        k_rank, k_world, k_rankid = K, 1, 0
-    else:
-        n_local = 1
-        k_rank, k_world, k_rankid = K, world, rank
-    is_auv = args.workload in AUV_WORKLOADS
-    sigma = (80.0 if is_auv else 0.25) * np.eye(a, dtype=np.float32)
-    rng = np.random.default_rng(5)
-    goal = None
-    if n_ctrl > 1:
-        goal = rng.uniform(-1, 1, (n_ctrl, s)).astype(np.float32)[rank * n_local:(rank + 1) * n_local]
+    name = args.workload
+    is_auv, is_mlp = name in AUV_WORKLOADS, name in MLP_WORKLOADS
     # a non-default torch stream: the library launches on it, and torch.cuda.Event records on it
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
-    ctrl = ControllerBase(k_rank, T, 0.1, 1.0, s, a, lam=1.0, sigma=sigma, goal=goal, seed=1, device=local_rank,
-                          rank=k_rankid, world=k_world, n_controllers=n_local,
-                          goal_per_controller=(n_ctrl > 1), stream=stream, model=("auv" if is_auv else "point_mass"))
-    if is_auv:
-        ctrl.setAuvModel(auv_params(), rk=2)
-        ctrl.setActionCost("python", gamma=1.0, upsilon=1.0)
-    is_mlp = args.workload in MLP_WORKLOADS
-    if is_mlp:
-        ctrl.setMlp(glorot_mlp(s, a))
+    ctrl, x, info = make_controller(name, local_rank, stream, args.philox_rounds, rank=rank, world=world, k_override=args.k_override)
+    K, T, s, a, n_ctrl, n_local, k_world = (info[k] for k in ("K", "T", "s", "a", "n_ctrl", "n_local", "k_world"))
     exchange = k_world > 1
-    if exchange and args.exchange == "peer":
-        # fused exchange: all-gather the CUDA IPC handles of the mailboxes once, then no collective call at all
-        ok = True
-        try:
-            handles = [None] * world
-            dist.all_gather_object(handles, ctrl.peerHandle())
-            ctrl.peerAttach(handles)
-        except Exception as e:                      # noqa: BLE001  (IPC not permitted / no peer access)
-            ok = False
-            print(f"[bench] rank {rank}: peer exchange unavailable ({e}); using nccl", file=sys.stderr)
-        flag = torch.tensor([1 if ok else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            if ok:
-                raise SystemExit("peer exchange attached on some ranks only")
-            args.exchange = "nccl"
-    if exchange:
-        if args.exchange == "peer":
-            pass
-        elif args.exchange == "nccl":
+
+    def wire_exchange(c):
+        """Fused exchange: all-gather the CUDA IPC handles of the mailboxes once, then no collective call at all."""
+        mode = args.exchange
+        if mode == "peer":
+            ok = True
+            try:
+                handles = [None] * world
+                dist.all_gather_object(handles, c.peerHandle())
+                c.peerAttach(handles)
+            except Exception as e:                      # noqa: BLE001  (IPC not permitted / no peer access)
+                ok = False
+                print(f"[bench] rank {rank}: peer exchange unavailable ({e}); using nccl", file=sys.stderr)
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if ok:
+                    raise SystemExit("peer exchange attached on some ranks only")
+                mode = "nccl"
+        if mode == "nccl":
             uid = [comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
-            ctrl.commInit(uid[0])
-        else:
+            c.commInit(uid[0])
+        return mode
+
+    send = recv = None
+    if exchange:
+        if args.exchange == "torch":
             stride = ctrl.exchangeStride()
             send = torch.zeros(stride, device=dev)
             recv = torch.zeros(world * stride, device=dev)
             ctrl.setExchangeBuffers(send.data_ptr(), recv.data_ptr())
-
-    x = np.zeros((n_local, s), np.float32) if n_ctrl == 1 else \
-        rng.uniform(-1, 1, (n_ctrl, s)).astype(np.float32)[rank * n_local:(rank + 1) * n_local]
-    if is_auv:
-        x[:, 6] = 1.0                               # identity attitude (a zero quaternion is not a state)
-        x[:, 0] = 1.0
+        else:
+            args.exchange = wire_exchange(ctrl)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def one_update(eps_ptr=None):
-        ctrl.enqueueUpdate(eps_ptr)
+    def one_update(eps_ptr=None, c=None):
+        c = c or ctrl
+        c.enqueueUpdate(eps_ptr)
         if exchange and args.exchange != "peer":             # peer: the update kernel exchanges and finishes itself
             if args.exchange == "nccl":
-                ctrl.enqueueExchange()                       # in-library ncclAllGather on the same stream
+                c.enqueueExchange()                          # in-library ncclAllGather on the same stream
             else:
                 dist.all_gather_into_tensor(recv, send)
-            ctrl.enqueueFinish()
+            c.enqueueFinish()
 
     def barrier():
         torch.cuda.synchronize()
@@ -383,15 +580,14 @@ def main():
             return ctrl.fetchAction()
         return ctrl.next(x)                             # the public synchronous call (in-library exchange)
 
-    act = None
     for _ in range(args.warmup):
-        act = api_next()
+        api_next()
     barrier()
     lat = []
     t_all0 = time.perf_counter()
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        act = api_next()
+        api_next()
         lat.append(time.perf_counter() - t0)
     e2e_s = time.perf_counter() - t_all0
     barrier()
@@ -402,94 +598,144 @@ def main():
     e2e_value = units_per_step * args.steps / e2e_s
     lat_ms = sorted(1e3 * v for v in lat)
     pct = lambda q: lat_ms[min(len(lat_ms) - 1, int(q * len(lat_ms)))]
+    clocks = sampler.stop() if sampler else None
+    nonzero_frac = nonzero_weight_frac(ctrl, n_local, 1.0)
+
+    # ---- N > 1: a correctness witness for the multi-rank path ------------------------------------------
+    parity = None
+    if world > 1:
+        # (i) every rank holds the bit-identical sequence after the timed region (same payloads merged in the same order)
+        seq_np = np.ascontiguousarray(ctrl.getSequence(), np.float32)
+        seq = torch.from_numpy(seq_np.view(np.int32).copy()).to(dev)
+        allseq = [torch.empty_like(seq) for _ in range(world)]
+        dist.all_gather(allseq, seq)
+        parity = {"finite": bool(np.isfinite(seq_np).all())}
+        if n_ctrl == 1:
+            parity["sequences_bit_identical_across_ranks"] = all(bool(torch.equal(allseq[0], t)) for t in allseq[1:])
+        if exchange:
+            # (ii) a reduced-K update sharded over all ranks (same exchange path) against ONE handle on rank 0 that owns all
+            # the samples: the Philox counter carries the global sample index, so both draw the same noise
+            from mppi_tf_b200 import ControllerBase
+            kc = 65536
+            sig = 0.25 * np.eye(a, dtype=np.float32)
+            xs = np.linspace(-0.5, 0.5, s).astype(np.float32)
+            U0 = (0.1 * np.sin(np.arange(T * a, dtype=np.float32))).reshape(T, a)
+            sh = ControllerBase(kc, T, 0.1, 1.0, s, a, sigma=sig, seed=7, device=local_rank, rank=rank, world=world, stream=stream,
+                                philox_rounds=args.philox_rounds)
+            try:
+                if args.exchange == "torch":
+                    sh.setExchangeBuffers(send.data_ptr(), recv.data_ptr())
+                else:
+                    wire_exchange(sh)
+                sh.setSequence(U0)
+                sh.setState(xs)
+                one_update(c=sh)
+                sh.fetchAction()
+                u_sh = np.ascontiguousarray(sh.getUpdate(), np.float32)
+            finally:
+                sh.close()
+            tsh = torch.from_numpy(u_sh.view(np.int32).copy()).to(dev)
+            allu = [torch.empty_like(tsh) for _ in range(world)]
+            dist.all_gather(allu, tsh)
+            parity["reduced_k_bit_identical_across_ranks"] = all(bool(torch.equal(allu[0], t)) for t in allu[1:])
+            if rank == 0:
+                one = ControllerBase(kc, T, 0.1, 1.0, s, a, sigma=sig, seed=7, device=local_rank, stream=stream,
+                                     philox_rounds=args.philox_rounds)
+                try:
+                    one.setSequence(U0)
+                    one.next(xs)
+                    u_one = one.getUpdate()
+                finally:
+                    one.close()
+                err = float(np.abs(u_sh.astype(np.float64) - u_one).max() / np.abs(u_one).max())
+                parity.update({"reduced_k": kc, "sharded_vs_single_handle_rel_err": err, "tolerance": 1e-5})
+        barrier()
+        if rank == 0:
+            parity["ok"] = bool(parity["finite"] and parity.get("sequences_bit_identical_across_ranks", True) and
+                                parity.get("reduced_k_bit_identical_across_ranks", True) and
+                                parity.get("sharded_vs_single_handle_rel_err", 0.0) <= 1e-5)
 
     # ---- HBM-bound injected-noise kernel (N = 1 only; inputs resident in HBM) -------------------------
     inj = None
+    n_eps = n_local * K * T * a
     if world == 1 and not args.no_injected and not is_mlp:
-        n_eps = n_local * K * T * a
         g = torch.Generator(device=dev).manual_seed(1234)
         eps = torch.randn(n_eps, device=dev, generator=g) * (80.0 if is_auv else 0.25)
-        isteps = max(10, min(args.steps, 50))
-        for _ in range(3):
-            one_update(eps.data_ptr())
-        torch.cuda.synchronize()
-        iev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(isteps)]
-        for i in range(isteps):
-            flush.zero_()
-            iev[i][0].record()
-            one_update(eps.data_ptr())
-            iev[i][1].record()
-        torch.cuda.synchronize()
-        ims = [e0.elapsed_time(e1) for e0, e1 in iev]
+        ims = time_updates(torch, ctrl, flush, max(10, min(args.steps, 50)), 3, eps.data_ptr())
         inj = statistics.mean(ims)
         del eps
-    clocks = sampler.stop() if sampler else None
-    # fraction of this rank's samples whose fp32 softmin weight is non-zero after the last update: the weighted
-    # noise sum revisits only those (an exact optimisation: 0 * z adds nothing), so the number is part of the workload
-    c_last = np.asarray(ctrl.getCosts(), np.float64).reshape(n_local, -1)
-    nonzero_frac = float(np.mean((c_last - c_last.min(1, keepdims=True)) * 1.4426950408889634 / 1.0 < 126.0))
+    ctrl.close()
+
+    # ---- N = 1: the same workload with dense weights, and the other BASELINE configs -------------------
+    peak, peak_src = measured_peaks()
+    dense = others = None
+    if world == 1 and not args.no_side and not args.k_override and rank == 0:
+        if name == "cfg3":
+            d = side_config(torch, "cfg3", local_rank, stream, flush, args.philox_rounds, 20, peak, peak_src, lam=DENSE_LAMBDA)
+            dense = {"lambda": DENSE_LAMBDA, "ms_per_step": d["ms_per_step"], "value": d["value"], "roofline_frac": d["roofline"]["frac"],
+                     "nonzero_weight_frac": d["nonzero_weight_frac"],
+                     "note": "every sample carries weight: the weighted noise sum regenerates all K*T*a normals a second time"}
+        others = {}
+        for other in ("cfg1", "cfg2", "cfg4", "cfg5"):
+            if other != name:
+                others[other] = side_config(torch, other, local_rank, stream, flush, args.philox_rounds, 20, peak, peak_src)
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
         ms_step = total_ms / args.steps
         kernel_ms = statistics.mean(per_step_ms)
-        b_alg = bytes_alg(K // k_world, T, a, n_local)          # per launch (this rank's shard)
-        achieved = b_alg / (kernel_ms * 1e-3) / 1e9
+        kname = philox_kernel_name(info, name)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if n_ctrl == 1 else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "K": K, "T": T, "s_dim": s, "a_dim": a, "n_controllers": n_ctrl,
-                       "mode": "philox (fresh noise regenerated in registers every update)",
-                       "sharding": f"K/{k_world} samples per rank" if n_ctrl == 1 else f"{n_local} controllers per rank",
-                       "exchange": (args.exchange if exchange else "none"),
-                       "l2": "flushed between timed iterations (256 MiB write, untimed)",
-                       "nonzero_weight_frac": round(nonzero_frac, 4)},
+            "vs_baseline": None, "dtype": "bf16" if is_mlp else "f32", "data": "synthetic",
+            "config": workload_config(name, args.k_override),
+            "run": {"mode": f"philox4x32-{args.philox_rounds} noise generated in registers every update, never stored "
+                            f"(library default: 10 rounds; both pinned on Random123's known-answer vectors)",
+                    "sharding": f"K/{k_world} samples per rank" if n_ctrl == 1 else f"{n_local} controllers per rank",
+                    "exchange": (args.exchange if exchange else "none"),
+                    "nonzero_weight_frac": round(nonzero_frac, 4)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * s * n_local),
                     "d2h_bytes_per_step": int(4 * a * n_local),
                     "latency_ms": {"p10": pct(0.10), "p50": pct(0.50), "p90": pct(0.90)}},
             "gpu_launches": args.steps * (2 if (exchange and args.exchange != "peer") else 1),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "rollout_philox_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(args.workload, "rollout_philox_kernel") if world == 1 and not args.k_override else None,
-                         "peak_source": peak_src,
-                         "note": "effective GB/s on the algorithmic bytes 4*a*K*T + 4*K; the Philox kernel moves "
-                                 "almost no HBM bytes and runs at the scheduler-dispatch bound of its instruction mix (DESIGN.md 3.1, profiles/)"},
+            "roofline": roofline_of(name, info, kernel_ms, peak, peak_src, kname, world),
         }
+        if not is_mlp:
+            line["roofline"]["note"] = ("effective GB/s on the algorithmic bytes 4*a*K*T + 4*K (what a stored-noise implementation "
+                                        "must move); the kernel itself moves almost no HBM bytes: its bound is the schedulers' "
+                                        "dispatch rate for its instruction mix (DESIGN.md 3.1, profiles/)")
         if is_auv:
-            line["config"]["mode"] = "philox noise + Fossen dynamics (Heun), fp32"
-            line["roofline"]["kernel"] = "rollout_auv_kernel"
-            line["roofline"]["traffic"] = None
-            line["roofline"]["note"] = ("effective GB/s on the algorithmic bytes 4*a*K*T + 4*K; the kernel is bound by its fp32 FFMA "
-                                        "chains (DESIGN.md 3.5: 70 % issue-active, 45 % of the FFMA peak)")
+            line["run"]["mode"] = f"philox4x32-{args.philox_rounds} noise + Fossen dynamics (Heun), fp32"
         if is_mlp:
-            tpeak, tsrc = measured_tensor_peak()
-            tf = MLP_FLOPS_PER_SAMPLE_STEP * (K // k_world) * T / (kernel_ms * 1e-3) / 1e12
-            line["dtype"] = "bf16"
-            line["config"]["mode"] = "philox noise + bf16 tcgen05 MLP rollout (fp32 state and accumulation)"
-            line["roofline"] = {"bound": "tensor", "kernel": "rollout_mlp_kernel", "achieved": tf, "peak": tpeak,
-                                "unit": "TFLOP/s", "frac": tf / tpeak,
-                                "traffic": measured_traffic(args.workload, "rollout_mlp_kernel") if world == 1 and not args.k_override else None,
-                                "peak_source": tsrc,
-                                "note": "algorithmic flops 2*(9*128+128*128+128*6) = 36608 per sample-step (unpadded)"}
+            line["run"]["mode"] = f"philox4x32-{args.philox_rounds} noise + bf16 tcgen05 MLP rollout (fp32 state and accumulation)"
         if inj is not None:
             ia = bytes_alg(K, T, a, n_local) / (inj * 1e-3) / 1e9
-            line["roofline_injected"] = {"bound": "hbm", "kernel": "rollout_auv_kernel<injected>" if is_auv else "rollout_injected_kernel", "achieved": ia,
-                                         "peak": peak, "unit": "GB/s", "frac": ia / peak,
-                                         "traffic": measured_traffic(args.workload, "rollout_injected_kernel") if not args.k_override else None,
+            line["roofline_injected"] = {"bound": "hbm", "kernel": "rollout_auv_kernel<injected>" if is_auv else "rollout_injected_kernel",
+                                         "achieved": ia, "peak": peak, "unit": "GB/s", "frac": ia / peak,
+                                         "traffic": measured_traffic(name, "rollout_injected_kernel") if not args.k_override else None,
                                          "ms_per_launch": inj,
                                          "inputs": "eps resident in HBM" + (" (larger than L2)" if 4 * n_eps > 126e6 else " (L2 flushed)")}
-        if not args.no_cpu_baseline and world == 1 and is_auv:
-            r = cpu_auv_throughput(K, T)
-            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"]}
-        elif not args.no_cpu_baseline and world == 1 and not is_mlp:
-            r = cpu_port_throughput(K, T, s, a, steps=3, warmup=1, budget_s=15.0)
-            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-                                    "sample": r["sample"]}
+        if dense is not None:
+            line["dense_weights"] = dense
+        if others is not None:
+            line["other_configs"] = others
+        if parity is not None:
+            line["parity_check"] = parity
+        if not args.no_cpu_baseline and world == 1:
+            if is_auv:
+                r = cpu_auv_throughput(K, T)
+                line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"]}
+            elif is_mlp:
+                line["cpu_baseline"] = cpu_mlp_run(K, T, s, a)
+            else:
+                r = cpu_port_run(K, T, s, a, n_ctrl, steps=3, warmup=1, budget_s=15.0)
+                line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"]}
+                line["cpu_baseline_c"] = cpu_c_run(K, T, s, a, n_ctrl)
+            if others and "cfg4" in others:
+                others["cfg4"]["cpu_baseline"] = cpu_mlp_run(262144, 50, 6, 3, budget_s=6.0)
         print(json.dumps(line), flush=True)
-    ctrl.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -82,6 +82,11 @@ typedef struct {
     int model;             /* mppi_model_kind at construction: MPPI_MODEL_POINT_MASS (0, default) or MPPI_MODEL_AUV
                             * (s_dim = 13, a_dim = 6; mppi_set_auv_model must follow).  MPPI_MODEL_MLP is selected
                             * later, by mppi_set_mlp on a point-mass handle. */
+    int philox_rounds;     /* rounds of the Philox4x32 noise generator: 10 (Random123's default and the generator behind
+                            * TensorFlow's RandomNormal; 0 means 10) or 7 (the shortest variant of Salmon et al. that passes
+                            * BigCrush; SURVEY.md section 7 allows a cheaper generator: parity is checked on injected noise
+                            * and on store-then-replay of whatever stream was drawn).  Both are pinned on Random123's
+                            * known-answer vectors (tests/golden/kats.py). */
 } mppi_config;
 
 /* Fill *cfg with the reference constructor's defaults for the given sizes. */
@@ -132,7 +137,12 @@ int mppi_synchronize(mppi_handle *h);
 /* ---- controller state ---------------------------------------------------------------------- */
 /* replaces ControllerBase::setGoal (src/controller_base.cpp:126-133) — and takes effect, which
  * the reference's does not (the goal is baked into the graph as a Const, src/cost_base.cpp:57). */
-int mppi_set_goal(mppi_handle *h, const float *goal_host);       /* [s] or [n][s] */
+int mppi_set_goal(mppi_handle *h, const float *goal_host);       /* [s] (shared goal) or [n][s] (goal_per_controller): the
+                                                                  * handle's mode decides how many floats are read */
+/* The same with the row count stated: n_rows = 1 sets the goal of every controller (broadcast on goal_per_controller
+ * handles); n_rows = n_controllers needs a goal_per_controller handle (MPPI_ERR_BAD_ARG otherwise).  The C++ and Python
+ * ControllerBase::setGoal go through this entry, so a size that does not fit the handle's mode is never read past. */
+int mppi_set_goal_n(mppi_handle *h, const float *goal_host, int n_rows);
 int mppi_set_lambda(mppi_handle *h, float lambda);
 int mppi_set_sigma(mppi_handle *h, const float *sigma_host);     /* [a][a], must be invertible */
 /* Python-twin extras (/root/reference/scripts/src):
@@ -312,6 +322,9 @@ int mppi_shift(int T, int a, const float *cur, const float *init, int nb, float 
  * out [n_calls][4] for counter (call0 + i, sample, update, stream). */
 int mppi_philox_raw(int device, uint64_t seed, uint32_t call0, uint32_t sample, uint32_t update,
                     uint32_t stream, int n_calls, uint32_t *out);
+/* The same with the round count (7 or 10) of mppi_config.philox_rounds. */
+int mppi_philox_raw_rounds(int device, uint64_t seed, uint32_t call0, uint32_t sample, uint32_t update,
+                           uint32_t stream, int n_calls, int rounds, uint32_t *out);
 
 /* Library/version info: returns a static string such as "mppi_b200 0.1 sm_100a". */
 const char *mppi_version(void);

@@ -29,6 +29,7 @@ class MppiConfig(C.Structure):
         ("n_controllers", C.c_int), ("goal_per_controller", C.c_int),
         ("stream", C.c_void_p),
         ("model", C.c_int),
+        ("philox_rounds", C.c_int),
     ]
 
 
@@ -72,6 +73,7 @@ SYMBOLS = {
     "mppi_fetch_action": (_i, [_H, _fp]),
     "mppi_synchronize": (_i, [_H]),
     "mppi_set_goal": (_i, [_H, _fp]),
+    "mppi_set_goal_n": (_i, [_H, _fp, _i]),
     "mppi_set_lambda": (_i, [_H, _f]),
     "mppi_set_sigma": (_i, [_H, _fp]),
     "mppi_set_action_cost": (_i, [_H, _i, _f, _f]),
@@ -126,6 +128,7 @@ SYMBOLS = {
     "mppi_get_new": (_i, [_i, _i, _fp, _i, _fp]),
     "mppi_shift": (_i, [_i, _i, _fp, _fp, _i, _fp]),
     "mppi_philox_raw": (_i, [_i, _u64, _u32, _u32, _u32, _u32, _i, C.POINTER(_u32)]),
+    "mppi_philox_raw_rounds": (_i, [_i, _u64, _u32, _u32, _u32, _u32, _i, _i, C.POINTER(_u32)]),
 }
 
 _lib = None

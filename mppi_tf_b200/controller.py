@@ -158,17 +158,23 @@ class ControllerBase:
     Extra keyword arguments expose what the reference hard-codes in its constructor
     (lambda=1, sigma=I, goal=(1,0,..), Q=1; src/controller_base.cpp:37-69) and the B200 additions:
     rank/world sample sharding, n_controllers batching, an external CUDA stream.
+
+    `mass` behaves as in the reference's C++ class and in include/controller_base.hpp: it is stored and NOT forwarded
+    to the model, which is built with mass 1 (src/controller_base.cpp:32,68).  `model_mass` (or setModelMass) sets the
+    mass the dynamics use.
     """
 
     def __init__(self, k, tau, dt, mass, s_dim, a_dim, lam=1.0, sigma=None, goal=None, Q=None, seed=1,
-                 device=-1, rank=0, world=1, n_controllers=1, goal_per_controller=False, stream=None, model="point_mass"):
+                 device=-1, rank=0, world=1, n_controllers=1, goal_per_controller=False, stream=None, model="point_mass",
+                 philox_rounds=10, model_mass=1.0):
         self._lib = _capi.load()
         self.k, self.tau, self.dt, self.mass, self.s_dim, self.a_dim = k, tau, dt, mass, s_dim, a_dim
         self.n = n_controllers
         self.device = device
         self._lam = float(lam)
+        self._goal_per_controller = bool(goal_per_controller)
         cfg = MppiConfig()
-        self._lib.mppi_config_default(C.byref(cfg), k, tau, dt, mass, s_dim, a_dim)
+        self._lib.mppi_config_default(C.byref(cfg), k, tau, dt, float(model_mass), s_dim, a_dim)
         cfg.lambda_ = lam
         keep = []
         for name, val in (("sigma", sigma), ("goal", goal), ("q", Q)):
@@ -183,6 +189,7 @@ class ControllerBase:
         cfg.goal_per_controller = 1 if goal_per_controller else 0
         cfg.stream = stream
         cfg.model = {"point_mass": _capi.MODEL_POINT_MASS, "auv": _capi.MODEL_AUV}[model]
+        cfg.philox_rounds = int(philox_rounds)
         self._h = C.c_void_p()
         check(self._lib.mppi_create(C.byref(cfg), C.byref(self._h)))
         self.k_local = self._lib.mppi_k_local(self._h)
@@ -211,12 +218,20 @@ class ControllerBase:
         return self._shape_out(self._action)
 
     def setGoal(self, goal):
-        """ControllerBase::setGoal — src/controller_base.cpp:126-133 (size mismatch -> False)."""
+        """ControllerBase::setGoal — src/controller_base.cpp:126-133 (size mismatch -> False).  [s_dim] sets the goal of
+        every controller of the handle; [n, s_dim] one goal each, on handles created with goal_per_controller."""
         g = _f32(goal).ravel()
-        if g.size not in (self.s_dim, self.n * self.s_dim):
+        if g.size == self.s_dim:
+            rows = 1
+        elif g.size == self.n * self.s_dim and self._goal_per_controller:
+            rows = self.n
+        else:
             return False
-        check(self._lib.mppi_set_goal(self._h, _ptr(g)), self._h)
+        check(self._lib.mppi_set_goal_n(self._h, _ptr(g), rows), self._h)
         return True
+
+    def setModelMass(self, mass):
+        check(self._lib.mppi_set_mass(self._h, float(mass)), self._h)
 
     # ---- parity / debug ---------------------------------------------------------------------------
     def nextWithNoise(self, x, eps):
@@ -466,9 +481,9 @@ def comm_unique_id():
     return bytes(buf.raw)
 
 
-def philox_raw(seed, call0, sample, update, stream, n_calls, device=-1):
+def philox_raw(seed, call0, sample, update, stream, n_calls, device=-1, rounds=10):
     lib = _capi.load()
     out = np.empty((n_calls, 4), np.uint32)
-    check(lib.mppi_philox_raw(device, seed, call0, sample, update, stream, n_calls,
-                              out.ctypes.data_as(C.POINTER(C.c_uint32))))
+    check(lib.mppi_philox_raw_rounds(device, seed, call0, sample, update, stream, n_calls, int(rounds),
+                                     out.ctypes.data_as(C.POINTER(C.c_uint32))))
     return out

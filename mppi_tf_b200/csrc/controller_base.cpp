@@ -50,7 +50,7 @@ bool ControllerBase::setGoal(std::vector<float> goal)
         std::cerr << "Wrong goal size, it should match the state dimension: " << m_s_dim << std::endl;
         return false;
     }
-    return mppi_set_goal(m_h, goal.data()) == MPPI_OK;
+    return mppi_set_goal_n(m_h, goal.data(), 1) == MPPI_OK;     // every controller of the handle gets this goal
 }
 
 std::vector<float> ControllerBase::next(std::vector<float> x)

@@ -100,7 +100,8 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
         float x[kAuvS];
 #pragma unroll
         for (int i = 0; i < kAuvS; i++) x[i] = x0[i];
-        float S = C0;
+        KahanSum Sk_;                               // per-step costs added with compensation (mppi_device.cuh)
+        Sk_.init(C0);
         if (PHILOX) {
             // flattened [T][6] row: call c yields normals 4c .. 4c+3; two steps = three calls
             uint32_t call = 0;
@@ -115,7 +116,9 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
                     float n[A];
 #pragma unroll
                     for (int j = 0; j < A; j++) n[j] = z[tt * A + j];
-                    auv_rollout_step<true, RK>(p, P, sUV + (t + tt) * RS, n, g, x, S);
+                    float S1 = 0.f;
+                    auv_rollout_step<true, RK>(p, P, sUV + (t + tt) * RS, n, g, x, S1);
+                    Sk_.add(S1);
                 }
             }
             if (t < p.T) {
@@ -125,7 +128,9 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
                 float n[A];
 #pragma unroll
                 for (int j = 0; j < A; j++) n[j] = z[j];
-                auv_rollout_step<true, RK>(p, P, sUV + t * RS, n, g, x, S);
+                float S1 = 0.f;
+                auv_rollout_step<true, RK>(p, P, sUV + t * RS, n, g, x, S1);
+                Sk_.add(S1);
             }
         } else {
             const float2 *row = reinterpret_cast<const float2 *>(eps + (size_t)k * TA);   // TA = 6 T: 8-byte aligned rows
@@ -137,10 +142,13 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
                     n[2 * j] = v.x;
                     n[2 * j + 1] = v.y;
                 }
-                auv_rollout_step<false, RK>(p, P, sUV + t * RS, n, g, x, S);
+                float S1 = 0.f;
+                auv_rollout_step<false, RK>(p, P, sUV + t * RS, n, g, x, S1);
+                Sk_.add(S1);
             }
         }
-        S += auv_state_cost(p.cost_kind, p.q, g, p.ell, x);          // terminal cost on top of step T-1's
+        Sk_.add(auv_state_cost(p.cost_kind, p.q, g, p.ell, x));      // terminal cost on top of step T-1's
+        const float S = Sk_.s;
         costs[k] = S;
         bmin = fminf(bmin, S);
         bmax = fmaxf(bmax, S);

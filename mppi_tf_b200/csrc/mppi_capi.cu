@@ -15,6 +15,7 @@
 #include "mppi_internal.h"
 #include "mppi_auv.cuh"
 #include "mppi_mlp.cuh"
+#include "mppi_linear.cuh"
 
 using namespace mppi;
 
@@ -73,6 +74,12 @@ struct mppi_handle {
     int cost_kind = 0;            // 0 StaticCost, 1 ElipseCost (mppi_set_ellipse_cost)
     float ell[12] = {0};
     uint64_t seed = 1;
+    int rounds = 10;              // Philox4x32-R (mppi_config.philox_rounds)
+    int kernel_variant = 0;       // developer knob MPPI_PHILOX_KERNEL: 0 pick, 1 regenerating superposition kernel, 2 resident-tile
+                                  // kernel, 3 direct-form kernels only
+    bool last_fast = false;       // the last update ran in the superposition form: costs / beta on the device are relative to d_cost_base
+    float *d_cost_base = nullptr;
+    size_t smem_sm = 0;
     uint32_t update_counter = 0, last_update = 0;
     bool have_philox_update = false, last_philox = true, pending_finish = false;
     int device = 0, num_sms = 148;
@@ -169,6 +176,19 @@ void derive_sigma(mppi_handle *h)
         }
 }
 
+// Superposition form (mppi_linear.cuh): point-mass model, diagonal Sigma, q > 0, StaticCost, no noise-quadratic term.
+bool fast_eligible(const mppi_handle *h, const float *eps_dev)
+{
+    if (h->auv || h->mlp || h->kernel_variant == 3) return false;
+    if (h->cost_kind != 0 || h->tau > kFastMaxT) return false;
+    if (!eps_dev && !h->sigma_diag) return false; // Philox mode folds the (diagonal) scale into the noise response; injected
+                                                  // noise arrives scaled, any Sigma
+    if (h->cost_form == MPPI_ACTION_COST_PYTHON && h->upsilon != 1.0f && h->lambda != 0.f) return false;   // kappa != 0
+    for (int i = 0; i < h->s; i++)
+        if (!(h->q[i] > 0.f)) return false;
+    return true;
+}
+
 RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
 {
     RolloutParams p;
@@ -226,6 +246,19 @@ RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
         p.rk0[r] = p.key0 + (uint32_t)r * kPhiloxW0;
         p.rk1[r] = p.key1 + (uint32_t)r * kPhiloxW1;
     }
+    p.rounds = h->rounds;
+    p.fast = fast_eligible(h, eps_dev) ? 1 : 0;
+    p.z_scale = 1.0f;
+    p.cost_base = h->d_cost_base;
+    if (p.fast) {
+        p.z_scale = eps_dev ? 1.0f : kZScale;     // injected mode: n = eps, nothing folded
+        for (int j = 0; j < a; j++) {
+            const float sqp = p.sqrt_q[2 * j], sqv = p.sqrt_q[2 * j + 1], sg = eps_dev ? 1.0f : p.sigma[j * a + j];
+            p.fa1[j] = p.dt * sqp / sqv;
+            p.fb1[j] = p.z_scale * sqp * p.c_pu * sg;
+            p.fb2[j] = p.z_scale * sqv * p.c_vu * sg;
+        }
+    }
     p.x_inline = (h->n_ctrl == 1);
     if (p.x_inline) memcpy(p.x0, h->h_x, sizeof(float) * h->s);
     p.x = h->d_x;
@@ -278,6 +311,7 @@ void mppi_config_default(mppi_config *cfg, int k, int tau, float dt, float mass,
     cfg->k = k; cfg->tau = tau; cfg->dt = dt; cfg->mass = mass; cfg->s_dim = s_dim; cfg->a_dim = a_dim;
     cfg->lambda = 1.0f;       // src/controller_base.cpp:40
     cfg->seed = 1;            // RandomNormal::Seed(1), src/controller_base.cpp:199
+    cfg->philox_rounds = 10;  // Philox4x32-10, the generator behind TensorFlow's RandomNormal
     cfg->device = -1;
     cfg->rank = 0; cfg->world = 1; cfg->n_controllers = 1;
 }
@@ -312,6 +346,17 @@ int mppi_create(const mppi_config *cfg, mppi_handle **out)
     if (rc != MPPI_OK) { g_last_error = h->err; delete h; return rc; }
     h->num_sms = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->smem_sm = prop.sharedMemPerMultiprocessor;
+    if (cfg->philox_rounds != 0 && cfg->philox_rounds != 7 && cfg->philox_rounds != 10) {
+        delete h;
+        return fail(nullptr, MPPI_ERR_BAD_ARG, "philox_rounds must be 0 (= 10), 7 or 10");
+    }
+    h->rounds = cfg->philox_rounds ? cfg->philox_rounds : 10;
+    if (const char *kv = getenv("MPPI_PHILOX_KERNEL")) {
+        if (!strcmp(kv, "regen")) h->kernel_variant = 1;
+        else if (!strcmp(kv, "resident")) h->kernel_variant = 2;
+        else if (!strcmp(kv, "direct")) h->kernel_variant = 3;
+    }
 
     h->k = cfg->k; h->tau = cfg->tau; h->s = cfg->s_dim; h->a = cfg->a_dim;
     h->n_ctrl = n_ctrl; h->rank = cfg->rank; h->world = world;
@@ -365,6 +410,8 @@ int mppi_create(const mppi_config *cfg, mppi_handle **out)
     CU_TRY_C(cudaMalloc(&h->d_gather, sizeof(float) * (size_t)world * n_ctrl * h->stride));
     CU_TRY_C(cudaMalloc(&h->d_stats, sizeof(float) * 2 * n_ctrl));
     CU_TRY_C(cudaMalloc(&h->d_norm, sizeof(float) * 2 * n_ctrl));
+    CU_TRY_C(cudaMalloc(&h->d_cost_base, sizeof(float) * n_ctrl));
+    CU_TRY_C(cudaMemset(h->d_cost_base, 0, sizeof(float) * n_ctrl));
     CU_TRY_C(cudaMalloc(&h->d_counters, sizeof(unsigned int) * n_ctrl));
     CU_TRY_C(cudaMemset(h->d_counters, 0, sizeof(unsigned int) * n_ctrl));
     CU_TRY_C(cudaMemset(h->d_U, 0, sizeof(float) * n_ctrl * h->TA));
@@ -410,6 +457,7 @@ int mppi_destroy(mppi_handle *h)
     cudaFree(h->d_x); cudaFree(h->d_goal); cudaFree(h->d_U); cudaFree(h->d_Unew); cudaFree(h->d_next);
     cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_counters);
     cudaFree(h->d_norm);
+    cudaFree(h->d_cost_base);
     cudaFree(h->d_eps_tmp);
     cudaFree(h->d_wblob);
     cudaFree(h->d_fvec);
@@ -474,6 +522,11 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
             if (e == cudaErrorInvalidConfiguration)
                 return fail(h, MPPI_ERR_UNSUPPORTED, "injected-noise mode: one 32-sample tile of tau*a_dim floats does not fit shared memory");
             CU_TRY(h, e);
+        } else if (p.fast) {
+            cudaError_t e = launch_rollout_philox_fast(p, h->a, h->kernel_variant, h->num_sms, h->smem_sm, h->smem_optin, h->stream, &gx);
+            if (e == cudaErrorInvalidConfiguration)
+                return fail(h, MPPI_ERR_UNSUPPORTED, "tau*a_dim is too large for the per-CTA shared-memory tables of the update kernel (about 2400 floats on this device)");
+            CU_TRY(h, e);
         } else {
             cudaError_t e = launch_rollout_philox(p, h->a, h->num_sms, h->smem_optin, h->stream, &gx);
             if (e == cudaErrorInvalidConfiguration)
@@ -482,6 +535,7 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
         }
     }
     h->last_philox = (eps_dev == nullptr);
+    h->last_fast = p.fast != 0;
     if (!eps_dev) {
         h->have_philox_update = true;
         h->last_update = h->update_counter;
@@ -625,6 +679,18 @@ int mppi_set_goal(mppi_handle *h, const float *goal_host)
     if (!h || !goal_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
     return h2d(h, h->d_goal, goal_host, (size_t)(h->goal_per_ctrl ? h->n_ctrl : 1) * h->s);
 }
+int mppi_set_goal_n(mppi_handle *h, const float *goal_host, int n_rows)
+{
+    if (!h || !goal_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    if (n_rows == 1) {
+        if (!h->goal_per_ctrl) return h2d(h, h->d_goal, goal_host, (size_t)h->s);
+        std::vector<float> all((size_t)h->n_ctrl * h->s);
+        for (int c = 0; c < h->n_ctrl; c++) memcpy(all.data() + (size_t)c * h->s, goal_host, sizeof(float) * h->s);
+        return h2d(h, h->d_goal, all.data(), all.size());
+    }
+    if (n_rows == h->n_ctrl && h->goal_per_ctrl) return h2d(h, h->d_goal, goal_host, (size_t)h->n_ctrl * h->s);
+    return fail(h, MPPI_ERR_BAD_ARG, "mppi_set_goal_n: n_rows must be 1, or n_controllers on a goal_per_controller handle");
+}
 int mppi_set_lambda(mppi_handle *h, float lambda)
 {
     if (!h || !(lambda > 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "lambda must be > 0");
@@ -712,10 +778,28 @@ int mppi_get_update(mppi_handle *h, float *U_new_host)
     if (!h || !U_new_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
     return d2h(h, U_new_host, h->d_Unew, (size_t)h->n_ctrl * h->TA);
 }
+// On the superposition path the device keeps S_k - C and beta - C (C: the cost part all samples of a controller share):
+// it is added back here, in fp32, exactly as the device would have rounded C + (S_k - C).
+static int cost_bases(mppi_handle *h, std::vector<float> &base)
+{
+    base.assign((size_t)h->n_ctrl, 0.f);
+    if (!h->last_fast) return MPPI_OK;
+    return d2h(h, base.data(), h->d_cost_base, base.size());
+}
 int mppi_get_costs(mppi_handle *h, float *costs_host)
 {
     if (!h || !costs_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
-    return d2h(h, costs_host, h->d_costs, (size_t)h->n_ctrl * h->K_local);
+    int rc = d2h(h, costs_host, h->d_costs, (size_t)h->n_ctrl * h->K_local);
+    if (rc) return rc;
+    std::vector<float> base;
+    rc = cost_bases(h, base);
+    if (rc) return rc;
+    if (h->last_fast)
+        for (int c = 0; c < h->n_ctrl; c++) {
+            float *row = costs_host + (size_t)c * h->K_local;
+            for (int k = 0; k < h->K_local; k++) row[k] = base[c] + row[k];
+        }
+    return MPPI_OK;
 }
 int mppi_get_weight_stats(mppi_handle *h, float *beta, float *eta)
 {
@@ -723,7 +807,10 @@ int mppi_get_weight_stats(mppi_handle *h, float *beta, float *eta)
     std::vector<float> st(2 * (size_t)h->n_ctrl);
     int rc = d2h(h, st.data(), h->d_stats, st.size());
     if (rc) return rc;
-    for (int c = 0; c < h->n_ctrl; c++) { beta[c] = st[2 * c]; eta[c] = st[2 * c + 1]; }
+    std::vector<float> base;
+    rc = cost_bases(h, base);
+    if (rc) return rc;
+    for (int c = 0; c < h->n_ctrl; c++) { beta[c] = base[c] + st[2 * c]; eta[c] = st[2 * c + 1]; }
     return MPPI_OK;
 }
 int mppi_set_update_counter(mppi_handle *h, uint32_t counter)
@@ -1406,12 +1493,18 @@ int mppi_shift(int T, int a, const float *cur, const float *init, int nb, float 
 int mppi_philox_raw(int device, uint64_t seed, uint32_t call0, uint32_t sample, uint32_t update, uint32_t stream,
                     int n_calls, uint32_t *out)
 {
-    if (!out || n_calls <= 0) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad philox_raw argument");
+    return mppi_philox_raw_rounds(device, seed, call0, sample, update, stream, n_calls, 10, out);
+}
+
+int mppi_philox_raw_rounds(int device, uint64_t seed, uint32_t call0, uint32_t sample, uint32_t update, uint32_t stream,
+                           int n_calls, int rounds, uint32_t *out)
+{
+    if (!out || n_calls <= 0 || (rounds != 7 && rounds != 10)) return fail(nullptr, MPPI_ERR_BAD_ARG, "bad philox_raw argument");
     int rc = stage_device(device);
     if (rc) return rc;
     DevBuf d;
     CU_TRY_S(d.alloc(sizeof(uint32_t) * 4 * (size_t)n_calls));
-    CU_TRY_S(launch_philox_raw(seed, call0, sample, update, stream, n_calls, d.as<uint32_t>(), 0));
+    CU_TRY_S(launch_philox_raw(seed, call0, sample, update, stream, n_calls, rounds, d.as<uint32_t>(), 0));
     CU_TRY_S(cudaMemcpy(out, d.p, sizeof(uint32_t) * 4 * (size_t)n_calls, cudaMemcpyDeviceToHost));
     return MPPI_OK;
 }

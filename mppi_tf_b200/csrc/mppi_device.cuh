@@ -52,6 +52,19 @@ struct RolloutParams {
     // Philox key / counter words
     uint32_t key0, key1, update;
     uint32_t rk0[10], rk1[10];              // Philox round keys key + r * W (hoisted to the host)
+    int rounds;                             // Philox4x32-R: 10 (Random123 / TensorFlow's RandomNormal) or 7 (the shortest
+                                            // Crush-resistant variant of Salmon et al.; mppi_config.philox_rounds)
+    // Superposition form of the rollout (diagonal Sigma, q > 0, StaticCost, no noise-quadratic term; mppi_linear.cuh):
+    // the state splits into the noise-free trajectory (per-CTA tables) and a noise-driven part (P, V) per sample,
+    //   P' = P + fa1 V + fb1 n,  V' = V + fb2 n,  S = C + sum_t w_t (P_t^2 + V_t^2) + sum_t L_t . n_t
+    // n = z / z_scale is what the generator returns without its last multiply (z_scale = sqrt(2 ln 2) folded into
+    // fb1, fb2, L and applied once more in apply_update); z_scale = 1 on every other path.
+    int fast;
+    float *cost_base;                       // [n_ctrl]: on the superposition path costs[] holds S_k - C and the weights are
+                                            // formed from those differences (the part all samples share never enters an
+                                            // exponent); C is added back on the host (mppi_get_costs / mppi_get_weight_stats)
+    float z_scale;
+    float fa1[kMaxA], fb1[kMaxA], fb2[kMaxA];
     // single-controller fast path: state passed by value (no H2D copy)
     int x_inline;
     float x0[kMaxS];
@@ -99,10 +112,11 @@ constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
 
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1)
+                                               uint32_t k0, uint32_t k1, int rounds = 10)
 {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
+        if (r >= rounds) break;
         const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
         const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -118,12 +132,14 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 }
 
 // Same generator with the ten round keys read from the kernel parameter block (constant bank
-// operands of LOP3: no per-call key arithmetic, no registers).
+// operands of LOP3: no per-call key arithmetic, no registers).  `rounds` (7 or 10) is grid-uniform: rounds 8-10 sit
+// behind one uniform branch.
 __device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                  const uint32_t (&rk0)[10], const uint32_t (&rk1)[10])
+                                                  const uint32_t (&rk0)[10], const uint32_t (&rk1)[10], int rounds = 10)
 {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
+        if (r == 7 && rounds <= 7) break;
         const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
         const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk0[r];
@@ -184,7 +200,7 @@ __device__ __forceinline__ void normals_from_words(const uint4 x, float z[4])
 __device__ __forceinline__ void normals4(uint32_t call, uint32_t k, uint32_t stream, const RolloutParams &p,
                                          float z[4])
 {
-    normals_from_words(philox4x32_10_rk(call, k, p.update, stream, p.rk0, p.rk1), z);
+    normals_from_words(philox4x32_10_rk(call, k, p.update, stream, p.rk0, p.rk1, p.rounds), z);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -219,6 +235,8 @@ __device__ __forceinline__ uint4 philox_call_table(uint32_t call, uint32_t strea
     const uint64_t q0 = (uint64_t)kPhiloxM0 * T0;                                     // round 3, uniform half
     return make_uint4(c3p ^ p.rk1[1], (uint32_t)p1 ^ p.rk0[2], (uint32_t)(q0 >> 32) ^ p.rk1[2], (uint32_t)q0 ^ p.rk1[3]);
 }
+// R = 7 / 10: compile-time round count (the superposition kernels); R = 0: p.rounds decides behind a uniform branch
+template <int R = 0>
 __device__ __forceinline__ uint4 philox4x32_10_tab(const uint4 t, const PhiloxSample s, const RolloutParams &p)
 {
     uint32_t c0, c1, c2, c3;
@@ -239,6 +257,7 @@ __device__ __forceinline__ uint4 philox4x32_10_tab(const uint4 t, const PhiloxSa
     }
 #pragma unroll
     for (int r = 4; r < 10; r++) {
+        if (R == 0 ? (r == 7 && p.rounds <= 7) : (r >= R)) break;
         const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
         const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ p.rk0[r];
@@ -252,7 +271,46 @@ __device__ __forceinline__ uint4 philox4x32_10_tab(const uint4 t, const PhiloxSa
 }
 __device__ __forceinline__ void normals4_tab(const uint4 *tab, uint32_t call, const PhiloxSample s, const RolloutParams &p, float z[4])
 {
-    normals_from_words(philox4x32_10_tab(tab[call], s, p), z);
+    normals_from_words(philox4x32_10_tab<0>(tab[call], s, p), z);
+}
+// The superposition kernels' generator: compile-time rounds, and the normals WITHOUT Box-Muller's sqrt(2 ln 2):
+// n = z / kZScale (RolloutParams::z_scale).  One Philox call -> float4 (n0, n1, n2, n3).
+constexpr float kZScale = 1.1774100225154747f;      // sqrt(2 ln 2)
+__device__ __forceinline__ float4 normals_unscaled_from_words(const uint4 x)
+{
+    const float2 fa = make_float2(bits_to_1_2(x.x), bits_to_1_2(x.z));
+    const float2 fb = make_float2(bits_to_1_2(x.y), bits_to_1_2(x.w));
+    const float2 u1 = __ffma2_rn(fa, make_float2(-1.f, -1.f), make_float2(2.f, 2.f));                       // (0, 1]
+    const float2 th = __ffma2_rn(fb, make_float2(6.2831853071795865f, 6.2831853071795865f),
+                                 make_float2(-6.2831853071795865f, -6.2831853071795865f));                  // [0, 2pi)
+    float2 l2, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2.x) : "f"(u1.x));                   // <= 0; u1 is never denormal
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2.y) : "f"(u1.y));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(-l2.x));                  // the negation is an operand modifier
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(-l2.y));
+    float2 csA, csB;
+    __sincosf(th.x, &csA.y, &csA.x);
+    __sincosf(th.y, &csB.y, &csB.x);
+    const float2 zA = __fmul2_rn(make_float2(r.x, r.x), csA);
+    const float2 zB = __fmul2_rn(make_float2(r.y, r.y), csB);
+    return make_float4(zA.x, zA.y, zB.x, zB.y);
+}
+template <int R>
+__device__ __forceinline__ float4 normals4_fast(const uint4 *tab, uint32_t call, const PhiloxSample s, const RolloutParams &p)
+{
+    return normals_unscaled_from_words(philox4x32_10_tab<R>(tab[call], s, p));
+}
+// The standard normals a handle's update kernel saw, from the plain generator (mppi_dump_noise, store-then-replay):
+// on the superposition path z = z_scale * n, elsewhere the Box-Muller of normals_from_words.
+__device__ __forceinline__ void normals4_as_used(uint32_t call, uint32_t k, uint32_t stream, const RolloutParams &p, float z[4])
+{
+    const uint4 x = philox4x32_10_rk(call, k, p.update, stream, p.rk0, p.rk1, p.rounds);
+    if (p.fast) {
+        const float4 n = normals_unscaled_from_words(x);
+        z[0] = p.z_scale * n.x; z[1] = p.z_scale * n.y; z[2] = p.z_scale * n.z; z[3] = p.z_scale * n.w;
+    } else {
+        normals_from_words(x, z);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -401,6 +459,21 @@ struct CostAcc {
     float a;
     __device__ __forceinline__ void zero() { a2 = make_float2(0.f, 0.f); a = 0.f; }
     __device__ __forceinline__ float total() const { return (a2.x + a2.y) + a; }
+};
+
+// Compensated (Kahan) running sum for the per-sample cost of the direct-form kernels: the steps of a block are summed from
+// zero (small values, small roundings) and the block sums are added with the lost low-order part carried along, so the
+// total is as good as its final fp32 rounding instead of collecting one rounding at ulp(S) per term.
+struct KahanSum {
+    float s, c;
+    __device__ __forceinline__ void init(float v) { s = v; c = 0.f; }
+    __device__ __forceinline__ void add(float v)
+    {
+        const float y = v - c;
+        const float t = s + y;
+        c = (t - s) - y;
+        s = t;
+    }
 };
 
 // q(x) of the selected state-cost functor, added into S

@@ -15,6 +15,27 @@ cudaError_t launch_rollout_injected(RolloutParams p, int a, int num_sms, size_t 
 cudaError_t launch_finish(RolloutParams p, int a, bool philox, const float *gathered, cudaStream_t st);
 cudaError_t launch_dump_noise(RolloutParams p, int a, float *out_dev, cudaStream_t st);
 int max_grid_x(int K_local, int n_ctrl, int num_sms);
+int philox_grid_x(int K_local, int n_ctrl, int num_sms);
+
+// mppi_rollout_fast.cu: the superposition kernels (p.fast set by the host).  variant: 0 = pick, 1 = regenerating kernel,
+// 2 = resident-tile kernel (cudaErrorInvalidConfiguration when the rows are too long for it)
+cudaError_t launch_rollout_philox_fast(RolloutParams p, int a, int variant, int num_sms, size_t smem_sm, size_t smem_limit,
+                                       cudaStream_t st, int *grid_x_out);
+bool resident_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sms, size_t smem_sm, size_t smem_cta_limit, int *nw_out,
+                       int *rs_out, int *cw_out, int *grid_x_out, size_t *smem_out);
+
+#define MPPI_DISPATCH_A(a, ...)                  \
+    switch (a) {                                 \
+        case 1: { constexpr int A_ = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int A_ = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int A_ = 3; __VA_ARGS__; } break; \
+        case 4: { constexpr int A_ = 4; __VA_ARGS__; } break; \
+        case 5: { constexpr int A_ = 5; __VA_ARGS__; } break; \
+        case 6: { constexpr int A_ = 6; __VA_ARGS__; } break; \
+        case 7: { constexpr int A_ = 7; __VA_ARGS__; } break; \
+        case 8: { constexpr int A_ = 8; __VA_ARGS__; } break; \
+        default: return cudaErrorInvalidValue;   \
+    }
 bool injected_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sms, size_t smem_limit,
                        int *ng_out, int *c_out, int *nbuf_out, int *grid_x_out, size_t *smem_out);
 
@@ -75,7 +96,7 @@ cudaError_t launch_update_stages(int k, int T, int a, float lambda, const float 
 cudaError_t launch_vector_op(int op, int k, const float *in, float s0, float s1, float *out, cudaStream_t st);
 cudaError_t launch_weighted_noise(int k, int TA, const float *weights, const float *noise, float *out, cudaStream_t st);
 cudaError_t launch_philox_raw(uint64_t seed, uint32_t call0, uint32_t sample, uint32_t update, uint32_t stream,
-                              int n_calls, uint32_t *out, cudaStream_t st);
+                              int n_calls, int rounds, uint32_t *out, cudaStream_t st);
 
 // Host helper: inverse of an a x a matrix (Gauss-Jordan, double); returns false when singular.
 bool invert_matrix(const float *m, int n, float *inv);

@@ -20,12 +20,10 @@
 #include "mppi_device.cuh"
 #include "mppi_internal.h"
 #include "mppi_update.cuh"
+#include "mppi_philox_sum.cuh"
+#include "mppi_linear.cuh"
 
 namespace mppi {
-
-constexpr int kPhiloxThreads = 512;
-constexpr int kPhiloxCtasPerSm = 2;
-constexpr int kListCap = 256;          // list entries per warp: the CTA's non-zero-weight list holds 8 iterations of samples
 
 template <int A>
 __device__ __forceinline__ void load_uv(const float *uv_row, Vec<A> &U, Vec<A> &w)
@@ -157,17 +155,11 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     constexpr int RS = RowU<A>::RS;
     constexpr int NW = kPhiloxThreads / 32;
     extern __shared__ float4 smem_f4[];
-    float *smem = reinterpret_cast<float *>(smem_f4);
     const int TA = p.TA, TAp = (TA + 31) & ~31;
-    uint2 *sList = reinterpret_cast<uint2 *>(smem);          // [NW * kListCap] non-zero-weight samples of the CTA (fixed offset)
-    float *sUV = smem + 2 * NW * kListCap;                   // [T][RS]
-    float *sAcc = sUV + p.T * RS;        // [NW][TAp]  per-warp chunk sums
-    float *sN = sAcc + NW * TAp;         // [TAp]
-    float *sWork = sN + TAp;             // [TAp]
-    float *sScale = sWork + TAp;         // [kMaxParts]
-    float *sRed = sScale + kMaxParts;    // [64]
-    float4 *sScratch = reinterpret_cast<float4 *>(sRed + 64);   // [kPhiloxThreads] merge scratch
-    uint4 *sTab = reinterpret_cast<uint4 *>(sScratch + kPhiloxThreads);   // [ceil(TA/4)] per-call uniform Philox words
+    PhiloxSmem sm;
+    sm.carve(reinterpret_cast<float *>(smem_f4), p.T, RS, TAp);
+    float *sUV = sm.sUV, *sWork = sm.sWork, *sRed = sm.sRed;
+    uint4 *sTab = sm.sTab;
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     stage_u<A>(p, ctrl, sUV);
@@ -199,9 +191,9 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
         PointMass<A> x;
         x.init(x0);
         CostAcc S, Sw;
-        S.zero();
+        KahanSum Sk_;                               // block sums added with compensation (mppi_device.cuh)
+        Sk_.init(C0);
         Sw.zero();
-        S.a = C0;
         const float *uv = sUV;
         uint32_t call = 0;
         for (int tb = 0; tb < nfull; tb++) {       // full blocks of 4 steps = A Philox calls, no guards
@@ -209,14 +201,17 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
 #pragma unroll
             for (int c = 0; c < A; c++) normals4_tab(sTab, call + c, ps, p, &z[4 * c]);
             call += A;
+            S.zero();
 #pragma unroll
             for (int tt = 0; tt < 4; tt++) {
                 Vec<A> n;
                 vec_from<A>(&z[tt * A], n);
                 rollout_step<A, true, DIAG, QUAD, COST>(x, S, Sw, uv + tt * RS, n, p, mc, sigd);
             }
+            Sk_.add(S.total());
             uv += 4 * RS;
         }
+        S.zero();
         if (trem) {                                 // tail: T % 4 steps (calls past the row end read table entries that exist: ceil)
             float z[4 * A];
 #pragma unroll
@@ -231,7 +226,8 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
                 }
         }
         add_state_cost<A, COST>(x, mc, p, S);    // terminal cost on top of step T-1's (src/controller_base.cpp:271-272)
-        const float Sk = fmaf(p.w_scale, Sw.total(), S.total());
+        Sk_.add(fmaf(p.w_scale, Sw.total(), S.total()));
+        const float Sk = Sk_.s;
         costs[k] = Sk;
         bmin = fminf(bmin, Sk);
         bmax = fmaxf(bmax, Sk);
@@ -252,131 +248,8 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
     const float nil = weight_scale(p, ctrl, beta_fixed);
     if (p.norm_mode == 2) beta_c = beta_fixed;
 
-    // ---- phase 2: sum_k e_k z_k, regenerating z from the same counters ----------------------------
-    // Only samples whose weight is non-zero in fp32 are revisited (with lambda of the order of the cost
-    // spread most weights underflow: e_k = 0 contributes exactly nothing).  Each warp compacts its own
-    // samples, in order, into a private list of (sample, weight) and walks that list with all 32 lanes.
-    const int ncall = (TA + 3) >> 2;
-    const int nchunk = (ncall + 7) >> 3;
-    float eta = 0.f;
-    // CTA-uniform: can any weight of this CTA underflow at all?  (false also for NaN and for the weight
-    // pass of a normalised update, whose exponents are bounded by 1/lambda)
-    const bool sparse = (max_c - beta_c) * fabsf(nil) > 125.f;
-    if (!sparse) {
-        // dense weights: every thread walks its own samples, chunk by chunk
-        for (int ch = 0; ch < nchunk; ch++) {
-            float2 acc2[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) acc2[i] = make_float2(0.f, 0.f);
-            const bool full = (ch * 8 + 8 <= ncall);    // warp-uniform: all 8 calls of the chunk exist
-            for (int k = kfirst; k < kend; k += kstride) {
-                const PhiloxSample ps = philox_sample(phA, (uint32_t)(p.k_offset + k));
-                const float e = weight_exp(costs[k], beta_c, nil);
-                const float2 e2 = make_float2(e, e);
-                if (ch == 0) eta += e;
-#pragma unroll
-                for (int c8 = 0; c8 < 8; c8++) {
-                    if (full || ch * 8 + c8 < ncall) {
-                        float z[4];
-                        normals4_tab(sTab, (uint32_t)(ch * 8 + c8), ps, p, z);
-                        acc2[2 * c8] = __ffma2_rn(e2, make_float2(z[0], z[1]), acc2[2 * c8]);
-                        acc2[2 * c8 + 1] = __ffma2_rn(e2, make_float2(z[2], z[3]), acc2[2 * c8 + 1]);
-                    }
-                }
-            }
-            float acc[32];
-#pragma unroll
-            for (int i = 0; i < 16; i++) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
-            const float r = warp_transpose_sum32(acc, lane);
-            sAcc[warp * TAp + ch * 32 + lane] = r;
-        }
-    } else {
-        // sparse weights: the CTA compacts its samples, in order (warp-major, then iteration), into one
-        // shared-memory list of (global sample index, weight); the warps then share the list 32 entries
-        // at a time.  Deterministic: the list order depends only on the data.
-        float *myacc = sAcc + warp * TAp;
-        for (int j = lane; j < TAp; j += 32) myacc[j] = 0.f;
-        int *sCnt = reinterpret_cast<int *>(sRed);                                   // [NW] per-warp counts
-        constexpr int BI = kListCap / 32;                                            // iterations per batch
-        const int k_cta = 32 * w_lo;
-        const int n_it_cta = (kend - k_cta + kstride - 1) / kstride;                 // CTA-uniform
-        const unsigned lt = (1u << lane) - 1u;
-        for (int b0 = 0; b0 < n_it_cta; b0 += BI) {
-            const int kb = k_cta + b0 * kstride + 32 * warp;                         // this warp's first sample of the batch
-            const int nit = min(BI, n_it_cta - b0);
-            int cnt_w = 0;
-#pragma unroll 1
-            for (int it = 0; it < nit; it++) {
-                const int k = kb + it * kstride + lane;
-                float e = 0.f;
-                if (k < kend) e = weight_exp(costs[k], beta_c, nil);
-                eta += e;
-                cnt_w += __popc(__ballot_sync(0xffffffffu, e != 0.f));
-            }
-            if (lane == 0) sCnt[warp] = cnt_w;
-            __syncthreads();
-            int off = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < NW; w++) {
-                const int c = sCnt[w];
-                if (w < warp) off += c;
-                total += c;
-            }
-#pragma unroll 1
-            for (int it = 0; it < nit; it++) {
-                const int k = kb + it * kstride + lane;
-                float e = 0.f;
-                if (k < kend) e = weight_exp(costs[k], beta_c, nil);
-                const unsigned m = __ballot_sync(0xffffffffu, e != 0.f);
-                if (e != 0.f) sList[off + __popc(m & lt)] = make_uint2((uint32_t)(p.k_offset + k), __float_as_uint(e));
-                off += __popc(m);
-            }
-            __syncthreads();
-            if (32 * warp < total) {                                                  // warp-uniform
-                for (int ch = 0; ch < nchunk; ch++) {
-                    float2 acc2[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) acc2[i] = make_float2(0.f, 0.f);
-                    const bool full = (ch * 8 + 8 <= ncall);
-                    for (int i0 = 32 * warp; i0 < total; i0 += 32 * NW) {
-                        const uint2 ent = (i0 + lane < total) ? sList[i0 + lane] : make_uint2(0u, 0u);   // padding lanes: weight 0
-                        const PhiloxSample ps = philox_sample(phA, ent.x);
-                        const float e = __uint_as_float(ent.y);
-                        const float2 e2 = make_float2(e, e);
-#pragma unroll
-                        for (int c8 = 0; c8 < 8; c8++) {
-                            if (full || ch * 8 + c8 < ncall) {
-                                float z[4];
-                                normals4_tab(sTab, (uint32_t)(ch * 8 + c8), ps, p, z);
-                                acc2[2 * c8] = __ffma2_rn(e2, make_float2(z[0], z[1]), acc2[2 * c8]);
-                                acc2[2 * c8 + 1] = __ffma2_rn(e2, make_float2(z[2], z[3]), acc2[2 * c8 + 1]);
-                            }
-                        }
-                    }
-                    float acc[32];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
-                    const float r = warp_transpose_sum32(acc, lane);
-                    myacc[ch * 32 + lane] += r;
-                }
-            }
-            __syncthreads();                         // list and counts are reused by the next batch / the reductions below
-        }
-    }
-    eta = warp_sum(eta);
-    if (lane == 0) sRed[warp] = eta;
-    __syncthreads();
-    float eta_c = 0.f;
-#pragma unroll
-    for (int w = 0; w < NW; w++) eta_c += sRed[w];
-    for (int j = tid; j < TA; j += kPhiloxThreads) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < NW; w++) s += sAcc[w * TAp + j];
-        sN[j] = s;
-    }
-    __syncthreads();
-    publish_and_finish<A, true>(p, ctrl, beta_c, eta_c, sN, sWork, sScale, sRed, sScratch, kPhiloxThreads);
+    // ---- phase 2: sum_k e_k z_k, regenerating z from the same counters (mppi_philox_sum.cuh) ----------
+    philox_weighted_sum_and_finish<A, GenPlain>(p, ctrl, costs, w_lo, kfirst, kend, beta_c, max_c, nil, phA, sm);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -427,11 +300,13 @@ __device__ __forceinline__ void load_block(const float *row, int tb, int TA, flo
     }
 }
 
-template <int A, bool TMA, bool QUAD, int COST>
+// FAST: the superposition form of mppi_linear.cuh (q > 0, StaticCost, no noise-quadratic term; any Sigma, the noise arrives
+// scaled): per-controller tables instead of the staged (U_t, w_t) rows, six FMAs per axis-step, costs[] relative to C.
+template <int A, bool TMA, bool QUAD, int COST, bool FAST>
 __global__ void __launch_bounds__(512, 1)
 rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedLaunch L)
 {
-    constexpr int RS = Row<A>::RS;
+    constexpr int RS = FAST ? ((A + 3) & ~3) : Row<A>::RS;
     extern __shared__ float4 smem_f4[];
     float *smem = reinterpret_cast<float *>(smem_f4);
     const int TA = p.TA, TAp = (TA + 31) & ~31;
@@ -475,10 +350,21 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
             fence_mbar_init();
         }
     }
-    stage_sequence<A, false>(p, ctrl, sUV);
+    if (!FAST) stage_sequence<A, false>(p, ctrl, sUV);
     for (int i = tid; i < NG * TAp; i += blockDim.x) sAccG[i] = 0.f;
     __syncthreads();
+    float C0 = 0.f;
+    if (FAST) {
+        // tables first (their scratch is the tile pool), then the first loads
+        if (p.norm_mode != 2) {
+            float Cb = build_linear_tables<A, false>(p, ctrl, sUV, sTiles, sRed);
+            Cb += stage_c0<A>(p, ctrl, sWork, sRed);
+            if (blockIdx.x == 0 && tid == 0) p.cost_base[ctrl] = Cb;
+        }
+        __syncthreads();
+    }
     if (TMA && tid == 0) {
+        if (FAST) fence_proxy_async();           // generic-proxy writes to the pool (table scratch) before the bulk copies land
         for (int seq = 0; seq < NBUF && seq < nseq; seq++) issue(seq);
     }
 
@@ -486,7 +372,9 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
     Vec<A> sigd;
     float x0[2 * A];
     thread_consts<A>(p, ctrl, mc, sigd, x0);
-    const float C0 = stage_c0<A>(p, ctrl, sWork, sRed);
+    FastConsts<A> fc;
+    if (FAST) fc.init(p);
+    if (!FAST) C0 = stage_c0<A>(p, ctrl, sWork, sRed);
     float beta_fixed = 0.f;
     const float nil = weight_scale(p, ctrl, beta_fixed);
 
@@ -508,7 +396,7 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
     Vec<A> CU, DU;
     CU.fill(0.f);
     DU.fill(0.f);
-    if (C > 1) {
+    if (C > 1 && !FAST) {
         const int s0 = 4 * tb0, s1 = min(p.T, 4 * tb1);
         for (int t = s0; t < s1; t++) {
 #pragma unroll
@@ -576,14 +464,21 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
                     const float dtcvu = p.dt * p.c_vu;
     #pragma unroll
                     for (int i = 0; i < A; i++) {
-                        const float Ci = Cs.get(i) + CU.get(i);
-                        const float Di = (Ds.get(i) - (float)extra * Cs.get(i)) + DU.get(i);
-                        myb[(2 * i) * 32] = fmaf(p.c_pu, Ci, dtcvu * Di);
-                        myb[(2 * i + 1) * 32] = p.c_vu * Ci;
+                        if (FAST) {           // zero-state response of the noise-driven part (P, V): no U part
+                            const float Ci = Cs.get(i), Di = Ds.get(i) - (float)extra * Cs.get(i);
+                            myb[(2 * i) * 32] = fmaf(p.fb1[i], Ci, (p.fa1[i] * p.fb2[i]) * Di);
+                            myb[(2 * i + 1) * 32] = p.fb2[i] * Ci;
+                        } else {
+                            const float Ci = Cs.get(i) + CU.get(i);
+                            const float Di = (Ds.get(i) - (float)extra * Cs.get(i)) + DU.get(i);
+                            myb[(2 * i) * 32] = fmaf(p.c_pu, Ci, dtcvu * Di);
+                            myb[(2 * i + 1) * 32] = p.c_vu * Ci;
+                        }
                     }
                     group_barrier(bar_id, bar_n);
-                    // true incoming state: x0 pushed through chunks 0..cw-1 (free response + zero-state response)
-                    x.init(x0);
+                    // true incoming state: x0 pushed through chunks 0..cw-1 (free response + zero-state response);
+                    // FAST: x holds (P, V), which start at zero and whose free response is P += n a1 V
+                    if (FAST) x.zero(); else x.init(x0);
                     for (int cc = 0; cc < cw; cc++) {
                         const int s0 = 4 * min(nblk, cc * nb), s1 = min(p.T, 4 * min(nblk, cc * nb + nb));
                         const float ndt = (float)(s1 - s0) * p.dt;
@@ -591,27 +486,32 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
     #pragma unroll
                         for (int i = 0; i < A; i++) {
                             const float vi = x.v.get(i);
-                            x.p.set(i, fmaf(ndt, vi, x.p.get(i)) + ob[(2 * i) * 32]);
+                            const float fr = FAST ? (float)(s1 - s0) * p.fa1[i] : ndt;
+                            x.p.set(i, fmaf(fr, vi, x.p.get(i)) + ob[(2 * i) * 32]);
                             x.v.set(i, vi + ob[(2 * i + 1) * 32]);
                         }
                     }
                 } else {
-                    x.init(x0);
+                    if (FAST) x.zero(); else x.init(x0);
                 }
 
                 // ---- pass 2: rollout with costs over this warp's chunk ----------------------------------
-                CostAcc Sa;
+                CostAcc Sa, Sl;
                 Sa.zero();
-                if (cw == 0) Sa.a = C0;
+                Sl.zero();
+                KahanSum Sk_;                       // direct form: block sums added with compensation
+                Sk_.init(cw == 0 ? C0 : 0.f);
                 for (int tb = tb0; tb < tb1; tb++) {
                     float e[4 * A];
+                    if (!FAST) { Sk_.add(Sa.total()); Sa.zero(); }
                     if (4 * tb + 4 <= p.T) {
                         load_block<A, TMA, false>(row, tb, TA, e);
     #pragma unroll
                         for (int tt = 0; tt < 4; tt++) {
                             Vec<A> n;
                             vec_from<A>(&e[tt * A], n);
-                            rollout_step<A, false, false, QUAD, COST>(x, Sa, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
+                            if (FAST) fast_step<A>(x.p, x.v, Sa, Sl, sUV + (4 * tb + tt) * RS, n, fc);
+                            else rollout_step<A, false, false, QUAD, COST>(x, Sa, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
                         }
                     } else {
                         load_block<A, TMA, true>(row, tb, TA, e);
@@ -620,12 +520,17 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
                             if (4 * tb + tt < p.T) {
                                 Vec<A> n;
                                 vec_from<A>(&e[tt * A], n);
-                                rollout_step<A, false, false, QUAD, COST>(x, Sa, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
+                                if (FAST) fast_step<A>(x.p, x.v, Sa, Sl, sUV + (4 * tb + tt) * RS, n, fc);
+                                else rollout_step<A, false, false, QUAD, COST>(x, Sa, Sa, sUV + (4 * tb + tt) * RS, n, p, mc, sigd);
                             }
                     }
                 }
-                if (tb1 == nblk && tb0 < tb1) add_state_cost<A, COST>(x, mc, p, Sa);   // terminal cost (src/controller_base.cpp:271-272)
-                S = Sa.total();
+                if (tb1 == nblk && tb0 < tb1) {                  // terminal cost (src/controller_base.cpp:271-272)
+                    if (FAST) fast_terminal<A>(x.p, x.v, Sa);
+                    else add_state_cost<A, COST>(x, mc, p, Sa);
+                }
+                if (!FAST) Sk_.add(Sa.total());
+                S = FAST ? Sa.total() + Sl.total() : Sk_.s;
                 if (C > 1) {
                     sS[(grp * C + cw) * 32 + lane] = S;
                     group_barrier(bar_id, bar_n);
@@ -766,7 +671,7 @@ __global__ void dump_noise_kernel(const __grid_constant__ RolloutParams p, float
          i += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(i / ncall), call = (int)(i - (long long)k * ncall);
         float z[4];
-        normals4((uint32_t)call, (uint32_t)(p.k_offset + k), (uint32_t)ctrl, p, z);
+        normals4_as_used((uint32_t)call, (uint32_t)(p.k_offset + k), (uint32_t)ctrl, p, z);
         float *row = out + ((size_t)ctrl * p.K_local + k) * p.TA;
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -800,13 +705,6 @@ __global__ void scale_noise_kernel(const __grid_constant__ RolloutParams p, floa
 // -------------------------------------------------------------------------------------------------
 // Host launchers
 // -------------------------------------------------------------------------------------------------
-static size_t philox_smem_bytes(int A, int T, int TA)
-{
-    const int RS = (A + 3) & ~3, TAp = (TA + 31) & ~31, NW = kPhiloxThreads / 32;
-    return sizeof(float) * ((size_t)T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 64) + sizeof(float4) * kPhiloxThreads +
-           sizeof(uint2) * NW * kListCap + sizeof(uint4) * (size_t)((TA + 3) >> 2);
-}
-
 template <int A, bool DIAG, bool QUAD, int COST>
 static cudaError_t launch_philox_V(const RolloutParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
@@ -832,19 +730,6 @@ static cudaError_t launch_philox_A(const RolloutParams &p, dim3 grid, cudaStream
     return launch_philox_V<A, false, false, 0>(p, grid, smem, st);
 }
 
-#define MPPI_DISPATCH_A(a, ...)                  \
-    switch (a) {                                 \
-        case 1: { constexpr int A_ = 1; __VA_ARGS__; } break; \
-        case 2: { constexpr int A_ = 2; __VA_ARGS__; } break; \
-        case 3: { constexpr int A_ = 3; __VA_ARGS__; } break; \
-        case 4: { constexpr int A_ = 4; __VA_ARGS__; } break; \
-        case 5: { constexpr int A_ = 5; __VA_ARGS__; } break; \
-        case 6: { constexpr int A_ = 6; __VA_ARGS__; } break; \
-        case 7: { constexpr int A_ = 7; __VA_ARGS__; } break; \
-        case 8: { constexpr int A_ = 8; __VA_ARGS__; } break; \
-        default: return cudaErrorInvalidValue;   \
-    }
-
 int philox_grid_x(int K_local, int n_ctrl, int num_sms)
 {
     const int ctas_total = num_sms * kPhiloxCtasPerSm;
@@ -860,6 +745,7 @@ int philox_grid_x(int K_local, int n_ctrl, int num_sms)
 
 cudaError_t launch_rollout_philox(RolloutParams p, int a, int num_sms, size_t smem_limit, cudaStream_t st, int *grid_x_out)
 {
+    if (p.fast) return cudaErrorInvalidValue;        // the superposition kernels are launched by launch_rollout_philox_fast
     // 16 per-warp rows of T*a partial sums + the sequence and call tables must fit one CTA's shared memory
     // (T*a up to about 2400 on a 227 KB part)
     if (philox_smem_bytes(a, p.T, p.TA) > smem_limit) return cudaErrorInvalidConfiguration;
@@ -920,12 +806,12 @@ bool injected_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sm
     return true;
 }
 
-template <int A, bool TMA, bool QUAD, int COST>
+template <int A, bool TMA, bool QUAD, int COST, bool FAST = false>
 static cudaError_t launch_injected_V(const RolloutParams &p, InjectedLaunch L, dim3 grid, size_t smem, cudaStream_t st)
 {
-    cudaError_t err = ensure_dyn_smem<rollout_injected_kernel<A, TMA, QUAD, COST>>(smem);
+    cudaError_t err = ensure_dyn_smem<rollout_injected_kernel<A, TMA, QUAD, COST, FAST>>(smem);
     if (err != cudaSuccess) return err;
-    rollout_injected_kernel<A, TMA, QUAD, COST><<<grid, L.ng * L.c * 32, smem, st>>>(p, L);
+    rollout_injected_kernel<A, TMA, QUAD, COST, FAST><<<grid, L.ng * L.c * 32, smem, st>>>(p, L);
     return cudaGetLastError();
 }
 
@@ -942,6 +828,7 @@ static cudaError_t launch_injected_A(const RolloutParams &p, InjectedLaunch L, d
         }
     }
     if (p.quad) return tma ? launch_injected_V<A, true, true, 0>(p, L, grid, smem, st) : launch_injected_V<A, false, true, 0>(p, L, grid, smem, st);
+    if (p.fast) return tma ? launch_injected_V<A, true, false, 0, true>(p, L, grid, smem, st) : launch_injected_V<A, false, false, 0, true>(p, L, grid, smem, st);
     return tma ? launch_injected_V<A, true, false, 0>(p, L, grid, smem, st) : launch_injected_V<A, false, false, 0>(p, L, grid, smem, st);
 }
 

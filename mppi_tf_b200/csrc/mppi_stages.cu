@@ -181,10 +181,10 @@ __global__ void weighted_noise_kernel(int k, int TA, const float *weights, const
 }
 
 __global__ void philox_raw_kernel(uint32_t key0, uint32_t key1, uint32_t call0, uint32_t sample, uint32_t update,
-                                  uint32_t stream, int n_calls, uint32_t *out)
+                                  uint32_t stream, int n_calls, int rounds, uint32_t *out)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_calls; i += gridDim.x * blockDim.x) {
-        const uint4 x = philox4x32_10(call0 + (uint32_t)i, sample, update, stream, key0, key1);
+        const uint4 x = philox4x32_10(call0 + (uint32_t)i, sample, update, stream, key0, key1, rounds);
         out[4 * i] = x.x; out[4 * i + 1] = x.y; out[4 * i + 2] = x.z; out[4 * i + 3] = x.w;
     }
 }
@@ -255,10 +255,10 @@ cudaError_t launch_weighted_noise(int k, int TA, const float *weights, const flo
 }
 
 cudaError_t launch_philox_raw(uint64_t seed, uint32_t call0, uint32_t sample, uint32_t update, uint32_t stream,
-                              int n_calls, uint32_t *out, cudaStream_t st)
+                              int n_calls, int rounds, uint32_t *out, cudaStream_t st)
 {
     philox_raw_kernel<<<blocks_for(n_calls, 256), 256, 0, st>>>((uint32_t)seed, (uint32_t)(seed >> 32), call0, sample,
-                                                               update, stream, n_calls, out);
+                                                               update, stream, n_calls, rounds, out);
     return cudaGetLastError();
 }
 

@@ -270,7 +270,7 @@ template <int A, bool PHILOX>
 __device__ void apply_update(const RolloutParams &p, int ctrl, Merged m, float *sN, float *sOut)
 {
     const int TA = p.TA;
-    const float inv_eta = 1.0f / m.eta;
+    const float inv_eta = (PHILOX ? p.z_scale : 1.0f) / m.eta;     // sN holds sum e n, n = z / z_scale (1 off the superposition path)
     float *U = p.U + (size_t)ctrl * TA;
     for (int i = threadIdx.x; i < TA; i += blockDim.x) {
         const int t = i / A, j = i - t * A;

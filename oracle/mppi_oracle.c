@@ -73,10 +73,12 @@ int orc_num_threads(void)
 #define PHILOX_W0 0x9E3779B9u
 #define PHILOX_W1 0xBB67AE85u
 
-void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+/* Philox4x32-R: R = 10 is Random123's default (and TensorFlow's); R = 7 is the shortest variant Salmon et al. report as
+ * passing BigCrush (mppi_config.philox_rounds). */
+void orc_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4])
 {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < rounds; r++) {
         uint64_t p0 = (uint64_t)PHILOX_M0 * c0, p1 = (uint64_t)PHILOX_M1 * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
         uint32_t n1 = (uint32_t)p1;
@@ -87,6 +89,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { orc_philox4x32_r(ctr, key, 10, out); }
 
 static float u01_from_bits(uint32_t x)
 {
@@ -97,8 +100,8 @@ static float u01_from_bits(uint32_t x)
 }
 
 /* Standard normals z[n_per_sample] for samples [k0,k1) (row-major [k1-k0][n_per_sample]). */
-void orc_philox_normals(uint64_t seed, uint32_t update, uint32_t stream, uint32_t k0, uint32_t k1,
-                        int n_per_sample, float *z)
+void orc_philox_normals_r(uint64_t seed, uint32_t update, uint32_t stream, uint32_t k0, uint32_t k1,
+                          int n_per_sample, int rounds, float *z)
 {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     int ncall = (n_per_sample + 3) / 4;
@@ -106,7 +109,7 @@ void orc_philox_normals(uint64_t seed, uint32_t update, uint32_t stream, uint32_
         for (int c = 0; c < ncall; c++) {
             uint32_t ctr[4] = {(uint32_t)c, k, update, stream}, x[4];
             float n[4];
-            orc_philox4x32_10(ctr, key, x);
+            orc_philox4x32_r(ctr, key, rounds, x);
             for (int h = 0; h < 2; h++) {
                 double u1 = 2.0 - (double)u01_from_bits(x[2 * h]);
                 double th = 6.283185307179586 * ((double)u01_from_bits(x[2 * h + 1]) - 1.0);
@@ -117,4 +120,9 @@ void orc_philox_normals(uint64_t seed, uint32_t update, uint32_t stream, uint32_
             for (int j = 0; j < 4; j++)
                 if (4 * c + j < n_per_sample) z[(size_t)(k - k0) * n_per_sample + 4 * c + j] = n[j];
         }
+}
+void orc_philox_normals(uint64_t seed, uint32_t update, uint32_t stream, uint32_t k0, uint32_t k1,
+                        int n_per_sample, float *z)
+{
+    orc_philox_normals_r(seed, update, stream, k0, k1, n_per_sample, 10, z);
 }

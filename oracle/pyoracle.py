@@ -367,20 +367,20 @@ class Oracle:
 
 
 # --- noise stream specification (integer part is a bit-exact contract) ---------------------
-def philox4x32_10(ctr, key):
+def philox4x32_10(ctr, key, rounds=10):
     lib = load()
     c = (C.c_uint32 * 4)(*[int(v) & 0xFFFFFFFF for v in ctr])
     k = (C.c_uint32 * 2)(*[int(v) & 0xFFFFFFFF for v in key])
     o = (C.c_uint32 * 4)()
-    lib.orc_philox4x32_10(c, k, o)
+    lib.orc_philox4x32_r(c, k, C.c_int(rounds), o)
     return [int(v) for v in o]
 
 
-def philox_normals(seed, update, stream, k0, k1, n_per_sample):
+def philox_normals(seed, update, stream, k0, k1, n_per_sample, rounds=10):
     lib = load()
     z = np.empty((k1 - k0, n_per_sample), np.float32)
-    lib.orc_philox_normals(C.c_uint64(seed), C.c_uint32(update), C.c_uint32(stream),
-                           C.c_uint32(k0), C.c_uint32(k1), C.c_int(n_per_sample), _p(z))
+    lib.orc_philox_normals_r(C.c_uint64(seed), C.c_uint32(update), C.c_uint32(stream),
+                             C.c_uint32(k0), C.c_uint32(k1), C.c_int(n_per_sample), C.c_int(rounds), _p(z))
     return z
 
 

@@ -270,3 +270,14 @@ PHILOX_KATS = [
     dict(ctr=[0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], key=[0xa4093822, 0x299f31d0],
          out=[0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
 ]
+
+# Philox4x32-7 (mppi_config.philox_rounds = 7): the seven-round lines of the same Random123 kat_vectors file
+# ("philox4x32 7 <ctr> <key> <out>": zeros, all ones, and the digits of pi).
+PHILOX7_KATS = [
+    dict(ctr=[0, 0, 0, 0], key=[0, 0],
+         out=[0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]),
+    dict(ctr=[0xffffffff] * 4, key=[0xffffffff] * 2,
+         out=[0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662]),
+    dict(ctr=[0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], key=[0xa4093822, 0x299f31d0],
+         out=[0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a]),
+]

@@ -208,6 +208,8 @@ def test_philox_kats():
     from oracle.pyoracle import philox4x32_10
     for kat in kats.PHILOX_KATS:
         assert philox4x32_10(kat["ctr"], kat["key"]) == kat["out"]
+    for kat in kats.PHILOX7_KATS:                       # the seven-round variant (mppi_config.philox_rounds = 7)
+        assert philox4x32_10(kat["ctr"], kat["key"], rounds=7) == kat["out"]
 
 
 def test_philox_normals_moments():
@@ -218,6 +220,9 @@ def test_philox_normals_moments():
     # rows independent of how the sample range is split (global sample index in the counter)
     z2 = philox_normals(seed=1, update=0, stream=0, k0=100, k1=110, n_per_sample=60)
     np.testing.assert_array_equal(z2, z[100:110].astype(np.float32))
+    z7 = philox_normals(seed=1, update=0, stream=0, k0=0, k1=4096, n_per_sample=60, rounds=7).astype(np.float64)
+    assert abs(z7.mean()) < 0.01 and abs(z7.var() - 1) < 0.01 and abs((z7 ** 4).mean() - 3) < 0.1
+    assert np.abs(z7 - z).max() > 1.0                    # a different stream
 
 
 # ---- MLP dynamics (parity unpinned in the reference; structure check only) ------------------------

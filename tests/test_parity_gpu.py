@@ -132,6 +132,40 @@ def test_set_goal_changes_the_update(oracle64):
     assert rel_err(act, ref["next"]) < 2e-5
 
 
+def test_set_goal_on_batched_handles(oracle64):
+    """setGoal never reads past the buffer it is given: [s] broadcasts to every controller, [n, s] needs a
+    goal_per_controller handle, anything else is refused."""
+    from mppi_tf_b200 import ControllerBase
+    n, k, tau, a = 3, 512, 8, 1
+    cfg = make_cfg(k, tau, 2, a)
+    rng = np.random.default_rng(12)
+    xs = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    eps = np.stack([parity_noise(k, tau, a, cfg["sigma"], seed=40 + c) for c in range(n)])
+    U0 = np.zeros((tau, a), np.float32)
+    per = ControllerBase(k, tau, cfg["dt"], 1.0, 2, a, sigma=cfg["sigma"], n_controllers=n, goal_per_controller=True)
+    shared = ControllerBase(k, tau, cfg["dt"], 1.0, 2, a, sigma=cfg["sigma"], n_controllers=n)
+    try:
+        assert shared.setGoal(np.zeros((n, 2))) is False            # a shared-goal handle takes [s] only
+        assert per.setGoal(np.zeros(5)) is False
+        one = np.array([-0.5, 0.25], np.float32)
+        assert per.setGoal(one) is True and shared.setGoal(one) is True      # broadcast / shared
+        a_per, a_sh = per.nextWithNoise(xs, eps), shared.nextWithNoise(xs, eps)
+        np.testing.assert_array_equal(a_per, a_sh)
+        for c in range(n):
+            ref = oracle64.mppi_update(dict(cfg, goal=one), xs[c], U0, eps[c])
+            assert rel_err(a_per[c], ref["next"]) < 2e-5
+        goals = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        assert per.setGoal(goals) is True
+        per.setSequence(np.zeros((n, tau, a), np.float32))
+        a2 = per.nextWithNoise(xs, eps)
+        for c in range(n):
+            ref = oracle64.mppi_update(dict(cfg, goal=goals[c]), xs[c], U0, eps[c])
+            assert rel_err(a2[c], ref["next"]) < 2e-5
+    finally:
+        per.close()
+        shared.close()
+
+
 def test_setters_lambda_sigma_q(oracle64):
     cfg = make_cfg(1024, 10, 4, 2)
     x0, U0, eps_unit = _inputs(cfg, seed=6)

@@ -35,8 +35,9 @@ def parity_noise(k, tau, a, sigma, seed=1234):
 
 def controller_from_cfg(cfg, **kw):
     from mppi_tf_b200 import ControllerBase
+    # the positional `mass` is not forwarded to the model (reference quirk, src/controller_base.cpp:68): model_mass is
     return ControllerBase(cfg["k"], cfg["tau"], cfg["dt"], cfg["mass"], cfg["s_dim"], cfg["a_dim"],
-                          lam=cfg["lambda"], sigma=cfg["sigma"], goal=cfg["goal"], Q=cfg["q"], **kw)
+                          lam=cfg["lambda"], sigma=cfg["sigma"], goal=cfg["goal"], Q=cfg["q"], model_mass=cfg["mass"], **kw)
 
 
 def rel_err(got, want):
