@@ -377,7 +377,7 @@ def make_controller(name, dev_index, stream, rounds, lam=1.0, rank=0, world=1, k
 
 def nonzero_weight_frac(ctrl, n_local, lam):
     c = np.asarray(ctrl.getCosts(), np.float64).reshape(n_local, -1)
-    return float(np.mean((c - c.min(1, keepdims=True)) * 1.4426950408889634 / lam < 126.0))
+    return float(np.mean((c - c.min(1, keepdims=True)) * 1.4426950408889634 / lam < 50.0))      # the kernels drop weights below 2^-50 of the best sample (mppi_device.cuh: sample_weight)
 
 
 def time_updates(torch, ctrl, flush, steps, warmup, eps_ptr=None):
@@ -426,6 +426,18 @@ def side_config(torch, name, dev_index, stream, flush, rounds, steps, peak, peak
         out = {"workload": WORKLOADS[name][0], "ms_per_step": m, "value": units / (m * 1e-3), "steps": steps, "lambda": lam,
                "roofline": roofline_of(name, info, m, peak, peak_src, philox_kernel_name(info, name)),
                "nonzero_weight_frac": round(nonzero_weight_frac(ctrl, info["n_local"], lam), 4)}
+        if out["nonzero_weight_frac"] < 0.5:
+            # almost every weight vanishes at lambda = 1 (costs spread over far more than 50 lambda): time the same workload
+            # once more with lambda of the order of the cost spread, so that the weighted noise sum is not for free
+            c = np.asarray(ctrl.getCosts(), np.float64).reshape(info["n_local"], -1)
+            c = c[np.isfinite(c).all(1)] if np.isfinite(c).any() else c
+            lam2 = float(max(np.median(c.max(1) - c.min(1)) / 30.0, 1e-3))
+            ctrl.setLambda(lam2)
+            ms2 = statistics.mean(time_updates(torch, ctrl, flush, max(5, steps // 2), 3))
+            out["dense_weights"] = {"lambda": lam2, "ms_per_step": ms2, "value": units / (ms2 * 1e-3),
+                                    "roofline_frac": roofline_of(name, info, ms2, peak, peak_src, philox_kernel_name(info, name))["frac"],
+                                    "nonzero_weight_frac": round(nonzero_weight_frac(ctrl, info["n_local"], lam2), 4)}
+            ctrl.setLambda(lam)
         # latency through the synchronous public call (host buffers)
         lat = []
         for i in range(5 + steps):

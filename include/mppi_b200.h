@@ -326,6 +326,13 @@ int mppi_philox_raw(int device, uint64_t seed, uint32_t call0, uint32_t sample, 
 int mppi_philox_raw_rounds(int device, uint64_t seed, uint32_t call0, uint32_t sample, uint32_t update,
                            uint32_t stream, int n_calls, int rounds, uint32_t *out);
 
+/* Developer knobs: per-CTA %globaltimer stamps of the update kernel's phases (12 per CTA, nanoseconds: start, tables built,
+ * rollout done, weighted sum done, partial published, partials merged, peer payloads in, update applied, then internal stamps)
+ * of the last update, [n_controllers][grid.x][12]; mppi_last_grid_x = grid.x of the last update launch. */
+int mppi_debug_trace(mppi_handle *h, int on);
+int mppi_debug_get_trace(mppi_handle *h, unsigned long long *out, int n_ctas);
+int mppi_last_grid_x(const mppi_handle *h);
+
 /* Library/version info: returns a static string such as "mppi_b200 0.1 sm_100a". */
 const char *mppi_version(void);
 

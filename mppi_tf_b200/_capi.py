@@ -128,6 +128,9 @@ SYMBOLS = {
     "mppi_get_new": (_i, [_i, _i, _fp, _i, _fp]),
     "mppi_shift": (_i, [_i, _i, _fp, _fp, _i, _fp]),
     "mppi_philox_raw": (_i, [_i, _u64, _u32, _u32, _u32, _u32, _i, C.POINTER(_u32)]),
+    "mppi_debug_trace": (_i, [_H, _i]),
+    "mppi_debug_get_trace": (_i, [_H, C.POINTER(C.c_uint64), _i]),
+    "mppi_last_grid_x": (_i, [_H]),
     "mppi_philox_raw_rounds": (_i, [_i, _u64, _u32, _u32, _u32, _u32, _i, _i, C.POINTER(_u32)]),
 }
 

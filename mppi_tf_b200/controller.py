@@ -387,6 +387,17 @@ class ControllerBase:
         check(self._lib.mppi_set_ellipse3d_cost(self._h, _ptr(_f32(normal).ravel()), _ptr(_f32(a_vec).ravel()), _ptr(_f32(axis).ravel()),
                                                 _ptr(_f32(center).ravel()), float(speed), float(m_state), float(m_vel)), self._h)
 
+    # ---- developer knobs ------------------------------------------------------------------------------
+    def debugTrace(self, on=True):
+        check(self._lib.mppi_debug_trace(self._h, int(bool(on))), self._h)
+
+    def getTrace(self):
+        """[n, grid_x, 12] uint64 nanosecond stamps of the last update's phases (see include/mppi_b200.h)."""
+        gx = self._lib.mppi_last_grid_x(self._h)
+        out = np.zeros((self.n * gx, 12), np.uint64)
+        check(self._lib.mppi_debug_get_trace(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), self.n * gx), self._h)
+        return out.reshape(self.n, gx, 12)
+
     # ---- asynchronous halves (bench / multi-rank) ---------------------------------------------------
     def setState(self, x):
         x = _f32(x).reshape(self.n, self.s_dim)

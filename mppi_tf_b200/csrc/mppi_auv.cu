@@ -182,7 +182,7 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
             for (int i = 0; i < 32; i++) acc[i] = 0.f;
             for (int wg = w_lo + warp; wg < w_hi; wg += NW) {
                 const int k = 32 * wg + lane;
-                const float e = (k < p.K_local) ? weight_exp(costs[k], beta_c, nil) : 0.f;
+                const float e = (k < p.K_local) ? sample_weight(costs[k], beta_c, nil) : 0.f;
                 if (ch == 0) eta += e;
                 if (__ballot_sync(0xffffffffu, e != 0.f) == 0u) continue;        // the whole group underflowed
                 const uint32_t kg = (uint32_t)(p.k_offset + k);
@@ -207,7 +207,7 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
             for (int i = 0; i < 8; i++) acc[i] = 0.f;
             for (int wg = w_lo + warp; wg < w_hi; wg += NW) {
                 const int k = 32 * wg + lane;
-                const float e = (k < p.K_local) ? weight_exp(costs[k], beta_c, nil) : 0.f;
+                const float e = (k < p.K_local) ? sample_weight(costs[k], beta_c, nil) : 0.f;
                 if (cb == 0) eta += e;
                 unsigned live = __ballot_sync(0xffffffffu, e != 0.f);
                 while (live) {

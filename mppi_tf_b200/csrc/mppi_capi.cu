@@ -16,6 +16,7 @@
 #include "mppi_auv.cuh"
 #include "mppi_mlp.cuh"
 #include "mppi_linear.cuh"
+#include "mppi_update.cuh"
 
 using namespace mppi;
 
@@ -71,7 +72,8 @@ struct mppi_handle {
     float inv_sigma[kMaxA * kMaxA];
     bool normalize = false;
     float *d_norm = nullptr;
-    int cost_kind = 0;            // 0 StaticCost, 1 ElipseCost (mppi_set_ellipse_cost)
+    int cost_kind = 0;            // 0 StaticCost, 1 ElipseCost (mppi_set_ellipse_cost), 2 StaticQuatCost, 3 ElipseCost3D
+    float q10[kMaxS] = {0};       // StaticQuatCost weights, kept apart from q so that mppi_set_static_cost finds q untouched
     float ell[12] = {0};
     uint64_t seed = 1;
     int rounds = 10;              // Philox4x32-R (mppi_config.philox_rounds)
@@ -80,13 +82,16 @@ struct mppi_handle {
     bool last_fast = false;       // the last update ran in the superposition form: costs / beta on the device are relative to d_cost_base
     float *d_cost_base = nullptr;
     size_t smem_sm = 0;
+    unsigned long long *d_trace = nullptr;      // developer knob: phase time stamps (mppi_debug_trace)
+    size_t trace_ctas = 0;
     uint32_t update_counter = 0, last_update = 0;
     bool have_philox_update = false, last_philox = true, pending_finish = false;
     int device = 0, num_sms = 148;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int max_gx = 1;
+    int max_gx = 1, last_gx = 0, max_groups = 1;
+    float *d_partials2 = nullptr;
     // device buffers
     float *d_x = nullptr, *d_goal = nullptr, *d_U = nullptr, *d_Unew = nullptr, *d_next = nullptr;
     float *d_costs = nullptr, *d_partials = nullptr, *d_payload = nullptr, *d_gather = nullptr, *d_stats = nullptr;
@@ -95,6 +100,12 @@ struct mppi_handle {
     bool ext_exchange = false;
     // pinned host staging
     float *h_x = nullptr, *h_next = nullptr;
+    // batched handles copy the states H2D asynchronously: two staging buffers, each guarded by the event of its last copy,
+    // so an asynchronous caller (set_state / enqueue_update in a loop) never overwrites a buffer the DMA still reads
+    float *h_xs[2] = {nullptr, nullptr};
+    cudaEvent_t x_ev[2] = {nullptr, nullptr};
+    bool x_ev_armed[2] = {false, false};
+    int x_idx = 0;
     // zero-copy result path (n_ctrl == 1): mapped pinned [a floats | pad | completion word]
     float *h_zc = nullptr, *d_zc = nullptr;
     unsigned int zc_epoch = 0;
@@ -200,13 +211,14 @@ RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
     p.n_ctrl = h->n_ctrl;
     p.n_iter = 1;
     p.world = h->world;
+    p.max_parts = h->max_gx;
     p.dt = h->dt;
     p.c_pu = (h->dt * h->dt) / 2.0f / h->mass;
     p.c_vu = h->dt / h->mass;
     p.lambda = h->lambda;
     p.neg_inv_lambda_log2e = -kLog2e / h->lambda;
-    memcpy(p.q, h->q, sizeof(p.q));
-    for (int i = 0; i < kMaxS; i++) p.sqrt_q[i] = sqrtf(h->q[i] > 0.f ? h->q[i] : 0.f);
+    memcpy(p.q, h->cost_kind == 2 ? h->q10 : h->q, sizeof(p.q));
+    for (int i = 0; i < kMaxS; i++) p.sqrt_q[i] = sqrtf(p.q[i] > 0.f ? p.q[i] : 0.f);
     const int a = h->a;
     const bool py = h->cost_form == MPPI_ACTION_COST_PYTHON;
     for (int i = 0; i < a * a; i++) p.sigma[i] = h->upsilon * h->sigma[i];   // sampling scale: eps = (upsilon Sigma) z
@@ -259,6 +271,7 @@ RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
             p.fb2[j] = p.z_scale * sqv * p.c_vu * sg;
         }
     }
+    p.trace = h->d_trace;
     p.x_inline = (h->n_ctrl == 1);
     if (p.x_inline) memcpy(p.x0, h->h_x, sizeof(float) * h->s);
     p.x = h->d_x;
@@ -268,13 +281,15 @@ RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
     p.next = h->d_next;
     p.costs = h->d_costs;
     p.partials = h->d_partials;
+    p.partials2 = h->d_partials2;
+    p.max_groups = h->max_groups;
     p.payload = h->d_payload;
     p.stats = h->d_stats;
     p.counters = h->d_counters;
     p.eps = eps_dev;
     if (h->d_zc && h->zc_request) {
         p.next_host = h->d_zc;
-        p.done_host = reinterpret_cast<unsigned int *>(h->d_zc + 16);
+        p.done_host = nullptr;
         p.done_epoch = h->zc_epoch;
     }
     p.peer_on = h->peer_on ? 1 : 0;
@@ -405,20 +420,26 @@ int mppi_create(const mppi_config *cfg, mppi_handle **out)
     CU_TRY_C(cudaMalloc(&h->d_Unew, sizeof(float) * n_ctrl * h->TA));
     CU_TRY_C(cudaMalloc(&h->d_next, sizeof(float) * n_ctrl * a));
     CU_TRY_C(cudaMalloc(&h->d_costs, sizeof(float) * (size_t)n_ctrl * h->K_local));
+    h->max_groups = (h->max_gx + kMergeGroup - 1) / kMergeGroup;
     CU_TRY_C(cudaMalloc(&h->d_partials, sizeof(float) * (size_t)n_ctrl * h->max_gx * h->stride));
+    CU_TRY_C(cudaMalloc(&h->d_partials2, sizeof(float) * (size_t)n_ctrl * h->max_groups * h->stride));
     CU_TRY_C(cudaMalloc(&h->d_payload, sizeof(float) * (size_t)n_ctrl * h->stride));
     CU_TRY_C(cudaMalloc(&h->d_gather, sizeof(float) * (size_t)world * n_ctrl * h->stride));
     CU_TRY_C(cudaMalloc(&h->d_stats, sizeof(float) * 2 * n_ctrl));
     CU_TRY_C(cudaMalloc(&h->d_norm, sizeof(float) * 2 * n_ctrl));
     CU_TRY_C(cudaMalloc(&h->d_cost_base, sizeof(float) * n_ctrl));
     CU_TRY_C(cudaMemset(h->d_cost_base, 0, sizeof(float) * n_ctrl));
-    CU_TRY_C(cudaMalloc(&h->d_counters, sizeof(unsigned int) * n_ctrl));
-    CU_TRY_C(cudaMemset(h->d_counters, 0, sizeof(unsigned int) * n_ctrl));
+    CU_TRY_C(cudaMalloc(&h->d_counters, sizeof(unsigned int) * (size_t)n_ctrl * (1 + h->max_groups)));
+    CU_TRY_C(cudaMemset(h->d_counters, 0, sizeof(unsigned int) * (size_t)n_ctrl * (1 + h->max_groups)));
     CU_TRY_C(cudaMemset(h->d_U, 0, sizeof(float) * n_ctrl * h->TA));
     CU_TRY_C(cudaMemset(h->d_Unew, 0, sizeof(float) * n_ctrl * h->TA));
     CU_TRY_C(cudaMemset(h->d_stats, 0, sizeof(float) * 2 * n_ctrl));
     CU_TRY_C(cudaMemset(h->d_x, 0, sizeof(float) * n_ctrl * s));
-    CU_TRY_C(cudaMallocHost(&h->h_x, sizeof(float) * n_ctrl * s));
+    CU_TRY_C(cudaMallocHost(&h->h_xs[0], sizeof(float) * n_ctrl * s));
+    CU_TRY_C(cudaMallocHost(&h->h_xs[1], sizeof(float) * n_ctrl * s));
+    CU_TRY_C(cudaEventCreateWithFlags(&h->x_ev[0], cudaEventDisableTiming));
+    CU_TRY_C(cudaEventCreateWithFlags(&h->x_ev[1], cudaEventDisableTiming));
+    h->h_x = h->h_xs[0];
     CU_TRY_C(cudaMallocHost(&h->h_next, sizeof(float) * n_ctrl * a));
     if (n_ctrl == 1) {
         if (cudaHostAlloc(&h->h_zc, 128, cudaHostAllocMapped) == cudaSuccess &&
@@ -431,7 +452,8 @@ int mppi_create(const mppi_config *cfg, mppi_handle **out)
             h->d_zc = nullptr;
         }
     }
-    memset(h->h_x, 0, sizeof(float) * n_ctrl * s);
+    memset(h->h_xs[0], 0, sizeof(float) * n_ctrl * s);
+    memset(h->h_xs[1], 0, sizeof(float) * n_ctrl * s);
 
     std::vector<float> goal(n_goal);
     for (size_t i = 0; i < n_goal; i++)
@@ -455,15 +477,19 @@ int mppi_destroy(mppi_handle *h)
     cudaFree(h->d_mailbox); cudaFree(h->d_peer_status);
     if (h->h_peer_status) cudaFreeHost(h->h_peer_status);
     cudaFree(h->d_x); cudaFree(h->d_goal); cudaFree(h->d_U); cudaFree(h->d_Unew); cudaFree(h->d_next);
-    cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_counters);
+    cudaFree(h->d_costs); cudaFree(h->d_partials); cudaFree(h->d_partials2); cudaFree(h->d_stats); cudaFree(h->d_counters);
     cudaFree(h->d_norm);
     cudaFree(h->d_cost_base);
+    cudaFree(h->d_trace);
     cudaFree(h->d_eps_tmp);
     cudaFree(h->d_wblob);
     cudaFree(h->d_fvec);
     cudaFree(h->d_params); cudaFree(h->d_adam_m); cudaFree(h->d_adam_v); cudaFree(h->d_train_work); cudaFree(h->d_loss);
     if (!h->ext_exchange) { cudaFree(h->d_payload); cudaFree(h->d_gather); }
-    if (h->h_x) cudaFreeHost(h->h_x);
+    for (int i = 0; i < 2; i++) {
+        if (h->h_xs[i]) cudaFreeHost(h->h_xs[i]);
+        if (h->x_ev[i]) cudaEventDestroy(h->x_ev[i]);
+    }
     if (h->h_next) cudaFreeHost(h->h_next);
     if (h->h_zc) cudaFreeHost(h->h_zc);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -490,9 +516,18 @@ int mppi_set_state(mppi_handle *h, const float *x_host)
 {
     if (!h || !x_host) return fail(h, MPPI_ERR_BAD_ARG, "null handle/state");
     CU_TRY(h, cudaSetDevice(h->device));
-    memcpy(h->h_x, x_host, sizeof(float) * h->n_ctrl * h->s);
-    if (h->n_ctrl > 1)
+    if (h->n_ctrl > 1) {
+        const int i = h->x_idx;
+        if (h->x_ev_armed[i]) CU_TRY(h, cudaEventSynchronize(h->x_ev[i]));     // the copy that last read this buffer is done
+        h->h_x = h->h_xs[i];
+        memcpy(h->h_x, x_host, sizeof(float) * h->n_ctrl * h->s);
         CU_TRY(h, cudaMemcpyAsync(h->d_x, h->h_x, sizeof(float) * h->n_ctrl * h->s, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaEventRecord(h->x_ev[i], h->stream));
+        h->x_ev_armed[i] = true;
+        h->x_idx ^= 1;
+    } else {
+        memcpy(h->h_x, x_host, sizeof(float) * h->s);      // travels by value in the kernel parameter block
+    }
     h->x_staged = true;
     return MPPI_OK;
 }
@@ -536,6 +571,7 @@ int mppi_enqueue_update(mppi_handle *h, const float *eps_dev)
     }
     h->last_philox = (eps_dev == nullptr);
     h->last_fast = p.fast != 0;
+    h->last_gx = gx;
     if (!eps_dev) {
         h->have_philox_update = true;
         h->last_update = h->update_counter;
@@ -584,18 +620,30 @@ int mppi_fetch_action(mppi_handle *h, float *action_host)
     // into mapped pinned memory; wait for the word instead of copying and synchronising the stream
     const bool finish_in_kernel = (h->world <= 1) || h->peer_on;
     if (h->zc_armed && h->h_zc && finish_in_kernel && !h->pending_finish) {
-        volatile unsigned int *done = reinterpret_cast<volatile unsigned int *>(h->h_zc + 16);
+        // slot i = {action_i, epoch} (i < a), slot 8 = {exchange status, epoch}: each an 8-byte store of the finishing CTA
+        volatile unsigned int *zc = reinterpret_cast<volatile unsigned int *>(h->h_zc);
+        auto all_in = [&]() {
+            if (zc[2 * 8 + 1] != h->zc_epoch) return false;
+            for (int i = 0; i < h->a; i++)
+                if (zc[2 * i + 1] != h->zc_epoch) return false;
+            return true;
+        };
         bool seen = false;
         for (long long spin = 0; spin < (1LL << 34); spin++) {
-            if (*done == h->zc_epoch) { seen = true; break; }
+            if (all_in()) { seen = true; break; }
             if ((spin & 0xfffff) == 0xfffff && cudaStreamQuery(h->stream) != cudaErrorNotReady) break;   // finished or failed
         }
         h->zc_armed = false;
-        if (seen || *done == h->zc_epoch) {
+        if (seen || all_in()) {
             std::atomic_thread_fence(std::memory_order_acquire);
-            memcpy(action_host, h->h_zc, sizeof(float) * h->a);
-            if (h->peer_on && reinterpret_cast<volatile unsigned int *>(h->h_zc)[8] != 0u)
-                return fail(h, MPPI_ERR_COMM, "fused exchange: a peer's payload did not arrive in time (is every rank calling the update?)");
+            for (int i = 0; i < h->a; i++) {
+                const unsigned int w = zc[2 * i];
+                memcpy(action_host + i, &w, sizeof(float));
+            }
+            if (h->peer_on && zc[2 * 8] != 0u) {
+                cudaMemsetAsync(h->d_peer_status, 0, sizeof(unsigned int), h->stream);    // reported: the next update starts clean
+                return fail(h, MPPI_ERR_COMM, "fused exchange: a peer's payload did not arrive in time (is every rank calling the update?); the sequence was left unchanged");
+            }
             return MPPI_OK;
         }
         CU_TRY(h, cudaStreamSynchronize(h->stream));    // surfaces the launch failure, if any; else fall through
@@ -606,8 +654,10 @@ int mppi_fetch_action(mppi_handle *h, float *action_host)
         CU_TRY(h, cudaMemcpyAsync(h->h_peer_status, h->d_peer_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     memcpy(action_host, h->h_next, sizeof(float) * h->n_ctrl * h->a);
-    if (h->peer_on && *h->h_peer_status != 0u)
-        return fail(h, MPPI_ERR_COMM, "fused exchange: a peer's payload did not arrive in time (is every rank calling the update?)");
+    if (h->peer_on && *h->h_peer_status != 0u) {
+        cudaMemsetAsync(h->d_peer_status, 0, sizeof(unsigned int), h->stream);            // reported: the next update starts clean
+        return fail(h, MPPI_ERR_COMM, "fused exchange: a peer's payload did not arrive in time (is every rank calling the update?); the sequence was left unchanged");
+    }
     return MPPI_OK;
 }
 
@@ -751,7 +801,6 @@ int mppi_set_sigma(mppi_handle *h, const float *sigma_host)
 int mppi_set_q(mppi_handle *h, const float *q_host)
 {
     if (!h || !q_host) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
-    if (h->cost_kind == 2) return fail(h, MPPI_ERR_STATE, "StaticQuatCost is active: its weights are set by mppi_set_quat_cost");
     for (int i = 0; i < h->s; i++)
         if (!(q_host[i] >= 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "q must be non-negative (diag of a PSD Q)");
     memcpy(h->q, q_host, sizeof(float) * h->s);
@@ -819,6 +868,34 @@ int mppi_set_update_counter(mppi_handle *h, uint32_t counter)
     h->update_counter = counter;
     return MPPI_OK;
 }
+
+// Developer knob: %globaltimer stamps of the update kernel's phases (see RolloutParams::trace), [n_controllers][grid.x][12]
+// nanoseconds of the LAST update.  mppi_debug_trace(h, 1) arms it (a few stores per CTA), (h, 0) disarms.
+int mppi_debug_trace(mppi_handle *h, int on)
+{
+    if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_trace);
+    h->d_trace = nullptr;
+    h->trace_ctas = 0;
+    if (on) {
+        h->trace_ctas = (size_t)h->n_ctrl * h->max_gx;
+        CU_TRY(h, cudaMalloc(&h->d_trace, sizeof(unsigned long long) * kTraceSlots * h->trace_ctas));
+        CU_TRY(h, cudaMemset(h->d_trace, 0, sizeof(unsigned long long) * kTraceSlots * h->trace_ctas));
+    }
+    return MPPI_OK;
+}
+int mppi_debug_get_trace(mppi_handle *h, unsigned long long *out, int n_ctas)
+{
+    if (!h || !out || n_ctas <= 0) return fail(h, MPPI_ERR_BAD_ARG, "bad argument");
+    if (!h->d_trace || (size_t)n_ctas > h->trace_ctas) return fail(h, MPPI_ERR_STATE, "trace not armed (mppi_debug_trace) or too many CTAs asked for");
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaMemcpyAsync(out, h->d_trace, sizeof(unsigned long long) * kTraceSlots * n_ctas, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+int mppi_last_grid_x(const mppi_handle *h) { return h ? h->last_gx : 0; }
 
 int mppi_dump_noise(mppi_handle *h, float *eps_host)
 {
@@ -900,8 +977,8 @@ int mppi_peer_attach(mppi_handle *h, const void *handles)
         h->peer_base[r] = ptr;
         h->peer_opened[r] = true;
     }
+    if (!h->peer_on) h->epoch = 0;      // a re-attach keeps counting: flags of earlier epochs can never match a later one
     h->peer_on = true;
-    h->epoch = 0;
     return MPPI_OK;
 }
 int mppi_comm_unique_id(void *id128)
@@ -1022,8 +1099,8 @@ int mppi_set_quat_cost(mppi_handle *h, const float *q10)
     if (!h->auv) return fail(h, MPPI_ERR_UNSUPPORTED, "StaticQuatCost is defined on the 13-dimensional AUV state");
     for (int i = 0; i < 10; i++)
         if (!(q10[i] >= 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "q must be non-negative (diag of a PSD Q)");
-    memset(h->q, 0, sizeof(h->q));
-    memcpy(h->q, q10, sizeof(float) * 10);
+    memset(h->q10, 0, sizeof(h->q10));
+    memcpy(h->q10, q10, sizeof(float) * 10);
     h->cost_kind = 2;
     return MPPI_OK;
 }

@@ -25,6 +25,7 @@ struct RolloutParams {
     int n_ctrl;
     int n_iter;       // samples per thread in the Philox kernel
     int world;        // > 1: the last CTA writes the rank payload instead of applying the update
+    int max_parts;    // partial records per controller the handle has room for: every launcher keeps grid.x within it
     // model (ModelBase: A = blkdiag([[1,dt],[0,1]]), B = blkdiag([[dt^2/2],[dt]]) / mass)
     float dt, c_pu, c_vu;
     // cost (CostBase): lambda, diag(Q), Sigma (scale) and lambda * Sigma^-T (action cost)
@@ -76,9 +77,11 @@ struct RolloutParams {
     float *next;             // [n_ctrl][a]
     float *costs;            // [n_ctrl][K_local]
     float *partials;         // [n_ctrl][gridDim.x][stride]
+    float *partials2;        // [n_ctrl][max_groups][stride]  group records of the two-level merge (mppi_update.cuh)
+    int max_groups;
     float *payload;          // [n_ctrl][stride]   (world > 1)
     float *stats;            // [n_ctrl][2]        beta, eta of the last update
-    unsigned int *counters;  // [n_ctrl] last-CTA election
+    unsigned int *counters;  // [n_ctrl][1 + max_groups] last-CTA election: top level, then one counter per merge group
     const float *eps;        // injected noise [n_ctrl][K_local][T][a] or nullptr
     // fused exchange over peer memory (world > 1, mppi_peer_attach): every rank's mailbox
     //   mail [2][world][n_ctrl][stride] floats, flag [2][world][n_ctrl] epochs, mapped into this process
@@ -89,10 +92,24 @@ struct RolloutParams {
     unsigned int *peer_status;   // set != 0 if a peer's payload did not arrive in time
     // zero-copy result (single controller): the finishing CTA also stores the action into mapped pinned host
     // memory and publishes `done_epoch`, so the synchronous next() needs neither a D2H copy nor a stream sync
+    // developer knob (MPPI_TRACE=1 at mppi_create, mppi_debug_trace): %globaltimer stamps [n_ctrl][gridDim.x][12] of the phases
+    //   0 start, 1 tables built, 2 rollout done, 3 weighted sum done, 4 partial published, 5 partials merged (last CTA),
+    //   6 peer payloads in (last CTA), 7 update applied (last CTA); 8 weights / list built, 9 list walked (regenerating kernels)
+    unsigned long long *trace;
     float *next_host;            // device alias of the mapped host buffer [a], or nullptr
     unsigned int *done_host;     // device alias of the mapped completion word
     unsigned int done_epoch;
 };
+
+constexpr int kTraceSlots = 12;
+__device__ __forceinline__ void trace_stamp(const RolloutParams &p, int ctrl, int slot)
+{
+    if (p.trace != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[((size_t)ctrl * gridDim.x + blockIdx.x) * kTraceSlots + slot] = t;
+    }
+}
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
 {
@@ -346,14 +363,26 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane)
     return v[0];
 }
 
-// exp(-(S - beta)/lambda) through one MUFU.EX2 with the max-shift already applied.  Flush-to-zero on
-// purpose: a weight below 2^-126 of the block's best sample is exactly 0.0f, and the kernels skip
-// zero-weight samples in the weighted noise sum (0 * z adds exactly nothing).
+// exp(-(S - beta)/lambda) through one MUFU.EX2 with the max-shift already applied (flush-to-zero).  Used for the
+// rescaling of partial sums (CTA / warp / rank records), where nothing is cut.
 __device__ __forceinline__ float weight_exp(float S, float beta, float neg_inv_lambda_log2e)
 {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((S - beta) * neg_inv_lambda_log2e));
     return r;
+}
+// The weight of ONE SAMPLE relative to the best sample seen so far by its CTA (or warp).  Weights below 2^-50 of that
+// best one are set to exactly 0 and the kernels skip zero-weight samples in the weighted noise sum: over K <= 2^20
+// samples the dropped mass is below 2^-30 = 9.3e-10 of eta - under one fp32 ulp (6e-8) of the sums it would enter, where
+// such terms are rounded away one by one anyway.  (Round 1 cut at fp32 underflow, 2^-126; the samples between the two
+// cuts are the bulk of what the weighted sum used to revisit: 22 % -> 7 % of K at config 3's inputs.)
+constexpr float kWeightCutLog2 = 50.0f;
+__device__ __forceinline__ float sample_weight(float S, float beta, float neg_inv_lambda_log2e)
+{
+    const float a = (S - beta) * neg_inv_lambda_log2e;      // <= 0 (up to rounding), log2 of the weight
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return a < -kWeightCutLog2 ? 0.f : r;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -485,6 +514,34 @@ __device__ __forceinline__ void add_state_cost(const PointMass<A> &x, const Mode
     } else {
         x.state_cost(mc, S.a2, S.a);
     }
+}
+
+// Thread-block clusters: rank / size of this CTA's cluster (1 when the kernel was launched without a cluster dimension),
+// the cluster barrier, and a load from the same shared-memory address of another CTA of the cluster (DSMEM).
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float *local_smem_ptr, uint32_t rank)
+{
+    uint32_t remote;
+    float v;
+    // not volatile: the loads of a reduction are independent and must be free to overlap (they are fenced by cluster_sync)
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(local_smem_ptr)), "r"(rank));
+    asm("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
+    return v;
 }
 
 // mbarrier / bulk-copy (TMA) helpers -----------------------------------------------------------

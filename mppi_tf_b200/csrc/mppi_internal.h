@@ -22,7 +22,7 @@ int philox_grid_x(int K_local, int n_ctrl, int num_sms);
 cudaError_t launch_rollout_philox_fast(RolloutParams p, int a, int variant, int num_sms, size_t smem_sm, size_t smem_limit,
                                        cudaStream_t st, int *grid_x_out);
 bool resident_geometry(int A, int T, int TA, int K_local, int n_ctrl, int num_sms, size_t smem_sm, size_t smem_cta_limit, int *nw_out,
-                       int *rs_out, int *cw_out, int *grid_x_out, size_t *smem_out);
+                       int *rs_out, int *cw_out, int *grid_x_out, size_t *smem_out, bool *latency_out);
 
 #define MPPI_DISPATCH_A(a, ...)                  \
     switch (a) {                                 \

@@ -20,7 +20,7 @@
 
 namespace mppi {
 
-constexpr int kFastMaxT = 256;     // the tables are built with O(T) work per entry; longer horizons take the direct form
+constexpr int kFastMaxT = 1024;    // the tables are built by 2T dependent steps per axis; longer horizons take the direct form
 
 template <int A>
 struct FastConsts {
@@ -78,67 +78,99 @@ __device__ __forceinline__ void fast_terminal(const Vec<A> &P, const Vec<A> &V, 
 
 // Builds the per-controller tables in shared memory; every thread of the CTA must call it (contains CTA barriers).
 //   sL   [T][RS]   L_tau (zero padded), RS = RowU<A>::RS
-//   sD   scratch, >= 2 * A * T floats (D_p, D_v of steps 1..T), free afterwards
+//   sD   scratch, >= (3 A + 1) T floats: U staged [T][A], then D_p / D_v of steps 1..T [T][2A], then T partial sums
 //   sRed scratch, >= 1 float
-// `lin_scale`: w_scale * z_scale (Philox mode, n = z / z_scale) or 1 with `lin_from_w` set (injected mode: the action-cost
-// vector is lambda Sigma^-T U_t, computed here from p.lam_inv_sigma_T).  Returns C (without C0), CTA-uniform, fixed order.
+// Philox mode: L = G + w_scale z_scale U (n = z / z_scale); injected mode: L = G + lambda Sigma^-T U (n = eps).
+// The forward (noise-free trajectory) and backward (adjoint) passes are the model's own recurrences, one thread per
+// axis — 2T dependent steps of two or three FMAs, about a microsecond at T = 100 — and the sum C = sum_t w_t |D_t|^2
+// is taken over per-step partials in a fixed order.  Returns C (without C0), CTA-uniform.
 template <int A, bool PHILOX>
 __device__ __forceinline__ float build_linear_tables(const RolloutParams &p, int ctrl, float *sL, float *sD, float *sRed)
 {
     constexpr int RS = (A + 3) & ~3;
     const int T = p.T, tid = threadIdx.x, nthr = blockDim.x;
     const float *U = p.U + (size_t)ctrl * p.TA;
-    const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * 2 * A : 0);
-    const float *xp = p.x + (size_t)ctrl * 2 * A;
-    const float dtcvu = p.dt * p.c_vu;
-    // forward: noise-free deviations at t = 1..T, one (t, axis) item per thread, closed form
-    //   v_t = v_0 + c_vu sum_{tau<t} U_tau ;  p_t = p_0 + t dt v_0 + sum_{tau<t} [c_pu + dt c_vu (t-1-tau)] U_tau
-    for (int it = tid; it < T * A; it += nthr) {
-        const int t = it / A + 1, j = it - (t - 1) * A;
-        float su = 0.f, sp = 0.f;
-        for (int tau = 0; tau < t; tau++) {
-            const float u = U[tau * A + j];
-            su += u;
-            sp = fmaf(fmaf(dtcvu, (float)(t - 1 - tau), p.c_pu), u, sp);
+    float *sU = sD;                                   // [T][A]
+    float *sDev = sD + A * T;                         // [T][2A]: D_p[A], D_v[A] of step t + 1
+    float *sC = sDev + 2 * A * T;                     // [T]
+    // goal and state of this thread's axis: loaded before the barrier, together with the sequence (one L2 round trip)
+    float gpj = 0.f, gvj = 0.f, pj = 0.f, vj = 0.f;
+    if (tid < A) {
+        const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * 2 * A : 0);
+        const float *xp = p.x + (size_t)ctrl * 2 * A;
+        gpj = gp[2 * tid];
+        gvj = gp[2 * tid + 1];
+        pj = p.x_inline ? p.x0[2 * tid] : xp[2 * tid];
+        vj = p.x_inline ? p.x0[2 * tid + 1] : xp[2 * tid + 1];
+    }
+    for (int i = tid; i < T * A; i += nthr) sU[i] = U[i];
+    for (int i = tid; i < T * RS; i += nthr) sL[i] = 0.f;
+    __syncthreads();
+    if (tid < A) {
+        const int j = tid;
+        const float sqp = p.sqrt_q[2 * j], sqv = p.sqrt_q[2 * j + 1];
+        // forward: x' = A x + (B/m) U_t, exactly the model step (src/model_base.cpp:53-82); eight steps at a time so that the
+        // shared-memory loads of a chunk are in flight together (the recurrence itself is two dependent FMAs per step)
+        constexpr int CH = 8;
+        for (int t0 = 0; t0 < T; t0 += CH) {
+            float u[CH];
+#pragma unroll
+            for (int i = 0; i < CH; i++) u[i] = (t0 + i < T) ? sU[(t0 + i) * A + j] : 0.f;
+            float dp[CH], dv[CH];
+#pragma unroll
+            for (int i = 0; i < CH; i++) {
+                pj = fmaf(p.c_pu, u[i], fmaf(p.dt, vj, pj));
+                vj = fmaf(p.c_vu, u[i], vj);
+                dp[i] = sqp * (pj - gpj);
+                dv[i] = sqv * (vj - gvj);
+            }
+#pragma unroll
+            for (int i = 0; i < CH; i++)
+                if (t0 + i < T) {
+                    sDev[2 * (t0 + i) * A + j] = dp[i];
+                    sDev[(2 * (t0 + i) + 1) * A + j] = dv[i];
+                }
         }
-        const float p0 = p.x_inline ? p.x0[2 * j] : xp[2 * j], v0 = p.x_inline ? p.x0[2 * j + 1] : xp[2 * j + 1];
-        const float pt = fmaf((float)t * p.dt, v0, p0) + sp;
-        const float vt = fmaf(p.c_vu, su, v0);
-        sD[(2 * (t - 1)) * A + j] = p.sqrt_q[2 * j] * (pt - gp[2 * j]);
-        sD[(2 * (t - 1) + 1) * A + j] = p.sqrt_q[2 * j + 1] * (vt - gp[2 * j + 1]);
+        // backward: aP_t = g_P,t + aP_{t+1}; aV_t = g_V,t + aV_{t+1} + a1 aP_{t+1}; g = 2 w_t D_t; G_tau = b1 aP_{tau+1} + b2 aV_{tau+1}
+        const float a1 = p.fa1[j], b1 = p.fb1[j], b2 = p.fb2[j];
+        float aP = 0.f, aV = 0.f;
+        for (int t0 = T; t0 >= 1; t0 -= CH) {                      // steps t0, t0-1, .. t0-CH+1
+            float dp[CH], dv[CH], lin[CH];
+#pragma unroll
+            for (int i = 0; i < CH; i++) {
+                const int t = t0 - i;
+                dp[i] = (t >= 1) ? sDev[2 * (t - 1) * A + j] : 0.f;
+                dv[i] = (t >= 1) ? sDev[(2 * (t - 1) + 1) * A + j] : 0.f;
+                lin[i] = 0.f;
+                if (t >= 1) {
+                    if (PHILOX) {
+                        lin[i] = p.w_scale * p.z_scale * sU[(t - 1) * A + j];
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < A; l++) lin[i] = fmaf(p.lam_inv_sigma_T[j * A + l], sU[(t - 1) * A + l], lin[i]);
+                    }
+                }
+            }
+            float Lv[CH];
+#pragma unroll
+            for (int i = 0; i < CH; i++) {
+                const int t = t0 - i;
+                const float w2 = (t == T) ? 4.f : 2.f;
+                const float aPn = fmaf(w2, dp[i], aP);
+                aV = fmaf(a1, aP, fmaf(w2, dv[i], aV));
+                aP = aPn;
+                Lv[i] = fmaf(b1, aP, fmaf(b2, aV, lin[i]));
+            }
+#pragma unroll
+            for (int i = 0; i < CH; i++)
+                if (t0 - i >= 1) sL[(t0 - i - 1) * RS + j] = Lv[i];
+        }
     }
     __syncthreads();
-    // backward: G_tau = 2 sum_{t>tau} w_t [D_p,t (b1 + a1 b2 (t-1-tau)) + D_v,t b2]
-    for (int it = tid; it < T * RS; it += nthr) {
-        const int tau = it / RS, j = it - tau * RS;
-        float L = 0.f;
-        if (j < A) {
-            const float a1b2 = p.fa1[j] * p.fb2[j];
-            float g = 0.f;
-            for (int t = tau + 1; t <= T; t++) {
-                const float w = (t == T) ? 4.f : 2.f;
-                const float dp = sD[(2 * (t - 1)) * A + j], dv = sD[(2 * (t - 1) + 1) * A + j];
-                g = fmaf(w, fmaf(dp, fmaf(a1b2, (float)(t - 1 - tau), p.fb1[j]), dv * p.fb2[j]), g);
-            }
-            float lin;
-            if (PHILOX) {
-                lin = p.w_scale * p.z_scale * U[tau * A + j];
-            } else {
-                lin = 0.f;
-#pragma unroll
-                for (int l = 0; l < A; l++) lin = fmaf(p.lam_inv_sigma_T[j * A + l], U[tau * A + l], lin);
-            }
-            L = g + lin;
-        }
-        sL[it] = L;
-    }
-    // C = sum_t w_t |D_t|^2: per-step partials, summed in a fixed order by warp 0
-    __syncthreads();                                 // everyone is done reading... (sD is read again below: no writes yet)
-    float *sC = sD + 2 * A * T;                      // [T] partials (the caller sizes sD as 2*A*T + T)
     for (int t = tid; t < T; t += nthr) {
         float c = 0.f;
 #pragma unroll
-        for (int j = 0; j < 2 * A; j++) { const float d = sD[2 * t * A + j]; c = fmaf(d, d, c); }
+        for (int j = 0; j < 2 * A; j++) { const float d = sDev[2 * t * A + j]; c = fmaf(d, d, c); }
         sC[t] = (t == T - 1) ? 2.f * c : c;
     }
     __syncthreads();

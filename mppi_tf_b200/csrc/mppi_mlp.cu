@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
     // zero-weight compaction as in rollout_philox_kernel: a weight that underflowed to 0.0f adds exactly
     // nothing, so only the other samples are revisited (per-warp ordered lists; dense loop when no weight
     // of the CTA can underflow)
-    const bool sparse = (max_c - beta_c) * fabsf(nil) > 125.f;         // CTA-uniform
+    const bool sparse = (max_c - beta_c) * fabsf(nil) > kWeightCutLog2;         // CTA-uniform
     float *myacc = sAcc + warp * TAp;
     for (int j = lane; j < TAp; j += 32) myacc[j] = 0.f;
     uint2 *wlist = sList + warp * kMlpListCap;
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) rollout_mlp_kernel(const __gri
         for (int it = 0; it < nit; it++) {
             const int k = kb + it * kMlpThreads + lane;
             float e = 0.f;
-            if (k < k_hi) e = weight_exp(costs[k], beta_c, nil);
+            if (k < k_hi) e = sample_weight(costs[k], beta_c, nil);
             eta += e;
             const bool keep = sparse ? (e != 0.f) : (k < k_hi);
             const unsigned m = __ballot_sync(0xffffffffu, keep);

@@ -85,7 +85,7 @@ __device__ __forceinline__ void philox_weighted_sum_and_finish(const RolloutPara
     float eta = 0.f;
     // CTA-uniform: can any weight of this CTA underflow at all?  (false also for NaN and for the weight
     // pass of a normalised update, whose exponents are bounded by 1/lambda)
-    const bool sparse = (max_c - beta_c) * fabsf(nil) > 125.f;
+    const bool sparse = (max_c - beta_c) * fabsf(nil) > kWeightCutLog2;
     if (!sparse) {
         for (int ch = 0; ch < nchunk; ch++) {
             float2 acc2[16];
@@ -94,7 +94,7 @@ __device__ __forceinline__ void philox_weighted_sum_and_finish(const RolloutPara
             const bool full = (ch * 8 + 8 <= ncall);    // warp-uniform: all 8 calls of the chunk exist
             for (int k = kfirst; k < kend; k += kstride) {
                 const PhiloxSample ps = philox_sample(phA, (uint32_t)(p.k_offset + k));
-                const float e = weight_exp(costs[k], beta_c, nil);
+                const float e = sample_weight(costs[k], beta_c, nil);
                 const float2 e2 = make_float2(e, e);
                 if (ch == 0) eta += e;
 #pragma unroll
@@ -128,7 +128,7 @@ __device__ __forceinline__ void philox_weighted_sum_and_finish(const RolloutPara
             for (int it = 0; it < nit; it++) {
                 const int k = kb + it * kstride + lane;
                 float e = 0.f;
-                if (k < kend) e = weight_exp(costs[k], beta_c, nil);
+                if (k < kend) e = sample_weight(costs[k], beta_c, nil);
                 eta += e;
                 cnt_w += __popc(__ballot_sync(0xffffffffu, e != 0.f));
             }
@@ -145,12 +145,13 @@ __device__ __forceinline__ void philox_weighted_sum_and_finish(const RolloutPara
             for (int it = 0; it < nit; it++) {
                 const int k = kb + it * kstride + lane;
                 float e = 0.f;
-                if (k < kend) e = weight_exp(costs[k], beta_c, nil);
+                if (k < kend) e = sample_weight(costs[k], beta_c, nil);
                 const unsigned m = __ballot_sync(0xffffffffu, e != 0.f);
                 if (e != 0.f) sm.sList[off + __popc(m & lt)] = make_uint2((uint32_t)(p.k_offset + k), __float_as_uint(e));
                 off += __popc(m);
             }
             __syncthreads();
+            trace_stamp(p, ctrl, 8);
             // work items (chunk, entry group), chunk-major; warp w takes the contiguous range [n w / NW, n (w+1) / NW)
             const int n_groups = (total + 31) >> 5;
             const int n_items = n_groups * nchunk;
@@ -189,6 +190,7 @@ __device__ __forceinline__ void philox_weighted_sum_and_finish(const RolloutPara
             }
             if (cur_ch >= 0) flush(cur_ch);
             __syncthreads();                         // list and counts are reused by the next batch / the reductions below
+            trace_stamp(p, ctrl, 9);
         }
     }
     eta = warp_sum(eta);

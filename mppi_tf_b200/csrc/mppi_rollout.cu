@@ -499,11 +499,13 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
                 CostAcc Sa, Sl;
                 Sa.zero();
                 Sl.zero();
-                KahanSum Sk_;                       // direct form: block sums added with compensation
+                KahanSum Sk_;                       // block sums (4 steps, from zero) added with compensation
                 Sk_.init(cw == 0 ? C0 : 0.f);
                 for (int tb = tb0; tb < tb1; tb++) {
                     float e[4 * A];
-                    if (!FAST) { Sk_.add(Sa.total()); Sa.zero(); }
+                    Sk_.add(FAST ? Sa.total() + Sl.total() : Sa.total());
+                    Sa.zero();
+                    Sl.zero();
                     if (4 * tb + 4 <= p.T) {
                         load_block<A, TMA, false>(row, tb, TA, e);
     #pragma unroll
@@ -529,8 +531,8 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
                     if (FAST) fast_terminal<A>(x.p, x.v, Sa);
                     else add_state_cost<A, COST>(x, mc, p, Sa);
                 }
-                if (!FAST) Sk_.add(Sa.total());
-                S = FAST ? Sa.total() + Sl.total() : Sk_.s;
+                Sk_.add(FAST ? Sa.total() + Sl.total() : Sa.total());
+                S = Sk_.s;
                 if (C > 1) {
                     sS[(grp * C + cw) * 32 + lane] = S;
                     group_barrier(bar_id, bar_n);
@@ -560,7 +562,7 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
                 }
                 beta_g = m;
             }
-            const float ek = (lane < rows) ? weight_exp(S, beta_g, nil) : 0.f;
+            const float ek = (lane < rows) ? sample_weight(S, beta_g, nil) : 0.f;
             eta_lane += ek;
             // rows whose weight is exactly zero (fp32 underflow) add nothing: when they are the majority,
             // visit the others only (bit scan); otherwise the unrolled dense loop is cheaper per row
@@ -749,7 +751,8 @@ cudaError_t launch_rollout_philox(RolloutParams p, int a, int num_sms, size_t sm
     // 16 per-warp rows of T*a partial sums + the sequence and call tables must fit one CTA's shared memory
     // (T*a up to about 2400 on a 227 KB part)
     if (philox_smem_bytes(a, p.T, p.TA) > smem_limit) return cudaErrorInvalidConfiguration;
-    const int gx = philox_grid_x(p.K_local, p.n_ctrl, num_sms);
+    int gx = philox_grid_x(p.K_local, p.n_ctrl, num_sms);
+    if (p.max_parts > 0 && gx > p.max_parts) gx = p.max_parts;
     p.n_iter = (p.K_local + gx * kPhiloxThreads - 1) / (gx * kPhiloxThreads);
     if (grid_x_out) *grid_x_out = gx;
     dim3 grid(gx, p.n_ctrl);
@@ -848,6 +851,7 @@ cudaError_t launch_rollout_injected(RolloutParams p, int a, int num_sms, size_t 
             if (grown <= smem_limit) { L.ng = ng; L.c = c; L.nbuf = nb; smem = grown; }
         }
     }
+    if (p.max_parts > 0 && gx > p.max_parts) gx = p.max_parts;
     if (grid_x_out) *grid_x_out = gx;
     // TMA path needs 16-byte aligned tiles and rows: T*a % 4 == 0 and an aligned base pointer.
     const bool tma = (p.TA % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.eps) & 15u) == 0);
@@ -856,10 +860,15 @@ cudaError_t launch_rollout_injected(RolloutParams p, int a, int num_sms, size_t 
     return cudaSuccess;
 }
 
+// Upper bound of grid.x over every update kernel (the handle sizes its partial-record buffer with it and passes it back
+// as RolloutParams::max_parts): the regenerating kernels use at most 2 CTAs per SM, the injected and resident kernels at
+// most 4 resident CTAs per SM, shared among the controllers.
 int max_grid_x(int K_local, int n_ctrl, int num_sms)
 {
     int g1 = philox_grid_x(K_local, n_ctrl, num_sms);
-    int g2 = num_sms * 4;
+    int g2 = (num_sms * 8) / (n_ctrl > 0 ? n_ctrl : 1);
+    if (g2 < 1) g2 = 1;
+    if (g2 > kMaxParts) g2 = kMaxParts;
     return g1 > g2 ? g1 : g2;
 }
 

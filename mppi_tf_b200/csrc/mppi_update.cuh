@@ -6,7 +6,10 @@
 
 namespace mppi {
 
-constexpr int kMaxParts = 1024;   // CTA partials (or ranks) one merge can take
+constexpr int kMaxParts = 1024;   // CTA partials per controller
+constexpr int kMergeGroup = 16;   // two-level merge: the last CTA of every group of 16 merges the group's records, the last
+                                  // group merges the group records - the serial tail after the last CTA finishes is two
+                                  // short merges (16 and <= 64 records) instead of one over every CTA of the grid
 
 // Per-step uniforms staged in shared memory, one row per step:
 //   [0, A)      U_t   mean action (src/controller_base.cpp:205-208)
@@ -100,14 +103,15 @@ __device__ inline void publish_minmax(const RolloutParams &p, int ctrl, float bm
     if (threadIdx.x == 0) { mine[0] = bmin; mine[1] = bmax; }
     __threadfence();
     __syncthreads();
+    unsigned int *ctr = p.counters + (size_t)ctrl * (1 + p.max_groups);
     if (threadIdx.x == 0) {
-        const unsigned prev = atomicAdd(&p.counters[ctrl], 1u);
+        const unsigned prev = atomicAdd(ctr, 1u);
         s_last_mm = (prev == (unsigned)nparts - 1u);
     }
     __syncthreads();
     if (!s_last_mm) return;
     __threadfence();
-    if (threadIdx.x == 0) p.counters[ctrl] = 0u;
+    if (threadIdx.x == 0) *ctr = 0u;
     const float *parts = p.partials + (size_t)ctrl * nparts * stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     float lo = kInf, hi = -kInf;
@@ -194,8 +198,27 @@ __device__ inline Merged merge_parts(const float *parts, size_t part_stride, int
                               float4 *sScratch, int scratch_f4)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    float b = kInf;
-    for (int c = tid; c < nparts; c += blockDim.x) b = fminf(b, __ldcg(parts + c * part_stride));
+    const int ncol4 = (TA + 3) >> 2;               // records are padded to whole quads (partial_stride)
+    int nsl = (int)blockDim.x / ncol4;
+    if (nsl > scratch_f4 / ncol4) nsl = scratch_f4 / ncol4;
+    if (nsl > nparts) nsl = nparts;
+    if (nsl < 1) nsl = 1;
+    // The merge is the serial tail of every update and its cost is L2 round trips, so everything that does not depend
+    // on beta is requested first: the first eight records of this thread's first (slice, column quad) item ...
+    const bool has_item = tid < ncol4 * nsl;
+    const int sl0 = has_item ? tid / ncol4 : 0, c40 = has_item ? tid - sl0 * ncol4 : 0;
+    float4 pre[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int c = sl0 + i * nsl;
+        pre[i] = (has_item && c < nparts) ? __ldcg(reinterpret_cast<const float4 *>(parts + 4 + 4 * c40 + (size_t)c * part_stride))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // ... and (beta, eta) of the records, one 8-byte load each
+    float2 be = make_float2(kInf, 0.f);
+    if (tid < nparts) be = __ldcg(reinterpret_cast<const float2 *>(parts + (size_t)tid * part_stride));
+    float b = be.x;
+    for (int c = tid + blockDim.x; c < nparts; c += blockDim.x) b = fminf(b, __ldcg(parts + c * part_stride));
     b = warp_min(b);
     if (lane == 0) sRed[warp] = b;
     __syncthreads();
@@ -203,7 +226,12 @@ __device__ inline Merged merge_parts(const float *parts, size_t part_stride, int
     for (int w = 1; w < nw; w++) beta = fminf(beta, sRed[w]);
     __syncthreads();
     float e = 0.f;
-    for (int c = tid; c < nparts; c += blockDim.x) {
+    if (tid < nparts) {
+        const float sc = (be.x == kInf) ? 0.f : weight_exp(be.x, beta, neg_inv_lambda_log2e);
+        sScale[tid] = sc;
+        e = sc * be.y;
+    }
+    for (int c = tid + blockDim.x; c < nparts; c += blockDim.x) {
         const float bc = __ldcg(parts + c * part_stride);
         const float sc = (bc == kInf) ? 0.f : weight_exp(bc, beta, neg_inv_lambda_log2e);
         sScale[c] = sc;
@@ -215,17 +243,24 @@ __device__ inline Merged merge_parts(const float *parts, size_t part_stride, int
     float eta = 0.f;
     for (int w = 0; w < nw; w++) eta += sRed[w];
 
-    const int ncol4 = (TA + 3) >> 2;               // records are padded to whole quads (partial_stride)
-    int nsl = (int)blockDim.x / ncol4;
-    if (nsl > scratch_f4 / ncol4) nsl = scratch_f4 / ncol4;
-    if (nsl > nparts) nsl = nparts;
-    if (nsl < 1) nsl = 1;
+    // column sums: work item (slice, column quad) sums every nsl-th record, eight 16-byte loads in flight, in order
     for (int it = tid; it < ncol4 * nsl; it += blockDim.x) {
         const int sl = it / ncol4, c4 = it - sl * ncol4;
         const float *col = parts + 4 + 4 * c4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int c = sl;
-        for (; c + 7 * nsl < nparts; c += 8 * nsl) {      // 8 independent loads in flight, accumulated in order
+        if (it == tid) {                                   // the prefetched batch
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (c + i * nsl < nparts) {
+                    const float w = sScale[c + i * nsl];
+                    acc.x = fmaf(w, pre[i].x, acc.x); acc.y = fmaf(w, pre[i].y, acc.y);
+                    acc.z = fmaf(w, pre[i].z, acc.z); acc.w = fmaf(w, pre[i].w, acc.w);
+                }
+            }
+            c += 8 * nsl;
+        }
+        for (; c + 7 * nsl < nparts; c += 8 * nsl) {
             float4 v[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) v[i] = __ldcg(reinterpret_cast<const float4 *>(col + (size_t)(c + i * nsl) * part_stride));
@@ -296,14 +331,14 @@ __device__ void apply_update(const RolloutParams &p, int ctrl, Merged m, float *
         p.stats[2 * ctrl + 1] = m.eta;
     }
     if (p.next_host != nullptr) {              // zero-copy result for the host (grid-uniform; n_ctrl == 1)
-        if (threadIdx.x < A) p.next_host[threadIdx.x] = sOut[threadIdx.x];
-        if (threadIdx.x == A)                   // the exchange status travels with the action (word 8 of the block)
-            reinterpret_cast<unsigned int *>(p.next_host)[8] = p.peer_on ? *reinterpret_cast<volatile unsigned int *>(p.peer_status) : 0u;
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned int *>(p.done_host) = p.done_epoch;
+        // Every word travels with the update's epoch in ONE 8-byte store to mapped pinned memory (slot i = {action_i, epoch},
+        // slot 8 = {exchange status, epoch}): a slot is valid as soon as its epoch shows, whatever order the stores arrive
+        // in, so no system-scope fence (a PCIe round trip each) is needed before the host may read.
+        if (threadIdx.x < A || threadIdx.x == 8) {
+            const unsigned int val = threadIdx.x < A ? __float_as_uint(sOut[threadIdx.x])
+                                                     : (p.peer_on ? *reinterpret_cast<volatile unsigned int *>(p.peer_status) : 0u);
+            unsigned int *slot = reinterpret_cast<unsigned int *>(p.next_host) + 2 * threadIdx.x;
+            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(val), "r"(p.done_epoch) : "memory");
         }
     }
 }
@@ -316,26 +351,109 @@ __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_
                                    float *sWork, float *sScale, float *sRed, float4 *sScratch, int scratch_f4)
 {
     __shared__ int s_is_last;
-    const int TA = p.TA, stride = partial_stride(TA), nparts = gridDim.x;
-    if (nparts == 1 && p.world == 1) {          // a single CTA owns the controller: nothing to merge
+    const int TA = p.TA, stride = partial_stride(TA);
+    int nparts = gridDim.x, part = blockIdx.x;
+    trace_stamp(p, ctrl, 3);
+    // Launched as thread-block clusters (small grids: latency matters, capacity does not): the CTAs of a cluster - always
+    // the same controller - are reduced over distributed shared memory first, by the rank-0 CTA, and only that CTA
+    // goes on: cluster-size times fewer partial records, and none at all when one cluster owns the controller.
+    const uint32_t cs = cluster_nctarank();
+    if (cs > 1) {
+        const uint32_t cr = cluster_ctarank();
+        if (threadIdx.x == 0) { sRed[0] = beta_c; sRed[1] = eta_c; }
+        cluster_sync();
+        if (cr == 0) {
+            float br[8], er[8];
+            float b = beta_c;
+#pragma unroll
+            for (uint32_t r = 1; r < 8; r++) {
+                br[r] = (r < cs) ? ld_dsmem(sRed, r) : kInf;
+                er[r] = (r < cs) ? ld_dsmem(sRed + 1, r) : 0.f;
+            }
+#pragma unroll
+            for (uint32_t r = 1; r < 8; r++) b = fminf(b, br[r]);
+            const float nil = p.neg_inv_lambda_log2e;
+            const float sc0 = (beta_c == kInf) ? 0.f : weight_exp(beta_c, b, nil);
+            float eta = sc0 * eta_c;
+#pragma unroll
+            for (uint32_t r = 1; r < 8; r++) {
+                br[r] = (br[r] == kInf) ? 0.f : weight_exp(br[r], b, nil);      // now the scale of rank r (0 beyond the cluster)
+                eta = fmaf(br[r], er[r], eta);
+            }
+            for (int j = threadIdx.x; j < TA; j += blockDim.x) {
+                float v[8];
+#pragma unroll
+                for (uint32_t r = 1; r < 8; r++) v[r] = (r < cs) ? ld_dsmem(sN + j, r) : 0.f;   // all in flight together
+                float acc = sc0 * sN[j];
+#pragma unroll
+                for (uint32_t r = 1; r < 8; r++)
+                    if (r < cs) acc = fmaf(br[r], v[r], acc);                                   // fixed order
+                sN[j] = acc;
+            }
+            beta_c = b;
+            eta_c = eta;
+        }
+        cluster_sync();                         // the peers' shared memory has been read: they may leave
+        if (cr != 0) return;
+        nparts = gridDim.x / cs;
+        part = blockIdx.x / cs;
+    }
+    if (nparts == 1 && p.world == 1) {          // a single CTA (or cluster) owns the controller: nothing to merge
         apply_update<A, PHILOX>(p, ctrl, Merged{beta_c, eta_c}, sN, sWork);
+        trace_stamp(p, ctrl, 7);
         return;
     }
-    float *mine = p.partials + ((size_t)ctrl * nparts + blockIdx.x) * stride;
+    float *mine = p.partials + ((size_t)ctrl * nparts + part) * stride;
     if (threadIdx.x == 0) { mine[0] = beta_c; mine[1] = eta_c; }
     for (int j = threadIdx.x; j < TA; j += blockDim.x) mine[4 + j] = sN[j];
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned prev = atomicAdd(&p.counters[ctrl], 1u);
-        s_is_last = (prev == (unsigned)nparts - 1u);
+    trace_stamp(p, ctrl, 4);
+    unsigned int *ctr = p.counters + (size_t)ctrl * (1 + p.max_groups);
+    const int ngroups = (nparts + kMergeGroup - 1) / kMergeGroup;
+    const bool two_level = nparts > 2 * kMergeGroup && ngroups <= p.max_groups;
+    Merged m;
+    if (!two_level) {
+        if (threadIdx.x == 0) {
+            const unsigned prev = atomicAdd(ctr, 1u);
+            s_is_last = (prev == (unsigned)nparts - 1u);
+        }
+        __syncthreads();
+        if (!s_is_last) return;
+        __threadfence();
+        if (threadIdx.x == 0) *ctr = 0u;
+        m = merge_parts(p.partials + (size_t)ctrl * nparts * stride, stride, nparts, TA,
+                        p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
+    } else {
+        const int gi = part / kMergeGroup, g0 = gi * kMergeGroup;
+        const int gn = min(kMergeGroup, nparts - g0);
+        if (threadIdx.x == 0) {
+            const unsigned prev = atomicAdd(ctr + 1 + gi, 1u);
+            s_is_last = (prev == (unsigned)gn - 1u);
+        }
+        __syncthreads();
+        if (!s_is_last) return;
+        __threadfence();
+        if (threadIdx.x == 0) ctr[1 + gi] = 0u;
+        const Merged mg = merge_parts(p.partials + ((size_t)ctrl * nparts + g0) * stride, stride, gn, TA,
+                                      p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
+        float *grec = p.partials2 + ((size_t)ctrl * p.max_groups + gi) * stride;
+        if (threadIdx.x == 0) { grec[0] = mg.beta; grec[1] = mg.eta; }
+        for (int j = threadIdx.x; j < TA; j += blockDim.x) grec[4 + j] = sN[j];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned prev = atomicAdd(ctr, 1u);
+            s_is_last = (prev == (unsigned)ngroups - 1u);
+        }
+        __syncthreads();
+        if (!s_is_last) return;
+        __threadfence();
+        if (threadIdx.x == 0) *ctr = 0u;
+        m = merge_parts(p.partials2 + (size_t)ctrl * p.max_groups * stride, stride, ngroups, TA,
+                        p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
     }
-    __syncthreads();
-    if (!s_is_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) p.counters[ctrl] = 0u;
-    Merged m = merge_parts(p.partials + (size_t)ctrl * nparts * stride, stride, nparts, TA,
-                           p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
+    trace_stamp(p, ctrl, 5);
     if (p.world > 1 && p.peer_on) {
         // Fused exchange: this CTA writes the rank payload straight into every rank's mailbox over NVLink,
         // raises its flag there, waits for the other ranks' flags in its own mailbox and finishes the update
@@ -363,10 +481,22 @@ __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_
             }
         }
         __syncthreads();
+        trace_stamp(p, ctrl, 6);
+        if (*reinterpret_cast<volatile unsigned int *>(p.peer_status) != 0u) {
+            // a payload is missing: leave U untouched (merging a stale mailbox would let the ranks' sequences diverge) and
+            // hand the status to a host that waits on the zero-copy slots; mppi_fetch_action reports MPPI_ERR_COMM and
+            // clears the word
+            if (p.next_host != nullptr && (tid < A || tid == 8)) {
+                unsigned int *slot = reinterpret_cast<unsigned int *>(p.next_host) + 2 * tid;
+                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(tid == 8 ? 1u : 0u), "r"(p.done_epoch) : "memory");
+            }
+            return;
+        }
         const float *mail = p.peer_mail[p.rank] + ((size_t)par * world * p.n_ctrl + ctrl) * stride;
         Merged mw = merge_parts(mail, (size_t)p.n_ctrl * stride, world, TA, p.neg_inv_lambda_log2e, sN, sScale, sRed,
                                 sScratch, scratch_f4);
         apply_update<A, PHILOX>(p, ctrl, mw, sN, sWork);
+        trace_stamp(p, ctrl, 7);
         return;
     }
     if (p.world > 1) {
@@ -376,6 +506,7 @@ __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_
         return;
     }
     apply_update<A, PHILOX>(p, ctrl, m, sN, sWork);
+    trace_stamp(p, ctrl, 7);
 }
 
 }  // namespace mppi

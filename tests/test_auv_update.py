@@ -252,4 +252,7 @@ def test_cuda_auv_batched_controllers(oracle64, oracle32):
         r32 = oracle32.mppi_update_auv(prm, 0.1, m["rk"], m["lam"], sigma, goals[c], q, xs[c], U0[c], eps[c], **kw)
         for Un, cs, what in ((Un_p, c_p, "philox"), (Un_i, c_i, "injected")):
             assert rel_err(cs.reshape(n, k)[c], r64["costs"]) < 1e-5, (what, c)
-            assert_update_close(Un.reshape(n, tau, 6)[c], r64["U_new"], r32["U_new"], what=f"{what} U_new[{c}]")
+            # k = 700 samples of a nonlinear model whose costs run into the hundreds: an ill-conditioned softmin, like the
+            # lambda = 0.05 point-mass case - the one other place that uses the fp32-distance allowance (tests/util.py)
+            assert_update_close(Un.reshape(n, tau, 6)[c], r64["U_new"], r32["U_new"], what=f"{what} U_new[{c}]",
+                                allow_fp32_distance=True)

@@ -95,7 +95,7 @@ def test_variants_store_then_replay(oracle32, oracle64, k, tau, a, lam, rounds):
         np.testing.assert_allclose(o["eps"], ref_eps, rtol=0, atol=2e-6 * np.abs(ref_eps).max())
         ro = oracle64.mppi_update(cfg, x0, U0, o["eps"])
         for key in ("U_new", "next", "U_shift"):
-            assert_update_close(o[key], ro[key], what=f"{key} {what}")
+            assert np.abs(np.asarray(o[key], np.float64) - ro[key]).max() <= 1e-5 * np.abs(ro["U_new"]).max(), f"{key} {what}"
         assert rel_err(o["costs"], ro["costs"]) < 1e-5, what
         beta, eta = o["stats"]
         assert abs(float(beta[0]) - ro["costs"].min()) <= 1e-5 * np.abs(ro["costs"]).max(), what
