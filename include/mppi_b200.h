@@ -166,6 +166,11 @@ int mppi_set_static_cost(mppi_handle *h);
  * exchanged through the fused peer-memory mailboxes: call mppi_peer_attach first (MPPI_ERR_UNSUPPORTED otherwise). */
 int mppi_set_normalize_cost(mppi_handle *h, int on);
 int mppi_set_q(mppi_handle *h, const float *q_host);             /* [s] */
+/* clip_act of the Python twin (controllers/controller_base.py:500-504, models/model_base.py:121-126): the updated sequence is
+ * clipped to [act_min, act_max] per action axis before the next action is taken and the sequence shifted,
+ * U' = clip(U + sum_k w_k eps_k).  n = 1 (one limit for every axis, the reference's default shape) or n = a_dim; on = 0 turns
+ * the clipping off again (the state at the reference's HEAD, where the call is commented out, :455-456). */
+int mppi_set_action_limits(mppi_handle *h, int on, int n, const float *act_min, const float *act_max);
 int mppi_set_mass(mppi_handle *h, float mass);                   /* model mass in B = [dt^2/2; dt] / mass */
 int mppi_set_sequence(mppi_handle *h, const float *U_host);      /* m_U, [n][T][a] */
 int mppi_get_sequence(mppi_handle *h, float *U_host);            /* shifted sequence kept for the next call */
@@ -318,6 +323,11 @@ int mppi_weighted_noise(int device, int k, int TA, const float *weights, const f
 /* ControllerBase::mGetNew / mShift (src/controller_base.cpp:310-329) */
 int mppi_get_new(int T, int a, const float *cur, int nb, float *out);
 int mppi_shift(int T, int a, const float *cur, const float *init, int nb, float *out);
+/* Savitzky-Golay smoothing of a sequence [T][a] along T (host code, double precision) - the pass the Python twin runs on its
+ * action sequence when `filterSeq` is set: scipy.signal.savgol_filter(seq, window, polyorder, deriv=0, axis=0), mode
+ * "interp" (/root/reference/scripts/src/controllers/controller_base.py:281-291 uses window 10, polyorder 9).  Like the
+ * reference, the result is a filtered COPY: the controller's own sequence is not touched.  window <= T, polyorder < window. */
+int mppi_savgol_filter(int T, int a, const float *U, int window, int polyorder, float *out);
 /* Raw Philox4x32-10 words of the noise stream (integer contract, bit-exact vs the oracle):
  * out [n_calls][4] for counter (call0 + i, sample, update, stream). */
 int mppi_philox_raw(int device, uint64_t seed, uint32_t call0, uint32_t sample, uint32_t update,

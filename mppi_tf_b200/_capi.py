@@ -83,6 +83,8 @@ SYMBOLS = {
     "mppi_cost_action_py": (_i, [_i, _i, _i, _f, _f, _f, _fp, _fp, _fp, _fp]),
     "mppi_cost_state_ellipse": (_i, [_i, _i, _fp] + [_f] * 7 + [_fp]),
     "mppi_set_q": (_i, [_H, _fp]),
+    "mppi_set_action_limits": (_i, [_H, _i, _i, _fp, _fp]),
+    "mppi_savgol_filter": (_i, [_i, _i, _fp, _i, _i, _fp]),
     "mppi_set_mass": (_i, [_H, _f]),
     "mppi_set_sequence": (_i, [_H, _fp]),
     "mppi_get_sequence": (_i, [_H, _fp]),

@@ -306,6 +306,26 @@ class ControllerBase:
         """norm_arg of the Python twin (controller_base.py:468-474): exponent -(S - beta)/(lambda max(S - beta))."""
         check(self._lib.mppi_set_normalize_cost(self._h, int(bool(on))), self._h)
 
+    def setActionLimits(self, act_min=None, act_max=None):
+        """clip_act of the Python twin (controller_base.py:500-504): the updated sequence is clipped to [act_min, act_max]
+        (scalars or [a_dim]) before the next action is taken; None, None turns the clipping off."""
+        if act_min is None and act_max is None:
+            check(self._lib.mppi_set_action_limits(self._h, 0, 1, None, None), self._h)
+            return
+        lo, hi = _f32(np.atleast_1d(act_min)).ravel(), _f32(np.atleast_1d(act_max)).ravel()
+        assert lo.size == hi.size
+        check(self._lib.mppi_set_action_limits(self._h, 1, lo.size, _ptr(lo), _ptr(hi)), self._h)
+
+    def filterSequence(self, window=10, polyorder=9):
+        """The Savitzky-Golay pass of the Python twin (controller_base.py:281-291): a filtered COPY of the current sequence
+        (the reference stores it aside too); scipy.signal.savgol_filter semantics, mode "interp"."""
+        U = _f32(self.getSequence()).reshape(self.n, self.tau, self.a_dim)
+        out = np.empty_like(U)
+        for c in range(self.n):
+            check(self._lib.mppi_savgol_filter(self.tau, self.a_dim, _ptr(np.ascontiguousarray(U[c])), int(window), int(polyorder),
+                                               _ptr(out[c])))
+        return out[0] if self.n == 1 else out
+
     def setQ(self, q):
         check(self._lib.mppi_set_q(self._h, _ptr(_f32(q))), self._h)
 

@@ -72,6 +72,8 @@ struct mppi_handle {
     float inv_sigma[kMaxA * kMaxA];
     bool normalize = false;
     float *d_norm = nullptr;
+    bool clip = false;            // mppi_set_action_limits
+    float act_min[kMaxA], act_max[kMaxA];
     int cost_kind = 0;            // 0 StaticCost, 1 ElipseCost (mppi_set_ellipse_cost), 2 StaticQuatCost, 3 ElipseCost3D
     float q10[kMaxS] = {0};       // StaticQuatCost weights, kept apart from q so that mppi_set_static_cost finds q untouched
     float ell[12] = {0};
@@ -248,6 +250,8 @@ RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
     }
     p.norm_mode = 0;
     p.norm = h->d_norm;
+    p.clip = h->clip ? 1 : 0;
+    if (h->clip) { memcpy(p.act_min, h->act_min, sizeof(p.act_min)); memcpy(p.act_max, h->act_max, sizeof(p.act_max)); }
     p.cost_kind = h->cost_kind;
     memcpy(p.ell, h->ell, sizeof(p.ell));
     p.goal_per_ctrl = h->goal_per_ctrl;
@@ -787,6 +791,20 @@ int mppi_set_normalize_cost(mppi_handle *h, int on)
         return fail(h, MPPI_ERR_UNSUPPORTED, "cost normalisation needs the global cost range before any weight: with world > 1 it "
                                               "runs over the fused peer-memory exchange only (mppi_peer_attach first)");
     h->normalize = on != 0;
+    return MPPI_OK;
+}
+int mppi_set_action_limits(mppi_handle *h, int on, int n, const float *act_min, const float *act_max)
+{
+    if (!h) return fail(h, MPPI_ERR_BAD_ARG, "null handle");
+    if (!on) { h->clip = false; return MPPI_OK; }
+    if (!act_min || !act_max || (n != 1 && n != h->a)) return fail(h, MPPI_ERR_BAD_ARG, "limits: n must be 1 or a_dim");
+    for (int j = 0; j < h->a; j++) {
+        const float lo = act_min[n == 1 ? 0 : j], hi = act_max[n == 1 ? 0 : j];
+        if (!(lo <= hi)) return fail(h, MPPI_ERR_BAD_ARG, "limits: act_min must not exceed act_max");
+        h->act_min[j] = lo;
+        h->act_max[j] = hi;
+    }
+    h->clip = true;
     return MPPI_OK;
 }
 int mppi_set_sigma(mppi_handle *h, const float *sigma_host)

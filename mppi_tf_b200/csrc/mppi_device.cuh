@@ -48,6 +48,8 @@ struct RolloutParams {
     // 3 = ElipseCost3D (elipse_cost.py:99-246): ell = {plane quaternion (x,y,z,w), 1/a, 1/b, -a/b, b/a, speed^2, m_state, m_vel}
     int cost_kind;
     float ell[12];
+    int clip;                               // clip_act (controller_base.py:500-504): U' = clip(U + Delta, act_min, act_max)
+    float act_min[kMaxA], act_max[kMaxA];
     int norm_mode;                          // cost normalisation: 0 off, 1 = cost pass (min/max only), 2 = weight pass
     float *norm;                            // [n_ctrl][2] beta, max(S - beta) written by pass 1, read by pass 2
     // Philox key / counter words

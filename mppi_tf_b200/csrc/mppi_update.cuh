@@ -317,7 +317,8 @@ __device__ void apply_update(const RolloutParams &p, int ctrl, Merged m, float *
         } else {
             d = sN[i];
         }
-        const float un = U[i] + d * inv_eta;
+        float un = U[i] + d * inv_eta;
+        if (p.clip) un = fminf(fmaxf(un, p.act_min[j]), p.act_max[j]);      // tf.clip_by_value (controller_base.py:500-504)
         sOut[i] = un;
         p.U_new[(size_t)ctrl * TA + i] = un;
     }
