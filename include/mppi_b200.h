@@ -217,8 +217,13 @@ int mppi_peer_attach(mppi_handle *h, const void *handles /* [world][64] */);
 /* x' = x + (W3^T relu(W2^T relu(W1^T X + b1) + b2) + b3) * Ystd + Ymean,
  * X = (concat(x, u) - Xmean) / Xstd; weights in Keras layout [in][out]
  * (behaviour of /root/reference/scripts/src/models/nn_model.py:54-60,215-239,289-304).
- * Switches the handle to MPPI_MODEL_MLP; bf16 tensor-core rollout, fp32 state.  This build supports
- * hidden = 128 and s + a <= 16 (a <= 5). */
+ * Switches the handle to MPPI_MODEL_MLP; bf16 tensor-core rollout, fp32 state.  hidden = 1..128 (the tensor-core tiles are
+ * 128 wide: narrower networks - the reference's use 32 units - are zero padded, which is exact: a padded unit outputs
+ * relu(0) = 0 and its gradients vanish), two hidden layers, point-mass state layout, s + a <= 15 (a <= 5: the input tile has
+ * 16 columns, one of which carries the bias).  This is the BASELINE config-4 network (2 x 128 on the point_mass3d state), a
+ * new specification derived from the reference's NNModel family: NNModel.build_step_graph itself raises NotImplementedError
+ * (nn_model.py:101-117).  The reference's one concrete learned model, NNAUVModel (three hidden layers of 32 on the AUV state
+ * without its position, nn_model.py:181-304), is a separate model kind: mppi_set_nn_auv_model below. */
 int mppi_set_mlp(mppi_handle *h, int hidden, const float *W1, const float *b1, const float *W2,
                  const float *b2, const float *W3, const float *b3, const float *Xmean,
                  const float *Xstd, const float *Ymean, const float *Ystd);
@@ -239,6 +244,18 @@ int mppi_mlp_predict(mppi_handle *h, int kst, int k, const float *state, const f
 int mppi_mlp_train_step(mppi_handle *h, int n, const float *state, const float *action, const float *next_state,
                         float learning_rate, float *loss_out);
 int mppi_mlp_set_adam(mppi_handle *h, float beta1, float beta2, float epsilon);
+/* The learner's loop, LearnerBase.train (learners/learner_base.py:324-358): `epochs` times { augment_data (:455-467) when
+ * augment_samples > 0: every transition repeated augment_samples times with Gaussian noise of standard deviation
+ * augment_sigma on the normalised inputs (Philox, key = seed), the normalised target kept; then Adam on the normalised MSE }.
+ * batch_size <= 0: one full-batch step per epoch, as the reference runs it (its batchSize argument is never used,
+ * :146-153,470); batch_size > 0: consecutive minibatches of the epoch's data (an extension).  The data are uploaded once and
+ * the steps run back to back on the handle's stream.  losses_out (may be NULL, room for epochs * ceil(n_epoch / batch)
+ * floats) receives the loss before every step; *n_steps_out (may be NULL) their number.  Deviation: the reference hands the
+ * augmented data to the step DE-normalised (:463-467) although the step expects normalised data; both agree for the
+ * default normalisation (mean 0, std 1, nn_model.py:65-69). */
+int mppi_mlp_train(mppi_handle *h, int n, const float *state, const float *action, const float *next_state, int epochs,
+                   int batch_size, float learning_rate, int augment_samples, float augment_sigma, uint64_t seed, float *losses_out,
+                   int *n_steps_out);
 int mppi_mlp_get_weights(mppi_handle *h, float *W1, float *b1, float *W2, float *b2, float *W3, float *b3);
 
 /* ---- AUV (Fossen) dynamics and the quaternion goal cost -------------- */

@@ -108,6 +108,7 @@ SYMBOLS = {
     "mppi_mlp_predict": (_i, [_H, _i, _i, _fp, _fp, _fp]),
     "mppi_mlp_train_step": (_i, [_H, _i, _fp, _fp, _fp, _f, _fp]),
     "mppi_mlp_set_adam": (_i, [_H, _f, _f, _f]),
+    "mppi_mlp_train": (_i, [_H, _i, _fp, _fp, _fp, _i, _i, _f, _i, _f, _u64, _fp, C.POINTER(_i)]),
     "mppi_mlp_get_weights": (_i, [_H] + [_fp] * 6),
     "mppi_set_auv_model": (_i, [_H, C.POINTER(MppiAuvParams)]),
     "mppi_auv_predict": (_i, [_H, _i, _i, _fp, _fp, _fp]),

@@ -338,6 +338,7 @@ class ControllerBase:
         Xmean/Xstd [s+a], Ymean/Ystd [s].  Switches the rollout to the tensor-core MLP model."""
         keep = {k: _f32(v) for k, v in mlp.items()}
         H = keep["b1"].size
+        self._mlp_hidden = H
         opt = lambda k: _ptr(keep[k]) if k in keep else None
         check(self._lib.mppi_set_mlp(self._h, H, _ptr(keep["W1"]), _ptr(keep["b1"]), _ptr(keep["W2"]), _ptr(keep["b2"]),
                                      _ptr(keep["W3"]), _ptr(keep["b3"]), opt("Xmean"), opt("Xstd"), opt("Ymean"),
@@ -352,11 +353,25 @@ class ControllerBase:
                                             C.byref(loss)), self._h)
         return loss.value
 
+    def mlpTrain(self, state, action, next_state, epochs=1, learning_rate=0.1, batch_size=-1, augment_samples=0, augment_sigma=0.001,
+                 seed=1):
+        """LearnerBase.train (learner_base.py:324-358): epochs x { augment_data, Adam step(s) on the normalised MSE }.
+        batch_size = -1 is the reference's one full-batch step per epoch.  Returns the loss before every step."""
+        st, ac, nx = _f32(state).reshape(-1, self.s_dim), _f32(action).reshape(-1, self.a_dim), _f32(next_state).reshape(-1, self.s_dim)
+        assert st.shape[0] == ac.shape[0] == nx.shape[0]
+        n_ep = st.shape[0] * (augment_samples if augment_samples > 0 else 1)
+        bs = batch_size if 0 < batch_size < n_ep else n_ep
+        losses = np.empty(epochs * ((n_ep + bs - 1) // bs), np.float32)
+        nsteps = C.c_int(0)
+        check(self._lib.mppi_mlp_train(self._h, st.shape[0], _ptr(st), _ptr(ac), _ptr(nx), int(epochs), int(batch_size), float(learning_rate),
+                                       int(augment_samples), float(augment_sigma), int(seed), _ptr(losses), C.byref(nsteps)), self._h)
+        return losses[:nsteps.value]
+
     def mlpSetAdam(self, beta1=0.9, beta2=0.999, epsilon=1e-7):
         check(self._lib.mppi_mlp_set_adam(self._h, float(beta1), float(beta2), float(epsilon)), self._h)
 
-    def mlpGetWeights(self, hidden=128):
-        s, a, H = self.s_dim, self.a_dim, hidden
+    def mlpGetWeights(self, hidden=None):
+        s, a, H = self.s_dim, self.a_dim, (hidden or getattr(self, "_mlp_hidden", 128))
         out = dict(W1=np.empty((s + a, H), np.float32), b1=np.empty(H, np.float32), W2=np.empty((H, H), np.float32),
                    b2=np.empty(H, np.float32), W3=np.empty((H, s), np.float32), b3=np.empty(s, np.float32))
         check(self._lib.mppi_mlp_get_weights(self._h, *[_ptr(out[k]) for k in ("W1", "b1", "W2", "b2", "W3", "b3")]), self._h)

@@ -127,6 +127,7 @@ struct mppi_handle {
     AuvParams auv_prm;
     // learned-MLP dynamics (mppi_set_mlp)
     bool mlp = false;
+    int mlp_hidden = 128;         // logical width; the device always runs 128-wide tiles (zero padded)
     void *d_wblob = nullptr;
     float *d_fvec = nullptr;
     // learner side (mppi_mlp_train_step): fp32 master weights + Adam state, W1 b1 W2 b2 W3 b3 back to back
@@ -1223,9 +1224,25 @@ int mppi_set_mlp(mppi_handle *h, int hidden, const float *W1, const float *b1, c
 {
     if (!h || !W1 || !b1 || !W2 || !b2 || !W3 || !b3) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
     if (h->auv) return fail(h, MPPI_ERR_UNSUPPORTED, "mppi_set_mlp needs a point-mass handle (s_dim = 2 a_dim)");
-    if (hidden != kMlpH) return fail(h, MPPI_ERR_UNSUPPORTED, "this build supports hidden = 128 only");
+    if (hidden < 1 || hidden > kMlpH) return fail(h, MPPI_ERR_UNSUPPORTED, "hidden must be in 1..128");
     if (h->s + h->a + 1 > kMlpKin || h->a > 5) return fail(h, MPPI_ERR_UNSUPPORTED, "MLP path needs s + a <= 15 (a <= 5)");
     CU_TRY(h, cudaSetDevice(h->device));
+    // Narrower networks (the reference's models use 32 units, nn_model.py:54-60) run on the 128-wide tensor-core tiles with
+    // zero padding: a padded unit has zero weights and bias, so it outputs relu(0) = 0, feeds nothing forward, and its
+    // gradients are exactly zero - the padded network IS the narrow one, in the rollout and under training.
+    std::vector<float> pW1, pb1, pW2, pb2, pW3;
+    if (hidden != kMlpH) {
+        const int in_ = h->s + h->a, H = hidden;
+        pW1.assign((size_t)in_ * kMlpH, 0.f); pb1.assign(kMlpH, 0.f); pW2.assign((size_t)kMlpH * kMlpH, 0.f);
+        pb2.assign(kMlpH, 0.f); pW3.assign((size_t)kMlpH * h->s, 0.f);
+        for (int i = 0; i < in_; i++) memcpy(&pW1[(size_t)i * kMlpH], W1 + (size_t)i * H, sizeof(float) * H);
+        memcpy(pb1.data(), b1, sizeof(float) * H);
+        for (int i = 0; i < H; i++) memcpy(&pW2[(size_t)i * kMlpH], W2 + (size_t)i * H, sizeof(float) * H);
+        memcpy(pb2.data(), b2, sizeof(float) * H);
+        memcpy(pW3.data(), W3, sizeof(float) * (size_t)H * h->s);
+        W1 = pW1.data(); b1 = pb1.data(); W2 = pW2.data(); b2 = pb2.data(); W3 = pW3.data();
+    }
+    h->mlp_hidden = hidden;
     std::vector<uint8_t> blob(kWBlobBytes);
     mlp_pack_weights(h->s, h->a, W1, b1, W2, b2, W3, b3, blob.data());
     std::vector<float> fv(kFvecFloats, 0.f);
@@ -1317,6 +1334,69 @@ int mppi_mlp_train_step(mppi_handle *h, int n, const float *state, const float *
     return MPPI_OK;
 }
 
+// The learner's loop (LearnerBase.train, learner_base.py:324-358): `epochs` times { optional augment_data (:455-467), then
+// Adam steps on the normalised MSE (_train_step, :469-496) }.  batch_size <= 0 is the reference's behaviour - ONE full-batch
+// step per epoch (its batchSize argument is accepted and never used, :146-153,470); batch_size > 0 walks the epoch's data
+// in consecutive minibatches (an extension).  The data stay on the device for the whole call; losses_out (may be NULL)
+// receives the loss before every step, [epochs * steps_per_epoch].
+int mppi_mlp_train(mppi_handle *h, int n, const float *state, const float *action, const float *next_state, int epochs,
+                   int batch_size, float learning_rate, int augment_samples, float augment_sigma, uint64_t seed, float *losses_out,
+                   int *n_steps_out)
+{
+    if (!h || !state || !action || !next_state || n <= 0 || epochs <= 0) return fail(h, MPPI_ERR_BAD_ARG, "bad mlp_train argument");
+    if (!h->mlp) return fail(h, MPPI_ERR_STATE, "mppi_set_mlp has not been called");
+    if (augment_samples < 0 || augment_sigma < 0.f) return fail(h, MPPI_ERR_BAD_ARG, "augmentation needs samples >= 0, sigma >= 0");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int s = h->s, a = h->a;
+    const bool aug = augment_samples > 0;
+    const long long n_ep = aug ? (long long)n * augment_samples : n;
+    if (n_ep > (1LL << 28)) return fail(h, MPPI_ERR_UNSUPPORTED, "epoch data too large");
+    const int bs = (batch_size > 0 && batch_size < n_ep) ? batch_size : (int)n_ep;
+    const int steps_per_epoch = (int)((n_ep + bs - 1) / bs);
+    const size_t need = train_work_floats(s, a, bs);
+    if (need > h->train_work_cap) {
+        cudaFree(h->d_train_work);
+        h->d_train_work = nullptr;
+        h->train_work_cap = 0;
+        CU_TRY(h, cudaMalloc(&h->d_train_work, sizeof(float) * need));
+        h->train_work_cap = need;
+    }
+    DevBuf raw, augb, losses;
+    const size_t row = (size_t)(2 * s + a);
+    CU_TRY(h, raw.alloc(sizeof(float) * row * n));
+    if (aug) CU_TRY(h, augb.alloc(sizeof(float) * row * (size_t)n_ep));
+    CU_TRY(h, losses.alloc(sizeof(float) * (size_t)epochs * steps_per_epoch));
+    float *dx = raw.as<float>(), *du = dx + (size_t)n * s, *dxn = du + (size_t)n * a;
+    CU_TRY(h, cudaMemcpyAsync(dx, state, sizeof(float) * (size_t)n * s, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(du, action, sizeof(float) * (size_t)n * a, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(dxn, next_state, sizeof(float) * (size_t)n * s, cudaMemcpyHostToDevice, h->stream));
+    float *ex = dx, *eu = du, *exn = dxn;
+    if (aug) {
+        ex = augb.as<float>();
+        eu = ex + (size_t)n_ep * s;
+        exn = eu + (size_t)n_ep * a;
+    }
+    for (int e = 0; e < epochs; e++) {
+        if (aug)
+            CU_TRY(h, launch_augment(n, augment_samples, s, a, dx, du, dxn, h->d_fvec, augment_sigma, seed, (uint32_t)e, ex, eu, exn, h->stream));
+        for (int b = 0; b < steps_per_epoch; b++) {
+            const long long lo = (long long)b * bs;
+            const int nb = (int)((n_ep - lo) < bs ? (n_ep - lo) : bs);
+            h->adam_t++;
+            const double t = (double)h->adam_t;
+            const float lr_t = (float)((double)learning_rate * sqrt(1.0 - pow((double)h->adam_b2, t)) / (1.0 - pow((double)h->adam_b1, t)));
+            CU_TRY(h, launch_train_step(s, a, nb, ex + lo * s, eu + lo * a, exn + lo * s, h->d_fvec, h->d_params, h->d_adam_m, h->d_adam_v,
+                                        lr_t, h->adam_b1, h->adam_b2, h->adam_eps, h->d_train_work,
+                                        losses.as<float>() + (size_t)e * steps_per_epoch + b, h->stream));
+        }
+    }
+    CU_TRY(h, launch_pack_blob(s, a, h->d_params, h->d_wblob, h->stream));     // the rollout sees the new weights
+    if (n_steps_out) *n_steps_out = epochs * steps_per_epoch;
+    if (losses_out) return d2h(h, losses_out, losses.as<float>(), (size_t)epochs * steps_per_epoch);
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
 int mppi_mlp_get_weights(mppi_handle *h, float *W1, float *b1, float *W2, float *b2, float *W3, float *b3)
 {
     if (!h || !W1 || !b1 || !W2 || !b2 || !W3 || !b3) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
@@ -1326,11 +1406,14 @@ int mppi_mlp_get_weights(mppi_handle *h, float *W1, float *b1, float *W2, float 
     int rc = d2h(h, params.data(), h->d_params, params.size());
     if (rc) return rc;
     const float *p = params.data();
-    memcpy(W1, p, sizeof(float) * in * kMlpH); p += (size_t)in * kMlpH;
-    memcpy(b1, p, sizeof(float) * kMlpH); p += kMlpH;
-    memcpy(W2, p, sizeof(float) * kMlpH * kMlpH); p += (size_t)kMlpH * kMlpH;
-    memcpy(b2, p, sizeof(float) * kMlpH); p += kMlpH;
-    memcpy(W3, p, sizeof(float) * kMlpH * h->s); p += (size_t)kMlpH * h->s;
+    const int H = h->mlp_hidden;                    // the caller's buffers have the logical width
+    for (int i = 0; i < in; i++) memcpy(W1 + (size_t)i * H, p + (size_t)i * kMlpH, sizeof(float) * H);
+    p += (size_t)in * kMlpH;
+    memcpy(b1, p, sizeof(float) * H); p += kMlpH;
+    for (int i = 0; i < H; i++) memcpy(W2 + (size_t)i * H, p + (size_t)i * kMlpH, sizeof(float) * H);
+    p += (size_t)kMlpH * kMlpH;
+    memcpy(b2, p, sizeof(float) * H); p += kMlpH;
+    memcpy(W3, p, sizeof(float) * H * h->s); p += (size_t)kMlpH * h->s;
     memcpy(b3, p, sizeof(float) * h->s);
     return MPPI_OK;
 }

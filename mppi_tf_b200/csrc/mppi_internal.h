@@ -80,6 +80,9 @@ cudaError_t launch_train_step(int s, int a, int n, const float *x, const float *
                               float *params, float *adam_m, float *adam_v, float lr_t, float b1, float b2, float eps,
                               float *work, float *loss_dev, cudaStream_t st);
 
+cudaError_t launch_augment(int n, int samples, int s, int a, const float *x, const float *u, const float *xnext, const float *norm,
+                           float sigma, uint64_t seed, uint32_t epoch, float *xo, float *uo, float *xno, cudaStream_t st);
+
 // mppi_stages.cu  (device pointers)
 cudaError_t launch_model_step(float mass, float dt, int s, int a, int kst, int k, const float *state,
                               const float *action, float *out, int mode, cudaStream_t st);

@@ -219,6 +219,44 @@ cudaError_t launch_train_step(int s, int a, int n, const float *x, const float *
     return cudaGetLastError();
 }
 
+// augment_data of the learner (learner_base.py:455-467): every transition is repeated `samples` times and Gaussian noise of
+// standard deviation sigma is added to the NORMALISED inputs; the normalised target is kept.  In raw coordinates:
+// x' = x + d_x Xstd_x, u' = u + d_u Xstd_u, xnext' = xnext + (x' - x).  Noise: Philox4x32-10, counter (input column quad,
+// augmented row, epoch, 0xA6), key = seed.  norm: the fvec block (Xmean [0,16), 1/Xstd [16,32), ...).
+__global__ void augment_kernel(int n, int samples, int s, int a, const float *x, const float *u, const float *xnext, const float *norm,
+                               float sigma, uint32_t key0, uint32_t key1, uint32_t epoch, float *xo, float *uo, float *xno)
+{
+    const int in = s + a, nq = (in + 3) >> 2;
+    const long long total = (long long)n * samples * nq;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / nq;
+        const int q = (int)(i - row * nq);
+        const long long src = row / samples;
+        float z[4];
+        normals_from_words(philox4x32_10((uint32_t)q, (uint32_t)row, epoch, 0xA6u, key0, key1), z);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int col = 4 * q + c;
+            if (col >= in) break;
+            const float d = sigma * z[c] / norm[16 + col];            // norm[16 + col] = 1 / Xstd
+            if (col < s) {
+                const float xv = x[src * s + col];
+                xo[row * s + col] = xv + d;
+                xno[row * s + col] = xnext[src * s + col] + ((xv + d) - xv);
+            } else {
+                uo[row * a + (col - s)] = u[src * a + (col - s)] + d;
+            }
+        }
+    }
+}
+
+cudaError_t launch_augment(int n, int samples, int s, int a, const float *x, const float *u, const float *xnext, const float *norm,
+                           float sigma, uint64_t seed, uint32_t epoch, float *xo, float *uo, float *xno, cudaStream_t st)
+{
+    augment_kernel<<<592, 256, 0, st>>>(n, samples, s, a, x, u, xnext, norm, sigma, (uint32_t)seed, (uint32_t)(seed >> 32), epoch, xo, uo, xno);
+    return cudaGetLastError();
+}
+
 size_t train_work_floats(int s, int a, int n)
 {
     return (size_t)n * ((s + a) + 3 * (size_t)s + 4 * (size_t)kMlpH) + mlp_param_count(s, a) + 1024 + 16;

@@ -67,3 +67,78 @@ def test_train_needs_a_model():
         assert e.value.code == _capi.MPPI_ERR_STATE
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("hidden", [32, 64])
+def test_narrow_networks_run_zero_padded(oracle64, hidden):
+    """hidden = 32 / 64 (the reference's networks use 32 units): the 128-wide tiles are zero padded, exactly - predict,
+    a full update and training steps all follow the narrow network."""
+    a, s = 3, 6
+    mlp, x, u, xn = _problem(11 + hidden, n=1500, s=s, a=a, H=hidden)
+    cfg = make_cfg(2048, 16, s, a, lam=2.0)
+    c = controller_from_cfg(cfg)
+    try:
+        c.setMlp(mlp)
+        got = c.mlpPredict(x[:400], u[:400])
+        want = np.stack([oracle64.mlp_step(mlp, x[i], u[i]) for i in range(400)])
+        assert rel_err(got - x[:400], want - x[:400]) < 2e-2
+        tr = AdamTrainer(mlp)
+        for it in range(4):
+            got_l = c.mlpTrainStep(x, u, xn, 2e-3)
+            want_l = tr.step(x, u, xn, 2e-3)
+            assert abs(got_l - want_l) <= 2e-5 * abs(want_l), (it, got_l, want_l)
+        w = c.mlpGetWeights()
+        for k in KEYS:
+            assert w[k].shape == np.asarray(mlp[k]).shape
+            moved = tr.w[k] - np.asarray(mlp[k], np.float64)
+            assert rel_err(w[k] - np.asarray(mlp[k], np.float32), moved) < 2e-2, k
+        # a full update with the trained narrow network
+        rng = np.random.default_rng(hidden)
+        x0 = rng.uniform(-1, 1, s).astype(np.float32)
+        U0 = (0.2 * rng.standard_normal((16, a))).astype(np.float32)
+        from tests.util import parity_noise
+        eps = parity_noise(2048, 16, a, cfg["sigma"])
+        c.setSequence(U0)
+        c.nextWithNoise(x0, eps)
+        ref = oracle64.mppi_update_mlp(cfg, tr.weights(), x0, U0, eps)
+        assert rel_err(c.getUpdate(), ref["U_new"]) < 2e-2
+    finally:
+        c.close()
+
+
+def test_train_loop_unpinned_matches_repeated_steps():
+    """mppi_mlp_train (LearnerBase.train): epochs of full-batch steps == the same number of single steps; minibatches ==
+    the oracle stepping over consecutive slices; augmentation with sigma = 0 changes nothing (repeated rows, same mean
+    gradient) and with sigma > 0 is deterministic in the seed.  (Training parity is unpinned in the reference: no golden
+    vector of a training step exists and TensorFlow's GradientTape cannot run here.)"""
+    a, s = 2, 4
+    mlp, x, u, xn = _problem(5, n=900, s=s, a=a)
+    c = controller_from_cfg(make_cfg(256, 4, s, a))
+    try:
+        c.setMlp(mlp)
+        tr = AdamTrainer(mlp)
+        got = c.mlpTrain(x, u, xn, epochs=6, learning_rate=2e-3)
+        want = [tr.step(x, u, xn, 2e-3) for _ in range(6)]
+        np.testing.assert_allclose(got, want, rtol=3e-5)
+        c.setMlp(mlp)                                             # resets the weights and the optimizer
+        tr = AdamTrainer(mlp)
+        got = c.mlpTrain(x, u, xn, epochs=2, learning_rate=1e-3, batch_size=400)
+        want = [tr.step(x[i:i + 400], u[i:i + 400], xn[i:i + 400], 1e-3) for _ in range(2) for i in (0, 400, 800)]
+        assert len(got) == 6
+        np.testing.assert_allclose(got, want, rtol=3e-5)
+        c.setMlp(mlp)
+        tr = AdamTrainer(mlp)
+        got = c.mlpTrain(x, u, xn, epochs=3, learning_rate=1e-3, augment_samples=5, augment_sigma=0.0)
+        want = [tr.step(x, u, xn, 1e-3) for _ in range(3)]
+        np.testing.assert_allclose(got, want, rtol=3e-5)
+        c.setMlp(mlp)
+        l1 = c.mlpTrain(x, u, xn, epochs=3, learning_rate=1e-3, augment_samples=5, augment_sigma=0.05, seed=9)
+        c.setMlp(mlp)
+        l2 = c.mlpTrain(x, u, xn, epochs=3, learning_rate=1e-3, augment_samples=5, augment_sigma=0.05, seed=9)
+        c.setMlp(mlp)
+        l3 = c.mlpTrain(x, u, xn, epochs=3, learning_rate=1e-3, augment_samples=5, augment_sigma=0.05, seed=10)
+        np.testing.assert_array_equal(l1, l2)
+        assert not np.array_equal(l1, l3)
+        assert abs(l1[0] - want[0]) < 0.2 * want[0] and l1[0] != want[0]      # noisy inputs: a nearby, different loss
+    finally:
+        c.close()
