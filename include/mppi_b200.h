@@ -276,6 +276,17 @@ typedef struct {
  * acc = M^-1 (u - C(nu) nu - D(nu) nu - g(q)) (auv_model.py:285-333,450-559).  The rigid-body mass matrix uses the
  * reference's transposed skew of cog (tf_skew_op, :23-40) and its rk = 4 branch is reproduced as written. */
 int mppi_set_auv_model(mppi_handle *h, const mppi_auv_params *prm);
+/* The reference's own LEARNED model of the AUV in place of the Fossen equations: NNAUVModel
+ * (/root/reference/scripts/src/models/nn_model.py:181-304): X = (concat(state[3:13], action) - Xmean) / Xstd (prepare_data,
+ * :289-293: the position is dropped, 16 inputs), n_hidden Dense(hidden, relu) layers and a linear Dense(13) (the reference
+ * builds 3 x 32, :54-60), delta = out * Ystd + Ymean, next = state + delta (a plain add: the quaternion is not renormalised,
+ * :303-304).  W[l] / b[l], l = 0 .. n_hidden, in Keras layout [in][out]: W[0] [16][hidden], W[l] [hidden][hidden],
+ * W[n_hidden] [hidden][13]; Xmean / Xstd [16], Ymean / Ystd [13] (NULL = 0 / 1).  n_hidden = 1..4, hidden = 1..32 (zero padded
+ * to 32: exact).  Replaces the model of an MPPI_MODEL_AUV handle; rollout, costs, exchange and mppi_auv_predict work as
+ * with the Fossen model.  fp32 CUDA-core kernel (3 kFLOP per sample-step in 32-wide layers is too thin for the 128-row
+ * tcgen05 tile of the config-4 MLP kernel). */
+int mppi_set_nn_auv_model(mppi_handle *h, int n_hidden, int hidden, const float *const *W, const float *const *b, const float *Xmean,
+                          const float *Xstd, const float *Ymean, const float *Ystd);
 /* AUVModel.build_step_graph on a batch (the model's predict): state [kst][13], kst in {1, k}; action [k][6]. */
 int mppi_auv_predict(mppi_handle *h, int kst, int k, const float *state, const float *action, float *out);
 /* StaticQuatCost (scripts/src/costs/static_cost.py:73-159) as the state cost of an AUV handle:

@@ -112,6 +112,7 @@ SYMBOLS = {
     "mppi_mlp_get_weights": (_i, [_H] + [_fp] * 6),
     "mppi_set_auv_model": (_i, [_H, C.POINTER(MppiAuvParams)]),
     "mppi_auv_predict": (_i, [_H, _i, _i, _fp, _fp, _fp]),
+    "mppi_set_nn_auv_model": (_i, [_H, _i, _i, C.POINTER(_fp), C.POINTER(_fp), _fp, _fp, _fp, _fp]),
     "mppi_set_quat_cost": (_i, [_H, _fp]),
     "mppi_cost_state_quat": (_i, [_i, _i, _fp, _fp, _fp, _fp]),
     "mppi_set_ellipse3d_cost": (_i, [_H, _fp, _fp, _fp, _fp, _f, _f, _f]),

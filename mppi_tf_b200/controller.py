@@ -403,6 +403,20 @@ class ControllerBase:
         p.rk = int(parameters.get("rk", 1) if rk is None else rk)
         check(self._lib.mppi_set_auv_model(self._h, C.byref(p)), self._h)
 
+    def setNnAuvModel(self, nn):
+        """The reference's learned AUV model (NNAUVModel, scripts/src/models/nn_model.py:181-304) as the dynamics of an "auv"
+        controller: nn = dict(W=[W0, .., W_last], b=[b0, ..], Xmean, Xstd, Ymean, Ystd), Keras-layout weights, W0 [16, H],
+        hidden layers [H, H], W_last [H, 13]."""
+        Ws = [_f32(w) for w in nn["W"]]
+        bs = [_f32(v).ravel() for v in nn["b"]]
+        n_hidden, H = len(Ws) - 1, Ws[0].shape[1]
+        assert Ws[0].shape[0] == 16 and Ws[-1].shape == (H, 13) and all(w.shape == (H, H) for w in Ws[1:-1])
+        Wp = (_fp * len(Ws))(*[_ptr(w) for w in Ws])
+        bp = (_fp * len(bs))(*[_ptr(v) for v in bs])
+        opt = {k: _f32(nn[k]).ravel() for k in ("Xmean", "Xstd", "Ymean", "Ystd") if k in nn and nn[k] is not None}
+        g = lambda k: _ptr(opt[k]) if k in opt else None
+        check(self._lib.mppi_set_nn_auv_model(self._h, n_hidden, H, Wp, bp, g("Xmean"), g("Xstd"), g("Ymean"), g("Ystd")), self._h)
+
     def auvPredict(self, state, action):
         """AUVModel.build_step_graph (auv_model.py:285-306): state [k|1, 13], action [k, 6] -> [k, 13]."""
         st = _f32(state).reshape(-1, 13)

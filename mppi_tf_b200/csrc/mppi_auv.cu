@@ -30,7 +30,7 @@ namespace mppi {
 
 // n = z (Philox mode: eps = sigma z formed here) or eps (injected mode)
 template <bool PHILOX, int RK>
-__device__ __forceinline__ void auv_rollout_step(const RolloutParams &p, const AuvParams &P, const float *uv_row,
+__device__ __forceinline__ void auv_rollout_step(const RolloutParams &p, const AuvParams &P, const float *sNN, const float *uv_row,
                                                  const float (&n)[kAuvA], const float *g, float (&x)[kAuvS], float &S)
 {
     constexpr int A = kAuvA, H = Row<A>::H;
@@ -51,7 +51,8 @@ __device__ __forceinline__ void auv_rollout_step(const RolloutParams &p, const A
 #pragma unroll
     for (int j = 0; j < A; j++) ac = fmaf(uv_row[H + j], n[j], ac);
     if (p.quad) ac += quad_cost<A>(p, n);                   // grid-uniform
-    auv_step<RK>(P, x, u);
+    if (RK == 0) nn_auv_step(sNN, P.nn_hidden, x, u);       // the learned model (NNAUVModel)
+    else auv_step<RK>(P, x, u);
     S += auv_state_cost(p.cost_kind, p.q, g, p.ell, x) + ac;
 }
 
@@ -71,8 +72,11 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
     float *sRed = sScale + kMaxParts;     // [64]
     float *sGX = sRed + 64;               // [32] goal at 0, initial state at 16 (broadcast reads instead of 26 registers)
     float4 *sScratch = reinterpret_cast<float4 *>(sGX + 32);    // [kAuvThreads]
+    float *sNN = reinterpret_cast<float *>(sScratch + kAuvThreads);   // RK == 0: the learned model's blob
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (RK == 0)
+        for (int i = tid; i < nn_auv_blob_floats(P.nn_hidden); i += kAuvThreads) sNN[i] = P.nn_blob[i];
     stage_sequence<A, PHILOX>(p, ctrl, sUV);
     if (tid < kAuvS) {
         sGX[tid] = p.goal[(p.goal_per_ctrl ? (size_t)ctrl * kAuvS : 0) + tid];
@@ -117,7 +121,7 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < A; j++) n[j] = z[tt * A + j];
                     float S1 = 0.f;
-                    auv_rollout_step<true, RK>(p, P, sUV + (t + tt) * RS, n, g, x, S1);
+                    auv_rollout_step<true, RK>(p, P, sNN, sUV + (t + tt) * RS, n, g, x, S1);
                     Sk_.add(S1);
                 }
             }
@@ -129,7 +133,7 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < A; j++) n[j] = z[j];
                 float S1 = 0.f;
-                auv_rollout_step<true, RK>(p, P, sUV + t * RS, n, g, x, S1);
+                auv_rollout_step<true, RK>(p, P, sNN, sUV + t * RS, n, g, x, S1);
                 Sk_.add(S1);
             }
         } else {
@@ -143,7 +147,7 @@ rollout_auv_kernel(const __grid_constant__ RolloutParams p, const __grid_constan
                     n[2 * j + 1] = v.y;
                 }
                 float S1 = 0.f;
-                auv_rollout_step<false, RK>(p, P, sUV + t * RS, n, g, x, S1);
+                auv_rollout_step<false, RK>(p, P, sNN, sUV + t * RS, n, g, x, S1);
                 Sk_.add(S1);
             }
         }
@@ -254,7 +258,8 @@ __global__ void __launch_bounds__(256) auv_predict_kernel(const __grid_constant_
         for (int j = 0; j < kAuvS; j++) x[j] = xs[j];
 #pragma unroll
         for (int j = 0; j < kAuvA; j++) u[j] = action[(size_t)i * kAuvA + j];
-        if (P.rk == 2) auv_step<2>(P, x, u);
+        if (P.rk == 0) nn_auv_step(P.nn_blob, P.nn_hidden, x, u);      // weights straight from global memory (L1-cached)
+        else if (P.rk == 2) auv_step<2>(P, x, u);
         else if (P.rk == 4) auv_step<4>(P, x, u);
         else auv_step<1>(P, x, u);
 #pragma unroll
@@ -282,7 +287,8 @@ static cudaError_t launch_auv_V(const RolloutParams &p, const AuvParams &P, int 
 {
     constexpr int RS = Row<kAuvA>::RS, NW = THREADS / 32;
     const int TAp = (p.TA + 31) & ~31;
-    const size_t smem = sizeof(float) * ((size_t)p.T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 64 + 32) + sizeof(float4) * THREADS;
+    const size_t smem = sizeof(float) * ((size_t)p.T * RS + (size_t)NW * TAp + 2 * TAp + kMaxParts + 64 + 32) + sizeof(float4) * THREADS +
+                        (RK == 0 ? sizeof(float) * nn_auv_blob_floats(P.nn_hidden) : 0);
     int per_ctrl = num_sms * CTAS / (p.n_ctrl > 0 ? p.n_ctrl : 1);
     if (per_ctrl < 1) per_ctrl = 1;
     const int need = (p.K_local + 63) / 64;        // at least two warps of samples per CTA
@@ -325,6 +331,7 @@ static cudaError_t launch_auv_G(const RolloutParams &p, const AuvParams &P, int 
 template <bool PHILOX>
 static cudaError_t launch_auv_R(const RolloutParams &p, const AuvParams &P, int num_sms, cudaStream_t st, int *grid_x_out)
 {
+    if (P.rk == 0) return launch_auv_G<PHILOX, 0>(p, P, num_sms, st, grid_x_out);
     if (P.rk == 2) return launch_auv_G<PHILOX, 2>(p, P, num_sms, st, grid_x_out);
     if (P.rk == 4) return launch_auv_G<PHILOX, 4>(p, P, num_sms, st, grid_x_out);
     return launch_auv_G<PHILOX, 1>(p, P, num_sms, st, grid_x_out);

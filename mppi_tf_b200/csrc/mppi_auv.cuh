@@ -17,7 +17,9 @@ struct AuvParams {
     float Mtot[36], invM[36];  // rigid body + added mass (with the reference's transposed skew of cog), inverse
     float Dl[36], dq[6], Dlf[36];
     float dt;
-    int rk;                    // 1, 2 or 4
+    int rk;                    // 1, 2 or 4; 0 = the learned model below (NNAUVModel) instead of the Fossen equations
+    const float *nn_blob;      // device, nn_auv_blob_floats(nn_hidden) floats (mppi_set_nn_auv_model)
+    int nn_hidden;             // hidden layers (1..kNnMaxHidden), each kNnW wide on the device (narrower ones zero padded)
 };
 constexpr int kAuvParamWords = sizeof(AuvParams) / 4;
 
@@ -81,6 +83,64 @@ __device__ __forceinline__ void auv_state_dot(const AuvParams &P, const float (&
         for (int c = 0; c < 6; c++) acc = fmaf(P.invM[6 * r + c], rhs[c], acc);
         xd[7 + r] = acc;
     }
+}
+
+// ---- the reference's learned AUV model as a dynamics functor (NNAUVModel, scripts/src/models/nn_model.py:181-304) ----
+//   X = (concat(x[3:13], u) - Xmean) / Xstd ; h = relu(h W_l + b_l) per hidden layer ; d = (h W_o + b_o) Ystd + Ymean ; x <- x + d
+// (prepare_data :289-293, Sequential of Dense layers :54-60, denormalizeY :295-297, next_state :303-304: a plain add, the
+// quaternion is not renormalised).  Weights sit in shared memory (every thread reads the same address: broadcast LDS.128),
+// activations in registers; fp32 FFMA throughout - about 3 kFLOP per sample-step of mostly 32 x 32 layers, too thin for
+// the 128-row tensor-core tile the config-4 kernel is built around.
+// Blob: [0,16) Xmean, [16,32) 1/Xstd, [32,48) Ystd, [48,64) Ymean, W_0 [16][32], b_0 [32], then per further hidden layer
+// W [32][32], b [32], then W_out [32][16] (13 columns used), b_out [16].
+constexpr int kNnW = 32, kNnIn = 16, kNnOutPad = 16, kNnMaxHidden = 4;
+__host__ __device__ inline int nn_auv_blob_floats(int n_hidden)
+{
+    return 64 + kNnIn * kNnW + kNnW + (n_hidden - 1) * (kNnW * kNnW + kNnW) + kNnW * kNnOutPad + kNnOutPad;
+}
+
+template <int NIN, int NOUT>
+__device__ __forceinline__ void nn_dense(const float *W, const float (&in)[kNnW], float (&out)[kNnW])
+{
+    const float *b = W + NIN * NOUT;
+#pragma unroll
+    for (int o = 0; o < NOUT; o += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(b + o);
+        out[o] = v.x; out[o + 1] = v.y; out[o + 2] = v.z; out[o + 3] = v.w;
+    }
+#pragma unroll
+    for (int q = 0; q < NIN; q++) {
+        const float xq = in[q];
+#pragma unroll
+        for (int o = 0; o < NOUT; o += 4) {
+            const float4 w = *reinterpret_cast<const float4 *>(W + q * NOUT + o);
+            out[o] = fmaf(xq, w.x, out[o]); out[o + 1] = fmaf(xq, w.y, out[o + 1]);
+            out[o + 2] = fmaf(xq, w.z, out[o + 2]); out[o + 3] = fmaf(xq, w.w, out[o + 3]);
+        }
+    }
+}
+
+static __device__ __noinline__ void nn_auv_step(const float *nn, int n_hidden, float (&x)[kAuvS], const float (&u)[kAuvA])
+{
+    float a0[kNnW], a1[kNnW];
+#pragma unroll
+    for (int j = 0; j < 10; j++) a0[j] = (x[3 + j] - nn[j]) * nn[16 + j];
+#pragma unroll
+    for (int j = 0; j < kAuvA; j++) a0[10 + j] = (u[j] - nn[10 + j]) * nn[26 + j];
+    const float *W = nn + 64;
+    nn_dense<kNnIn, kNnW>(W, a0, a1);
+#pragma unroll
+    for (int o = 0; o < kNnW; o++) a0[o] = fmaxf(a1[o], 0.f);
+    W += kNnIn * kNnW + kNnW;
+    for (int l = 1; l < n_hidden; l++) {            // grid-uniform trip count
+        nn_dense<kNnW, kNnW>(W, a0, a1);
+#pragma unroll
+        for (int o = 0; o < kNnW; o++) a0[o] = fmaxf(a1[o], 0.f);
+        W += kNnW * kNnW + kNnW;
+    }
+    nn_dense<kNnW, kNnOutPad>(W, a0, a1);
+#pragma unroll
+    for (int j = 0; j < kAuvS; j++) x[j] += fmaf(a1[j], nn[32 + j], nn[48 + j]);
 }
 
 // x <- step(x, u): explicit Euler / Heun / the reference's rk-4 variant, then quaternion normalisation.

@@ -125,6 +125,7 @@ struct mppi_handle {
     // AUV (Fossen) dynamics (cfg.model = MPPI_MODEL_AUV + mppi_set_auv_model)
     bool auv = false, auv_ready = false;
     AuvParams auv_prm;
+    float *d_nn_blob = nullptr;   // learned AUV model (mppi_set_nn_auv_model)
     // learned-MLP dynamics (mppi_set_mlp)
     bool mlp = false;
     int mlp_hidden = 128;         // logical width; the device always runs 128-wide tiles (zero padded)
@@ -488,6 +489,7 @@ int mppi_destroy(mppi_handle *h)
     cudaFree(h->d_trace);
     cudaFree(h->d_eps_tmp);
     cudaFree(h->d_wblob);
+    cudaFree(h->d_nn_blob);
     cudaFree(h->d_fvec);
     cudaFree(h->d_params); cudaFree(h->d_adam_m); cudaFree(h->d_adam_v); cudaFree(h->d_train_work); cudaFree(h->d_loss);
     if (!h->ext_exchange) { cudaFree(h->d_payload); cudaFree(h->d_gather); }
@@ -1091,6 +1093,49 @@ int mppi_set_auv_model(mppi_handle *h, const mppi_auv_params *prm)
     if (!h->auv) return fail(h, MPPI_ERR_STATE, "handle was not created with cfg.model = MPPI_MODEL_AUV");
     if (prm->rk != 1 && prm->rk != 2 && prm->rk != 4) return fail(h, MPPI_ERR_BAD_ARG, "rk must be 1, 2 or 4");
     if (!derive_auv(prm, h->dt, &h->auv_prm)) return fail(h, MPPI_ERR_BAD_ARG, "total mass matrix is singular");
+    h->auv_ready = true;
+    return MPPI_OK;
+}
+
+int mppi_set_nn_auv_model(mppi_handle *h, int n_hidden, int hidden, const float *const *W, const float *const *b, const float *Xmean,
+                          const float *Xstd, const float *Ymean, const float *Ystd)
+{
+    if (!h || !W || !b) return fail(h, MPPI_ERR_BAD_ARG, "null argument");
+    if (!h->auv) return fail(h, MPPI_ERR_STATE, "handle was not created with cfg.model = MPPI_MODEL_AUV");
+    if (n_hidden < 1 || n_hidden > kNnMaxHidden || hidden < 1 || hidden > kNnW)
+        return fail(h, MPPI_ERR_UNSUPPORTED, "the learned AUV model takes 1..4 hidden layers of 1..32 units");
+    for (int l = 0; l <= n_hidden; l++)
+        if (!W[l] || !b[l]) return fail(h, MPPI_ERR_BAD_ARG, "null layer");
+    CU_TRY(h, cudaSetDevice(h->device));
+    std::vector<float> blob((size_t)nn_auv_blob_floats(n_hidden), 0.f);
+    for (int i = 0; i < 16; i++) {
+        blob[i] = Xmean ? Xmean[i] : 0.f;
+        const float sd = Xstd ? Xstd[i] : 1.f;
+        if (!(sd != 0.f)) return fail(h, MPPI_ERR_BAD_ARG, "Xstd must be non-zero");
+        blob[16 + i] = 1.0f / sd;
+    }
+    for (int i = 0; i < kAuvS; i++) { blob[32 + i] = Ystd ? Ystd[i] : 1.f; blob[48 + i] = Ymean ? Ymean[i] : 0.f; }
+    // zero padding of narrower layers is exact: a padded unit has zero weights and bias, outputs relu(0) = 0 and feeds nothing on
+    float *dst = blob.data() + 64;
+    int n_in = kNnIn, w_in = kNnIn;                           // logical / padded input width of the layer
+    for (int l = 0; l <= n_hidden; l++) {
+        const int n_out = (l == n_hidden) ? kAuvS : hidden, w_out = (l == n_hidden) ? kNnOutPad : kNnW;
+        for (int q = 0; q < n_in; q++)
+            for (int o = 0; o < n_out; o++) dst[(size_t)q * w_out + o] = W[l][(size_t)q * n_out + o];
+        for (int o = 0; o < n_out; o++) dst[(size_t)w_in * w_out + o] = b[l][o];
+        dst += (size_t)w_in * w_out + w_out;
+        n_in = n_out;
+        w_in = w_out;
+    }
+    if (h->d_nn_blob) { cudaFree(h->d_nn_blob); h->d_nn_blob = nullptr; }
+    CU_TRY(h, cudaMalloc(&h->d_nn_blob, sizeof(float) * blob.size()));
+    CU_TRY(h, cudaMemcpyAsync(h->d_nn_blob, blob.data(), sizeof(float) * blob.size(), cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    memset(&h->auv_prm, 0, sizeof(h->auv_prm));
+    h->auv_prm.dt = h->dt;
+    h->auv_prm.rk = 0;
+    h->auv_prm.nn_blob = h->d_nn_blob;
+    h->auv_prm.nn_hidden = n_hidden;
     h->auv_ready = true;
     return MPPI_OK;
 }

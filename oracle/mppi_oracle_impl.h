@@ -614,8 +614,46 @@ static void FN(orc_auv_state_dot)(const REAL *prm, const REAL *Mtot, const REAL 
 
 /* AUVModel.step — :285-306 (rk = 1, 2; the rk = 4 branch of the reference multiplies k4 by dt twice and is
  * restated as written) followed by normalize_quat :426-448 (tf.math.l2_normalize, epsilon 1e-12). */
+/* NNAUVModel.build_step_graph — /root/reference/scripts/src/models/nn_model.py:215-239 with prepare_data :289-293,
+ * denormalizeY :295-297 and next_state :303-304:
+ *   X = (concat(state[3:13], action) - Xmean) / Xstd ; h = relu(h W_l + b_l) for every hidden layer ; d = (h W_o + b_o) Ystd + Ymean
+ *   next = state + d                      (the quaternion is NOT renormalised)
+ * nn = [n_hidden, H, Xmean[16], Xstd[16], Ymean[13], Ystd[13], then per layer W [in][out] (Keras layout), b [out]]:
+ * in = 16 for the first layer, out = H for the hidden layers and 13 for the last one. */
+void FN(orc_nn_auv_step)(int k, const REAL *nn, const REAL *state, const REAL *action, REAL *out)
+{
+    const int nh = (int)nn[0], H = (int)nn[1];
+    const REAL *Xmean = nn + 2, *Xstd = Xmean + 16, *Ymean = Xstd + 16, *Ystd = Ymean + 13, *W0 = Ystd + 13;
+    for (int i = 0; i < k; i++) {
+        const REAL *x = state + 13 * i, *u = action + 6 * i;
+        REAL a0[ORC_MAX_H], a1[ORC_MAX_H];
+        for (int j = 0; j < 10; j++) a0[j] = (x[3 + j] - Xmean[j]) / Xstd[j];
+        for (int j = 0; j < 6; j++) a0[10 + j] = (u[j] - Xmean[10 + j]) / Xstd[10 + j];
+        const REAL *W = W0;
+        int n_in = 16;
+        for (int l = 0; l <= nh; l++) {
+            const int n_out = (l == nh) ? 13 : H;
+            const REAL *b = W + n_in * n_out;
+            for (int o = 0; o < n_out; o++) {
+                REAL acc = b[o];
+                for (int q = 0; q < n_in; q++) acc += a0[q] * W[q * n_out + o];
+                a1[o] = (l == nh) ? acc : (acc > (REAL)0 ? acc : (REAL)0);
+            }
+            for (int o = 0; o < n_out; o++) a0[o] = a1[o];
+            W = b + n_out;
+            n_in = n_out;
+        }
+        for (int j = 0; j < 13; j++) out[13 * i + j] = x[j] + (a0[j] * Ystd[j] + Ymean[j]);
+    }
+}
+
+/* rk = 0 selects the learned model: `prm` is then the nn vector of orc_nn_auv_step. */
 void FN(orc_auv_step)(int k, const REAL *prm, REAL dt, int rk, const REAL *state, const REAL *action, REAL *out)
 {
+    if (rk == 0) {
+        FN(orc_nn_auv_step)(k, prm, state, action, out);
+        return;
+    }
     REAL Mtot[36], invM[36];
     FN(orc_auv_mass)(prm, Mtot, invM);
     for (int i = 0; i < k; i++) {

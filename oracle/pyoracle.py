@@ -261,6 +261,37 @@ class Oracle:
                                sq(np.asarray(prm["linear_damping"], np.float64)), np.asarray(prm["quad_damping"], np.float64),
                                sq(np.asarray(prm["linear_damping_forward_speed"], np.float64))]).astype(np.float64)
 
+    @staticmethod
+    def nn_auv_pack(nn):
+        """Parameter vector of the learned AUV model (orc_nn_auv_step): nn = dict(W=[W0, ..], b=[b0, ..], Xmean, Xstd, Ymean,
+        Ystd) with Keras-layout weights, W0 [16, H], .., W_last [H, 13]."""
+        W, b = nn["W"], nn["b"]
+        parts = [[len(W) - 1, np.asarray(W[0]).shape[1]], nn["Xmean"], nn["Xstd"], nn["Ymean"], nn["Ystd"]]
+        for Wl, bl in zip(W, b):
+            parts += [np.asarray(Wl, np.float64).ravel(), np.asarray(bl, np.float64).ravel()]
+        return np.concatenate([np.asarray(v, np.float64).ravel() for v in parts])
+
+    def nn_auv_step(self, nn, state, action):
+        """NNAUVModel.build_step_graph (scripts/src/models/nn_model.py:215-239): state [k,13], action [k,6] -> [k,13]."""
+        st, ac = _c(np.asarray(state).reshape(-1, 13), self.dt), _c(np.asarray(action).reshape(-1, 6), self.dt)
+        out = np.empty_like(st)
+        self._fn("orc_nn_auv_step")(st.shape[0], _p(_c(self.nn_auv_pack(nn), self.dt)), _p(st), _p(ac), _p(out))
+        return out
+
+    def mppi_update_nn_auv(self, nn, lam, sigma, goal, q, x0, U, eps, gamma=None, upsilon=1.0, normalize=False, quat_cost=False):
+        """Python-controller update with the learned AUV model in place of AUVModel (rk = 0 in the C restatement)."""
+        eps = _c(eps, self.dt)
+        k, T, a = eps.shape
+        gamma = lam if gamma is None else gamma
+        Q = _c(np.diag(np.asarray(q, np.float64)) if quat_cost else np.asarray(q, np.float64), self.dt)
+        costs, U_new, nxt, U_shift = np.empty(k, self.dt), np.empty((T, a), self.dt), np.empty(a, self.dt), np.empty((T, a), self.dt)
+        self._fn("orc_mppi_update_auv")(k, T, _p(_c(self.nn_auv_pack(nn), self.dt)), self.creal(0.1), 0, self.creal(lam),
+                                        self.creal(gamma), self.creal(upsilon), int(bool(normalize)),
+                                        _p(_c(sigma, self.dt)), _p(_c(np.asarray(goal).ravel(), self.dt)), _p(Q),
+                                        int(bool(quat_cost)), _p(_c(x0, self.dt)), _p(_c(U, self.dt)), _p(eps), _p(costs),
+                                        _p(U_new), _p(nxt), _p(U_shift))
+        return dict(costs=costs, U_new=U_new, next=nxt, U_shift=U_shift)
+
     def auv_step(self, prm, dt, rk, state, action):
         """AUVModel.step (scripts/src/models/auv_model.py:285-306): state [k,13], action [k,6] -> [k,13]."""
         st, ac = _c(np.asarray(state).reshape(-1, 13), self.dt), _c(np.asarray(action).reshape(-1, 6), self.dt)

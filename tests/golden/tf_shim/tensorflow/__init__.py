@@ -212,3 +212,55 @@ summary = types.SimpleNamespace(create_file_writer=lambda *a, **k: None, scalar=
                                 histogram=lambda *a, **k: None)
 profiler = types.SimpleNamespace(experimental=types.SimpleNamespace(start=lambda *a, **k: None,
                                                                     stop=lambda *a, **k: None))
+
+
+# ---- tf.keras: just enough for NNModel / NNAUVModel (scripts/src/models/nn_model.py:54-60): Sequential of Dense layers,
+# forward only.  Weights are created on first use (Glorot uniform like Keras) and are plain numpy arrays the fixture
+# generator overwrites.
+class _Dense:
+    def __init__(self, units, activation=None, input_shape=None, kernel_regularizer=None, name=None):
+        self.units, self.activation, self.input_shape, self.name = int(units), activation, input_shape, name
+        self.kernel, self.bias = None, None
+
+    def build(self, n_in, rng):
+        lim = np.sqrt(6.0 / (n_in + self.units))
+        self.kernel = rng.uniform(-lim, lim, (n_in, self.units))
+        self.bias = np.zeros(self.units)
+
+    def __call__(self, x):
+        y = _a(x) @ self.kernel + self.bias
+        return np.maximum(y, 0.0) if self.activation == "relu" else y
+
+
+class _Sequential:
+    def __init__(self, layers):
+        self.layers = list(layers)
+        rng = np.random.default_rng(0)
+        n_in = int(self.layers[0].input_shape[0])
+        for layer in self.layers:
+            layer.build(n_in, rng)
+            n_in = layer.units
+
+    def __call__(self, x):
+        for layer in self.layers:
+            x = layer(x)
+        return x
+
+    @property
+    def trainable_variables(self):
+        out = []
+        for layer in self.layers:
+            out += [layer.kernel, layer.bias]
+        return out
+
+
+keras = types.SimpleNamespace(Sequential=_Sequential, layers=types.SimpleNamespace(Dense=_Dense),
+                              backend=types.SimpleNamespace(set_floatx=lambda name: None),
+                              models=types.SimpleNamespace(load_model=lambda path: None))
+
+
+def constant(x, dtype=None, name=None):
+    return _a(x, dtype)
+
+
+compat = types.SimpleNamespace(v1=types.SimpleNamespace(dimension_value=lambda d: d))

@@ -75,3 +75,13 @@ def _relative_angle(q1, q2, name=None):
 geometry = types.SimpleNamespace(transformation=types.SimpleNamespace(quaternion=types.SimpleNamespace(
     multiply=_multiply, rotate=_rotate, from_rotation_matrix=_from_rotation_matrix,
     between_two_vectors_3d=_between_two_vectors_3d, relative_angle=_relative_angle, conjugate=_conjugate)))
+
+
+# nn_model.py:10-17 patches tensorflow_graphics.util.shape._get_dim through sys.modules at import time
+import sys as _sys                                                                          # noqa: E402
+_shape_mod = types.ModuleType("tensorflow_graphics.util.shape")
+_util_mod = types.ModuleType("tensorflow_graphics.util")
+_util_mod.shape = _shape_mod
+_sys.modules.setdefault("tensorflow_graphics.util", _util_mod)
+_sys.modules.setdefault("tensorflow_graphics.util.shape", _shape_mod)
+util = _util_mod
