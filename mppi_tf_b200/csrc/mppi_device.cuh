@@ -5,6 +5,16 @@
 
 #include "../../include/mppi_b200.h"
 
+// Bounds checks of every computed shared / global index in the rollout kernels, compiled in by `make debug`
+// (-DMPPI_DEBUG_BOUNDS -> mppi_tf_b200/_build_dbg/libmppi_b200.so, loaded through MPPI_B200_LIB): the stand-in for
+// compute-sanitizer, which is closed on this pool.  A violated check traps the kernel (the launch then reports an error).
+#ifdef MPPI_DEBUG_BOUNDS
+#include <cassert>
+#define MPPI_CHECK(cond) assert(cond)
+#else
+#define MPPI_CHECK(cond) ((void)0)
+#endif
+
 namespace mppi {
 
 constexpr int kMaxA = MPPI_MAX_A;
@@ -560,19 +570,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// Bounded: a bulk copy that never completes (a bad address, a byte count that does not match expect_tx) would otherwise
+// spin for ever and take the GPU with it; after about 2^26 polls (seconds) the kernel traps and the launch reports an error.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 26); spin++) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    asm volatile("trap;");
 }
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (UBLKCP in SASS).
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)

@@ -110,6 +110,7 @@ __device__ __forceinline__ void philox_weighted_sum_and_finish(const RolloutPara
 #pragma unroll
             for (int i = 0; i < 16; i++) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
             const float r = warp_transpose_sum32(acc, lane);
+            MPPI_CHECK(ch * 32 + lane < TAp);
             sAcc[warp * TAp + ch * 32 + lane] = r;
         }
     } else {
@@ -147,6 +148,7 @@ __device__ __forceinline__ void philox_weighted_sum_and_finish(const RolloutPara
                 float e = 0.f;
                 if (k < kend) e = sample_weight(costs[k], beta_c, nil);
                 const unsigned m = __ballot_sync(0xffffffffu, e != 0.f);
+                MPPI_CHECK(e == 0.f || (off + __popc(m & lt) >= 0 && off + __popc(m & lt) < NW * kListCap));
                 if (e != 0.f) sm.sList[off + __popc(m & lt)] = make_uint2((uint32_t)(p.k_offset + k), __float_as_uint(e));
                 off += __popc(m);
             }
@@ -163,6 +165,7 @@ __device__ __forceinline__ void philox_weighted_sum_and_finish(const RolloutPara
 #pragma unroll
                 for (int i = 0; i < 16; i++) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
                 const float r = warp_transpose_sum32(acc, lane);
+                MPPI_CHECK(ch >= 0 && ch * 32 + lane < TAp);
                 myacc[ch * 32 + lane] += r;
             };
 #pragma unroll 1
@@ -174,6 +177,7 @@ __device__ __forceinline__ void philox_weighted_sum_and_finish(const RolloutPara
                     for (int i = 0; i < 16; i++) acc2[i] = make_float2(0.f, 0.f);
                     cur_ch = ch;
                 }
+                MPPI_CHECK(i0 >= 0 && i0 < total && total <= NW * kListCap && ch < nchunk);
                 const uint2 ent = (i0 + lane < total) ? sm.sList[i0 + lane] : make_uint2(0u, 0u);   // padding lanes: weight 0
                 const PhiloxSample ps = philox_sample(phA, ent.x);
                 const float e = __uint_as_float(ent.y);

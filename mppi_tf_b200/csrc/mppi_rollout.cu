@@ -228,6 +228,7 @@ rollout_philox_kernel(const __grid_constant__ RolloutParams p)
         add_state_cost<A, COST>(x, mc, p, S);    // terminal cost on top of step T-1's (src/controller_base.cpp:271-272)
         Sk_.add(fmaf(p.w_scale, Sw.total(), S.total()));
         const float Sk = Sk_.s;
+        MPPI_CHECK(k >= 0 && k < p.K_local);
         costs[k] = Sk;
         bmin = fminf(bmin, Sk);
         bmax = fmaxf(bmax, Sk);
@@ -412,6 +413,7 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
             const int b = TMA ? seq % NBUF : grp;          // cooperative-load fallback: a private buffer per group
             const int gt = seq * gridDim.x + blockIdx.x;
             const int rows = min(32, p.K_local - 32 * gt);
+            MPPI_CHECK(b >= 0 && b < NBUF && gt >= 0 && gt < n_tiles && rows >= 1 && rows <= 32);
             float *tile = sTiles + (size_t)b * tile_words;
             if (TMA) {
                 // A parity wait cannot tell phase n from phase n - 2: with a shared pool a group may get here before
@@ -540,6 +542,7 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
                     for (int cc = 0; cc < C; cc++) S += sS[(grp * C + cc) * 32 + lane];   // fixed order in every warp
                 }
             }
+            MPPI_CHECK(lane >= rows || 32 * gt + lane < p.K_local);
             if (p.norm_mode != 2 && cw == 0 && lane < rows) costs[32 * gt + lane] = S;
             if (p.norm_mode == 1) {                // cost pass: track (min, max), no weights yet
                 if (lane < rows) { gmin = fminf(gmin, S); gmax = fmaxf(gmax, S); }
@@ -594,6 +597,7 @@ rollout_injected_kernel(const __grid_constant__ RolloutParams p, const InjectedL
 #pragma unroll
                 for (int mm = 0; mm < 4; mm++) {
                     const int c = (cb + mm) * 32 + lane;
+                    MPPI_CHECK(!(cb + mm < cb1 && c < TA) || c < TAp);
                     if (cb + mm < cb1 && c < TA) accg[c] += a4[mm];
                 }
             }

@@ -55,6 +55,7 @@ __device__ __forceinline__ float fast_rollout(const RolloutParams &p, const uint
 #pragma unroll
         for (int c = 0; c < A; c++) {
             const float4 v = normals4_fast<R>(sTab, call + c, ps, p);
+            MPPI_CHECK((int)(call + c) < ncall);
             if (STORE) row[call + c] = v;
             z[4 * c] = v.x; z[4 * c + 1] = v.y; z[4 * c + 2] = v.z; z[4 * c + 3] = v.w;
         }
@@ -139,6 +140,7 @@ rollout_philox_fast_kernel(const __grid_constant__ RolloutParams p)
     for (int k = kfirst; k < kend && p.norm_mode != 2; k += kPhiloxThreads) {   // weight pass of a normalised update: costs are in HBM
         const PhiloxSample ps = philox_sample(phA, (uint32_t)(p.k_offset + k));
         const float Sk = fast_rollout<A, R, false>(p, sm.sTab, sm.sUV, ps, fc, nullptr);
+        MPPI_CHECK(k >= 0 && k < p.K_local);
         costs[k] = Sk;
         bmin = fminf(bmin, Sk);
         bmax = fmaxf(bmax, Sk);
@@ -229,6 +231,7 @@ rollout_philox_resident_kernel(const __grid_constant__ RolloutParams p, const Re
         const bool valid = k < p.K_local;
         // ---- rollout + cost; the normals of the row are left in the tile ------------------------------
         const PhiloxSample ps = philox_sample(phA, (uint32_t)(p.k_offset + k));
+        MPPI_CHECK(t >= 0 && t < n_tiles && ncall <= rs && (size_t)(warp + 1) * tile_f4 <= (size_t)NW * tile_f4);
         float S = fast_rollout<A, R, true>(p, sTab, sL, ps, fc, myrow);
         if (valid) costs[k] = S; else S = kInf;
         // ---- online max-shifted weights -----------------------------------------------------------------
@@ -255,6 +258,7 @@ rollout_philox_resident_kernel(const __grid_constant__ RolloutParams p, const Re
 #pragma unroll
                 for (int j = 0; j < NC; j++) {
                     if (c + 32 * j < ncall) {
+                        MPPI_CHECK((i * ng + g) < 32 && g * rs + c + i * rstep + 32 * j < tile_f4);
                         const float4 v = col[i * rstep + 32 * j];
                         const float2 lo = __ffma2_rn(w2, make_float2(v.x, v.y), make_float2(acc[j].x, acc[j].y));
                         const float2 hi = __ffma2_rn(w2, make_float2(v.z, v.w), make_float2(acc[j].z, acc[j].w));

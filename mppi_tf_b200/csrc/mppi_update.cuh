@@ -404,6 +404,7 @@ __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_
         trace_stamp(p, ctrl, 7);
         return;
     }
+    MPPI_CHECK(part >= 0 && part < nparts && nparts <= p.max_parts && ctrl < p.n_ctrl);
     float *mine = p.partials + ((size_t)ctrl * nparts + part) * stride;
     if (threadIdx.x == 0) { mine[0] = beta_c; mine[1] = eta_c; }
     for (int j = threadIdx.x; j < TA; j += blockDim.x) mine[4 + j] = sN[j];
@@ -428,6 +429,7 @@ __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_
     } else {
         const int gi = part / kMergeGroup, g0 = gi * kMergeGroup;
         const int gn = min(kMergeGroup, nparts - g0);
+        MPPI_CHECK(gi >= 0 && gi < ngroups && ngroups <= p.max_groups && gn >= 1);
         if (threadIdx.x == 0) {
             const unsigned prev = atomicAdd(ctr + 1 + gi, 1u);
             s_is_last = (prev == (unsigned)gn - 1u);
