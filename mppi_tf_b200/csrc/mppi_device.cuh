@@ -120,6 +120,13 @@ __device__ __forceinline__ void trace_stamp(const RolloutParams &p, int ctrl, in
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.trace[((size_t)ctrl * gridDim.x + blockIdx.x) * kTraceSlots + slot] = t;
+        if (slot == 0) {                                   // where the CTA runs: slot 10 = 1 + %smid, slot 11 = 1 + %warpid of thread 0
+            unsigned sm, wid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+            p.trace[((size_t)ctrl * gridDim.x + blockIdx.x) * kTraceSlots + 10] = 1ull + sm;
+            p.trace[((size_t)ctrl * gridDim.x + blockIdx.x) * kTraceSlots + 11] = 1ull + wid;
+        }
     }
 }
 

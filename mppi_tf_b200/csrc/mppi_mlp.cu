@@ -2,6 +2,7 @@
 // batched one-step `predict` stage used by ModelBase-style callers and by the unit tests.
 // Device building blocks: mppi_mlp.cuh.  The update logic (softmin partials, merge, shift) is the
 // same code the point-mass kernels use (mppi_update.cuh).
+#define MPPI_TAIL_INLINE        // setmaxnreg kernel: no function calls (mppi_update.cuh)
 #include "mppi_mlp.cuh"
 #include "mppi_internal.h"
 #include "mppi_update.cuh"

@@ -72,11 +72,13 @@ inline size_t philox_smem_bytes(int A, int T, int TA)
 template <int A, class Gen>
 __device__ __forceinline__ void philox_weighted_sum_and_finish(const RolloutParams &p, int ctrl, const float *costs, int w_lo, int kfirst,
                                                                int kend, float beta_c, float max_c, float nil, uint32_t phA,
-                                                               const PhiloxSmem &sm)
+                                                               const PhiloxSmem &sm, int vtid = -1)
 {
     constexpr int NW = kPhiloxThreads / 32;
     constexpr int kstride = kPhiloxThreads;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // vtid: the thread's index under the caller's (virtual) warp numbering, kfirst = 32 w_lo + vtid; every shared-memory row,
+    // list position and work range below is a function of it, so the result does not depend on the placement
+    const int tid = vtid >= 0 ? vtid : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int TA = p.TA, TAp = (TA + 31) & ~31;
     const int ncall = (TA + 3) >> 2;
     const int nchunk = (ncall + 7) >> 3;

@@ -114,6 +114,8 @@ rollout_philox_fast_kernel(const __grid_constant__ RolloutParams p)
     float *sRed = sm.sRed;
 
     const int ctrl = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ unsigned s_slot;                  // hardware warp slot of the CTA's first warp (read after the barriers below)
+    if (tid == 0) asm volatile("mov.u32 %0, %%warpid;" : "=r"(s_slot));
     trace_stamp(p, ctrl, 0);
     for (int c = tid; c < ((TA + 3) >> 2); c += kPhiloxThreads) sm.sTab[c] = philox_call_table((uint32_t)c, (uint32_t)ctrl, p);
     const uint32_t phA = philox_uniform_A(p);
@@ -132,7 +134,15 @@ rollout_philox_fast_kernel(const __grid_constant__ RolloutParams p)
     const int n_w = (p.K_local + 31) >> 5;
     const int w_lo = (int)((long long)n_w * blockIdx.x / gridDim.x);
     const int w_hi = (int)((long long)n_w * (blockIdx.x + 1) / gridDim.x);
-    const int kfirst = 32 * w_lo + tid;
+    // Which warps idle in the CTA's last (partly filled) iteration: the kernel is bound by the schedulers' dispatch rate, a
+    // warp runs on scheduler %warpid mod 4, and the two CTAs of an SM would both park their idle warps on the same schedulers
+    // (a K/8 shard of config 3 is one iteration of 13.8 tiles per CTA: 8 + 8 + 6 + 6 busy warps per scheduler instead of four
+    // times 7).  The CTA in the upper half of the SM's warp slots therefore rotates its warp numbering by the idle count.  Only
+    // the placement changes: samples, list order and summation order are functions of the virtual warp index.
+    const int idle = (NW - (w_hi - w_lo) % NW) % NW;
+    const int vwarp = (warp + ((s_slot >> 4) & 1) * idle) % NW;
+    const int vtid = 32 * vwarp + lane;
+    const int kfirst = 32 * w_lo + vtid;
     const int kend = min(p.K_local, 32 * w_hi);
 
     // ---- phase 1: rollout + cost ---------------------------------------------------------------
@@ -163,7 +173,7 @@ rollout_philox_fast_kernel(const __grid_constant__ RolloutParams p)
     if (p.norm_mode == 2) beta_c = beta_fixed;
 
     // ---- phase 2 (mppi_philox_sum.cuh) -----------------------------------------------------------
-    philox_weighted_sum_and_finish<A, GenFast<R>>(p, ctrl, costs, w_lo, kfirst, kend, beta_c, max_c, nil, phA, sm);
+    philox_weighted_sum_and_finish<A, GenFast<R>>(p, ctrl, costs, w_lo, kfirst, kend, beta_c, max_c, nil, phA, sm, vtid);
 }
 
 // -------------------------------------------------------------------------------------------------

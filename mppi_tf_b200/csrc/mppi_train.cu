@@ -3,10 +3,11 @@
 // (/root/reference/scripts/src/learners/learner_base.py:469-496, optimizer tf.optimizers.Adam :325),
 // for the network of mppi_mlp.cuh:   Xn = (concat(x, u) - Xmean)/Xstd,  Yn = ((x' - x) - Ymean)/Ystd,
 //   h1 = relu(Xn W1 + b1), h2 = relu(h1 W2 + b2), out = h2 W3 + b3,  loss = mean((out - Yn)^2).
-// fp32 throughout (the bf16 copy the rollout kernels stage is re-packed from the fp32 master weights after
-// every step).  This is the caller of the hot path, not the hot path: plain shared-memory-tiled kernels,
-// fixed summation order (deterministic).
+// fp32 accuracy throughout (the bf16 copy the rollout kernels stage is re-packed from the fp32 master weights after
+// every step); the seven GEMMs of a step run on the tensor cores as error-compensated tf32 products (gemm_kernel).  This is
+// the caller of the hot path, not the hot path: shared-memory-tiled kernels, fixed summation order (deterministic).
 #include <cuda_bf16.h>
+#include <mma.h>
 
 #include "mppi_internal.h"
 #include "mppi_mlp.cuh"
@@ -15,44 +16,83 @@ namespace mppi {
 
 namespace {
 
-constexpr int TS = 32;     // GEMM tile
+constexpr int TS = 32;     // GEMM tile (M, N and K step)
+constexpr int LDS_ = TS + 4;   // shared-memory leading dimension: a multiple of 4 floats (wmma), rows 16 apart stay 32-byte aligned
 
-// C[M][N] = op(A) op(B) (+ bias[N]) (relu), row-major.  TA: A is stored [K][M]; TB: B is stored [N][K].
+// C[M][N] = op(A) op(B) (+ bias[N]) (relu), row-major fp32.  TA: A is stored [K][M]; TB: B is stored [N][K].
+// The contraction runs on the tensor cores: wmma m16n16k8 with tf32 operands and fp32 accumulation, each fp32 operand split
+// exactly into three tf32 words (11 + 11 + 2 significant bits: the usual two-word "3xTF32" split keeps 22 of the 24 bits,
+// four times the rounding of an fp32 product, and Adam turns the gradient error of nearly dead units into weight
+// movement) and the six products above 2^-33 accumulated small to large - the learner works in fp32 because the
+// reference's does (Keras in float64), and a plain tf32 or bf16 product would put 1e-3 into every gradient.  Four warps per CTA, one 16 x 16 fragment each; fixed
+// summation order (deterministic).
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(TS * 8) gemm_kernel(int M, int N, int K, const float *A, const float *B, const float *bias,
-                                                      int relu, float *C)
+__global__ void __launch_bounds__(128) gemm_kernel(int M, int N, int K, const float *A, const float *B, const float *bias,
+                                                   int relu, float *C)
 {
-    __shared__ float sA[TS][TS + 1], sB[TS][TS + 1];
-    const int tx = threadIdx.x & (TS - 1), ty = threadIdx.x / TS;     // 32 x 8 threads, 4 rows each
+    using namespace nvcuda;
+    __shared__ __align__(32) float sA[TS][LDS_], sB[TS][LDS_], sC[TS][LDS_];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;                              // 2 x 2 warps
     const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // the tensor core's accumulator adds with truncation: a K-long chain drifts by about K 2^-24 relative.  Every 32-deep
+    // tile is therefore accumulated from zero and added to the running sum with an ordinary (round-to-nearest) fp32 add.
+    wmma::fragment<wmma::accumulator, 16, 16, 8, float> acc, part;
+    wmma::fill_fragment(acc, 0.f);
     for (int k0 = 0; k0 < K; k0 += TS) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int i = ty + 8 * r;                     // tile row
-            {   // sA[i][tx] = op(A)[m0 + i][k0 + tx]
-                const int m = m0 + i, k = k0 + tx;
-                sA[i][tx] = (m < M && k < K) ? (TA ? A[(size_t)k * M + m] : A[(size_t)m * K + k]) : 0.f;
+        wmma::fill_fragment(part, 0.f);
+        for (int i = tid; i < TS * TS; i += 128) {
+            const int r = i / TS, c = i - r * TS;
+            {   // sA[r][c] = op(A)[m0 + r][k0 + c]: consecutive threads walk the contiguous dimension of the source
+                const int rr = TA ? c : r, cc = TA ? r : c;               // TA: source rows are k
+                const int m = m0 + rr, k = k0 + cc;
+                sA[rr][cc] = (m < M && k < K) ? (TA ? A[(size_t)k * M + m] : A[(size_t)m * K + k]) : 0.f;
             }
-            {   // sB[i][tx] = op(B)[k0 + i][n0 + tx]
-                const int k = k0 + i, n = n0 + tx;
-                sB[i][tx] = (k < K && n < N) ? (TB ? B[(size_t)n * K + k] : B[(size_t)k * N + n]) : 0.f;
+            {   // sB[r][c] = op(B)[k0 + r][n0 + c]
+                const int rr = TB ? c : r, cc = TB ? r : c;               // TB: source rows are n
+                const int k = k0 + rr, n = n0 + cc;
+                sB[rr][cc] = (k < K && n < N) ? (TB ? B[(size_t)n * K + k] : B[(size_t)k * N + n]) : 0.f;
             }
         }
         __syncthreads();
-#pragma unroll 8
-        for (int kk = 0; kk < TS; kk++) {
-            const float b = sB[kk][tx];
 #pragma unroll
-            for (int r = 0; r < 4; r++) acc[r] = fmaf(sA[ty + 8 * r][kk], b, acc[r]);
+        for (int kk = 0; kk < TS; kk += 8) {
+            wmma::fragment<wmma::matrix_a, 16, 16, 8, wmma::precision::tf32, wmma::row_major> a_hi, a_lo, a_l2;
+            wmma::fragment<wmma::matrix_b, 16, 16, 8, wmma::precision::tf32, wmma::row_major> b_hi, b_lo, b_l2;
+            wmma::load_matrix_sync(a_hi, &sA[16 * wm][kk], LDS_);
+            wmma::load_matrix_sync(b_hi, &sB[kk][16 * wn], LDS_);
+#pragma unroll
+            for (int i = 0; i < a_hi.num_elements; i++) {
+                const float x = a_hi.x[i], hi = wmma::__float_to_tf32(x), lo = wmma::__float_to_tf32(x - hi);
+                a_hi.x[i] = hi;
+                a_lo.x[i] = lo;
+                a_l2.x[i] = (x - hi) - lo;                                 // at most two significant bits: exact in tf32
+            }
+#pragma unroll
+            for (int i = 0; i < b_hi.num_elements; i++) {
+                const float x = b_hi.x[i], hi = wmma::__float_to_tf32(x), lo = wmma::__float_to_tf32(x - hi);
+                b_hi.x[i] = hi;
+                b_lo.x[i] = lo;
+                b_l2.x[i] = (x - hi) - lo;
+            }
+            wmma::mma_sync(part, a_lo, b_lo, part);                        // 2^-22 terms
+            wmma::mma_sync(part, a_l2, b_hi, part);
+            wmma::mma_sync(part, a_hi, b_l2, part);
+            wmma::mma_sync(part, a_lo, b_hi, part);                        // 2^-11 terms
+            wmma::mma_sync(part, a_hi, b_lo, part);
+            wmma::mma_sync(part, a_hi, b_hi, part);
         }
+#pragma unroll
+        for (int i = 0; i < acc.num_elements; i++) acc.x[i] += part.x[i];
         __syncthreads();
     }
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int m = m0 + ty + 8 * r, n = n0 + tx;
+    wmma::store_matrix_sync(&sC[16 * wm][16 * wn], acc, LDS_, wmma::mem_row_major);
+    __syncthreads();
+    for (int i = tid; i < TS * TS; i += 128) {
+        const int r = i / TS, c = i - r * TS;
+        const int m = m0 + r, n = n0 + c;
         if (m < M && n < N) {
-            float v = acc[r] + (bias ? bias[n] : 0.f);
+            float v = sC[r][c] + (bias ? bias[n] : 0.f);
             if (relu) v = fmaxf(v, 0.f);
             C[(size_t)m * N + n] = v;
         }
@@ -63,7 +103,7 @@ template <bool TA, bool TB>
 cudaError_t gemm(int M, int N, int K, const float *A, const float *B, const float *bias, bool relu, float *C, cudaStream_t st)
 {
     dim3 grid((N + TS - 1) / TS, (M + TS - 1) / TS);
-    gemm_kernel<TA, TB><<<grid, TS * 8, 0, st>>>(M, N, K, A, B, bias, relu ? 1 : 0, C);
+    gemm_kernel<TA, TB><<<grid, 128, 0, st>>>(M, N, K, A, B, bias, relu ? 1 : 0, C);
     return cudaGetLastError();
 }
 

@@ -4,6 +4,16 @@
 #pragma once
 #include "mppi_device.cuh"
 
+// The merge of partial records runs once per launch, in one CTA, after everyone else has finished, up to three times in a
+// row (group, groups, ranks): a real function (one copy per kernel, warm on its second call) with rolled loops - the
+// tail's cost is instruction fetch and dependent L2 trips, not arithmetic.  A kernel that re-partitions its registers
+// with setmaxnreg (mppi_mlp.cu) cannot call functions: it defines MPPI_TAIL_INLINE before including this header.
+#ifdef MPPI_TAIL_INLINE
+#define MPPI_TAIL_FN inline
+#else
+#define MPPI_TAIL_FN __noinline__
+#endif
+
 namespace mppi {
 
 constexpr int kMaxParts = 1024;   // CTA partials per controller
@@ -193,7 +203,7 @@ struct Merged { float beta, eta; };
 // of every update (one CTA reads nparts x TA floats through L2), so they are spread over the whole CTA:
 // work item (slice, column quad) sums every nsl-th record with eight 16-byte loads in flight, then the
 // slices are added in a fixed order.
-__device__ inline Merged merge_parts(const float *parts, size_t part_stride, int nparts, int TA,
+static __device__ MPPI_TAIL_FN Merged merge_parts(const float *parts, size_t part_stride, int nparts, int TA,
                               float neg_inv_lambda_log2e, float *sN, float *sScale, float *sRed,
                               float4 *sScratch, int scratch_f4)
 {
@@ -207,9 +217,10 @@ __device__ inline Merged merge_parts(const float *parts, size_t part_stride, int
     // on beta is requested first: the first eight records of this thread's first (slice, column quad) item ...
     const bool has_item = tid < ncol4 * nsl;
     const int sl0 = has_item ? tid / ncol4 : 0, c40 = has_item ? tid - sl0 * ncol4 : 0;
-    float4 pre[8];
+    constexpr int PRE = 4;
+    float4 pre[PRE];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < PRE; i++) {
         const int c = sl0 + i * nsl;
         pre[i] = (has_item && c < nparts) ? __ldcg(reinterpret_cast<const float4 *>(parts + 4 + 4 * c40 + (size_t)c * part_stride))
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -218,11 +229,13 @@ __device__ inline Merged merge_parts(const float *parts, size_t part_stride, int
     float2 be = make_float2(kInf, 0.f);
     if (tid < nparts) be = __ldcg(reinterpret_cast<const float2 *>(parts + (size_t)tid * part_stride));
     float b = be.x;
+#pragma unroll 1
     for (int c = tid + blockDim.x; c < nparts; c += blockDim.x) b = fminf(b, __ldcg(parts + c * part_stride));
     b = warp_min(b);
     if (lane == 0) sRed[warp] = b;
     __syncthreads();
     float beta = sRed[0];
+#pragma unroll 1
     for (int w = 1; w < nw; w++) beta = fminf(beta, sRed[w]);
     __syncthreads();
     float e = 0.f;
@@ -231,6 +244,7 @@ __device__ inline Merged merge_parts(const float *parts, size_t part_stride, int
         sScale[tid] = sc;
         e = sc * be.y;
     }
+#pragma unroll 1
     for (int c = tid + blockDim.x; c < nparts; c += blockDim.x) {
         const float bc = __ldcg(parts + c * part_stride);
         const float sc = (bc == kInf) ? 0.f : weight_exp(bc, beta, neg_inv_lambda_log2e);
@@ -241,9 +255,11 @@ __device__ inline Merged merge_parts(const float *parts, size_t part_stride, int
     if (lane == 0) sRed[warp] = e;
     __syncthreads();
     float eta = 0.f;
+#pragma unroll 1
     for (int w = 0; w < nw; w++) eta += sRed[w];
 
     // column sums: work item (slice, column quad) sums every nsl-th record, eight 16-byte loads in flight, in order
+#pragma unroll 1
     for (int it = tid; it < ncol4 * nsl; it += blockDim.x) {
         const int sl = it / ncol4, c4 = it - sl * ncol4;
         const float *col = parts + 4 + 4 * c4;
@@ -251,26 +267,28 @@ __device__ inline Merged merge_parts(const float *parts, size_t part_stride, int
         int c = sl;
         if (it == tid) {                                   // the prefetched batch
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
+            for (int i = 0; i < PRE; i++) {
                 if (c + i * nsl < nparts) {
                     const float w = sScale[c + i * nsl];
                     acc.x = fmaf(w, pre[i].x, acc.x); acc.y = fmaf(w, pre[i].y, acc.y);
                     acc.z = fmaf(w, pre[i].z, acc.z); acc.w = fmaf(w, pre[i].w, acc.w);
                 }
             }
-            c += 8 * nsl;
+            c += PRE * nsl;
         }
-        for (; c + 7 * nsl < nparts; c += 8 * nsl) {
-            float4 v[8];
+#pragma unroll 1
+        for (; c + (PRE - 1) * nsl < nparts; c += PRE * nsl) {
+            float4 v[PRE];
 #pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = __ldcg(reinterpret_cast<const float4 *>(col + (size_t)(c + i * nsl) * part_stride));
+            for (int i = 0; i < PRE; i++) v[i] = __ldcg(reinterpret_cast<const float4 *>(col + (size_t)(c + i * nsl) * part_stride));
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
+            for (int i = 0; i < PRE; i++) {
                 const float w = sScale[c + i * nsl];
                 acc.x = fmaf(w, v[i].x, acc.x); acc.y = fmaf(w, v[i].y, acc.y);
                 acc.z = fmaf(w, v[i].z, acc.z); acc.w = fmaf(w, v[i].w, acc.w);
             }
         }
+#pragma unroll 1
         for (; c < nparts; c += nsl) {
             const float4 v = __ldcg(reinterpret_cast<const float4 *>(col + (size_t)c * part_stride));
             const float w = sScale[c];
@@ -289,8 +307,10 @@ __device__ inline Merged merge_parts(const float *parts, size_t part_stride, int
     __syncthreads();
     if (nsl > 1) {
         const float *sc = reinterpret_cast<const float *>(sScratch);
+#pragma unroll 1
         for (int j = tid; j < TA; j += blockDim.x) {
             float acc = 0.f;
+#pragma unroll 1
             for (int sl = 0; sl < nsl; sl++) acc += sc[(size_t)sl * 4 * ncol4 + j];
             sN[j] = acc;
         }

@@ -26,10 +26,20 @@ def test_train_steps_match_oracle(n, a):
         w = c.mlpGetWeights()
     finally:
         c.close()
+    worst, rms = {}, {}
     for k in KEYS:
         # five Adam steps of 1e-3 move every weight by about 5e-3: compare the MOVEMENT, not the weight
         moved = tr.w[k] - np.asarray(mlp[k], np.float64)
-        assert rel_err(w[k] - np.asarray(mlp[k], np.float32), moved) < 2e-2, k
+        diff = (w[k] - np.asarray(mlp[k], np.float32)).astype(np.float64) - moved
+        worst[k] = float(np.abs(diff).max() / np.abs(moved).max())
+        rms[k] = float(np.sqrt(np.mean(diff ** 2)) / np.sqrt(np.mean(moved ** 2)))
+    print("movement errors", n, a, "worst", {k: round(v, 5) for k, v in worst.items()}, "rms", {k: round(v, 6) for k, v in rms.items()})
+    # Adam divides by sqrt(v) + 1e-7: an entry whose gradient is a nearly cancelling sum over the batch (|g| ~ 1e-6 at n = 4096)
+    # turns the fp32 rounding of that sum into percents of ITS movement, whatever the summation order (SIMT chain or tensor-core
+    # tiles: the worst entry of W2 at n = 4096 is just under 2 % / 2.2 %, its rms error 2e-4) - the bar on the worst entry is 5e-2, the one on the whole
+    # tensor (rms) 2e-3
+    assert max(worst.values()) < 5e-2, worst
+    assert max(rms.values()) < 2e-3, rms
 
 
 def test_rollout_uses_the_trained_weights(oracle64):
