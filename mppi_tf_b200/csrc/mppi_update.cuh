@@ -419,116 +419,98 @@ __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_
         nparts = gridDim.x / cs;
         part = blockIdx.x / cs;
     }
-    if (nparts == 1 && p.world == 1) {          // a single CTA (or cluster) owns the controller: nothing to merge
-        apply_update<A, PHILOX>(p, ctrl, Merged{beta_c, eta_c}, sN, sWork);
-        trace_stamp(p, ctrl, 7);
-        return;
-    }
-    MPPI_CHECK(part >= 0 && part < nparts && nparts <= p.max_parts && ctrl < p.n_ctrl);
-    float *mine = p.partials + ((size_t)ctrl * nparts + part) * stride;
-    if (threadIdx.x == 0) { mine[0] = beta_c; mine[1] = eta_c; }
-    for (int j = threadIdx.x; j < TA; j += blockDim.x) mine[4 + j] = sN[j];
-    __threadfence();
-    __syncthreads();
-    trace_stamp(p, ctrl, 4);
-    unsigned int *ctr = p.counters + (size_t)ctrl * (1 + p.max_groups);
-    const int ngroups = (nparts + kMergeGroup - 1) / kMergeGroup;
-    const bool two_level = nparts > 2 * kMergeGroup && ngroups <= p.max_groups;
-    Merged m;
-    if (!two_level) {
-        if (threadIdx.x == 0) {
-            const unsigned prev = atomicAdd(ctr, 1u);
-            s_is_last = (prev == (unsigned)nparts - 1u);
-        }
-        __syncthreads();
-        if (!s_is_last) return;
-        __threadfence();
-        if (threadIdx.x == 0) *ctr = 0u;
-        m = merge_parts(p.partials + (size_t)ctrl * nparts * stride, stride, nparts, TA,
-                        p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
-    } else {
-        const int gi = part / kMergeGroup, g0 = gi * kMergeGroup;
-        const int gn = min(kMergeGroup, nparts - g0);
-        MPPI_CHECK(gi >= 0 && gi < ngroups && ngroups <= p.max_groups && gn >= 1);
-        if (threadIdx.x == 0) {
-            const unsigned prev = atomicAdd(ctr + 1 + gi, 1u);
-            s_is_last = (prev == (unsigned)gn - 1u);
-        }
-        __syncthreads();
-        if (!s_is_last) return;
-        __threadfence();
-        if (threadIdx.x == 0) ctr[1 + gi] = 0u;
-        const Merged mg = merge_parts(p.partials + ((size_t)ctrl * nparts + g0) * stride, stride, gn, TA,
-                                      p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
-        float *grec = p.partials2 + ((size_t)ctrl * p.max_groups + gi) * stride;
-        if (threadIdx.x == 0) { grec[0] = mg.beta; grec[1] = mg.eta; }
-        for (int j = threadIdx.x; j < TA; j += blockDim.x) grec[4 + j] = sN[j];
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned prev = atomicAdd(ctr, 1u);
-            s_is_last = (prev == (unsigned)ngroups - 1u);
-        }
-        __syncthreads();
-        if (!s_is_last) return;
-        __threadfence();
-        if (threadIdx.x == 0) *ctr = 0u;
-        m = merge_parts(p.partials2 + (size_t)ctrl * p.max_groups * stride, stride, ngroups, TA,
-                        p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
-    }
-    trace_stamp(p, ctrl, 5);
-    if (p.world > 1 && p.peer_on) {
-        // Fused exchange: this CTA writes the rank payload straight into every rank's mailbox over NVLink,
-        // raises its flag there, waits for the other ranks' flags in its own mailbox and finishes the update
-        // in the same launch - no collective call, no second kernel.  Buffers alternate with the epoch's
-        // parity, so a rank that races ahead cannot overwrite a payload that is still being read.
-        const int world = p.world, tid = threadIdx.x;
-        const uint32_t par = p.epoch & 1u;
-        const size_t slot = ((size_t)par * world + p.rank) * p.n_ctrl + ctrl;
-        for (int r = 0; r < world; r++) {
-            float *dst = p.peer_mail[r] + slot * stride;
-            if (tid == 0) { dst[0] = m.beta; dst[1] = m.eta; dst[2] = 0.f; dst[3] = 0.f; }
-            for (int j = tid; j < stride - 4; j += blockDim.x) dst[4 + j] = (j < TA) ? sN[j] : 0.f;
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid < world) st_release_sys(p.peer_flag[tid] + slot, p.epoch);
-        if (tid < world) {
-            const uint32_t *f = p.peer_flag[p.rank] + (((size_t)par * world + tid) * p.n_ctrl + ctrl);
-            const long long t0 = clock64();
-            while (ld_acquire_sys(f) != p.epoch) {
-                if (clock64() - t0 > (1LL << 31)) {            // about a second: a rank is missing, do not hang the GPU
-                    atomicExch(p.peer_status, 1u);
-                    break;
+    Merged m{beta_c, eta_c};
+    const int tid = threadIdx.x;
+    if (!(nparts == 1 && p.world == 1)) {       // else a single CTA (or cluster) owns the controller: nothing to merge
+        MPPI_CHECK(part >= 0 && part < nparts && nparts <= p.max_parts && ctrl < p.n_ctrl);
+        // record = {beta, eta, 0, 0, N[TA], 0 ..}
+        auto store_record = [&](float *dst, float b, float e) {
+#pragma unroll 1
+            for (int j = tid; j < stride; j += blockDim.x) dst[j] = j == 0 ? b : (j == 1 ? e : ((j >= 4 && j - 4 < TA) ? sN[j - 4] : 0.f));
+        };
+        // Last-arriver election after the CTA's stores: the barrier orders every thread's stores before thread 0's fence
+        // (cumulative), one fence and one atomic per CTA instead of a fence in every thread; the winner's fence and the
+        // second barrier order the atomic before the CTA's L2 loads.  CTA-wide (two barriers); true in the last CTA.
+        auto last_of = [&](unsigned int *counter, int n) {
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                const bool last = atomicAdd(counter, 1u) == (unsigned)n - 1u;
+                if (last) {
+                    __threadfence();
+                    *counter = 0u;              // ready for the next launch
                 }
+                s_is_last = last;
             }
+            __syncthreads();
+            return s_is_last != 0;
+        };
+        store_record(p.partials + ((size_t)ctrl * nparts + part) * stride, beta_c, eta_c);
+        trace_stamp(p, ctrl, 4);
+        unsigned int *ctr = p.counters + (size_t)ctrl * (1 + p.max_groups);
+        const int ngroups = (nparts + kMergeGroup - 1) / kMergeGroup;
+        const bool two_level = nparts > 2 * kMergeGroup && ngroups <= p.max_groups;
+        if (!two_level) {
+            if (!last_of(ctr, nparts)) return;
+            m = merge_parts(p.partials + (size_t)ctrl * nparts * stride, stride, nparts, TA,
+                            p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
+        } else {
+            const int gi = part / kMergeGroup, g0 = gi * kMergeGroup;
+            const int gn = min(kMergeGroup, nparts - g0);
+            MPPI_CHECK(gi >= 0 && gi < ngroups && ngroups <= p.max_groups && gn >= 1);
+            if (!last_of(ctr + 1 + gi, gn)) return;
+            const Merged mg = merge_parts(p.partials + ((size_t)ctrl * nparts + g0) * stride, stride, gn, TA,
+                                          p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
+            store_record(p.partials2 + ((size_t)ctrl * p.max_groups + gi) * stride, mg.beta, mg.eta);
+            if (!last_of(ctr, ngroups)) return;
+            m = merge_parts(p.partials2 + (size_t)ctrl * p.max_groups * stride, stride, ngroups, TA,
+                            p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
         }
-        __syncthreads();
-        trace_stamp(p, ctrl, 6);
-        if (*reinterpret_cast<volatile unsigned int *>(p.peer_status) != 0u) {
-            // a payload is missing: leave U untouched (merging a stale mailbox would let the ranks' sequences diverge) and
-            // hand the status to a host that waits on the zero-copy slots; mppi_fetch_action reports MPPI_ERR_COMM and
-            // clears the word
-            if (p.next_host != nullptr && (tid < A || tid == 8)) {
-                unsigned int *slot = reinterpret_cast<unsigned int *>(p.next_host) + 2 * tid;
-                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(tid == 8 ? 1u : 0u), "r"(p.done_epoch) : "memory");
-            }
+        trace_stamp(p, ctrl, 5);
+        if (p.world > 1 && !p.peer_on) {        // NCCL / caller-side exchange: the payload, then finish_kernel
+            store_record(p.payload + (size_t)ctrl * stride, m.beta, m.eta);
             return;
         }
-        const float *mail = p.peer_mail[p.rank] + ((size_t)par * world * p.n_ctrl + ctrl) * stride;
-        Merged mw = merge_parts(mail, (size_t)p.n_ctrl * stride, world, TA, p.neg_inv_lambda_log2e, sN, sScale, sRed,
-                                sScratch, scratch_f4);
-        apply_update<A, PHILOX>(p, ctrl, mw, sN, sWork);
-        trace_stamp(p, ctrl, 7);
-        return;
+        if (p.world > 1) {
+            // Fused exchange: this CTA writes the rank payload straight into every rank's mailbox over NVLink,
+            // raises its flag there, waits for the other ranks' flags in its own mailbox and finishes the update
+            // in the same launch - no collective call, no second kernel.  Buffers alternate with the epoch's
+            // parity, so a rank that races ahead cannot overwrite a payload that is still being read.
+            const int world = p.world;
+            const uint32_t par = p.epoch & 1u;
+            const size_t slot = ((size_t)par * world + p.rank) * p.n_ctrl + ctrl;
+#pragma unroll 1
+            for (int r = 0; r < world; r++) store_record(p.peer_mail[r] + slot * stride, m.beta, m.eta);
+            __syncthreads();
+            if (tid < world) {
+                __threadfence_system();         // cumulative over the CTA's stores (ordered by the barrier)
+                st_release_sys(p.peer_flag[tid] + slot, p.epoch);
+                const uint32_t *f = p.peer_flag[p.rank] + (((size_t)par * world + tid) * p.n_ctrl + ctrl);
+                const long long t0 = clock64();
+                while (ld_acquire_sys(f) != p.epoch) {
+                    if (clock64() - t0 > (1LL << 31)) {            // about a second: a rank is missing, do not hang the GPU
+                        atomicExch(p.peer_status, 1u);
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+            trace_stamp(p, ctrl, 6);
+            if (*reinterpret_cast<volatile unsigned int *>(p.peer_status) != 0u) {
+                // a payload is missing: leave U untouched (merging a stale mailbox would let the ranks' sequences diverge) and
+                // hand the status to a host that waits on the zero-copy slots; mppi_fetch_action reports MPPI_ERR_COMM and
+                // clears the word
+                if (p.next_host != nullptr && (tid < A || tid == 8)) {
+                    unsigned int *slot = reinterpret_cast<unsigned int *>(p.next_host) + 2 * tid;
+                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(tid == 8 ? 1u : 0u), "r"(p.done_epoch) : "memory");
+                }
+                return;
+            }
+            const float *mail = p.peer_mail[p.rank] + ((size_t)par * world * p.n_ctrl + ctrl) * stride;
+            m = merge_parts(mail, (size_t)p.n_ctrl * stride, world, TA, p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
+        }
     }
-    if (p.world > 1) {
-        float *pay = p.payload + (size_t)ctrl * stride;
-        if (threadIdx.x == 0) { pay[0] = m.beta; pay[1] = m.eta; pay[2] = 0.f; pay[3] = 0.f; }
-        for (int j = threadIdx.x; j < stride - 4; j += blockDim.x) pay[4 + j] = (j < TA) ? sN[j] : 0.f;
-        return;
-    }
-    apply_update<A, PHILOX>(p, ctrl, m, sN, sWork);
+    apply_update<A, PHILOX>(p, ctrl, m, sN, sWork);      // the one copy of it
     trace_stamp(p, ctrl, 7);
 }
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of the library in _build_alt (previous) against _build (current): event-timed updates and phase traces
 mkdir -p gpurun_out
-python -m pytest tests/test_train_gpu.py -q -m gpu -s 2>&1 | grep -i "movement\|passed\|failed"
+python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 for v in _build_alt _build; do
   export MPPI_B200_LIB=$PWD/mppi_tf_b200/$v/libmppi_b200.so
   for W in "--k-override 131072:shard" ":full" "--workload cfg2:cfg2" "--workload cfg1:cfg1" "--workload cfg5:cfg5"; do
