@@ -81,9 +81,9 @@ __device__ __forceinline__ void fast_terminal(const Vec<A> &P, const Vec<A> &V, 
 //   sD   scratch, >= (3 A + 1) T floats: U staged [T][A], then D_p / D_v of steps 1..T [T][2A], then T partial sums
 //   sRed scratch, >= 1 float
 // Philox mode: L = G + w_scale z_scale U (n = z / z_scale); injected mode: L = G + lambda Sigma^-T U (n = eps).
-// The forward (noise-free trajectory) and backward (adjoint) passes are the model's own recurrences, one thread per
-// axis — 2T dependent steps of two or three FMAs, about a microsecond at T = 100 — and the sum C = sum_t w_t |D_t|^2
-// is taken over per-step partials in a fixed order.  Returns C (without C0), CTA-uniform.
+// The forward (noise-free trajectory) and backward (adjoint) passes are the model's own recurrences, one warp per axis
+// as a blocked scan, and the sum C = sum_t w_t |D_t|^2 is taken over per-step partials in a fixed order.
+// Returns C (without C0), CTA-uniform.
 template <int A, bool PHILOX>
 __device__ __forceinline__ float build_linear_tables(const RolloutParams &p, int ctrl, float *sL, float *sD, float *sRed)
 {
@@ -93,77 +93,106 @@ __device__ __forceinline__ float build_linear_tables(const RolloutParams &p, int
     float *sU = sD;                                   // [T][A]
     float *sDev = sD + A * T;                         // [T][2A]: D_p[A], D_v[A] of step t + 1
     float *sC = sDev + 2 * A * T;                     // [T]
-    // goal and state of this thread's axis: loaded before the barrier, together with the sequence (one L2 round trip)
-    float gpj = 0.f, gvj = 0.f, pj = 0.f, vj = 0.f;
-    if (tid < A) {
-        const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * 2 * A : 0);
-        const float *xp = p.x + (size_t)ctrl * 2 * A;
-        gpj = gp[2 * tid];
-        gvj = gp[2 * tid + 1];
-        pj = p.x_inline ? p.x0[2 * tid] : xp[2 * tid];
-        vj = p.x_inline ? p.x0[2 * tid + 1] : xp[2 * tid + 1];
+    // Both passes are the model's own recurrences (src/model_base.cpp:53-82 forward, its adjoint backward), one warp per
+    // axis, as a blocked scan: lane l owns the contiguous chunk of L = ceil(T/32) steps, runs it from a zero state, the 32
+    // chunk responses are composed by a warp scan of the affine maps (x -> M^n x + b with M^n = [[1, n dt], [0, 1]] forward,
+    // [[1, 0], [n a1, 1]] for the adjoint) and the lane replays its chunk from its true incoming state: 2 L + 5 dependent
+    // steps per pass instead of T (T = 100: 13).
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5, L = (T + 31) >> 5;
+    // goal and state of the warp's first axis: loaded before the barrier, together with the sequence (one L2 round trip)
+    const float *gp = p.goal + (p.goal_per_ctrl ? (size_t)ctrl * 2 * A : 0);
+    const float *xp = p.x + (size_t)ctrl * 2 * A;
+    float gp0 = 0.f, gv0 = 0.f, p0 = 0.f, v0 = 0.f;
+    if (warp < A) {
+        gp0 = gp[2 * warp];
+        gv0 = gp[2 * warp + 1];
+        p0 = p.x_inline ? p.x0[2 * warp] : xp[2 * warp];
+        v0 = p.x_inline ? p.x0[2 * warp + 1] : xp[2 * warp + 1];
     }
     for (int i = tid; i < T * A; i += nthr) sU[i] = U[i];
     for (int i = tid; i < T * RS; i += nthr) sL[i] = 0.f;
     __syncthreads();
-    if (tid < A) {
-        const int j = tid;
-        const float sqp = p.sqrt_q[2 * j], sqv = p.sqrt_q[2 * j + 1];
-        // forward: x' = A x + (B/m) U_t, exactly the model step (src/model_base.cpp:53-82); eight steps at a time so that the
-        // shared-memory loads of a chunk are in flight together (the recurrence itself is two dependent FMAs per step)
-        constexpr int CH = 8;
-        for (int t0 = 0; t0 < T; t0 += CH) {
-            float u[CH];
-#pragma unroll
-            for (int i = 0; i < CH; i++) u[i] = (t0 + i < T) ? sU[(t0 + i) * A + j] : 0.f;
-            float dp[CH], dv[CH];
-#pragma unroll
-            for (int i = 0; i < CH; i++) {
-                pj = fmaf(p.c_pu, u[i], fmaf(p.dt, vj, pj));
-                vj = fmaf(p.c_vu, u[i], vj);
-                dp[i] = sqp * (pj - gpj);
-                dv[i] = sqv * (vj - gvj);
-            }
-#pragma unroll
-            for (int i = 0; i < CH; i++)
-                if (t0 + i < T) {
-                    sDev[2 * (t0 + i) * A + j] = dp[i];
-                    sDev[(2 * (t0 + i) + 1) * A + j] = dv[i];
-                }
+    for (int j = warp; j < A; j += nwarp) {                            // warp-uniform
+        if (j != warp) {
+            gp0 = gp[2 * j];
+            gv0 = gp[2 * j + 1];
+            p0 = p.x_inline ? p.x0[2 * j] : xp[2 * j];
+            v0 = p.x_inline ? p.x0[2 * j + 1] : xp[2 * j + 1];
         }
-        // backward: aP_t = g_P,t + aP_{t+1}; aV_t = g_V,t + aV_{t+1} + a1 aP_{t+1}; g = 2 w_t D_t; G_tau = b1 aP_{tau+1} + b2 aV_{tau+1}
+        const float sqp = p.sqrt_q[2 * j], sqv = p.sqrt_q[2 * j + 1];
+        const int t_lo = min(T, lane * L), t_hi = min(T, t_lo + L);      // this lane's steps [t_lo, t_hi)
+        // ---- forward: x' = A x + (B/m) U_t ------------------------------------------------------------------
+        float bp = 0.f, bv = 0.f;
+        for (int t = t_lo; t < t_hi; t++) {
+            const float u = sU[t * A + j];
+            bp = fmaf(p.c_pu, u, fmaf(p.dt, bv, bp));
+            bv = fmaf(p.c_vu, u, bv);
+        }
+        float sp = bp, sv = bv;                                         // inclusive scan: response of chunks 0 .. lane
+        int sn = t_hi - t_lo;                                           // ... and their step count
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float lp = __shfl_up_sync(0xffffffffu, sp, o), lv = __shfl_up_sync(0xffffffffu, sv, o);
+            const int ln = __shfl_up_sync(0xffffffffu, sn, o);
+            if (lane >= o) {                                            // left segment first, then (sp, sv, sn)
+                sp = sp + fmaf((float)sn * p.dt, lv, lp);
+                sv = sv + lv;
+                sn += ln;
+            }
+        }
+        {
+            float ip = __shfl_up_sync(0xffffffffu, sp, 1), iv = __shfl_up_sync(0xffffffffu, sv, 1);
+            if (lane == 0) { ip = 0.f; iv = 0.f; }
+            float pj = p0 + fmaf((float)t_lo * p.dt, v0, ip), vj = v0 + iv;     // state before step t_lo
+            for (int t = t_lo; t < t_hi; t++) {
+                const float u = sU[t * A + j];
+                pj = fmaf(p.c_pu, u, fmaf(p.dt, vj, pj));
+                vj = fmaf(p.c_vu, u, vj);
+                sDev[2 * t * A + j] = sqp * (pj - gp0);
+                sDev[(2 * t + 1) * A + j] = sqv * (vj - gv0);
+            }
+        }
+        __syncwarp();
+        // ---- backward (adjoint): aP_t = g_P,t + aP_{t+1}; aV_t = g_V,t + aV_{t+1} + a1 aP_{t+1}; g = 2 w_t D_t;
+        //      L_tau = b1 aP_{tau+1} + b2 aV_{tau+1} + (action-cost term).  Lane l walks steps t = T - l L down. ----------
         const float a1 = p.fa1[j], b1 = p.fb1[j], b2 = p.fb2[j];
-        float aP = 0.f, aV = 0.f;
-        for (int t0 = T; t0 >= 1; t0 -= CH) {                      // steps t0, t0-1, .. t0-CH+1
-            float dp[CH], dv[CH], lin[CH];
+        const int u_hi = max(0, T - lane * L), u_lo = max(0, u_hi - L);  // this lane's steps t in (u_lo, u_hi], downwards
+        float cP = 0.f, cV = 0.f;
+        for (int t = u_hi; t > u_lo; t--) {
+            const float w2 = (t == T) ? 4.f : 2.f;
+            const float dp = sDev[2 * (t - 1) * A + j], dv = sDev[(2 * (t - 1) + 1) * A + j];
+            cV = fmaf(a1, cP, fmaf(w2, dv, cV));
+            cP = fmaf(w2, dp, cP);
+        }
+        float aPs = cP, aVs = cV;
+        int an = u_hi - u_lo;
 #pragma unroll
-            for (int i = 0; i < CH; i++) {
-                const int t = t0 - i;
-                dp[i] = (t >= 1) ? sDev[2 * (t - 1) * A + j] : 0.f;
-                dv[i] = (t >= 1) ? sDev[(2 * (t - 1) + 1) * A + j] : 0.f;
-                lin[i] = 0.f;
-                if (t >= 1) {
-                    if (PHILOX) {
-                        lin[i] = p.w_scale * p.z_scale * sU[(t - 1) * A + j];
-                    } else {
-#pragma unroll
-                        for (int l = 0; l < A; l++) lin[i] = fmaf(p.lam_inv_sigma_T[j * A + l], sU[(t - 1) * A + l], lin[i]);
-                    }
-                }
+        for (int o = 1; o < 32; o <<= 1) {
+            const float lP = __shfl_up_sync(0xffffffffu, aPs, o), lV = __shfl_up_sync(0xffffffffu, aVs, o);
+            const int ln = __shfl_up_sync(0xffffffffu, an, o);
+            if (lane >= o) {                                            // earlier (higher-t) segment first
+                aVs = aVs + fmaf((float)an * a1, lP, lV);
+                aPs = aPs + lP;
+                an += ln;
             }
-            float Lv[CH];
-#pragma unroll
-            for (int i = 0; i < CH; i++) {
-                const int t = t0 - i;
+        }
+        {
+            float aP = __shfl_up_sync(0xffffffffu, aPs, 1), aV = __shfl_up_sync(0xffffffffu, aVs, 1);
+            if (lane == 0) { aP = 0.f; aV = 0.f; }
+            for (int t = u_hi; t > u_lo; t--) {
                 const float w2 = (t == T) ? 4.f : 2.f;
-                const float aPn = fmaf(w2, dp[i], aP);
-                aV = fmaf(a1, aP, fmaf(w2, dv[i], aV));
-                aP = aPn;
-                Lv[i] = fmaf(b1, aP, fmaf(b2, aV, lin[i]));
-            }
+                const float dp = sDev[2 * (t - 1) * A + j], dv = sDev[(2 * (t - 1) + 1) * A + j];
+                float lin = 0.f;
+                if (PHILOX) {
+                    lin = p.w_scale * p.z_scale * sU[(t - 1) * A + j];
+                } else {
 #pragma unroll
-            for (int i = 0; i < CH; i++)
-                if (t0 - i >= 1) sL[(t0 - i - 1) * RS + j] = Lv[i];
+                    for (int l = 0; l < A; l++) lin = fmaf(p.lam_inv_sigma_T[j * A + l], sU[(t - 1) * A + l], lin);
+                }
+                aV = fmaf(a1, aP, fmaf(w2, dv, aV));
+                aP = fmaf(w2, dp, aP);
+                sL[(t - 1) * RS + j] = fmaf(b1, aP, fmaf(b2, aV, lin));
+            }
         }
     }
     __syncthreads();
