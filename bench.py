@@ -14,7 +14,8 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   roofline           dominant kernel, effective HBM GB/s on the algorithmic bytes
   roofline_injected  the HBM-bound injected-noise kernel on the same workload (N = 1)
   dense_weights      the same workload with lambda large enough that every fp32 weight is non-zero (N = 1)
-  other_configs      BASELINE configs 1, 2, 4, 5 at their full sizes, ~20 updates each (N = 1)
+  other_configs      BASELINE configs 1, 2, 4, 5 at their full sizes, ~20 timed updates each, then a sampled burst of the
+                     same updates for `clocks` (SM clock, throttle reasons, peak power while that config runs) (N = 1)
   parity_check       N > 1: sequences bit-identical across ranks after the timed region, and a reduced-K sharded
                      update equal (1e-5) to a single-handle update on rank 0 that draws the same Philox stream
   cpu_baseline       the graph-faithful CPU port timed on this box (+ cpu_baseline_c: the OpenMP C restatement)
@@ -127,13 +128,17 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
+            try:
+                pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                pass
             for n, v in zip(names, r[5:9]):
                 if v.strip().lower() == "active":
                     reasons.add(n)
@@ -141,7 +146,7 @@ class ClockSampler:
             return None
         hi = [v for v in sm if v >= 0.5 * max(sm)]      # samples under load
         return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 def measured_traffic(workload, kernel):
@@ -422,10 +427,16 @@ def side_config(torch, name, dev_index, stream, flush, rounds, steps, peak, peak
         ctrl.setState(x)
         ms = time_updates(torch, ctrl, flush, steps, 5)
         m = statistics.mean(ms)
+        # clocks / power while this config runs: a sampled burst of >= 0.15 s of the same updates (nvidia-smi reports every 20 ms)
+        sampler = ClockSampler(dev_index)
+        sampler.start()
+        time.sleep(0.15)
+        time_updates(torch, ctrl, flush, int(min(2000, max(steps, 0.15 / (m * 1e-3 + 6e-5)))), 0)
+        side_clocks = sampler.stop()
         units = info["K"] * info["T"] * info["n_ctrl"]
         out = {"workload": WORKLOADS[name][0], "ms_per_step": m, "value": units / (m * 1e-3), "steps": steps, "lambda": lam,
                "roofline": roofline_of(name, info, m, peak, peak_src, philox_kernel_name(info, name)),
-               "nonzero_weight_frac": round(nonzero_weight_frac(ctrl, info["n_local"], lam), 4)}
+               "nonzero_weight_frac": round(nonzero_weight_frac(ctrl, info["n_local"], lam), 4), "clocks": side_clocks}
         if out["nonzero_weight_frac"] < 0.5:
             # almost every weight vanishes at lambda = 1 (costs spread over far more than 50 lambda): time the same workload
             # once more with lambda of the order of the cost spread, so that the weighted noise sum is not for free
