@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("n,a", [(257, 3), (4096, 3), (100, 1), (1000, 5)])
-def test_train_steps_match_oracle(n, a):
+def test_train_steps_unpinned_match_numpy_restatement(n, a):
     s = 2 * a
     mlp, x, u, xn = _problem(n + a, n=n, s=s, a=a)
     cfg = make_cfg(256, 4, s, a)

@@ -21,7 +21,7 @@ def _problem(seed=0, n=257, s=6, a=3, H=128):
     return mlp, x, u, xn
 
 
-def test_gradients_match_autograd():
+def test_unpinned_oracle_gradients_match_autograd():
     torch = pytest.importorskip("torch")
     mlp, x, u, xn = _problem()
     Xn, Yn = normalise(mlp, x, u, xn)
