@@ -269,7 +269,7 @@ __device__ __forceinline__ void mlp_mma_loop(MlpTile &t, int nsteps)
     for (int s = 0; s < nsteps; s++) {
         // layer 1: X[128 x 16] -> D (two N halves)
         MLP_TRACE(1, 0);
-        mbar_wait(&t.bars[kBarX], ph_x);
+        mbar_wait_spin(&t.bars[kBarX], ph_x);
         MLP_TRACE(1, 1);
         ph_x ^= 1;
         tc_fence_after();
@@ -282,13 +282,13 @@ __device__ __forceinline__ void mlp_mma_loop(MlpTile &t, int nsteps)
         __syncwarp();
         // layer 2: starts on K half 0 of A1 while the row warps still convert half 1
         MLP_TRACE(1, 2);
-        mbar_wait(&t.bars[kBarA0], ph_a);
+        mbar_wait_spin(&t.bars[kBarA0], ph_a);
         MLP_TRACE(1, 3);
         tc_fence_after();
         if (elect_one()) mlp_issue(t, kColD, kColA, kW1Bytes, kMlpSplitN ? 64 : 128, kMlpH, 0, KH0, true);
         __syncwarp();
         MLP_TRACE(1, 4);
-        mbar_wait(&t.bars[kBarA1], ph_a);
+        mbar_wait_spin(&t.bars[kBarA1], ph_a);
         MLP_TRACE(1, 5);
         ph_a ^= 1;
         tc_fence_after();
@@ -308,9 +308,9 @@ __device__ __forceinline__ void mlp_mma_loop(MlpTile &t, int nsteps)
         // output layer: one batch (nine tiny MMAs) once both K halves of A2 are in place - an early
         // start on half 0 would save 50 tensor cycles and cost a second issue batch (~200 cycles)
         MLP_TRACE(1, 6);
-        mbar_wait(&t.bars[kBarA0], ph_a);
+        mbar_wait_spin(&t.bars[kBarA0], ph_a);
         MLP_TRACE(1, 8);
-        mbar_wait(&t.bars[kBarA1], ph_a);
+        mbar_wait_spin(&t.bars[kBarA1], ph_a);
         MLP_TRACE(1, 9);
         ph_a ^= 1;
         tc_fence_after();
@@ -372,14 +372,14 @@ __device__ __forceinline__ void mlp_row_layer1(MlpTile &t, int part)
 {
     uint32_t o[16];
     MLP_TRACE(0, 2);
-    mbar_wait(&t.bars[kBarD0], t.ph_d);
+    mbar_wait_spin(&t.bars[kBarD0], t.ph_d);
     MLP_TRACE(0, 3);
     tc_fence_after();
     mlp_load_pack(t, 0, part, o);
     MLP_TRACE(0, 4);
     mlp_store_signal(t, 0, part, o);
     MLP_TRACE(0, 5);
-    mbar_wait(&t.bars[kBarD1], t.ph_d);
+    mbar_wait_spin(&t.bars[kBarD1], t.ph_d);
     MLP_TRACE(0, 6);
     tc_fence_after();
     mlp_load_pack(t, 1, part, o);
@@ -393,12 +393,12 @@ __device__ __forceinline__ void mlp_row_layer2(MlpTile &t, int part)
 {
     uint32_t o[16];
     MLP_TRACE(0, 8);
-    mbar_wait(&t.bars[kBarD0], t.ph_d);
+    mbar_wait_spin(&t.bars[kBarD0], t.ph_d);
     MLP_TRACE(0, 9);
     tc_fence_after();
     mlp_load_pack(t, 0, part, o);
     MLP_TRACE(0, 10);
-    mbar_wait(&t.bars[kBarD1], t.ph_d);
+    mbar_wait_spin(&t.bars[kBarD1], t.ph_d);
     MLP_TRACE(0, 11);
     tc_fence_after();
     mlp_store_signal(t, 0, part, o);
@@ -422,7 +422,7 @@ __device__ __forceinline__ void mlp_row_finish(MlpTile &t, float (&x)[S])
 {
     const float *ystd = t.fvec + 32, *ymean = t.fvec + 48;
     MLP_TRACE(0, 14);
-    mbar_wait(&t.bars[kBarD3], t.ph_d3);
+    mbar_wait_spin(&t.bars[kBarD3], t.ph_d3);
     MLP_TRACE(0, 15);
     t.ph_d3 ^= 1;
     tc_fence_after();
