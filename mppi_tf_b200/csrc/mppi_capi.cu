@@ -117,6 +117,7 @@ struct mppi_handle {
     // fused exchange over peer memory (mppi_peer_handle / mppi_peer_attach)
     void *d_mailbox = nullptr;            // [2][world][n_ctrl][stride] floats + [2][world][n_ctrl] epochs
     size_t mail_floats = 0;
+    size_t mail_ll_off = 0;               // byte offset of the tagged-word region inside the mailbox
     void *peer_base[kMaxWorld] = {nullptr};
     bool peer_opened[kMaxWorld] = {false};
     bool peer_on = false;
@@ -305,6 +306,7 @@ RolloutParams make_params(const mppi_handle *h, const float *eps_dev)
         for (int r = 0; r < h->world; r++) {
             p.peer_mail[r] = static_cast<float *>(h->peer_base[r]);
             p.peer_flag[r] = reinterpret_cast<uint32_t *>(static_cast<float *>(h->peer_base[r]) + h->mail_floats);
+            p.peer_ll[r] = reinterpret_cast<uint2 *>(static_cast<char *>(h->peer_base[r]) + h->mail_ll_off);
         }
         p.peer_status = h->d_peer_status;
     }
@@ -955,7 +957,9 @@ static int peer_alloc(mppi_handle *h)
     if (h->d_mailbox) return MPPI_OK;
     CU_TRY(h, cudaSetDevice(h->device));
     h->mail_floats = (size_t)2 * h->world * h->n_ctrl * h->stride;
-    const size_t bytes = sizeof(float) * h->mail_floats + sizeof(uint32_t) * 2 * h->world * h->n_ctrl;
+    // [float records + flags: the (min, max) exchange of a normalised update] [tagged words: the payload exchange]
+    h->mail_ll_off = (sizeof(float) * h->mail_floats + sizeof(uint32_t) * 2 * h->world * h->n_ctrl + 15) & ~(size_t)15;
+    const size_t bytes = h->mail_ll_off + sizeof(uint2) * h->mail_floats;
     CU_TRY(h, cudaMalloc(&h->d_mailbox, bytes));
     CU_TRY(h, cudaMemset(h->d_mailbox, 0, bytes));
     CU_TRY(h, cudaMalloc(&h->d_peer_status, sizeof(unsigned int)));

@@ -101,6 +101,7 @@ struct RolloutParams {
     uint32_t epoch;          // exchange epoch of this update (> 0, same on every rank); parity selects the buffer
     float *peer_mail[kMaxWorld];
     uint32_t *peer_flag[kMaxWorld];
+    uint2 *peer_ll[kMaxWorld];   // [2][world][n_ctrl][stride] tagged words {value, epoch}: the payload exchange (mppi_update.cuh)
     unsigned int *peer_status;   // set != 0 if a peer's payload did not arrive in time
     // zero-copy result (single controller): the finishing CTA also stores the action into mapped pinned host
     // memory and publishes `done_epoch`, so the synchronous next() needs neither a D2H copy nor a stream sync

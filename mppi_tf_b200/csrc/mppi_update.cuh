@@ -319,6 +319,108 @@ static __device__ MPPI_TAIL_FN Merged merge_parts(const float *parts, size_t par
     return Merged{beta, eta};
 }
 
+// -------------------------------------------------------------------------------------------------
+// Tagged words for the rank exchange: every 4-byte value of a rank payload travels over NVLink together with the
+// update's epoch in ONE 8-byte store (single-copy atomic), and the receiver polls the words in its own mailbox until
+// the epoch shows: no system fence (a round trip to the farthest peer) and no flag hand-over stand between the
+// sender's last store and the receiver's first load.  The region is zeroed at creation and epochs start at 1.
+// (The same scheme for the CTA records inside one GPU was measured slower than fence + atomic, section 3.4 of DESIGN.md.)
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ll_store(uint2 *dst, float v, uint32_t tag)
+{
+    asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+// two consecutive words {v0, tag0, v1, tag1}; src 16-byte aligned
+__device__ __forceinline__ uint4 ll_load2(const uint2 *src)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
+    return v;
+}
+// Polls until both words carry `tag`; after about a second the status word is raised and the poll gives up.
+__device__ __forceinline__ uint4 ll_wait2(const uint2 *src, uint4 v, uint32_t tag, unsigned int *status)
+{
+    if (v.y == tag && v.w == tag) return v;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (;;) {
+        v = ll_load2(src);
+        if (v.y == tag && v.w == tag) return v;
+        if (clock64() - t0 > (1LL << 31)) {
+            atomicExch(status, 1u);
+            return v;
+        }
+    }
+}
+// Merge of the `world` rank payloads in this rank's mailbox (tagged words), polling for them.  Same result contract as
+// merge_parts; records are added in rank order per column (independent of the CTA size, identical on every rank).
+static __device__ MPPI_TAIL_FN Merged merge_world_ll(const uint2 *base, size_t rec_stride, uint32_t tag, unsigned int *status, int world,
+                                                     int TA, float neg_inv_lambda_log2e, float *sN)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ncol4 = (TA + 3) >> 2;
+    // requested together: (beta, eta) of rank `lane` (every warp) and the first four ranks' words of this thread's column quad
+    uint4 hraw = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < world) hraw = ll_load2(base + (size_t)lane * rec_stride);
+    uint4 ra[4], rb[4];
+    if (tid < ncol4) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (q < world) {
+                const uint2 *src = base + (size_t)q * rec_stride + 4 + 4 * tid;
+                ra[q] = ll_load2(src);
+                rb[q] = ll_load2(src + 2);
+            }
+    }
+    float b = kInf, e = 0.f;
+    if (lane < world) {
+        const uint4 h = ll_wait2(base + (size_t)lane * rec_stride, hraw, tag, status);
+        b = __uint_as_float(h.x);
+        e = __uint_as_float(h.z);
+    }
+    const float beta = warp_min(b);
+    const float sc_lane = (b == kInf) ? 0.f : weight_exp(b, beta, neg_inv_lambda_log2e);
+    const float eta = warp_sum(sc_lane * e);
+#pragma unroll 1
+    for (int c0 = 0; c0 < ncol4; c0 += blockDim.x) {          // warp-uniform trip count (the weights travel by shuffle)
+        const int c4 = c0 + tid;
+        const bool live = c4 < ncol4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int r0 = 0; r0 < world; r0 += 4) {
+            if (live && (c0 | r0) != 0) {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (r0 + q < world) {
+                        const uint2 *src = base + (size_t)(r0 + q) * rec_stride + 4 + 4 * c4;
+                        ra[q] = ll_load2(src);
+                        rb[q] = ll_load2(src + 2);
+                    }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const bool on = r0 + q < world;                // warp-uniform
+                if (!on) continue;
+                const float w = __shfl_sync(0xffffffffu, sc_lane, r0 + q);
+                if (live) {
+                    const uint2 *src = base + (size_t)(r0 + q) * rec_stride + 4 + 4 * c4;
+                    const uint4 a = ll_wait2(src, ra[q], tag, status), bb = ll_wait2(src + 2, rb[q], tag, status);
+                    acc.x = fmaf(w, __uint_as_float(a.x), acc.x); acc.y = fmaf(w, __uint_as_float(a.z), acc.y);
+                    acc.z = fmaf(w, __uint_as_float(bb.x), acc.z); acc.w = fmaf(w, __uint_as_float(bb.z), acc.w);
+                }
+            }
+        }
+        if (live) {
+            const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (4 * c4 + i < TA) sN[4 * c4 + i] = a4[i];
+        }
+    }
+    __syncthreads();
+    return Merged{beta, eta};
+}
+
 // U' = U + Delta (src/controller_base.cpp:223), next = U'[0] (:327-329), U <- [U'[1:], 0] (:310-324).
 // In Philox mode sN holds sum e z, so Delta_t = Sigma (sN_t) / eta; injected mode sums eps directly.
 template <int A, bool PHILOX>
@@ -472,29 +574,24 @@ __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_
             return;
         }
         if (p.world > 1) {
-            // Fused exchange: this CTA writes the rank payload straight into every rank's mailbox over NVLink,
-            // raises its flag there, waits for the other ranks' flags in its own mailbox and finishes the update
-            // in the same launch - no collective call, no second kernel.  Buffers alternate with the epoch's
-            // parity, so a rank that races ahead cannot overwrite a payload that is still being read.
+            // Fused exchange: this CTA writes the rank payload as tagged words straight into every rank's mailbox over
+            // NVLink, polls its own mailbox for the other ranks' words and finishes the update in the same launch - no
+            // collective call, no second kernel, no system fence, no flag.  Buffers alternate with the epoch's parity, so
+            // a rank that races ahead (by at most one update: its next exchange needs this rank's next payload) cannot
+            // overwrite words that are still being read.
             const int world = p.world;
             const uint32_t par = p.epoch & 1u;
             const size_t slot = ((size_t)par * world + p.rank) * p.n_ctrl + ctrl;
 #pragma unroll 1
-            for (int r = 0; r < world; r++) store_record(p.peer_mail[r] + slot * stride, m.beta, m.eta);
-            __syncthreads();
-            if (tid < world) {
-                __threadfence_system();         // cumulative over the CTA's stores (ordered by the barrier)
-                st_release_sys(p.peer_flag[tid] + slot, p.epoch);
-                const uint32_t *f = p.peer_flag[p.rank] + (((size_t)par * world + tid) * p.n_ctrl + ctrl);
-                const long long t0 = clock64();
-                while (ld_acquire_sys(f) != p.epoch) {
-                    if (clock64() - t0 > (1LL << 31)) {            // about a second: a rank is missing, do not hang the GPU
-                        atomicExch(p.peer_status, 1u);
-                        break;
-                    }
-                }
+            for (int r = 0; r < world; r++) {
+                uint2 *dst = p.peer_ll[r] + slot * stride;
+#pragma unroll 1
+                for (int j = tid; j < stride; j += blockDim.x)
+                    ll_store(dst + j, j == 0 ? m.beta : (j == 1 ? m.eta : ((j >= 4 && j - 4 < TA) ? sN[j - 4] : 0.f)), p.epoch);
             }
-            __syncthreads();
+            __syncthreads();                    // the payload has been read out of sN
+            m = merge_world_ll(p.peer_ll[p.rank] + ((size_t)par * world * p.n_ctrl + ctrl) * stride, (size_t)p.n_ctrl * stride, p.epoch,
+                               p.peer_status, world, TA, p.neg_inv_lambda_log2e, sN);
             trace_stamp(p, ctrl, 6);
             if (*reinterpret_cast<volatile unsigned int *>(p.peer_status) != 0u) {
                 // a payload is missing: leave U untouched (merging a stale mailbox would let the ranks' sequences diverge) and
@@ -506,8 +603,6 @@ __device__ void publish_and_finish(const RolloutParams &p, int ctrl, float beta_
                 }
                 return;
             }
-            const float *mail = p.peer_mail[p.rank] + ((size_t)par * world * p.n_ctrl + ctrl) * stride;
-            m = merge_parts(mail, (size_t)p.n_ctrl * stride, world, TA, p.neg_inv_lambda_log2e, sN, sScale, sRed, sScratch, scratch_f4);
         }
     }
     apply_update<A, PHILOX>(p, ctrl, m, sN, sWork);      // the one copy of it
