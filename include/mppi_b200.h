@@ -203,8 +203,9 @@ int mppi_comm_unique_id(void *id128);
 int mppi_comm_init(mppi_handle *h, const void *id128);
 
 /* Fused exchange over peer memory (one box, NVLink / NVSwitch): instead of all-gather + finish, the last CTA
- * of the update kernel stores its payload into every rank's mailbox, signals, waits for the other ranks'
- * payloads and finishes the update in the same launch.  Every rank exports the 64-byte CUDA IPC handle of
+ * of the update kernel stores its payload into every rank's mailbox (every word together with the update's epoch in
+ * one 8-byte store: no fence, no flag), polls its own mailbox for the other ranks' payloads and finishes the update
+ * in the same launch.  Every rank exports the 64-byte CUDA IPC handle of
  * its mailbox (mppi_peer_handle), the caller all-gathers them (any host channel) and every rank attaches the
  * world handles in rank order (mppi_peer_attach; world <= MPPI_MAX_PEERS, one process per GPU).  After a
  * successful attach mppi_next needs no exchange call, and mppi_enqueue_exchange / _finish are no-ops.

@@ -96,7 +96,8 @@ struct RolloutParams {
     unsigned int *counters;  // [n_ctrl][1 + max_groups] last-CTA election: top level, then one counter per merge group
     const float *eps;        // injected noise [n_ctrl][K_local][T][a] or nullptr
     // fused exchange over peer memory (world > 1, mppi_peer_attach): every rank's mailbox
-    //   mail [2][world][n_ctrl][stride] floats, flag [2][world][n_ctrl] epochs, mapped into this process
+    //   mail [2][world][n_ctrl][stride] floats + flag [2][world][n_ctrl] epochs (the (min, max) exchange of a normalised update),
+    //   then the tagged words of the payload exchange; mapped into this process
     int peer_on, rank;
     uint32_t epoch;          // exchange epoch of this update (> 0, same on every rank); parity selects the buffer
     float *peer_mail[kMaxWorld];
