@@ -337,7 +337,8 @@ __device__ __forceinline__ uint4 ll_load2(const uint2 *src)
     asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
     return v;
 }
-// Polls until both words carry `tag`; after about a second the status word is raised and the poll gives up.
+// Polls until both words carry `tag`; after about a second the status word is raised and the poll gives up - and so does
+// every later poll of the CTA at once (a missing rank costs one timeout, not one per word).
 __device__ __forceinline__ uint4 ll_wait2(const uint2 *src, uint4 v, uint32_t tag, unsigned int *status)
 {
     if (v.y == tag && v.w == tag) return v;
@@ -346,7 +347,7 @@ __device__ __forceinline__ uint4 ll_wait2(const uint2 *src, uint4 v, uint32_t ta
     for (;;) {
         v = ll_load2(src);
         if (v.y == tag && v.w == tag) return v;
-        if (clock64() - t0 > (1LL << 31)) {
+        if (clock64() - t0 > (1LL << 31) || *reinterpret_cast<volatile unsigned int *>(status) != 0u) {
             atomicExch(status, 1u);
             return v;
         }
